@@ -1,0 +1,193 @@
+/* milb200.h — C ABI of the B200 (sm_100a) MIL-aggregator kernel library (libmilb200.so).
+ *
+ * The reference (KyleKWKim/LLM-guided-Multimodal-MIL) is pure Python: its "operator API" for this
+ * path is torch.nn.Linear / torch.softmax / torch.matmul / nn.LayerNorm called from nn.Modules
+ * (SURVEY.md §1, §8b).  There is no FFI upstream; each entry point below names the reference lines
+ * whose eager-PyTorch ops it replaces.  The Python host (package mil_b200) binds these with ctypes and
+ * wraps them in torch.autograd.Functions behind the reference's nn.Module interfaces.
+ *
+ * Conventions (all entry points)
+ *   - plain C: raw device pointers, sizes, a cudaStream_t passed as void*; no torch types.
+ *   - the caller allocates every output and the workspace (query sizes with *_workspace_bytes);
+ *     kernels never malloc/free and never synchronise; all work is enqueued on `stream`.
+ *   - return 0 on success, a negative MILB200_E* code otherwise; milb200_last_error() gives the text
+ *     (thread-local).  Nothing is launched when an argument check fails.
+ *   - matrices are row-major and densely packed unless a leading dimension is given.
+ *   - dtype: MILB200_F32 (SIMT fp32 kernels, <=1e-5 parity) or MILB200_BF16 (tcgen05/TMEM/TMA kernels,
+ *     fp32 accumulate).  Scores, statistics and all gradients of parameters are fp32.
+ *   - ragged bags: packed rows X[total_n, L] + CSR offsets[B+1] (int32, offsets[0]=0, non-decreasing,
+ *     offsets[B]=total_n; every bag non-empty).
+ */
+#ifndef MILB200_H_
+#define MILB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MILB200_VERSION 100
+
+enum { MILB200_F32 = 0, MILB200_BF16 = 1 };
+
+enum {
+  MILB200_OK = 0,
+  MILB200_EINVAL = -1,      /* bad shape / null pointer / unsupported size */
+  MILB200_EALIGN = -2,      /* pointer or row pitch not 16-byte aligned */
+  MILB200_EWORKSPACE = -3,  /* workspace too small */
+  MILB200_ECUDA = -4,       /* CUDA runtime / launch error */
+  MILB200_EUNSUPPORTED = -5 /* dtype/shape combination not built */
+};
+
+enum { MILB200_ACT_NONE = 0, MILB200_ACT_TANH = 1, MILB200_ACT_RELU = 2, MILB200_ACT_SIGMOID = 3 };
+
+int milb200_version(void);
+const char* milb200_last_error(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t milb200_launch_count(void);
+
+/* ---- gated-attention scores -------------------------------------------------------------------
+ * Replaces ABMIL.forward's attention_V / attention_U / attention_weights chain
+ * (model/dim1/ABMIL.py:52-54): s_i = (tanh(x_i Wv^T + bv) * sigmoid(x_i Wu^T + bu)) . ww + bw.
+ * Packed gate weights: Wcat[2D, L] rows [0,D) = attention_V.0.weight, rows [D,2D) = attention_U.0.weight
+ * (dtype of X); bcat[2D] fp32; ww[D] fp32 (attention_weights.weight row); bw[1] fp32 on device.       */
+int milb200_pack_gate_weights(const void* Wv, const void* Wu, const void* bv, const void* bu,
+                              int src_dtype, int L, int D, void* Wcat, int dst_dtype, float* bcat,
+                              void* stream);
+
+size_t milb200_gated_score_workspace_bytes(int64_t total_n, int L, int D, int dtype, int backward);
+
+int milb200_gated_score_fwd(const void* X, const void* Wcat, const float* bcat, const float* ww,
+                            const float* bw, float* scores, int64_t total_n, int L, int D, int dtype,
+                            void* workspace, size_t ws_bytes, void* stream);
+
+/* Backward of the line above (autograd of ABMIL.py:52-54).  dscores[total_n] is dL/ds.
+ * Recomputes V,U from X (nothing but s is kept from forward).  Outputs (fp32, overwritten):
+ * dWcat[2D,L], dbcat[2D], dww[D], dbw[1].  If dX != NULL it receives
+ *   dX_i = attn_i * dM[bag(i)] + dVpre_i Wv + dUpre_i Wu      (dtype of X)
+ * where attn/dM/offsets describe the pooling term (pass attn=NULL to get the GEMM term only).       */
+int milb200_gated_score_bwd(const void* X, const void* Wcat, const float* bcat, const float* ww,
+                            const float* bw, const float* dscores, const float* attn,
+                            const float* dM, const int32_t* offsets, int B, int64_t total_n, int L,
+                            int D, int dtype, float* dWcat, float* dbcat, float* dww, float* dbw,
+                            void* dX, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- ragged segmented softmax + attention-weighted instance sum ---------------------------------
+ * Replaces F.softmax(A, dim=1) and torch.matmul(A, x) (model/dim1/ABMIL.py:56-59), one launch for a
+ * whole CSR batch: M[b] = sum_i softmax_b(s)_i x_i.  Outputs: M[B,L] fp32; M_lowp[B,L] in X's dtype
+ * (may be NULL); argmax[B] int32 = index *within the bag* of the largest score, first index on ties
+ * (may be NULL); lse[B] fp32 = log sum exp of the bag's scores (may be NULL).                       */
+size_t milb200_pool_workspace_bytes(int64_t total_n, int B, int L);
+
+int milb200_segment_softmax_pool_fwd(const void* X, const float* scores, const int32_t* offsets, int B,
+                                     int64_t total_n, int L, int dtype, float* M, void* M_lowp,
+                                     int32_t* argmax, float* lse, void* workspace, size_t ws_bytes,
+                                     void* stream);
+
+/* Backward of the pooling w.r.t. the scores (and the attention weights needed for dX):
+ *   attn_i = softmax_b(s)_i (recomputed from s),  dscores_i = attn_i * (dM_b . x_i - dM_b . M_b).
+ * dM, M are [B,L] fp32.  attn (fp32[total_n]) may be NULL.                                          */
+int milb200_segment_softmax_pool_bwd(const void* X, const float* scores, const int32_t* offsets, int B,
+                                     int64_t total_n, int L, int dtype, const float* dM, const float* M,
+                                     float* dscores, float* attn, void* workspace, size_t ws_bytes,
+                                     void* stream);
+
+/* ---- dense linear layers ------------------------------------------------------------------------
+ * Y[m,n] = act(X[m,k] W[n,k]^T + bias[n])  — nn.Linear (+Tanh/ReLU) as used by fc_pathology,
+ * fc_CI2CT/fc_CI2Pth (model/aggregator.py:44,47,66), q/k/v/out projections
+ * (model/sam/transformer.py:430-432,448) and MLPBlock (model/sam/common.py:26).
+ * X, W, Y share `dtype`; bias fp32 (may be NULL).  If `add` != NULL the input is (X + add) — the
+ * `keys + key_pe` / `queries + query_pe` sums of transformer.py:291-292,303-304 fused into the load
+ * (fp32 path only; the bf16 path needs it pre-added).                                               */
+size_t milb200_linear_workspace_bytes(int64_t m, int n, int k, int dtype, int backward);
+
+int milb200_linear_fwd(const void* X, const void* add, const void* W, const float* bias, void* Y,
+                       int64_t m, int n, int k, int act, int dtype, void* workspace, size_t ws_bytes,
+                       void* stream);
+
+/* Backward: given dY (dtype) and the forward OUTPUT Y (for the activation derivative; unused for
+ * ACT_NONE), computes dX[m,k] (dtype, may be NULL), dW[n,k] fp32, dbias[n] fp32 (may be NULL).
+ * If accumulate != 0, dW/dbias are added to instead of overwritten.                                 */
+int milb200_linear_bwd(const void* X, const void* add, const void* W, const void* Y, const void* dY,
+                       void* dX, float* dW, float* dbias, int64_t m, int n, int k, int act, int dtype,
+                       int accumulate, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- LayerNorm over the last dim (nn.LayerNorm, eps 1e-5; transformer.py:288,295,300,307,118) ----
+ * Y = LN(X + R) * gamma + beta, R optional residual (may be NULL).  mean/rstd[m] fp32 are saved.    */
+int milb200_layernorm_fwd(const void* X, const void* R, const float* gamma, const float* beta, void* Y,
+                          float* mean, float* rstd, int64_t m, int n, int dtype, void* stream);
+/* dXR = dL/d(X+R) (same for both addends); dgamma/dbeta fp32[n] overwritten (or added to).          */
+int milb200_layernorm_bwd(const void* X, const void* R, const float* gamma, const float* mean,
+                          const float* rstd, const void* dY, void* dXR, float* dgamma, float* dbeta,
+                          int64_t m, int n, int dtype, int accumulate, void* workspace, size_t ws_bytes,
+                          void* stream);
+size_t milb200_layernorm_workspace_bytes(int64_t m, int n);
+
+/* ---- multi-head attention core (transformer.py:434-446): O = softmax(Q K^T / sqrt(c)) V per head ---
+ * Q[nq, H*c], K[nk, H*c], V[nk, H*c], O[nq, H*c] (dtype); lse[H, nq] fp32 saved for backward.
+ * One of nq / nk is small (text tokens, <= 16) on this path; both orientations are covered.          */
+size_t milb200_attention_workspace_bytes(int64_t nq, int64_t nk, int heads, int c, int backward);
+int milb200_attention_fwd(const void* Q, const void* K, const void* V, void* O, float* lse, int64_t nq,
+                          int64_t nk, int heads, int c, int dtype, void* workspace, size_t ws_bytes,
+                          void* stream);
+int milb200_attention_bwd(const void* Q, const void* K, const void* V, const void* O, const float* lse,
+                          const void* dO, void* dQ, void* dK, void* dV, int64_t nq, int64_t nk, int heads,
+                          int c, int dtype, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- CLIP-style logits and small losses -----------------------------------------------------------
+ * clip/model.py:359-365: logits_per_image = exp(logit_scale) * norm(I) norm(T)^T  ([bi,bt] fp32).    */
+int milb200_clip_logits_fwd(const void* I, const void* T, const float* logit_scale, float* logits,
+                            float* inv_norm_i, float* inv_norm_t, int bi, int bt, int d, int dtype,
+                            void* stream);
+int milb200_clip_logits_bwd(const void* I, const void* T, const float* logit_scale, const float* logits,
+                            const float* inv_norm_i, const float* inv_norm_t, const float* dlogits,
+                            void* dI, void* dT, float* dscale, int bi, int bt, int d, int dtype,
+                            void* stream);
+/* utils.py:277-282 (CLIPloss_v1): logits[i] = out @ feat[:,i,:]^T ([I,b,b]), CE over dim 1 against the
+ * identity, mean over I*b.  out[b,d] (dtype), feat[b,I,d] (dtype, frozen).  loss[1], dout[b,d] fp32.  */
+int milb200_cliploss_fwd_bwd(const void* out, const void* feat, float* logits, float* loss, float* dout,
+                             int b, int n_info, int d, int dtype, void* stream);
+/* sigmoid + BCELoss(mean) of aggregator.py:200 / train_ddp.py:99,319: prob = sigmoid(z),
+ * loss = mean BCE(prob, target), dz = (prob - target)/numel.  z,target,prob,dz fp32[n].             */
+int milb200_sigmoid_bce_fwd_bwd(const float* z, const float* target, float* prob, float* loss, float* dz,
+                                int n, void* stream);
+
+/* M[b] = sum_i x_i over CSR offsets, no softmax: what the reference computes when ABMIL.forward is handed a
+ * dense batch B>1 (softmax over the size-1 K axis, model/dim1/ABMIL.py:48,56-59) and in SwinUNETR_wMask's
+ * 3-crop pool (model/dim3/swinUNETR_wMask.py:60-67).  Workspace: milb200_pool_workspace_bytes.            */
+int milb200_segment_sum_fwd(const void* X, const int32_t* offsets, int B, int64_t total_n, int L, int dtype,
+                            float* M, void* M_lowp, void* workspace, size_t ws_bytes, void* stream);
+/* out[i,:] = (w ? w[i] : 1) * src[bag(i),:]  (src fp32 [B,L], out [total_n,L] in dtype): backward of the
+ * sum pool, and the a_i * dM term of the gated pool's dX.                                                */
+int milb200_bag_broadcast(const float* src, const float* w, const int32_t* offsets, int B, int64_t total_n,
+                          int L, int dtype, void* out, void* stream);
+
+/* ---- elementwise glue -----------------------------------------------------------------------------*/
+/* nn.Dropout(p) in train mode (ABMIL.py:49; aggregator.py:129): out = keep ? x/(1-p) : 0.  The Philox4x32-10
+ * mask is a pure function of (seed, offset, element index): the same call on a gradient is the backward,
+ * nothing is stored.  It cannot reproduce torch's own mask bit for bit.                       */
+int milb200_dropout(const void* x, void* out, int64_t n, float p, uint64_t seed, uint64_t offset, int dtype,
+                    void* stream);
+/* dtype conversion fp32 <-> bf16 and a 2-D transpose out[cols,rows] = in[rows,cols]^T (weight repacking).  */
+int milb200_cast(const void* in, int src_dtype, void* out, int dst_dtype, int64_t n, void* stream);
+int milb200_transpose(const void* in, void* out, int rows, int cols, int dtype, void* stream);
+/* out = a + b (broadcast none); any of the three dtypes per `dtype`. (keys + key_pe, residual adds)   */
+int milb200_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
+/* on-device sinusoidal table pe[n_pos, dim] (model/aggregator.py:99-106), written in `dtype`.         */
+int milb200_sinusoid_pe(void* pe, int64_t n_pos, int dim, int dtype, void* stream);
+/* (B,C,T,H*W) -> (T,C) mean over the trailing axis then transpose (transformer.py:93), fwd and bwd.    */
+int milb200_ct_tokens_fwd(const void* fmap, void* tokens, int c, int t, int hw, int dtype, void* stream);
+int milb200_ct_tokens_bwd(const void* dtokens, void* dfmap, int c, int t, int hw, int dtype, void* stream);
+
+/* ---- optimiser (train_ddp.py:111-118): fused Adam over one flat fp32 buffer -----------------------
+ * g is first scaled by grad_scale (1/world after the NCCL sum = DDP's average).                      */
+int milb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                      float lr, float beta1, float beta2, float eps, float weight_decay,
+                      float grad_scale, int step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MILB200_H_ */

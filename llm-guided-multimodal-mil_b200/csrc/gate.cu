@@ -1,0 +1,441 @@
+// gate.cu — C-ABI entry points for the gated-attention score (ABMIL.py:52-54) forward/backward and for
+// the dense linear layers (nn.Linear sites of aggregator.py / sam/transformer.py), dispatching between
+// the tcgen05 kernels (bf16) and the FFMA kernels (fp32, or shapes the tensor-core tiles do not cover).
+#include <algorithm>
+
+#include "simt_gemm.cuh"
+#include "tc_gemm.cuh"
+
+namespace milb200 {
+
+bool force_simt();
+int transpose2d(const void* in, void* out, int rows, int cols, int dtype, cudaStream_t st);
+
+constexpr int64_t SIMT_ROW_CHUNK = 32768;  // bounds the fp32 pre-activation workspace of the FFMA path
+
+// ---- FFMA-path gate kernels (one warp per instance) -------------------------------------------
+__global__ void __launch_bounds__(256)
+k_gate_fwd(const float* __restrict__ Z, const float* __restrict__ ww, const float* __restrict__ bw,
+           float* __restrict__ scores, int64_t rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* z = Z + r * 2 * D;
+  float p = 0.f;
+  for (int d = lane; d < D; d += 32) p = fmaf(tanhf(z[d]) * sigmoid_precise(z[D + d]), __ldg(ww + d), p);
+  p = warp_sum(p);
+  if (lane == 0) scores[r] = p + __ldg(bw);
+}
+
+constexpr int GATE_MAX_DPL = 8;  // D <= 256 on the FFMA path
+
+// in place: Z (pre-activations, bias included) -> dZ = [dVpre | dUpre]; column sums accumulate atomically
+__global__ void __launch_bounds__(256)
+k_gate_bwd(float* __restrict__ Z, const float* __restrict__ ww, const float* __restrict__ dscores, int64_t rows, int D,
+           float* __restrict__ dbcat, float* __restrict__ dww, float* __restrict__ dbw) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * 8;
+  float sv[GATE_MAX_DPL], su[GATE_MAX_DPL], sw[GATE_MAX_DPL];
+#pragma unroll
+  for (int j = 0; j < GATE_MAX_DPL; ++j) sv[j] = su[j] = sw[j] = 0.f;
+  float sds = 0.f;
+  for (int64_t r = warp0; r < rows; r += nwarps) {
+    float* z = Z + r * 2 * D;
+    const float ds = __ldg(dscores + r);
+    sds += ds;
+#pragma unroll
+    for (int j = 0; j < GATE_MAX_DPL; ++j) {
+      int d = lane + j * 32;
+      if (d < D) {
+        float V = tanhf(z[d]), U = sigmoid_precise(z[D + d]);
+        float g = ds * __ldg(ww + d);
+        float dv = g * U * (1.f - V * V), du = g * V * U * (1.f - U);
+        z[d] = dv;
+        z[D + d] = du;
+        sv[j] += dv;
+        su[j] += du;
+        sw[j] += ds * V * U;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < GATE_MAX_DPL; ++j) {
+    int d = lane + j * 32;
+    if (d < D) {
+      atomicAdd(dbcat + d, sv[j]);
+      atomicAdd(dbcat + D + d, su[j]);
+      atomicAdd(dww + d, sw[j]);
+    }
+  }
+  if (lane == 0) atomicAdd(dbw, sds);
+}
+
+__global__ void k_colsum_finalize(const float* __restrict__ ws, int nrec, int stride, float* __restrict__ dbcat,
+                                  float* __restrict__ dww, float* __restrict__ dbw, int D) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > 3 * D) return;
+  float a = 0.f;
+  for (int r = 0; r < nrec; ++r) a += ws[static_cast<int64_t>(r) * stride + c];
+  if (c < 2 * D) dbcat[c] = a;
+  else if (c < 3 * D) dww[c - 2 * D] = a;
+  else dbw[0] = a;
+}
+
+// dYpre = dY * act'(Y)   (Y is the activation OUTPUT)
+template <typename T>
+__global__ void k_act_bwd(const T* __restrict__ Y, const T* __restrict__ dY, T* __restrict__ out, int64_t n, int act) {
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) {
+    float y = to_f32<T>(Y[i]), g = to_f32<T>(dY[i]);
+    if (act == MILB200_ACT_TANH) g *= (1.f - y * y);
+    else if (act == MILB200_ACT_RELU) g = y > 0.f ? g : 0.f;
+    else if (act == MILB200_ACT_SIGMOID) g *= y * (1.f - y);
+    out[i] = from_f32<T>(g);
+  }
+}
+
+// out[c] (+)= sum_r A[r, c]
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_colsum(const T* __restrict__ A, int64_t rows, int cols, float* __restrict__ out, int rows_per_block) {
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
+  const int64_t r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    float a = 0.f;
+    for (int64_t r = r0; r < r1; ++r) a += to_f32<T>(A[r * cols + c]);
+    atomicAdd(out + c, a);
+  }
+}
+
+static size_t simt_splits(int64_t K) {
+  int64_t s = K / 512;
+  if (s < 1) s = 1;
+  if (s > 64) s = 64;
+  return static_cast<size_t>(s);
+}
+
+static bool tc_gate_ok(int L, int D, int dtype) {
+  return dtype == MILB200_BF16 && D == tc::GATE_D && L >= 64 && L % 8 == 0 && !force_simt();
+}
+
+// ---- workspace layouts ---------------------------------------------------------------------------
+struct GateWs {
+  // tensor-core path
+  size_t dz, colsum, part, wT;
+  // FFMA path
+  size_t z, spart;
+  size_t total;
+};
+static GateWs gate_ws(int64_t total_n, int L, int D, int dtype, int backward) {
+  GateWs w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = align_up(off, 256);
+    off = o + bytes;
+    return o;
+  };
+  if (tc_gate_ok(L, D, dtype)) {
+    if (backward) {
+      w.dz = take(static_cast<size_t>(total_n) * 2 * D * 2);
+      w.colsum = take(sizeof(float) * tc::CS_STRIDE * static_cast<size_t>(tc::gated_dz_max_records()));
+      w.part = take(sizeof(float) * static_cast<size_t>(tc::gemm_tn_max_splits(2 * D, L)) * 2 * D * L);
+      w.wT = take(static_cast<size_t>(2) * D * L * 2);
+    }
+  } else {
+    int64_t rows = std::min<int64_t>(total_n, SIMT_ROW_CHUNK);
+    w.z = take(sizeof(float) * static_cast<size_t>(rows) * 2 * D);
+    if (backward) w.spart = take(sizeof(float) * simt_splits(rows) * 2 * D * L);
+  }
+  w.total = align_up(off, 256) + 256;
+  return w;
+}
+
+template <typename T>
+static int gate_fwd_simt(const T* X, const T* Wcat, const float* bcat, const float* ww, const float* bw, float* scores,
+                         int64_t total_n, int L, int D, char* ws, const GateWs& w, cudaStream_t st) {
+  float* Z = reinterpret_cast<float*>(ws + w.z);
+  for (int64_t r0 = 0; r0 < total_n; r0 += SIMT_ROW_CHUNK) {
+    int64_t rows = std::min<int64_t>(SIMT_ROW_CHUNK, total_n - r0);
+    simt::EpiStore<float> ep{Z, 2 * D, bcat, MILB200_ACT_NONE, nullptr, nullptr, nullptr, 0, 0};
+    int rc = simt::launch<T, T, true, true>(X + r0 * L, L, Wcat, L, rows, 2 * D, L, 1, ep, st);
+    if (rc) return rc;
+    k_gate_fwd<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(Z, ww, bw, scores + r0, rows, D);
+    MIL_LAUNCH_CHECK();
+  }
+  return MILB200_OK;
+}
+
+template <typename T>
+static int gate_bwd_simt(const T* X, const T* Wcat, const float* bcat, const float* ww, const float* dscores,
+                         const float* attn, const float* dM, const int32_t* offsets, int B, int64_t total_n, int L,
+                         int D, float* dWcat, float* dbcat, float* dww, float* dbw, T* dX, char* ws, const GateWs& w,
+                         cudaStream_t st) {
+  MIL_CHECK_ARG(D <= 32 * GATE_MAX_DPL, MILB200_EUNSUPPORTED, "gated_score_bwd (FFMA path): D=%d > %d", D, 32 * GATE_MAX_DPL);
+  float* Z = reinterpret_cast<float*>(ws + w.z);
+  float* part = reinterpret_cast<float*>(ws + w.spart);
+  MIL_CUDA(cudaMemsetAsync(dbcat, 0, sizeof(float) * 2 * D, st));
+  MIL_CUDA(cudaMemsetAsync(dww, 0, sizeof(float) * D, st));
+  MIL_CUDA(cudaMemsetAsync(dbw, 0, sizeof(float), st));
+  int chunk = 0;
+  for (int64_t r0 = 0; r0 < total_n; r0 += SIMT_ROW_CHUNK, ++chunk) {
+    int64_t rows = std::min<int64_t>(SIMT_ROW_CHUNK, total_n - r0);
+    simt::EpiStore<float> ep{Z, 2 * D, bcat, MILB200_ACT_NONE, nullptr, nullptr, nullptr, 0, 0};
+    int rc = simt::launch<T, T, true, true>(X + r0 * L, L, Wcat, L, rows, 2 * D, L, 1, ep, st);
+    if (rc) return rc;
+    unsigned blocks = static_cast<unsigned>(std::min<int64_t>((rows + 7) / 8, sm_count() * 4));
+    k_gate_bwd<<<blocks, 256, 0, st>>>(Z, ww, dscores + r0, rows, D, dbcat, dww, dbw);
+    MIL_LAUNCH_CHECK();
+    // dWcat[j, l] (+)= sum_i dZ[i, j] X[i, l]
+    int splits = static_cast<int>(simt_splits(rows));
+    simt::EpiPartial pe{part, 2 * D, L};
+    rc = simt::launch<float, T, false, false>(Z, 2 * D, X + r0 * L, L, 2 * D, L, rows, splits, pe, st);
+    if (rc) return rc;
+    rc = splitk_reduce(part, splits, static_cast<int64_t>(2) * D * L, dWcat, chunk > 0, st);
+    if (rc) return rc;
+    if (dX) {
+      // dX[i, l] = sum_j dZ[i, j] Wcat[j, l]  (+ attn_i * dM[bag(i), l])
+      simt::EpiStore<T> ex{dX + r0 * L, L, nullptr, MILB200_ACT_NONE, attn, dM, offsets, B, r0};
+      rc = simt::launch<float, T, true, false>(Z, 2 * D, Wcat, L, rows, L, 2 * D, 1, ex, st);
+      if (rc) return rc;
+    }
+  }
+  return MILB200_OK;
+}
+
+// ---- linear workspace ------------------------------------------------------------------------------
+struct LinWs {
+  size_t xin, dypre, wT, part, total;
+};
+static bool tc_linear_ok(int64_t m, int n, int k, int dtype) {
+  return dtype == MILB200_BF16 && !force_simt() && tc::gemm_store_supported(m, n, k);
+}
+static bool tc_linear_bwd_ok(int64_t m, int n, int k, int dtype) {
+  // dX = dYpre[m,n] . Wt[k,n]^T needs the reduction dim n >= 64; dW = dYpre^T X needs both >= 64
+  return dtype == MILB200_BF16 && !force_simt() && tc::gemm_store_supported(m, k, n) && tc::gemm_tn_supported(n, k);
+}
+static LinWs linear_ws(int64_t m, int n, int k, int dtype, int backward, int has_add) {
+  LinWs w{};
+  size_t off = 0;
+  const size_t e = elem_size(dtype);
+  auto take = [&](size_t bytes) {
+    size_t o = align_up(off, 256);
+    off = o + bytes;
+    return o;
+  };
+  if (has_add) w.xin = take(static_cast<size_t>(m) * k * e);
+  if (backward) {
+    w.dypre = take(static_cast<size_t>(m) * n * e);
+    w.wT = take(static_cast<size_t>(n) * k * e);
+    size_t splits = tc_linear_bwd_ok(m, n, k, dtype) ? static_cast<size_t>(tc::gemm_tn_max_splits(n, k)) : simt_splits(m);
+    w.part = take(sizeof(float) * splits * n * k);
+  }
+  w.total = align_up(off, 256) + 256;
+  return w;
+}
+
+}  // namespace milb200
+
+using namespace milb200;
+
+extern "C" {
+
+int milb200_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
+
+size_t milb200_gated_score_workspace_bytes(int64_t total_n, int L, int D, int dtype, int backward) {
+  if (total_n <= 0 || L <= 0 || D <= 0) return 256;
+  return gate_ws(total_n, L, D, dtype, backward).total;
+}
+
+int milb200_gated_score_fwd(const void* X, const void* Wcat, const float* bcat, const float* ww, const float* bw,
+                            float* scores, int64_t total_n, int L, int D, int dtype, void* workspace, size_t ws_bytes,
+                            void* stream) {
+  MIL_CHECK_ARG(X && Wcat && bcat && ww && bw && scores, MILB200_EINVAL, "gated_score_fwd: null pointer");
+  MIL_CHECK_ARG(total_n > 0 && L > 0 && D > 0, MILB200_EINVAL, "gated_score_fwd: total_n=%lld L=%d D=%d must be positive",
+                (long long)total_n, L, D);
+  MIL_CHECK_ARG(dtype == MILB200_F32 || dtype == MILB200_BF16, MILB200_EINVAL, "gated_score_fwd: bad dtype %d", dtype);
+  MIL_CHECK_ARG(aligned16(X) && aligned16(Wcat) && (L * elem_size(dtype)) % 16 == 0, MILB200_EALIGN,
+                "gated_score_fwd: X/Wcat must be 16-byte aligned with a 16-byte multiple row pitch");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tc_gate_ok(L, D, dtype)) return tc::gated_score(X, total_n, L, Wcat, bcat, ww, bw, scores, st);
+  GateWs w = gate_ws(total_n, L, D, dtype, 0);
+  MIL_CHECK_ARG(workspace && ws_bytes >= w.total, MILB200_EWORKSPACE, "gated_score_fwd: workspace %zu < %zu", ws_bytes, w.total);
+  char* ws = static_cast<char*>(workspace);
+  if (dtype == MILB200_BF16)
+    return gate_fwd_simt<__nv_bfloat16>((const __nv_bfloat16*)X, (const __nv_bfloat16*)Wcat, bcat, ww, bw, scores, total_n,
+                                        L, D, ws, w, st);
+  return gate_fwd_simt<float>((const float*)X, (const float*)Wcat, bcat, ww, bw, scores, total_n, L, D, ws, w, st);
+}
+
+int milb200_gated_score_bwd(const void* X, const void* Wcat, const float* bcat, const float* ww, const float* bw,
+                            const float* dscores, const float* attn, const float* dM, const int32_t* offsets, int B,
+                            int64_t total_n, int L, int D, int dtype, float* dWcat, float* dbcat, float* dww, float* dbw,
+                            void* dX, void* workspace, size_t ws_bytes, void* stream) {
+  (void)bw;
+  MIL_CHECK_ARG(X && Wcat && bcat && ww && dscores && dWcat && dbcat && dww && dbw, MILB200_EINVAL,
+                "gated_score_bwd: null pointer");
+  MIL_CHECK_ARG(total_n > 0 && L > 0 && D > 0, MILB200_EINVAL, "gated_score_bwd: bad shape");
+  MIL_CHECK_ARG(dtype == MILB200_F32 || dtype == MILB200_BF16, MILB200_EINVAL, "gated_score_bwd: bad dtype %d", dtype);
+  MIL_CHECK_ARG(attn == nullptr || (dM && offsets && B > 0), MILB200_EINVAL,
+                "gated_score_bwd: attn given without dM/offsets");
+  MIL_CHECK_ARG(aligned16(X) && aligned16(Wcat) && (L * elem_size(dtype)) % 16 == 0, MILB200_EALIGN,
+                "gated_score_bwd: X/Wcat must be 16-byte aligned with a 16-byte multiple row pitch");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GateWs w = gate_ws(total_n, L, D, dtype, 1);
+  MIL_CHECK_ARG(workspace && ws_bytes >= w.total, MILB200_EWORKSPACE, "gated_score_bwd: workspace %zu < %zu", ws_bytes, w.total);
+  char* ws = static_cast<char*>(workspace);
+  if (tc_gate_ok(L, D, dtype)) {
+    void* dZ = ws + w.dz;
+    float* colsum = reinterpret_cast<float*>(ws + w.colsum);
+    float* part = reinterpret_cast<float*>(ws + w.part);
+    int nrec = 0, splits = 0;
+    int rc = tc::gated_dz(X, total_n, L, Wcat, bcat, ww, dscores, dZ, colsum, &nrec, st);
+    if (rc) return rc;
+    k_colsum_finalize<<<(3 * D + 1 + 255) / 256, 256, 0, st>>>(colsum, nrec, tc::CS_STRIDE, dbcat, dww, dbw, D);
+    MIL_LAUNCH_CHECK();
+    rc = tc::gemm_tn_splitk(dZ, 2 * D, X, L, total_n, 2 * D, L, part, &splits, st);
+    if (rc) return rc;
+    rc = splitk_reduce(part, splits, static_cast<int64_t>(2) * D * L, dWcat, 0, st);
+    if (rc) return rc;
+    if (dX) {
+      void* wT = ws + w.wT;  // [L, 2D]: the K-contiguous B operand of dX = dZ . Wcat
+      rc = transpose2d(Wcat, wT, 2 * D, L, MILB200_BF16, st);
+      if (rc) return rc;
+      rc = tc::gemm_store(dZ, total_n, 2 * D, 2 * D, wT, L, 2 * D, nullptr, MILB200_ACT_NONE, dX, MILB200_BF16, L, attn, dM,
+                          offsets, B, st);
+      if (rc) return rc;
+    }
+    return MILB200_OK;
+  }
+  if (dtype == MILB200_BF16)
+    return gate_bwd_simt<__nv_bfloat16>((const __nv_bfloat16*)X, (const __nv_bfloat16*)Wcat, bcat, ww, dscores, attn, dM,
+                                        offsets, B, total_n, L, D, dWcat, dbcat, dww, dbw, (__nv_bfloat16*)dX, ws, w, st);
+  return gate_bwd_simt<float>((const float*)X, (const float*)Wcat, bcat, ww, dscores, attn, dM, offsets, B, total_n, L, D,
+                              dWcat, dbcat, dww, dbw, (float*)dX, ws, w, st);
+}
+
+// ---- dense linear ------------------------------------------------------------------------------------
+size_t milb200_linear_workspace_bytes(int64_t m, int n, int k, int dtype, int backward) {
+  if (m <= 0 || n <= 0 || k <= 0) return 256;
+  return linear_ws(m, n, k, dtype, backward, 1).total;
+}
+
+static int linear_check(const void* X, const void* W, int64_t m, int n, int k, int dtype) {
+  MIL_CHECK_ARG(X && W, MILB200_EINVAL, "linear: null pointer");
+  MIL_CHECK_ARG(m > 0 && n > 0 && k > 0, MILB200_EINVAL, "linear: m=%lld n=%d k=%d must be positive", (long long)m, n, k);
+  MIL_CHECK_ARG(dtype == MILB200_F32 || dtype == MILB200_BF16, MILB200_EINVAL, "linear: bad dtype %d", dtype);
+  return MILB200_OK;
+}
+
+}  // extern "C"
+template <typename T>
+static int linear_fwd_simt(const T* X, const T* W, const float* bias, T* Y, int64_t m, int n, int k, int act,
+                           cudaStream_t st) {
+  simt::EpiStore<T> ep{Y, n, bias, act, nullptr, nullptr, nullptr, 0, 0};
+  return simt::launch<T, T, true, true>(X, k, W, k, m, n, k, 1, ep, st);
+}
+
+extern "C" {
+int milb200_linear_fwd(const void* X, const void* add, const void* W, const float* bias, void* Y, int64_t m, int n,
+                       int k, int act, int dtype, void* workspace, size_t ws_bytes, void* stream) {
+  int rc = linear_check(X, W, m, n, k, dtype);
+  if (rc) return rc;
+  MIL_CHECK_ARG(Y != nullptr, MILB200_EINVAL, "linear_fwd: Y is null");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const void* xin = X;
+  if (add) {
+    LinWs w = linear_ws(m, n, k, dtype, 0, 1);
+    MIL_CHECK_ARG(workspace && ws_bytes >= w.total, MILB200_EWORKSPACE, "linear_fwd: workspace %zu < %zu", ws_bytes, w.total);
+    void* tmp = static_cast<char*>(workspace) + w.xin;
+    rc = milb200_add(X, add, tmp, m * k, dtype, stream);
+    if (rc) return rc;
+    xin = tmp;
+  }
+  if (tc_linear_ok(m, n, k, dtype) && aligned16(xin) && aligned16(W) && aligned16(Y))
+    return tc::gemm_store(xin, m, k, k, W, n, k, bias, act, Y, MILB200_BF16, n, nullptr, nullptr, nullptr, 0, st);
+  if (dtype == MILB200_BF16)
+    return linear_fwd_simt<__nv_bfloat16>((const __nv_bfloat16*)xin, (const __nv_bfloat16*)W, bias, (__nv_bfloat16*)Y, m,
+                                          n, k, act, st);
+  return linear_fwd_simt<float>((const float*)xin, (const float*)W, bias, (float*)Y, m, n, k, act, st);
+}
+
+}  // extern "C"
+template <typename T>
+static int linear_bwd_t(const T* Xin, const T* W, const T* Y, const T* dY, T* dX, float* dW, float* dbias, int64_t m,
+                        int n, int k, int act, int dtype, int accumulate, char* ws, const LinWs& w, cudaStream_t st) {
+  const T* dypre = dY;
+  if (act != MILB200_ACT_NONE) {
+    MIL_CHECK_ARG(Y != nullptr, MILB200_EINVAL, "linear_bwd: the forward output Y is required for act=%d", act);
+    T* tmp = reinterpret_cast<T*>(ws + w.dypre);
+    int64_t tot = m * n;
+    unsigned blocks = static_cast<unsigned>(std::min<int64_t>((tot + 255) / 256, sm_count() * 8));
+    k_act_bwd<T><<<blocks, 256, 0, st>>>(Y, dY, tmp, tot, act);
+    MIL_LAUNCH_CHECK();
+    dypre = tmp;
+  }
+  if (dbias) {
+    if (!accumulate) MIL_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * n, st));
+    int rpb = 128;
+    k_colsum<T><<<static_cast<unsigned>((m + rpb - 1) / rpb), 256, 0, st>>>(dypre, m, n, dbias, rpb);
+    MIL_LAUNCH_CHECK();
+  }
+  float* part = reinterpret_cast<float*>(ws + w.part);
+  const bool use_tc = tc_linear_bwd_ok(m, n, k, dtype) && aligned16(dypre) && aligned16(Xin) && aligned16(W);
+  int rc;
+  if (dW) {
+    int splits = 0;
+    if (use_tc) {
+      rc = tc::gemm_tn_splitk(dypre, n, Xin, k, m, n, k, part, &splits, st);
+    } else {
+      splits = static_cast<int>(simt_splits(m));
+      simt::EpiPartial pe{part, n, k};
+      rc = simt::launch<T, T, false, false>(dypre, n, Xin, k, n, k, m, splits, pe, st);
+    }
+    if (rc) return rc;
+    rc = splitk_reduce(part, splits, static_cast<int64_t>(n) * k, dW, accumulate, st);
+    if (rc) return rc;
+  }
+  if (dX) {
+    if (use_tc) {
+      T* wT = reinterpret_cast<T*>(ws + w.wT);  // [k, n]
+      rc = transpose2d(W, wT, n, k, dtype, st);
+      if (rc) return rc;
+      rc = tc::gemm_store(dypre, m, n, n, wT, k, n, nullptr, MILB200_ACT_NONE, dX, MILB200_BF16, k, nullptr, nullptr,
+                          nullptr, 0, st);
+    } else {
+      simt::EpiStore<T> ex{dX, k, nullptr, MILB200_ACT_NONE, nullptr, nullptr, nullptr, 0, 0};
+      rc = simt::launch<T, T, true, false>(dypre, n, W, k, m, k, n, 1, ex, st);
+    }
+    if (rc) return rc;
+  }
+  return MILB200_OK;
+}
+
+extern "C" {
+int milb200_linear_bwd(const void* X, const void* add, const void* W, const void* Y, const void* dY, void* dX,
+                       float* dW, float* dbias, int64_t m, int n, int k, int act, int dtype, int accumulate,
+                       void* workspace, size_t ws_bytes, void* stream) {
+  int rc = linear_check(X, W, m, n, k, dtype);
+  if (rc) return rc;
+  MIL_CHECK_ARG(dY != nullptr, MILB200_EINVAL, "linear_bwd: dY is null");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LinWs w = linear_ws(m, n, k, dtype, 1, add != nullptr);
+  MIL_CHECK_ARG(workspace && ws_bytes >= w.total, MILB200_EWORKSPACE, "linear_bwd: workspace %zu < %zu", ws_bytes, w.total);
+  char* ws = static_cast<char*>(workspace);
+  const void* xin = X;
+  if (add && dW) {
+    void* tmp = ws + w.xin;
+    rc = milb200_add(X, add, tmp, m * k, dtype, stream);
+    if (rc) return rc;
+    xin = tmp;
+  }
+  if (dtype == MILB200_BF16)
+    return linear_bwd_t<__nv_bfloat16>((const __nv_bfloat16*)xin, (const __nv_bfloat16*)W, (const __nv_bfloat16*)Y,
+                                       (const __nv_bfloat16*)dY, (__nv_bfloat16*)dX, dW, dbias, m, n, k, act, dtype,
+                                       accumulate, ws, w, st);
+  return linear_bwd_t<float>((const float*)xin, (const float*)W, (const float*)Y, (const float*)dY, (float*)dX, dW, dbias,
+                             m, n, k, act, dtype, accumulate, ws, w, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,570 @@
+// pool.cu — ragged segmented softmax + attention-weighted instance sum over CSR bag offsets,
+// forward and backward (replaces F.softmax(A, dim=1) and torch.matmul(A, x), model/dim1/ABMIL.py:56-59,
+// and their autograd).  Bandwidth-bound: X is streamed exactly once per pass with 128-bit loads.
+//
+// Forward = ONE kernel.  The packed rows are cut into fixed chunks of `ch` rows; a CTA owns one chunk
+// and walks the bag pieces inside it.  For every piece it computes a local (max, sum, weighted
+// accumulator) online-softmax partial; a bag that lies inside one chunk is finished on the spot, a bag
+// that spans chunks is finished by whichever CTA publishes its last piece (per-bag arrival counter),
+// which folds the partials in piece order, so the result is deterministic.
+#include <algorithm>
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace milb200 {
+
+constexpr int POOL_THREADS = 256;
+constexpr int POOL_MAX_CH = 128;
+
+struct PoolLayout {  // how the 256 threads of a CTA tile one row of V 16-byte vectors
+  int V, TPR, R, VPT;
+};
+static PoolLayout pool_layout(int L, int esz) {
+  PoolLayout p;
+  p.V = L * esz / 16;
+  p.VPT = (p.V + POOL_THREADS - 1) / POOL_THREADS;
+  int per = (p.V + p.VPT - 1) / p.VPT;
+  p.TPR = per;
+  p.R = POOL_THREADS / p.TPR;
+  if (p.R < 1) p.R = 1;
+  return p;
+}
+
+template <typename T> __device__ __forceinline__ float exp_t(float x);
+template <> __device__ __forceinline__ float exp_t<float>(float x) { return expf(x); }
+template <> __device__ __forceinline__ float exp_t<__nv_bfloat16>(float x) { return __expf(x); }
+
+struct PiecePartial {  // published per (chunk, bag) piece
+  float m, l;
+  int argmax;  // index within the bag
+  int pad;
+};
+
+template <typename T, int VPT>
+__global__ void __launch_bounds__(POOL_THREADS)
+k_pool_fwd(const T* __restrict__ X, const float* __restrict__ scores, const int32_t* __restrict__ offsets, int B,
+           int64_t total_n, int L, int ch, int V, int TPR, int R, float* __restrict__ M, T* __restrict__ M_lowp,
+           int32_t* __restrict__ argmax_out, float* __restrict__ lse_out, float* __restrict__ ws_acc,
+           PiecePartial* __restrict__ ws_ml, unsigned int* __restrict__ counters, int normalize) {
+  constexpr int VN = Vec16<T>::N;
+  extern __shared__ __align__(16) float smem[];
+  float* e_s = smem;                    // [POOL_MAX_CH] exp(s - m_piece)
+  float* red = smem + POOL_MAX_CH;      // [R][L] cross-row-group reduction, then the piece accumulator
+  __shared__ float wred_v[8];
+  __shared__ int wred_i[8];
+  __shared__ float piece_m, piece_l;
+  __shared__ int piece_arg, is_last;
+
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int64_t chunk = blockIdx.x;
+  const int64_t r0 = chunk * ch;
+  const int64_t r1 = (r0 + ch < total_n) ? r0 + ch : total_n;
+  const int rg = t / TPR, vt = t % TPR;
+  const bool active = rg < R;
+  const int64_t rowvecs = static_cast<int64_t>(V);
+  const uint4* Xv = reinterpret_cast<const uint4*>(X);
+
+  int b = find_bag(offsets, B, r0);
+  for (; b < B; ++b) {
+    const int64_t ob = __ldg(offsets + b), oe = __ldg(offsets + b + 1);
+    if (ob >= r1) break;
+    const int64_t s0 = ob > r0 ? ob : r0, s1 = oe < r1 ? oe : r1;
+    const int nseg = static_cast<int>(s1 - s0);
+    if (nseg <= 0) continue;  // empty bag: nothing to pool (contract: bags are non-empty)
+
+    // ---- piece max / first argmax ----
+    float sv = (t < nseg) ? (scores ? __ldg(scores + s0 + t) : 0.f) : -FLT_MAX;
+    int si = (t < nseg) ? t : 0x7fffffff;
+    {
+      float mv = sv;
+      int mi = si;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, mv, o);
+        int oi = __shfl_xor_sync(0xffffffffu, mi, o);
+        if (ov > mv || (ov == mv && oi < mi)) { mv = ov; mi = oi; }
+      }
+      if (lane == 0) { wred_v[warp] = mv; wred_i[warp] = mi; }
+    }
+    __syncthreads();
+    if (t == 0) {
+      float mv = wred_v[0];
+      int mi = wred_i[0];
+      for (int w = 1; w < POOL_THREADS / 32; ++w)
+        if (wred_v[w] > mv || (wred_v[w] == mv && wred_i[w] < mi)) { mv = wred_v[w]; mi = wred_i[w]; }
+      piece_m = mv;
+      piece_arg = mi + static_cast<int>(s0 - ob);
+    }
+    __syncthreads();
+    const float pm = piece_m;
+    float ev = (t < nseg) ? exp_t<T>(sv - pm) : 0.f;
+    if (t < nseg) e_s[t] = ev;
+    ev = warp_sum(ev);
+    __syncthreads();  // e_s visible; wred_v reads above are done
+    if (lane == 0) wred_v[warp] = ev;
+    __syncthreads();
+    if (t == 0) {
+      float l = 0.f;
+      for (int w = 0; w < POOL_THREADS / 32; ++w) l += wred_v[w];
+      piece_l = l;
+    }
+
+    // ---- weighted row sum: thread (rg, vt) owns vectors vt + j*TPR of rows rg, rg+R, ... ----
+    float acc[VPT][VN];
+#pragma unroll
+    for (int j = 0; j < VPT; ++j)
+#pragma unroll
+      for (int k = 0; k < VN; ++k) acc[j][k] = 0.f;
+    if (active) {
+      constexpr int UNR = (VPT == 1) ? 4 : 2;
+      int i = rg;
+      for (; i + (UNR - 1) * R < nseg; i += UNR * R) {
+        uint4 v[UNR][VPT];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u)
+#pragma unroll
+          for (int j = 0; j < VPT; ++j) {
+            int vec = vt + j * TPR;
+            v[u][j] = (vec < V) ? ldg_stream(Xv + (s0 + i + u * R) * rowvecs + vec) : make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+          float w = e_s[i + u * R];
+#pragma unroll
+          for (int j = 0; j < VPT; ++j) {
+            float f[VN];
+            Vec16<T>::unpack(v[u][j], f);
+#pragma unroll
+            for (int k = 0; k < VN; ++k) acc[j][k] = fmaf(w, f[k], acc[j][k]);
+          }
+        }
+      }
+      for (; i < nseg; i += R) {
+        float w = e_s[i];
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+          int vec = vt + j * TPR;
+          if (vec < V) {
+            float f[VN];
+            Vec16<T>::unpack(ldg_stream(Xv + (s0 + i) * rowvecs + vec), f);
+#pragma unroll
+            for (int k = 0; k < VN; ++k) acc[j][k] = fmaf(w, f[k], acc[j][k]);
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < VPT; ++j) {
+        int vec = vt + j * TPR;
+        if (vec < V) {
+#pragma unroll
+          for (int k = 0; k < VN; ++k) red[static_cast<int64_t>(rg) * L + vec * VN + k] = acc[j][k];
+        }
+      }
+    }
+    __syncthreads();
+    // fold row groups in fixed order into red[0][:]
+    for (int c = t; c < L; c += POOL_THREADS) {
+      float a = red[c];
+      for (int g = 1; g < R; ++g) a += red[static_cast<int64_t>(g) * L + c];
+      red[c] = a;
+    }
+    __syncthreads();
+
+    const int64_t c_first = ob / ch, c_last = (oe - 1) / ch;
+    const int pieces = static_cast<int>(c_last - c_first + 1);
+    if (pieces == 1) {
+      const float inv = normalize ? 1.f / piece_l : 1.f;
+      for (int c = t; c < L; c += POOL_THREADS) {
+        float mval = red[c] * inv;
+        M[static_cast<int64_t>(b) * L + c] = mval;
+        if (M_lowp) M_lowp[static_cast<int64_t>(b) * L + c] = from_f32<T>(mval);
+      }
+      if (t == 0) {
+        if (argmax_out) argmax_out[b] = piece_arg;
+        if (lse_out) lse_out[b] = piece_m + logf(piece_l);
+      }
+    } else {
+      const int64_t slot = chunk + b;  // unique per (chunk, bag) piece, monotone along the row order
+      for (int c = t; c < L; c += POOL_THREADS) ws_acc[slot * L + c] = red[c];
+      if (t == 0) {
+        PiecePartial pp;
+        pp.m = piece_m; pp.l = piece_l; pp.argmax = piece_arg; pp.pad = 0;
+        ws_ml[slot] = pp;
+      }
+      __threadfence();
+      __syncthreads();
+      if (t == 0) {
+        unsigned int old = atomicAdd(counters + b, 1u);
+        is_last = (old == static_cast<unsigned int>(pieces - 1));
+      }
+      __syncthreads();
+      if (is_last) {
+        __threadfence();
+        const int64_t slot0 = c_first + b;
+        float gm = -FLT_MAX;
+        int garg = 0;
+        for (int p = 0; p < pieces; ++p) {
+          PiecePartial pp = ws_ml[slot0 + p];
+          if (pp.m > gm) { gm = pp.m; garg = pp.argmax; }
+        }
+        float gl = 0.f;
+        for (int p = 0; p < pieces; ++p) {
+          PiecePartial pp = ws_ml[slot0 + p];
+          gl += pp.l * exp_t<T>(pp.m - gm);
+        }
+        const float inv = normalize ? 1.f / gl : 1.f;
+        for (int c = t; c < L; c += POOL_THREADS) {
+          float a = 0.f;
+          for (int p = 0; p < pieces; ++p) {
+            float sc = exp_t<T>(ws_ml[slot0 + p].m - gm);
+            a = fmaf(sc, __ldcg(ws_acc + (slot0 + p) * L + c), a);
+          }
+          float mval = a * inv;
+          M[static_cast<int64_t>(b) * L + c] = mval;
+          if (M_lowp) M_lowp[static_cast<int64_t>(b) * L + c] = from_f32<T>(mval);
+        }
+        if (t == 0) {
+          if (argmax_out) argmax_out[b] = garg;
+          if (lse_out) lse_out[b] = gm + logf(gl);
+        }
+      }
+    }
+    __syncthreads();  // smem (e_s, red, piece_*) is reused by the next piece
+  }
+}
+
+// ---- backward ------------------------------------------------------------------------------------
+// stats[b] = (lse_b, dM_b . M_b): softmax statistics are recomputed from the scores, not stored.
+__global__ void __launch_bounds__(256)
+k_pool_bwd_stats(const float* __restrict__ scores, const int32_t* __restrict__ offsets, int L,
+                 const float* __restrict__ dM, const float* __restrict__ M, float2* __restrict__ stats) {
+  __shared__ float red[8];
+  __shared__ float bc;
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int64_t ob = offsets[b], oe = offsets[b + 1];
+  float mx = -FLT_MAX;
+  for (int64_t i = ob + t; i < oe; i += 256) mx = fmaxf(mx, scores[i]);
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  if (t == 0) {
+    float v = red[0];
+    for (int w = 1; w < 8; ++w) v = fmaxf(v, red[w]);
+    bc = v;
+  }
+  __syncthreads();
+  mx = bc;
+  float sum = 0.f;
+  for (int64_t i = ob + t; i < oe; i += 256) sum += expf(scores[i] - mx);
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  float tot = 0.f;
+  if (t == 0) {
+    for (int w = 0; w < 8; ++w) tot += red[w];
+  }
+  float dot = 0.f;
+  for (int c = t; c < L; c += 256) dot = fmaf(dM[static_cast<int64_t>(b) * L + c], M[static_cast<int64_t>(b) * L + c], dot);
+  dot = warp_sum(dot);
+  __syncthreads();
+  if (lane == 0) red[warp] = dot;
+  __syncthreads();
+  if (t == 0) {
+    float d = 0.f;
+    for (int w = 0; w < 8; ++w) d += red[w];
+    stats[b] = make_float2(oe > ob ? mx + logf(tot) : 0.f, d);
+  }
+}
+
+constexpr int BWD_ROWS_PER_WARP = 16;
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(256)
+k_pool_bwd(const T* __restrict__ X, const float* __restrict__ scores, const int32_t* __restrict__ offsets, int B,
+           int64_t total_n, int L, int V, const float* __restrict__ dM, const float2* __restrict__ stats,
+           float* __restrict__ dscores, float* __restrict__ attn) {
+  constexpr int VN = Vec16<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int64_t gwarp = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t r0 = gwarp * BWD_ROWS_PER_WARP;
+  if (r0 >= total_n) return;
+  const int64_t r1 = (r0 + BWD_ROWS_PER_WARP < total_n) ? r0 + BWD_ROWS_PER_WARP : total_n;
+  const uint4* Xv = reinterpret_cast<const uint4*>(X);
+
+  int b = find_bag(offsets, B, r0);
+  int64_t bag_end = __ldg(offsets + b + 1);
+  float dm[NV][VN];
+  float lse = 0.f, cdot = 0.f;
+  auto load_bag = [&](int bag) {
+    float2 st = __ldg(stats + bag);
+    lse = st.x;
+    cdot = st.y;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      int vec = lane + j * 32;
+#pragma unroll
+      for (int k = 0; k < VN; ++k) dm[j][k] = (vec < V) ? __ldg(dM + static_cast<int64_t>(bag) * L + vec * VN + k) : 0.f;
+    }
+  };
+  load_bag(b);
+
+  int64_t i = r0;
+  for (; i + 1 < r1; i += 2) {
+    uint4 v0[NV], v1[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      int vec = lane + j * 32;
+      v0[j] = (vec < V) ? ldg_stream(Xv + i * V + vec) : make_uint4(0, 0, 0, 0);
+      v1[j] = (vec < V) ? ldg_stream(Xv + (i + 1) * V + vec) : make_uint4(0, 0, 0, 0);
+    }
+    float s0 = __ldg(scores + i), s1 = __ldg(scores + i + 1);
+    // row i
+    while (i >= bag_end) { ++b; bag_end = __ldg(offsets + b + 1); load_bag(b); }
+    float g = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float f[VN];
+      Vec16<T>::unpack(v0[j], f);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) g = fmaf(dm[j][k], f[k], g);
+    }
+    g = warp_sum(g);
+    float a = expf(s0 - lse);
+    if (lane == 0) {
+      dscores[i] = a * (g - cdot);
+      if (attn) attn[i] = a;
+    }
+    // row i+1
+    while (i + 1 >= bag_end) { ++b; bag_end = __ldg(offsets + b + 1); load_bag(b); }
+    g = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      float f[VN];
+      Vec16<T>::unpack(v1[j], f);
+#pragma unroll
+      for (int k = 0; k < VN; ++k) g = fmaf(dm[j][k], f[k], g);
+    }
+    g = warp_sum(g);
+    a = expf(s1 - lse);
+    if (lane == 0) {
+      dscores[i + 1] = a * (g - cdot);
+      if (attn) attn[i + 1] = a;
+    }
+  }
+  if (i < r1) {
+    while (i >= bag_end) { ++b; bag_end = __ldg(offsets + b + 1); load_bag(b); }
+    float g = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      int vec = lane + j * 32;
+      if (vec < V) {
+        float f[VN];
+        Vec16<T>::unpack(ldg_stream(Xv + i * V + vec), f);
+#pragma unroll
+        for (int k = 0; k < VN; ++k) g = fmaf(dm[j][k], f[k], g);
+      }
+    }
+    g = warp_sum(g);
+    float a = expf(__ldg(scores + i) - lse);
+    if (lane == 0) {
+      dscores[i] = a * (g - cdot);
+      if (attn) attn[i] = a;
+    }
+  }
+}
+
+// out[i, :] = (w ? w[i] : 1) * src[bag(i), :]   (dX of a plain sum pool; the pooling term of the gated dX)
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_bag_broadcast(const float* __restrict__ src, const float* __restrict__ w, const int32_t* __restrict__ offsets, int B,
+                int64_t total_n, int L, T* __restrict__ out) {
+  constexpr int VN = Vec16<T>::N;
+  const int V = L / VN;
+  const int64_t total = total_n * V;
+  for (int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t row = idx / V;
+    const int vec = static_cast<int>(idx % V);
+    const int b = find_bag(offsets, B, row);
+    const float a = w ? __ldg(w + row) : 1.f;
+    float f[VN];
+#pragma unroll
+    for (int k = 0; k < VN; ++k) f[k] = a * __ldg(src + static_cast<int64_t>(b) * L + vec * VN + k);
+    reinterpret_cast<uint4*>(out)[idx] = Vec16<T>::pack(f);
+  }
+}
+
+static int pool_chunk_rows(int64_t total_n) {
+  int64_t target = static_cast<int64_t>(sm_count()) * 4;
+  if (total_n >= target * 128) return 128;
+  if (total_n >= target * 64) return 64;
+  return 32;
+}
+
+struct PoolWs {
+  float* acc;
+  PiecePartial* ml;
+  unsigned int* counters;
+  float2* stats;
+  size_t bytes;
+};
+static PoolWs pool_ws(void* base, int64_t total_n, int B, int L) {
+  // sized for the smallest chunk (32 rows): slots <= ceil(total_n/32) + B
+  int64_t slots = (total_n + 31) / 32 + B + 1;
+  size_t off = 0;
+  PoolWs w;
+  char* p = static_cast<char*>(base);
+  w.counters = reinterpret_cast<unsigned int*>(p + off);
+  off = align_up(off + sizeof(unsigned int) * static_cast<size_t>(B), 256);
+  w.stats = reinterpret_cast<float2*>(p + off);
+  off = align_up(off + sizeof(float2) * static_cast<size_t>(B), 256);
+  w.ml = reinterpret_cast<PiecePartial*>(p + off);
+  off = align_up(off + sizeof(PiecePartial) * static_cast<size_t>(slots), 256);
+  w.acc = reinterpret_cast<float*>(p + off);
+  // partial accumulators are only written for bags that span chunks; with the chunk size picked by
+  // pool_chunk_rows the slot count is bounded by ceil(total_n / ch) + B
+  int ch = pool_chunk_rows(total_n);
+  int64_t acc_slots = (total_n + ch - 1) / ch + B + 1;
+  off = align_up(off + sizeof(float) * static_cast<size_t>(acc_slots) * L, 256);
+  w.bytes = off;
+  return w;
+}
+
+template <typename T>
+static int pool_fwd_t(const T* X, const float* scores, const int32_t* offsets, int B, int64_t total_n, int L, float* M,
+                      T* M_lowp, int32_t* argmax, float* lse, void* workspace, size_t ws_bytes, cudaStream_t st,
+                      int normalize = 1) {
+  PoolLayout pl = pool_layout(L, sizeof(T));
+  MIL_CHECK_ARG(pl.VPT <= 4, MILB200_EUNSUPPORTED, "pool: row of %d bytes exceeds the 16 KB limit", L * (int)sizeof(T));
+  PoolWs w = pool_ws(workspace, total_n, B, L);
+  MIL_CHECK_ARG(workspace && ws_bytes >= w.bytes, MILB200_EWORKSPACE, "pool_fwd: workspace %zu < %zu", ws_bytes, w.bytes);
+  MIL_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(unsigned int) * static_cast<size_t>(B), st));
+  int ch = pool_chunk_rows(total_n);
+  int64_t chunks = (total_n + ch - 1) / ch;
+  size_t smem = sizeof(float) * (POOL_MAX_CH + static_cast<size_t>(pl.R) * L);
+  auto launch = [&](auto kern) -> int {
+    if (smem > 48 * 1024) MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<static_cast<unsigned>(chunks), POOL_THREADS, smem, st>>>(X, scores, offsets, B, total_n, L, ch, pl.V, pl.TPR,
+                                                                   pl.R, M, M_lowp, argmax, lse, w.acc, w.ml, w.counters, normalize);
+    MIL_LAUNCH_CHECK();
+    return MILB200_OK;
+  };
+  switch (pl.VPT) {
+    case 1: return launch(k_pool_fwd<T, 1>);
+    case 2: return launch(k_pool_fwd<T, 2>);
+    default: return launch(k_pool_fwd<T, 4>);
+  }
+}
+
+template <typename T>
+static int pool_bwd_t(const T* X, const float* scores, const int32_t* offsets, int B, int64_t total_n, int L,
+                      const float* dM, const float* M, float* dscores, float* attn, void* workspace, size_t ws_bytes,
+                      cudaStream_t st) {
+  PoolWs w = pool_ws(workspace, total_n, B, L);
+  MIL_CHECK_ARG(workspace && ws_bytes >= w.bytes, MILB200_EWORKSPACE, "pool_bwd: workspace %zu < %zu", ws_bytes, w.bytes);
+  k_pool_bwd_stats<<<B, 256, 0, st>>>(scores, offsets, L, dM, M, w.stats);
+  MIL_LAUNCH_CHECK();
+  int V = L * static_cast<int>(sizeof(T)) / 16;
+  int nv = (V + 31) / 32;
+  MIL_CHECK_ARG(nv <= 16, MILB200_EUNSUPPORTED, "pool_bwd: row too long (L=%d)", L);
+  int64_t warps = (total_n + BWD_ROWS_PER_WARP - 1) / BWD_ROWS_PER_WARP;
+  unsigned blocks = static_cast<unsigned>((warps + 7) / 8);
+#define MIL_POOL_BWD(NVV)                                                                                   \
+  k_pool_bwd<T, NVV><<<blocks, 256, 0, st>>>(X, scores, offsets, B, total_n, L, V, dM, w.stats, dscores, attn)
+  if (nv <= 1) MIL_POOL_BWD(1);
+  else if (nv == 2) MIL_POOL_BWD(2);
+  else if (nv == 3) MIL_POOL_BWD(3);
+  else if (nv == 4) MIL_POOL_BWD(4);
+  else if (nv <= 6) MIL_POOL_BWD(6);
+  else if (nv <= 8) MIL_POOL_BWD(8);
+  else MIL_POOL_BWD(16);
+#undef MIL_POOL_BWD
+  MIL_LAUNCH_CHECK();
+  return MILB200_OK;
+}
+
+static int pool_check(const void* X, const float* scores, const int32_t* offsets, int B, int64_t total_n, int L, int dtype,
+                      bool need_scores = true) {
+  MIL_CHECK_ARG(X && (scores || !need_scores) && offsets, MILB200_EINVAL, "pool: null pointer");
+  MIL_CHECK_ARG(B > 0 && total_n > 0 && L > 0, MILB200_EINVAL, "pool: B=%d total_n=%lld L=%d must be positive", B,
+                (long long)total_n, L);
+  MIL_CHECK_ARG(dtype == MILB200_F32 || dtype == MILB200_BF16, MILB200_EINVAL, "pool: bad dtype %d", dtype);
+  MIL_CHECK_ARG((L * elem_size(dtype)) % 16 == 0, MILB200_EALIGN, "pool: row pitch %d bytes is not a multiple of 16",
+                L * elem_size(dtype));
+  MIL_CHECK_ARG(aligned16(X), MILB200_EALIGN, "pool: X must be 16-byte aligned");
+  MIL_CHECK_ARG(total_n < (1ll << 31), MILB200_EINVAL, "pool: total_n exceeds int32 CSR offsets");
+  return MILB200_OK;
+}
+
+}  // namespace milb200
+
+using namespace milb200;
+
+extern "C" {
+
+size_t milb200_pool_workspace_bytes(int64_t total_n, int B, int L) {
+  if (total_n <= 0 || B <= 0 || L <= 0) return 256;
+  return pool_ws(nullptr, total_n, B, L).bytes;
+}
+
+int milb200_segment_softmax_pool_fwd(const void* X, const float* scores, const int32_t* offsets, int B,
+                                     int64_t total_n, int L, int dtype, float* M, void* M_lowp, int32_t* argmax,
+                                     float* lse, void* workspace, size_t ws_bytes, void* stream) {
+  int rc = pool_check(X, scores, offsets, B, total_n, L, dtype);
+  if (rc) return rc;
+  MIL_CHECK_ARG(M != nullptr, MILB200_EINVAL, "pool_fwd: M is null");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == MILB200_BF16)
+    return pool_fwd_t<__nv_bfloat16>((const __nv_bfloat16*)X, scores, offsets, B, total_n, L, M, (__nv_bfloat16*)M_lowp,
+                                     argmax, lse, workspace, ws_bytes, st);
+  return pool_fwd_t<float>((const float*)X, scores, offsets, B, total_n, L, M, (float*)M_lowp, argmax, lse, workspace,
+                           ws_bytes, st);
+}
+
+/* M[b] = sum_i x_i over CSR offsets (no softmax): the reference's dense-batch behaviour (ABMIL.py:56-59 with
+ * B>1, where the softmax runs over a size-1 axis) and SwinUNETR_wMask's 3-crop pool. */
+int milb200_segment_sum_fwd(const void* X, const int32_t* offsets, int B, int64_t total_n, int L, int dtype, float* M,
+                            void* M_lowp, void* workspace, size_t ws_bytes, void* stream) {
+  int rc = pool_check(X, nullptr, offsets, B, total_n, L, dtype, false);
+  if (rc) return rc;
+  MIL_CHECK_ARG(M != nullptr, MILB200_EINVAL, "segment_sum_fwd: M is null");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == MILB200_BF16)
+    return pool_fwd_t<__nv_bfloat16>((const __nv_bfloat16*)X, nullptr, offsets, B, total_n, L, M, (__nv_bfloat16*)M_lowp,
+                                     nullptr, nullptr, workspace, ws_bytes, st, 0);
+  return pool_fwd_t<float>((const float*)X, nullptr, offsets, B, total_n, L, M, (float*)M_lowp, nullptr, nullptr, workspace,
+                           ws_bytes, st, 0);
+}
+
+/* out[i, :] = (w ? w[i] : 1) * src[bag(i), :], src fp32 [B, L], out [total_n, L] in `dtype`. */
+int milb200_bag_broadcast(const float* src, const float* w, const int32_t* offsets, int B, int64_t total_n, int L,
+                          int dtype, void* out, void* stream) {
+  MIL_CHECK_ARG(src && offsets && out && B > 0 && total_n > 0 && L > 0, MILB200_EINVAL, "bag_broadcast: bad arguments");
+  MIL_CHECK_ARG((L * elem_size(dtype)) % 16 == 0 && aligned16(out), MILB200_EALIGN, "bag_broadcast: misaligned output");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int64_t total = total_n * (L * elem_size(dtype) / 16);
+  unsigned blocks = static_cast<unsigned>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(sm_count()) * 16));
+  if (dtype == MILB200_BF16)
+    k_bag_broadcast<__nv_bfloat16><<<blocks, 256, 0, st>>>(src, w, offsets, B, total_n, L, (__nv_bfloat16*)out);
+  else
+    k_bag_broadcast<float><<<blocks, 256, 0, st>>>(src, w, offsets, B, total_n, L, (float*)out);
+  MIL_LAUNCH_CHECK();
+  return MILB200_OK;
+}
+
+int milb200_segment_softmax_pool_bwd(const void* X, const float* scores, const int32_t* offsets, int B,
+                                     int64_t total_n, int L, int dtype, const float* dM, const float* M,
+                                     float* dscores, float* attn, void* workspace, size_t ws_bytes, void* stream) {
+  int rc = pool_check(X, scores, offsets, B, total_n, L, dtype);
+  if (rc) return rc;
+  MIL_CHECK_ARG(dM && M && dscores, MILB200_EINVAL, "pool_bwd: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == MILB200_BF16)
+    return pool_bwd_t<__nv_bfloat16>((const __nv_bfloat16*)X, scores, offsets, B, total_n, L, dM, M, dscores, attn,
+                                     workspace, ws_bytes, st);
+  return pool_bwd_t<float>((const float*)X, scores, offsets, B, total_n, L, dM, M, dscores, attn, workspace, ws_bytes, st);
+}
+
+}  // extern "C"

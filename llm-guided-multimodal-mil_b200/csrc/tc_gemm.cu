@@ -1,0 +1,607 @@
+// tc_gemm.cu — hand-written sm_100a tensor-core GEMMs: TMA (cp.async.bulk.tensor, 128-byte swizzle)
+// feeds shared-memory stages, ONE thread issues tcgen05.mma with the fp32 accumulators in TMEM, four
+// epilogue warps read them back with tcgen05.ld and apply the fused epilogue.
+//
+//   k_gemm_kmajor<BN, Epi>   D[128 x BN] tiles of A[M,K] . B[N,K]^T  (both K-contiguous); persistent,
+//                            warp-specialised: warp0 = TMA producer, warp1 = MMA issuer, warp2 = TMEM
+//                            allocator, warps 4-7 = epilogue.  Epilogues:
+//                              EpiStore   bias + activation (+ rank-1 pooling term) -> bf16/fp32 store
+//                                         (nn.Linear sites: aggregator.py:44,47,66; transformer.py:430-448)
+//                              EpiScore   gated-attention score  (ABMIL.py:52-54), writes 4 B per instance
+//                              EpiDz      its backward: recompute V,U, emit dZ + column sums
+//   k_gemm_tn                split-K  D[128 x 512] = sum_k A[k, m] B[k, n]  (both operands MN-major):
+//                            dW = dZ^T X of the gate / linear backward.
+#include "tc_common.cuh"
+#include "tc_gemm.cuh"
+
+namespace milb200 {
+namespace tc {
+
+constexpr int BM = 128;      // rows per tile = TMEM lanes
+constexpr int BK = 64;       // bf16 per 128-byte swizzle span
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+
+template <int BN>
+struct TileCfg {
+  static constexpr int UMMA_N = (BN <= 256) ? BN : BN / 2;
+  static constexpr int N_MMA = BN / UMMA_N;
+  static constexpr int ACC_STAGES = (2 * BN <= 512) ? 2 : 1;
+  static constexpr int TMEM_COLS = (BN * ACC_STAGES <= 128) ? 128 : ((BN * ACC_STAGES <= 256) ? 256 : 512);
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
+  static_assert(UMMA_N % 16 == 0 && UMMA_N <= 256, "invalid UMMA N");
+  static_assert((UMMA_N * 128) % 1024 == 0, "B boxes must start on a swizzle-atom boundary");
+};
+
+constexpr int BAR_BYTES = 256;
+
+template <int BN, class Epi>
+constexpr size_t kmajor_smem_bytes() {
+  return 1024 + static_cast<size_t>(TileCfg<BN>::STAGES) * TileCfg<BN>::STAGE_BYTES + BAR_BYTES +
+         sizeof(float) * Epi::SMEM_FLOATS;
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogues
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == MILB200_ACT_TANH) return tanh_fast(v);
+  if (act == MILB200_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == MILB200_ACT_SIGMOID) return sigmoid_fast(v);
+  return v;
+}
+
+struct EpiStore {
+  struct Params {
+    void* out;
+    int out_bf16;
+    int64_t ldo;
+    const float* bias;
+    int act;
+    const float* attn;
+    const float* dM;
+    const int32_t* offsets;
+    int nbags;
+  };
+  static constexpr int SMEM_FLOATS = 0;
+  __device__ static void prologue(const Params&, float*, int) {}
+  __device__ EpiStore() {}
+  template <int BN>
+  __device__ __forceinline__ void tile(const Params& p, float*, uint32_t tacc, int64_t row, int64_t M, int n0, int N,
+                                       int lane) {
+    const bool row_ok = row < M;
+    float a = 0.f;
+    const float* dmrow = nullptr;
+    if (p.attn && row_ok) {
+      a = __ldg(p.attn + row);
+      dmrow = p.dM + static_cast<int64_t>(find_bag(p.offsets, p.nbags, row)) * p.ldo;
+    }
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      if (n0 + c >= N) break;  // warp-uniform
+      uint32_t r[32];
+      tmem_ld32(tacc + c, r);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        int n = n0 + c + j;
+        float x = __uint_as_float(r[j]);
+        if (n < N) {
+          if (p.bias) x += __ldg(p.bias + n);
+          x = apply_act(x, p.act);
+          if (dmrow) x = fmaf(a, __ldg(dmrow + n), x);
+        }
+        v[j] = x;
+      }
+      const int nvalid = (N - (n0 + c)) < 32 ? (N - (n0 + c)) : 32;  // multiple of 8 (N % 8 == 0)
+      if (p.out_bf16) {
+        __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + row * p.ldo + n0 + c;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8)
+          if (j < nvalid) *reinterpret_cast<uint4*>(o + j) = Vec16<__nv_bfloat16>::pack(v + j);
+      } else {
+        float* o = static_cast<float*>(p.out) + row * p.ldo + n0 + c;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          if (j < nvalid) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+    }
+  }
+  __device__ void finish(const Params&, int, int) {}
+};
+
+struct EpiScore {
+  struct Params {
+    const float* bcat;  // [384] = [bv | bu]
+    const float* ww;    // [192]
+    const float* bw;    // [1]
+    float* scores;
+  };
+  static constexpr int SMEM_FLOATS = 3 * GATE_D;
+  __device__ static void prologue(const Params& p, float* esm, int tid) {
+    for (int i = tid; i < 2 * GATE_D; i += NUM_THREADS) esm[i] = __ldg(p.bcat + i);
+    for (int i = tid; i < GATE_D; i += NUM_THREADS) esm[2 * GATE_D + i] = __ldg(p.ww + i);
+  }
+  __device__ EpiScore() {}
+  template <int BN>
+  __device__ __forceinline__ void tile(const Params& p, float* esm, uint32_t tacc, int64_t row, int64_t M, int, int,
+                                       int) {
+    static_assert(BN == 2 * GATE_D, "score epilogue expects the [V | U] 384-column tile");
+    float part = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < GATE_D; c += 16) {
+      uint32_t v[16], u[16];
+      tmem_ld16(tacc + c, v);
+      tmem_ld16(tacc + GATE_D + c, u);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; j += 4) {
+        float4 bv = *reinterpret_cast<const float4*>(esm + c + j);
+        float4 bu = *reinterpret_cast<const float4*>(esm + GATE_D + c + j);
+        float4 w = *reinterpret_cast<const float4*>(esm + 2 * GATE_D + c + j);
+        part = fmaf(tanh_fast(__uint_as_float(v[j]) + bv.x) * sigmoid_fast(__uint_as_float(u[j]) + bu.x), w.x, part);
+        part = fmaf(tanh_fast(__uint_as_float(v[j + 1]) + bv.y) * sigmoid_fast(__uint_as_float(u[j + 1]) + bu.y), w.y, part);
+        part = fmaf(tanh_fast(__uint_as_float(v[j + 2]) + bv.z) * sigmoid_fast(__uint_as_float(u[j + 2]) + bu.z), w.z, part);
+        part = fmaf(tanh_fast(__uint_as_float(v[j + 3]) + bv.w) * sigmoid_fast(__uint_as_float(u[j + 3]) + bu.w), w.w, part);
+      }
+    }
+    if (row < M) p.scores[row] = part + __ldg(p.bw);
+  }
+  __device__ void finish(const Params&, int, int) {}
+};
+
+// sum over the 32 lanes of a warp of 16 per-lane columns; lanes 2c and 2c+1 both return column c's total
+__device__ __forceinline__ float colsum16(float* v, int lane) {
+  bool hi = lane & 16;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float send = hi ? v[j] : v[j + 8], keep = hi ? v[j + 8] : v[j];
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  hi = lane & 8;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    float send = hi ? v[j] : v[j + 4], keep = hi ? v[j + 4] : v[j];
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  hi = lane & 4;
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    float send = hi ? v[j] : v[j + 2], keep = hi ? v[j + 2] : v[j];
+    v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  hi = lane & 2;
+  {
+    float send = hi ? v[0] : v[1], keep = hi ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+struct EpiDz {
+  struct Params {
+    const float* bcat;
+    const float* ww;
+    const float* dscores;
+    __nv_bfloat16* dZ;  // [M, 384]
+    float* colsum_ws;   // [gridDim.x * 4][CS_STRIDE]
+  };
+  static constexpr int SMEM_FLOATS = 3 * GATE_D;
+  __device__ static void prologue(const Params& p, float* esm, int tid) {
+    for (int i = tid; i < 2 * GATE_D; i += NUM_THREADS) esm[i] = __ldg(p.bcat + i);
+    for (int i = tid; i < GATE_D; i += NUM_THREADS) esm[2 * GATE_D + i] = __ldg(p.ww + i);
+  }
+  float colacc[3 * GATE_D / 16];  // [0,12) dVpre, [12,24) dUpre, [24,36) ds*V*U; column (lane>>1) of each chunk
+  float ds_acc;
+  __device__ EpiDz() {
+#pragma unroll
+    for (int i = 0; i < 3 * GATE_D / 16; ++i) colacc[i] = 0.f;
+    ds_acc = 0.f;
+  }
+  template <int BN>
+  __device__ __forceinline__ void tile(const Params& p, float* esm, uint32_t tacc, int64_t row, int64_t M, int, int,
+                                       int lane) {
+    static_assert(BN == 2 * GATE_D, "dz epilogue expects the [V | U] 384-column tile");
+    const bool row_ok = row < M;
+    const float ds = row_ok ? __ldg(p.dscores + row) : 0.f;
+    ds_acc += ds;
+    __nv_bfloat16* zrow = p.dZ + row * (2 * GATE_D);
+#pragma unroll
+    for (int ci = 0; ci < GATE_D / 16; ++ci) {
+      const int c = ci * 16;
+      uint32_t v[16], u[16];
+      tmem_ld16(tacc + c, v);
+      tmem_ld16(tacc + GATE_D + c, u);
+      tmem_ld_wait();
+      float dv[16], du[16], vu[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float V = tanh_fast(__uint_as_float(v[j]) + esm[c + j]);
+        float U = sigmoid_fast(__uint_as_float(u[j]) + esm[GATE_D + c + j]);
+        float g = ds * esm[2 * GATE_D + c + j];
+        float gu = g * U;
+        dv[j] = gu * (1.f - V * V);
+        du[j] = gu * V * (1.f - U);
+        vu[j] = ds * V * U;
+      }
+      if (row_ok) {
+        *reinterpret_cast<uint4*>(zrow + c) = Vec16<__nv_bfloat16>::pack(dv);
+        *reinterpret_cast<uint4*>(zrow + c + 8) = Vec16<__nv_bfloat16>::pack(dv + 8);
+        *reinterpret_cast<uint4*>(zrow + GATE_D + c) = Vec16<__nv_bfloat16>::pack(du);
+        *reinterpret_cast<uint4*>(zrow + GATE_D + c + 8) = Vec16<__nv_bfloat16>::pack(du + 8);
+      }
+      colacc[ci] += colsum16(dv, lane);
+      colacc[GATE_D / 16 + ci] += colsum16(du, lane);
+      colacc[2 * GATE_D / 16 + ci] += colsum16(vu, lane);
+    }
+  }
+  __device__ void finish(const Params& p, int q, int lane) {
+    float* rec = p.colsum_ws + (static_cast<int64_t>(blockIdx.x) * 4 + q) * CS_STRIDE;
+    if ((lane & 1) == 0) {
+#pragma unroll
+      for (int i = 0; i < 3 * GATE_D / 16; ++i) rec[i * 16 + (lane >> 1)] = colacc[i];
+    }
+    float s = warp_sum(ds_acc);
+    if (lane == 0) rec[3 * GATE_D] = s;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// K-major persistent GEMM
+// ---------------------------------------------------------------------------------------------
+template <int BN, class Epi>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int64_t M, int N, int K,
+              uint32_t b_box_bytes, typename Epi::Params ep) {
+  using Cfg = TileCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                       // [STAGES]
+  uint64_t* empty_bar = bars + Cfg::STAGES;        // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;    // [2]
+  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
+  float* esm = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + BAR_BYTES);
+  static_assert((2 * Cfg::STAGES + 4) * 8 + 8 <= BAR_BYTES, "barrier block overflow");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m_tiles = (M + BM - 1) / BM;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int64_t tiles = m_tiles * n_tiles;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + a, 1);
+      mbar_init(tempty_bar + a, 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  Epi::prologue(ep, esm, threadIdx.x);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t stage_tx = Cfg::A_BYTES + Cfg::N_MMA * b_box_bytes;
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t mt = tile / n_tiles;
+        const int nt = static_cast<int>(tile % n_tiles);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar + s, ph ^ 1);
+          uint8_t* sa = stage_base + s * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::A_BYTES;
+          mbar_arrive_expect_tx(full_bar + s, stage_tx);
+          tma_load_2d(sa, &tmA, full_bar + s, kb * BK, static_cast<int32_t>(mt * BM), kEvictFirst);
+#pragma unroll
+          for (int j = 0; j < Cfg::N_MMA; ++j)
+            tma_load_2d(sb + j * Cfg::UMMA_N * 128, &tmB, full_bar + s, kb * BK, nt * BN + j * Cfg::UMMA_N, kEvictLast);
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, Cfg::UMMA_N, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int64_t it = 0;
+      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const int acc = static_cast<int>(it % Cfg::ACC_STAGES);
+        const uint32_t acc_ph = static_cast<uint32_t>((it / Cfg::ACC_STAGES) & 1);
+        mbar_wait(tempty_bar + acc, acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + s * Cfg::STAGE_BYTES);
+          const uint32_t sb = sa + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = umma_desc_sw128(sa + k * UMMA_K * 2, 16, 1024);
+#pragma unroll
+            for (int j = 0; j < Cfg::N_MMA; ++j) {
+              const uint64_t db = umma_desc_sw128(sb + j * Cfg::UMMA_N * 128 + k * UMMA_K * 2, 16, 1024);
+              umma_bf16(tacc + j * Cfg::UMMA_N, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+          }
+          tc_commit(empty_bar + s);  // frees the smem stage once these MMAs have read it
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+        tc_commit(tfull_bar + acc);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===== epilogue warps: warp q may touch TMEM lanes [32q, 32q+32) =====
+    const int q = warp - EPI_WARP0;
+    Epi epi;
+    int64_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int64_t mt = tile / n_tiles;
+      const int nt = static_cast<int>(tile % n_tiles);
+      const int acc = static_cast<int>(it % Cfg::ACC_STAGES);
+      const uint32_t acc_ph = static_cast<uint32_t>((it / Cfg::ACC_STAGES) & 1);
+      mbar_wait(tfull_bar + acc, acc_ph);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+      epi.template tile<BN>(ep, esm, tacc, mt * BM + q * 32 + lane, M, nt * BN, N, lane);
+      tc_fence_before();
+      mbar_arrive(tempty_bar + acc);
+    }
+    epi.finish(ep, q, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, class Epi>
+static int launch_kmajor(const void* A, int64_t M, int K, int64_t lda, const void* B, int N, int64_t ldb,
+                         typename Epi::Params ep, int* grid_out, cudaStream_t st) {
+  using Cfg = TileCfg<BN>;
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16_2d(&tmA, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), BM);
+  if (rc) return rc;
+  const uint32_t box_rows = static_cast<uint32_t>(N < Cfg::UMMA_N ? N : Cfg::UMMA_N);
+  rc = make_tmap_bf16_2d(&tmB, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), box_rows);
+  if (rc) return rc;
+  auto kern = k_gemm_kmajor<BN, Epi>;
+  constexpr size_t smem = kmajor_smem_bytes<BN, Epi>();
+  static_assert(smem <= 232448, "shared memory budget exceeded");
+  MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  if (grid_out) *grid_out = grid;
+  kern<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, M, N, K, box_rows * 128u, ep);
+  MIL_LAUNCH_CHECK();
+  return MILB200_OK;
+}
+
+bool gemm_store_supported(int64_t M, int N, int K) { return M >= 1 && N >= 16 && N % 16 == 0 && K >= 64 && K % 8 == 0; }
+
+int gemm_store(const void* A, int64_t M, int K, int64_t lda, const void* W, int N, int64_t ldw, const float* bias,
+               int act, void* out, int out_dtype, int64_t ldo, const float* attn, const float* dM,
+               const int32_t* offsets, int nbags, cudaStream_t st) {
+  MIL_CHECK_ARG(gemm_store_supported(M, N, K), MILB200_EUNSUPPORTED, "tc gemm_store: unsupported shape M=%lld N=%d K=%d",
+                (long long)M, N, K);
+  MIL_CHECK_ARG(aligned16(out) && (ldo * (out_dtype == MILB200_BF16 ? 2 : 4)) % 16 == 0, MILB200_EALIGN,
+                "tc gemm_store: output must be 16-byte aligned");
+  EpiStore::Params ep{out, out_dtype == MILB200_BF16 ? 1 : 0, ldo, bias, act, attn, dM, offsets, nbags};
+  if (N <= 128) return launch_kmajor<128, EpiStore>(A, M, K, lda, W, N, ldw, ep, nullptr, st);
+  return launch_kmajor<256, EpiStore>(A, M, K, lda, W, N, ldw, ep, nullptr, st);
+}
+
+int gated_score(const void* X, int64_t n, int L, const void* Wcat, const float* bcat, const float* ww,
+                const float* bw, float* scores, cudaStream_t st) {
+  EpiScore::Params ep{bcat, ww, bw, scores};
+  return launch_kmajor<2 * GATE_D, EpiScore>(X, n, L, L, Wcat, 2 * GATE_D, L, ep, nullptr, st);
+}
+
+int gated_dz_max_records() { return sm_count() * 4; }
+
+int gated_dz(const void* X, int64_t n, int L, const void* Wcat, const float* bcat, const float* ww,
+             const float* dscores, void* dZ, float* colsum_ws, int* nrec, cudaStream_t st) {
+  EpiDz::Params ep{bcat, ww, dscores, static_cast<__nv_bfloat16*>(dZ), colsum_ws};
+  int grid = 0;
+  int rc = launch_kmajor<2 * GATE_D, EpiDz>(X, n, L, L, Wcat, 2 * GATE_D, L, ep, &grid, st);
+  if (nrec) *nrec = grid * 4;
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// split-K "TN" GEMM: D[mo, no] = sum_k A[k, mo] * B[k, no]
+// ---------------------------------------------------------------------------------------------
+constexpr int TN_BK = 32;                 // k rows per stage
+constexpr int TN_BNO = 512;               // output columns per CTA = all 512 TMEM columns
+constexpr int TN_BOX_BYTES = TN_BK * 128; // one [32 x 64] bf16 box
+constexpr int TN_A_BYTES = 2 * TN_BOX_BYTES;
+constexpr int TN_B_BYTES = (TN_BNO / 64) * TN_BOX_BYTES;
+constexpr int TN_STAGE_BYTES = TN_A_BYTES + TN_B_BYTES;
+constexpr int TN_STAGES = 5;
+constexpr size_t TN_SMEM = 1024 + static_cast<size_t>(TN_STAGES) * TN_STAGE_BYTES + BAR_BYTES;
+static_assert(TN_SMEM <= 232448, "TN smem budget");
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int64_t Kr, int Mo, int No,
+          int m_tiles, int n_tiles, int kb_per_split, float* __restrict__ part) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TN_STAGES * TN_STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + TN_STAGES;
+  uint64_t* tfull_bar = bars + 2 * TN_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TN_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x % (m_tiles * n_tiles);
+  const int split = blockIdx.x / (m_tiles * n_tiles);
+  const int mt = tile / n_tiles, nt = tile % n_tiles;
+  const int64_t total_kb = (Kr + TN_BK - 1) / TN_BK;
+  const int64_t kb0 = static_cast<int64_t>(split) * kb_per_split;
+  int64_t kb1 = kb0 + kb_per_split;
+  if (kb1 > total_kb) kb1 = total_kb;
+  const int nkb = kb1 > kb0 ? static_cast<int>(kb1 - kb0) : 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TN_STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(empty_bar + s, ph ^ 1);
+        uint8_t* sa = smem + s * TN_STAGE_BYTES;
+        uint8_t* sb = sa + TN_A_BYTES;
+        const int32_t krow = static_cast<int32_t>((kb0 + i) * TN_BK);
+        mbar_arrive_expect_tx(full_bar + s, TN_STAGE_BYTES);
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+          tma_load_2d(sa + j * TN_BOX_BYTES, &tmA, full_bar + s, mt * BM + j * 64, krow, kEvictNormal);
+#pragma unroll
+        for (int j = 0; j < TN_BNO / 64; ++j)
+          tma_load_2d(sb + j * TN_BOX_BYTES, &tmB, full_bar + s, nt * TN_BNO + j * 64, krow, kEvictNormal);
+        if (++s == TN_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nkb > 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, 256, 1, 1);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(full_bar + s, ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * TN_STAGE_BYTES);
+        const uint32_t sb = sa + TN_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TN_BK / UMMA_K; ++k) {
+          // MN-major, 128-byte swizzle: 8 k-rows x 128 B per atom; next 8 k-rows at SBO = 1024 B,
+          // next 64 m/n elements at LBO = one box
+          const uint64_t da = umma_desc_sw128(sa + k * 2048, TN_BOX_BYTES, 1024);
+#pragma unroll
+          for (int h = 0; h < TN_BNO / 256; ++h) {
+            const uint64_t db = umma_desc_sw128(sb + h * 4 * TN_BOX_BYTES + k * 2048, TN_BOX_BYTES, 1024);
+            umma_bf16(tmem_base + h * 256, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+        }
+        tc_commit(empty_bar + s);
+        if (++s == TN_STAGES) { s = 0; ph ^= 1; }
+      }
+      tc_commit(tfull_bar);
+    }
+  } else if (warp >= EPI_WARP0) {
+    const int q = warp - EPI_WARP0;
+    const int m = mt * BM + q * 32 + lane;
+    float* prow = part + (static_cast<int64_t>(split) * Mo + m) * No + nt * TN_BNO;
+    if (nkb > 0) {
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < TN_BNO; c += 32) {
+      if (nt * TN_BNO + c >= No) break;
+      uint32_t r[32];
+      if (nkb > 0) {
+        tmem_ld32(tacc + c, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (m < Mo) {
+        const int nvalid = (No - (nt * TN_BNO + c)) < 32 ? (No - (nt * TN_BNO + c)) : 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          if (j < nvalid)
+            *reinterpret_cast<float4*>(prow + c + j) =
+                make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                            __uint_as_float(r[j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+bool gemm_tn_supported(int Mo, int No) { return Mo >= 64 && Mo % 8 == 0 && No >= 64 && No % 8 == 0; }
+
+int gemm_tn_max_splits(int Mo, int No) {
+  int tiles = ((Mo + BM - 1) / BM) * ((No + TN_BNO - 1) / TN_BNO);
+  int s = sm_count() / tiles;
+  return s < 1 ? 1 : s;
+}
+
+int gemm_tn_splitk(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t Kr, int Mo, int No, float* part,
+                   int* splits_out, cudaStream_t st) {
+  MIL_CHECK_ARG(gemm_tn_supported(Mo, No), MILB200_EUNSUPPORTED, "tc gemm_tn: unsupported shape Mo=%d No=%d", Mo, No);
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16_2d(&tmA, A, static_cast<uint64_t>(Kr), static_cast<uint64_t>(Mo), static_cast<uint64_t>(lda), TN_BK);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, B, static_cast<uint64_t>(Kr), static_cast<uint64_t>(No), static_cast<uint64_t>(ldb), TN_BK);
+  if (rc) return rc;
+  const int m_tiles = (Mo + BM - 1) / BM, n_tiles = (No + TN_BNO - 1) / TN_BNO;
+  const int64_t total_kb = (Kr + TN_BK - 1) / TN_BK;
+  int splits = gemm_tn_max_splits(Mo, No);
+  if (splits > total_kb) splits = static_cast<int>(total_kb);
+  if (splits < 1) splits = 1;
+  const int kb_per_split = static_cast<int>((total_kb + splits - 1) / splits);
+  splits = static_cast<int>((total_kb + kb_per_split - 1) / kb_per_split);
+  if (splits_out) *splits_out = splits;
+  MIL_CUDA(cudaFuncSetAttribute(k_gemm_tn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TN_SMEM)));
+  k_gemm_tn<<<m_tiles * n_tiles * splits, NUM_THREADS, TN_SMEM, st>>>(tmA, tmB, Kr, Mo, No, m_tiles, n_tiles,
+                                                                      kb_per_split, part);
+  MIL_LAUNCH_CHECK();
+  return MILB200_OK;
+}
+
+}  // namespace tc
+}  // namespace milb200

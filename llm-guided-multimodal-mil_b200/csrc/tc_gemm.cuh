@@ -1,0 +1,37 @@
+// tc_gemm.cuh — host entry points of the tcgen05/TMEM/TMA GEMM kernels (bf16 operands, fp32 accumulate).
+#pragma once
+
+#include "common.cuh"
+
+namespace milb200 {
+namespace tc {
+
+constexpr int GATE_D = 192;           // gate width the fused kernels are built for (ABMIL default D)
+constexpr int CS_STRIDE = 592;        // per-warp column-sum record: 384 dZ cols + 192 (V*U) cols + sum(ds) + pad
+
+// Y[m, n] = act(A[m, :] . W[n, :] + bias[n]) (+ attn[m] * dM[bag(m), n]);  A [M,K] and W [N,K] are bf16,
+// K-contiguous.  out_dtype selects bf16 or fp32 output (ldo elements per row).
+int gemm_store(const void* A, int64_t M, int K, int64_t lda, const void* W, int N, int64_t ldw, const float* bias,
+               int act, void* out, int out_dtype, int64_t ldo, const float* attn, const float* dM,
+               const int32_t* offsets, int nbags, cudaStream_t st);
+bool gemm_store_supported(int64_t M, int N, int K);
+
+// s[i] = sum_d tanh(x_i.Wv_d + bv_d) * sigmoid(x_i.Wu_d + bu_d) * ww_d + bw     (D = 192)
+int gated_score(const void* X, int64_t n, int L, const void* Wcat, const float* bcat, const float* ww,
+                const float* bw, float* scores, cudaStream_t st);
+
+// Recompute V,U and emit dZ[n, 384] = [dL/dVpre | dL/dUpre] (bf16) for upstream dscores; per-warp column sums
+// (-> dbcat, dww, dbw) are written to colsum_ws[nrec][CS_STRIDE]; *nrec receives the record count.
+int gated_dz(const void* X, int64_t n, int L, const void* Wcat, const float* bcat, const float* ww,
+             const float* dscores, void* dZ, float* colsum_ws, int* nrec, cudaStream_t st);
+int gated_dz_max_records();
+
+// part[s][mo][no] = sum over the k rows of split s of A[k, mo] * B[k, no]   (A [Kr, Mo], B [Kr, No] bf16,
+// both row-major => both operands MN-major for the tensor core).  *splits receives the split count.
+int gemm_tn_splitk(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t Kr, int Mo, int No, float* part,
+                   int* splits, cudaStream_t st);
+int gemm_tn_max_splits(int Mo, int No);
+bool gemm_tn_supported(int Mo, int No);
+
+}  // namespace tc
+}  // namespace milb200
