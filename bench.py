@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py — bags/s forward+backward of the gated-attention MIL pool on ragged WSI-scale bags
+(BASELINE.json configs[1]: 1 B200, bf16, bags of 100..20000 instances x 1024-dim).
+
+One "step" = one packed CSR batch of `--bags` synthetic bags per rank through
+  gated-score GEMM (tcgen05) -> segmented softmax pool -> pool backward -> gate backward (dZ recompute,
+  split-K dW GEMM) -> [NCCL all-reduce of the flat gradient if N>1] -> fused Adam.
+`value` has the inputs resident in HBM; `e2e` goes through the same public call with HOST (pinned) inputs,
+H2D copy of the bags and D2H read of the pooled vectors inside the timed region.
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                      (CPU arm: the oracle's torch fp32 restatement)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+L_FEAT, D_GATE = 1024, 192
+LEN_LO, LEN_HI = 100, 20000
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return d, "measured"
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+def bag_lengths(n_bags, seed):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(LEN_LO, LEN_HI + 1, (n_bags,), generator=g)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's torch restatement of ABMIL.forward (fp32, autograd backward), bag at a time
+# ----------------------------------------------------------------------------------------------------
+def cpu_reference(lengths, steps, warmup, budget_s=20.0):
+    import torch
+    from oracle import fusion_oracle as fo
+    from oracle import mil_oracle as mo
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    p = mo.procedural_state(mo.abmil_shapes(L_FEAT, D_GATE), 1234)
+    sd = {"a." + k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in p.items()}
+    g = torch.Generator().manual_seed(1234)
+
+    def one_bag(n):
+        x = torch.randn(1, n, L_FEAT, generator=g)
+        for t in sd.values():
+            t.grad = None
+        t0 = time.perf_counter()
+        M = fo.abmil(sd, "a", x)
+        M.sum().backward()
+        return time.perf_counter() - t0
+
+    lens = [int(v) for v in lengths]
+    for i in range(min(warmup, 2)):
+        one_bag(lens[i % len(lens)])
+    # bounded sample: each "step" is a fixed subset of the workload's bags; stop inside the budget
+    per_step = max(1, min(len(lens), 4))
+    times, done_bags, t_begin = [], 0, time.perf_counter()
+    for s in range(max(1, steps)):
+        t = 0.0
+        for j in range(per_step):
+            t += one_bag(lens[(s * per_step + j) % len(lens)])
+        times.append(t)
+        done_bags += per_step
+        if time.perf_counter() - t_begin > budget_s:
+            break
+    total = sum(times)
+    return {"value": done_bags / total, "unit": "bags/s", "cores": cores, "kind": "port",
+            "sample": f"{done_bags} bags of the same length distribution (first {per_step} lengths per step, "
+                      f"{len(times)} steps), fp32, bag-at-a-time fwd+bwd (M.sum().backward()), "
+                      f"torch {torch.__version__} with {cores} threads",
+            "ms_per_step": 1e3 * total / len(times), "steps": len(times), "bags_per_step": per_step}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--bags", type=int, default=64, help="bags per rank per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--input-grad", action="store_true", help="also produce dX (instances are trainable upstream)")
+    args = ap.parse_args()
+    warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    config = {"workload": f"gated-attention MIL fwd+bwd, ragged bags {LEN_LO}-{LEN_HI} instances x {L_FEAT}-dim "
+                          f"(BASELINE configs[1]), {args.bags} bags/rank/step packed CSR, D={D_GATE}, "
+                          f"lengths randint seed 1234+rank",
+              "bags_per_rank": args.bags, "L": L_FEAT, "D": D_GATE, "parallelism": f"dp{world}",
+              "input_grad": bool(args.input_grad),
+              "cache": "inputs (~1.3 GB/rank) exceed the 126 MB L2, no flush needed",
+              "mode": "eval-mode semantics (no dropout), dM = ones, optimizer = fused Adam in the timed region"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        lengths = bag_lengths(args.bags, 1234)
+        cb = cpu_reference(lengths, args.steps, args.warmup, budget_s=60.0)
+        line = {"impl": "reference", "metric": "bags/sec fwd+bwd", "value": cb["value"], "unit": "bags/s",
+                "n_gpus": args.gpus, "steps": cb["steps"], "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config,
+                "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": cb["value"], "unit": "bags/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import mil_b200
+    from mil_b200 import _lib as Lb
+    from mil_b200.dp import AbmilTrainer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+
+    peaks, peak_src = load_peaks()
+    lengths = bag_lengths(args.bags, 1234 + rank)
+    offsets_h = torch.zeros(args.bags + 1, dtype=torch.int32)
+    offsets_h[1:] = lengths.cumsum(0).to(torch.int32)
+    total_n = int(offsets_h[-1])
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    X = torch.randn(total_n, L_FEAT, device=dev, generator=gen).to(torch.bfloat16)
+    offsets = offsets_h.to(dev)
+
+    # parameters: reference default init (nn.Linear), seed 1234 (config.py:103), replicated via broadcast
+    torch.manual_seed(1234)
+    module = mil_b200.ABMIL(None, L=L_FEAT, D=D_GATE).to(dev)
+    tr = AbmilTrainer(L_FEAT, D_GATE, torch.bfloat16, lr=1e-5, weight_decay=1e-7, device=dev, process_group=pg,
+                      world_size=world, need_input_grad=args.input_grad)
+    tr.load_from(module)
+    tr.broadcast_params()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    for _ in range(warmup):
+        tr.step(X, offsets)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    l0 = mil_b200.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        tr.step(X, offsets)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = mil_b200.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    total_bags = args.bags * world * args.steps
+    value = total_bags / (ms_max / 1e3)
+
+    # ---- end to end: host (pinned) inputs, H2D + D2H inside the timed region ----
+    X_h = torch.empty((total_n, L_FEAT), dtype=torch.bfloat16).pin_memory()
+    X_h.copy_(X)
+    off_pin = offsets_h.pin_memory()
+    M_h = torch.empty((args.bags, L_FEAT), dtype=torch.float32).pin_memory()
+    X_d = torch.empty_like(X)
+    off_d = torch.empty_like(offsets)
+
+    def e2e_step():
+        X_d.copy_(X_h, non_blocking=True)
+        off_d.copy_(off_pin, non_blocking=True)
+        M = tr.step(X_d, off_d)
+        M_h.copy_(M, non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the caller consumes the pooled vectors
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    e2e_value = args.bags * world * e2e_steps / (e2e_ms / 1e3)
+    h2d = X_h.numel() * 2 + off_pin.numel() * 4
+    d2h = M_h.numel() * 4
+
+    # ---- per-kernel roofline (timed alone, CUDA events on the launch stream, same inputs) ----
+    kernels = []
+    if rank == 0:
+        from mil_b200 import functional as F
+        v = tr._views(tr.params)
+        Wcat = tr._wcat_lp
+        hbm_peak = float(peaks.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"]))
+        tf_peak = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
+        s = F.gated_scores(X, Wcat, v["bcat"], v["ww"], v["bw"])
+        M, _, _, _ = F.segment_softmax_pool(X, s, offsets)
+        dM = torch.ones_like(M)
+        ds, _ = F.segment_softmax_pool_bwd(X, s, offsets, dM, M, False)
+
+        def timeit(fn, reps=10):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        n, Lf, D, B = total_n, L_FEAT, D_GATE, args.bags
+        gemm_flops = 2.0 * n * Lf * 2 * D
+        t_score = timeit(lambda: F.gated_scores(X, Wcat, v["bcat"], v["ww"], v["bw"]))
+        kernels.append({"name": "gated_score_fwd (k_gemm_kmajor<384,EpiScore>)", "ms": t_score, "bound": "tensor",
+                        "achieved": gemm_flops / t_score / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
+                        "algorithmic": "2*n*L*2D flop", "hbm_gbs": (n * Lf * 2 + n * 4) / t_score / 1e6})
+        t_pool = timeit(lambda: F.segment_softmax_pool(X, s, offsets))
+        pool_bytes = n * (Lf * 2 + 4) + B * Lf * 4 + (B + 1) * 4
+        kernels.append({"name": "segment_softmax_pool_fwd (k_pool_fwd)", "ms": t_pool, "bound": "hbm",
+                        "achieved": pool_bytes / t_pool / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                        "algorithmic": "n*(L*2+4) + B*L*4 + (B+1)*4 bytes"})
+        t_pbwd = timeit(lambda: F.segment_softmax_pool_bwd(X, s, offsets, dM, M, False))
+        pbwd_bytes = n * (Lf * 2 + 4 + 4) + 2 * B * Lf * 4 + (B + 1) * 4
+        kernels.append({"name": "segment_softmax_pool_bwd (k_pool_bwd)", "ms": t_pbwd, "bound": "hbm",
+                        "achieved": pbwd_bytes / t_pbwd / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                        "algorithmic": "n*(L*2+8) + 2*B*L*4 + (B+1)*4 bytes"})
+        Lb.lib().milb200_profile_enable(1)
+        acc = [0.0] * 4
+        reps = 10
+        for i in range(reps + 3):
+            F.gated_scores_bwd(X, Wcat, v["bcat"], v["ww"], v["bw"], ds, None, dM, offsets, False, grad_out=tr.grads)
+            buf = (ctypes.c_float * 8)()
+            k = Lb.lib().milb200_profile_read(buf, 8)
+            if i >= 3:
+                for j in range(min(k, 4)):
+                    acc[j] += buf[j] / reps
+        Lb.lib().milb200_profile_enable(0)
+        kernels.append({"name": "gate_bwd dZ recompute (k_gemm_kmajor<384,EpiDz>)", "ms": acc[0], "bound": "tensor",
+                        "achieved": gemm_flops / acc[0] / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
+                        "algorithmic": "2*n*L*2D flop", "hbm_gbs": (n * Lf * 2 + n * 2 * D * 2) / acc[0] / 1e6})
+        kernels.append({"name": "gate_bwd dW split-K (k_gemm_tn)", "ms": acc[1], "bound": "tensor",
+                        "achieved": gemm_flops / acc[1] / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
+                        "algorithmic": "2*n*L*2D flop", "hbm_gbs": (n * Lf * 2 + n * 2 * D * 2) / acc[1] / 1e6})
+        kernels.append({"name": "split-K reduce (k_splitk_reduce)", "ms": acc[2], "bound": "hbm", "achieved": None,
+                        "peak": hbm_peak, "unit": "GB/s"})
+        for kinfo in kernels:
+            kinfo["frac"] = (kinfo["achieved"] / kinfo["peak"]) if kinfo.get("achieved") else None
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_base = cpu_reference(lengths, steps=3, warmup=1, budget_s=20.0)
+        cpu_base = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        dom = max(kernels, key=lambda k: k["ms"])
+        roof = {"kernel": dom["name"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
+                "unit": dom["unit"], "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                "ms_per_launch": dom["ms"], "algorithmic": dom.get("algorithmic")}
+        line = {"metric": "bags/sec fwd+bwd", "value": value, "unit": "bags/s", "n_gpus": world, "steps": args.steps,
+                "warmup": warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+                "instances_per_step_per_rank": total_n, "gpu_launches": int(launches),
+                "e2e": {"value": e2e_value, "unit": "bags/s", "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+                "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_base, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -74,6 +74,12 @@ int milb200_gated_score_bwd(const void* X, const void* Wcat, const float* bcat, 
                             int D, int dtype, float* dWcat, float* dbcat, float* dww, float* dbw,
                             void* dX, void* workspace, size_t ws_bytes, void* stream);
 
+/* Bench hook: with profiling enabled the bf16 path of milb200_gated_score_bwd records CUDA events between its
+ * sub-kernels (dz recompute | dW split-K GEMM | split-K reduce | optional dX GEMM); profile_read waits for the
+ * last one and returns up to max_intervals durations in milliseconds (return value = count).              */
+void milb200_profile_enable(int on);
+int milb200_profile_read(float* ms, int max_intervals);
+
 /* ---- ragged segmented softmax + attention-weighted instance sum ---------------------------------
  * Replaces F.softmax(A, dim=1) and torch.matmul(A, x) (model/dim1/ABMIL.py:56-59), one launch for a
  * whole CSR batch: M[b] = sum_i softmax_b(s)_i x_i.  Outputs: M[B,L] fp32; M_lowp[B,L] in X's dtype

@@ -11,7 +11,18 @@ namespace milb200 {
 bool force_simt();
 int transpose2d(const void* in, void* out, int rows, int cols, int dtype, cudaStream_t st);
 
-constexpr int64_t SIMT_ROW_CHUNK = 32768;  // bounds the fp32 pre-activation workspace of the FFMA path
+constexpr int64_t SIMT_ROW_CHUNK = 32768;
+
+// ---- optional per-sub-kernel timing of gated_score_bwd (bench.py's roofline uses it) ------------
+constexpr int PROF_MAX = 8;
+static bool g_prof_on = false;
+static cudaEvent_t g_prof_ev[PROF_MAX];
+static int g_prof_n = 0;
+static void prof_mark(cudaStream_t st) {
+  if (!g_prof_on || g_prof_n >= PROF_MAX) return;
+  if (!g_prof_ev[g_prof_n]) cudaEventCreate(&g_prof_ev[g_prof_n]);
+  cudaEventRecord(g_prof_ev[g_prof_n++], st);
+}  // bounds the fp32 pre-activation workspace of the FFMA path
 
 // ---- FFMA-path gate kernels (one warp per instance) -------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -243,6 +254,19 @@ extern "C" {
 
 int milb200_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
 
+/* Developer/bench hook: when enabled, the tensor-core path of milb200_gated_score_bwd records CUDA events
+ * between its sub-kernels (dz recompute | dW split-K GEMM | split-K reduce | dX GEMM);
+ * milb200_profile_read synchronises on the last event and returns the interval durations in ms. */
+void milb200_profile_enable(int on) { g_prof_on = on != 0; g_prof_n = 0; }
+int milb200_profile_read(float* ms, int max_intervals) {
+  int n = g_prof_n - 1;
+  if (n <= 0 || !ms) return 0;
+  if (n > max_intervals) n = max_intervals;
+  cudaEventSynchronize(g_prof_ev[g_prof_n - 1]);
+  for (int i = 0; i < n; ++i) cudaEventElapsedTime(ms + i, g_prof_ev[i], g_prof_ev[i + 1]);
+  return n;
+}
+
 size_t milb200_gated_score_workspace_bytes(int64_t total_n, int L, int D, int dtype, int backward) {
   if (total_n <= 0 || L <= 0 || D <= 0) return 256;
   return gate_ws(total_n, L, D, dtype, backward).total;
@@ -290,14 +314,19 @@ int milb200_gated_score_bwd(const void* X, const void* Wcat, const float* bcat, 
     float* colsum = reinterpret_cast<float*>(ws + w.colsum);
     float* part = reinterpret_cast<float*>(ws + w.part);
     int nrec = 0, splits = 0;
+    g_prof_n = 0;
+    prof_mark(st);
     int rc = tc::gated_dz(X, total_n, L, Wcat, bcat, ww, dscores, dZ, colsum, &nrec, st);
     if (rc) return rc;
     k_colsum_finalize<<<(3 * D + 1 + 255) / 256, 256, 0, st>>>(colsum, nrec, tc::CS_STRIDE, dbcat, dww, dbw, D);
     MIL_LAUNCH_CHECK();
+    prof_mark(st);
     rc = tc::gemm_tn_splitk(dZ, 2 * D, X, L, total_n, 2 * D, L, part, &splits, st);
     if (rc) return rc;
+    prof_mark(st);
     rc = splitk_reduce(part, splits, static_cast<int64_t>(2) * D * L, dWcat, 0, st);
     if (rc) return rc;
+    prof_mark(st);
     if (dX) {
       void* wT = ws + w.wT;  // [L, 2D]: the K-contiguous B operand of dX = dZ . Wcat
       rc = transpose2d(Wcat, wT, 2 * D, L, MILB200_BF16, st);
@@ -305,6 +334,7 @@ int milb200_gated_score_bwd(const void* X, const void* Wcat, const float* bcat, 
       rc = tc::gemm_store(dZ, total_n, 2 * D, 2 * D, wT, L, 2 * D, nullptr, MILB200_ACT_NONE, dX, MILB200_BF16, L, attn, dM,
                           offsets, B, st);
       if (rc) return rc;
+      prof_mark(st);
     }
     return MILB200_OK;
   }

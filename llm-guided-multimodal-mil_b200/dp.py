@@ -1,0 +1,111 @@
+"""Data-parallel training step for the gated-attention MIL pool (train_ddp.py:79,346-348 shape):
+bags shard across ranks, parameters are replicated, and the ONLY exchange is one all-reduce of a flat
+fp32 gradient buffer per step, followed by a fused Adam kernel (the 1/world scaling of DDP's gradient
+average is folded into it).  The backward kernels write straight into the flat buffer, so there are no
+gradient buckets, hooks or unused-parameter bitmaps.
+
+Flat layout (fp32), chosen so that [Wv; Wu] is the contiguous Wcat operand the kernels want:
+    Wv (D*L) | Wu (D*L) | bv (D) | bu (D) | ww (D) | bw (1)
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib as L
+from . import functional as F
+
+
+class AbmilTrainer:
+    def __init__(self, L_feat=1024, D=192, compute_dtype=torch.bfloat16, lr=1e-5, betas=(0.9, 0.999), eps=1e-8,
+                 weight_decay=1e-7, device="cuda", process_group=None, world_size=1, need_input_grad=False):
+        self.L, self.D = L_feat, D
+        self.dtype = compute_dtype
+        self.device = torch.device(device)
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.pg, self.world = process_group, world_size
+        self.need_input_grad = need_input_grad
+        n = 2 * D * L_feat + 3 * D + 1
+        self.numel = n
+        self.params = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.step_count = 0
+        self._wcat_lp = (torch.empty((2 * D, L_feat), dtype=compute_dtype, device=self.device)
+                         if compute_dtype != torch.float32 else None)
+
+    # ---- views into the flat buffers -----------------------------------------------------------
+    def _views(self, flat):
+        D, Lf = self.D, self.L
+        o = 2 * D * Lf
+        return dict(Wcat=flat[:o].view(2 * D, Lf), bcat=flat[o:o + 2 * D], ww=flat[o + 2 * D:o + 3 * D],
+                    bw=flat[o + 3 * D:o + 3 * D + 1])
+
+    def load_from(self, module):
+        """Copy an ABMIL module's parameters (reference state_dict names) into the flat buffer."""
+        v = self._views(self.params)
+        D = self.D
+        with torch.no_grad():
+            v["Wcat"][:D].copy_(module.attention_V[0].weight)
+            v["Wcat"][D:].copy_(module.attention_U[0].weight)
+            v["bcat"][:D].copy_(module.attention_V[0].bias)
+            v["bcat"][D:].copy_(module.attention_U[0].bias)
+            v["ww"].copy_(module.attention_weights.weight.reshape(-1))
+            v["bw"].copy_(module.attention_weights.bias.reshape(-1))
+
+    def store_to(self, module):
+        v = self._views(self.params)
+        D = self.D
+        with torch.no_grad():
+            module.attention_V[0].weight.copy_(v["Wcat"][:D])
+            module.attention_U[0].weight.copy_(v["Wcat"][D:])
+            module.attention_V[0].bias.copy_(v["bcat"][:D])
+            module.attention_U[0].bias.copy_(v["bcat"][D:])
+            module.attention_weights.weight.copy_(v["ww"].view(1, D))
+            module.attention_weights.bias.copy_(v["bw"])
+
+    def grad_views(self):
+        return self._views(self.grads)
+
+    def broadcast_params(self):
+        """DDP's constructor broadcast (rank 0 -> all), once."""
+        if self.world > 1:
+            torch.distributed.broadcast(self.params, src=0, group=self.pg)
+
+    # ---- one training step ---------------------------------------------------------------------
+    def forward_backward(self, X, offsets, dM=None):
+        """Forward + backward of the pool over one packed CSR batch.  Upstream gradient dM defaults to ones
+        (loss = sum of the pooled vectors).  Returns (M fp32 [B, L], dX or None)."""
+        v = self._views(self.params)
+        if self._wcat_lp is not None:
+            L.check(L.lib().milb200_cast(L.ptr(v["Wcat"]), L.F32, L.ptr(self._wcat_lp), L.BF16,
+                                         v["Wcat"].numel(), L.stream_ptr()), "cast")
+            Wcat = self._wcat_lp
+        else:
+            Wcat = v["Wcat"]
+        s = F.gated_scores(X, Wcat, v["bcat"], v["ww"], v["bw"])
+        M, _, am, _ = F.segment_softmax_pool(X, s, offsets)
+        if dM is None:
+            if getattr(self, "_ones", None) is None or self._ones.shape != M.shape:
+                self._ones = torch.ones_like(M)
+            dM = self._ones
+        ds, attn = F.segment_softmax_pool_bwd(X, s, offsets, dM, M, want_attn=self.need_input_grad)
+        dX, *_ = F.gated_scores_bwd(X, Wcat, v["bcat"], v["ww"], v["bw"], ds, attn, dM, offsets,
+                                    self.need_input_grad, grad_out=self.grads)
+        self.last_argmax, self.last_scores = am, s
+        return M, dX
+
+    def reduce_and_update(self):
+        """all-reduce(sum) of the flat gradient over NCCL, then fused Adam with grad_scale = 1/world."""
+        if self.world > 1:
+            torch.distributed.all_reduce(self.grads, group=self.pg)
+        self.step_count += 1
+        L.check(L.lib().milb200_adam_step(L.ptr(self.params), L.ptr(self.grads), L.ptr(self.exp_avg),
+                                          L.ptr(self.exp_avg_sq), self.numel, self.lr, self.betas[0], self.betas[1],
+                                          self.eps, self.wd, 1.0 / self.world, self.step_count, L.stream_ptr()),
+                "adam_step")
+
+    def step(self, X, offsets, dM=None):
+        M, dX = self.forward_backward(X, offsets, dM)
+        self.reduce_and_update()
+        return M
