@@ -281,10 +281,10 @@ def main():
     if rank == 0:
         from mil_b200 import functional as F
         v = tr._views(tr.params)
-        Wcat = tr._wcat_lp
+        Wcat, bcat_c = tr._wcat_c, tr._bcat_c
         hbm_peak = float(peaks.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"]))
         tf_peak = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
-        s = F.gated_scores(X, Wcat, v["bcat"], v["ww"], v["bw"])
+        s = F.gated_scores(X, Wcat, bcat_c, v["ww"], v["bw"])
         M, _, _, _ = F.segment_softmax_pool(X, s, offsets)
         dM = torch.ones_like(M)
         ds, _ = F.segment_softmax_pool_bwd(X, s, offsets, dM, M, False)
@@ -303,7 +303,7 @@ def main():
 
         n, Lf, D, B = total_n, L_FEAT, D_GATE, args.bags
         gemm_flops = 2.0 * n * Lf * 2 * D
-        t_score = timeit(lambda: F.gated_scores(X, Wcat, v["bcat"], v["ww"], v["bw"]))
+        t_score = timeit(lambda: F.gated_scores(X, Wcat, bcat_c, v["ww"], v["bw"]))
         kernels.append({"name": "gated_score_fwd (k_gemm_kmajor<384,EpiScore>)", "ms": t_score, "bound": "tensor",
                         "achieved": gemm_flops / t_score / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
                         "algorithmic": "2*n*L*2D flop", "hbm_gbs": (n * Lf * 2 + n * 4) / t_score / 1e6})
@@ -321,7 +321,7 @@ def main():
         acc = [0.0] * 4
         reps = 10
         for i in range(reps + 3):
-            F.gated_scores_bwd(X, Wcat, v["bcat"], v["ww"], v["bw"], ds, None, dM, offsets, False, grad_out=tr.grads)
+            F.gated_scores_bwd(X, Wcat, bcat_c, v["ww"], v["bw"], ds, None, dM, offsets, False, grad_out=tr.grads)
             buf = (ctypes.c_float * 8)()
             k = Lb.lib().milb200_profile_read(buf, 8)
             if i >= 3:

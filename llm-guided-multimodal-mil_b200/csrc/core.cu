@@ -36,6 +36,8 @@ int sm_count() {
   return cached;
 }
 
+bool gate_layout_interleaved(int L, int D, int dtype);
+
 bool force_simt() {
   static int v = -1;
   if (v < 0) {
@@ -116,6 +118,31 @@ int splitk_reduce(const float* part, int splits, int64_t n, float* out, int accu
   // n is a multiple of 4 for every caller except tiny vectors; the tail loop handles the rest
   int64_t threads = (n + 3) / 4;
   k_splitk_reduce<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(part, splits, n, out, accumulate);
+  MIL_LAUNCH_CHECK();
+  return MILB200_OK;
+}
+
+// dWcat (natural [dWv; dWu] rows) = sum_s part[s] with part rows in the interleaved-halves order
+__global__ void k_splitk_reduce_gate(const float* __restrict__ part, int splits, int D, int L, int dh,
+                                     float* __restrict__ out) {
+  int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  const int64_t n = static_cast<int64_t>(2) * D * L;
+  if (i >= n) return;
+  const int r = static_cast<int>(i / L), c = static_cast<int>(i % L);
+  const bool is_u = r >= D;
+  const int d = is_u ? r - D : r;
+  const int pr = (d / dh) * 2 * dh + (is_u ? dh : 0) + d % dh;
+  const float* src = part + static_cast<int64_t>(pr) * L + c;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {
+    float4 p = *reinterpret_cast<const float4*>(src + static_cast<int64_t>(s) * n);
+    a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+  }
+  *reinterpret_cast<float4*>(out + i) = a;
+}
+int splitk_reduce_gate(const float* part, int splits, int D, int L, int dh, float* out, cudaStream_t st) {
+  int64_t threads = static_cast<int64_t>(2) * D * L / 4;  // L % 8 == 0 on this path
+  k_splitk_reduce_gate<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(part, splits, D, L, dh, out);
   MIL_LAUNCH_CHECK();
   return MILB200_OK;
 }
@@ -214,19 +241,36 @@ __global__ void k_sigmoid_bce(const float* __restrict__ z, const float* __restri
   }
 }
 
+// dh > 0: interleaved-halves row order [V 0..dh-1 | U 0..dh-1 | V dh..2dh-1 | U dh..2dh-1] (tensor-core gate tiles);
+// dh == 0: plain [V | U].
 template <typename TS, typename TD>
 __global__ void k_pack_gate(const TS* __restrict__ Wv, const TS* __restrict__ Wu, const TS* __restrict__ bv,
                             const TS* __restrict__ bu, int L, int D, TD* __restrict__ Wcat,
-                            float* __restrict__ bcat) {
+                            float* __restrict__ bcat, int dh) {
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   int64_t n = static_cast<int64_t>(2) * D * L;
+  auto src_of = [&](int r, bool& is_u) {
+    if (dh > 0) {
+      int h = r / (2 * dh), w = r % (2 * dh);
+      is_u = w >= dh;
+      return h * dh + (w % dh);
+    }
+    is_u = r >= D;
+    return is_u ? r - D : r;
+  };
   if (i < n) {
-    int64_t r = i / L;
+    int r = static_cast<int>(i / L);
     int c = static_cast<int>(i % L);
-    float v = (r < D) ? to_f32<TS>(Wv[r * L + c]) : to_f32<TS>(Wu[(r - D) * L + c]);
+    bool is_u;
+    int d = src_of(r, is_u);
+    float v = is_u ? to_f32<TS>(Wu[static_cast<int64_t>(d) * L + c]) : to_f32<TS>(Wv[static_cast<int64_t>(d) * L + c]);
     Wcat[i] = from_f32<TD>(v);
   }
-  if (i < 2 * D && bcat) bcat[i] = (i < D) ? to_f32<TS>(bv[i]) : to_f32<TS>(bu[i - D]);
+  if (i < 2 * D && bcat) {
+    bool is_u;
+    int d = src_of(static_cast<int>(i), is_u);
+    bcat[i] = is_u ? to_f32<TS>(bu[d]) : to_f32<TS>(bv[d]);
+  }
 }
 
 template <typename T>
@@ -311,16 +355,17 @@ int milb200_pack_gate_weights(const void* Wv, const void* Wu, const void* bv, co
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int64_t n = static_cast<int64_t>(2) * D * L;
   unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  const int dh = gate_layout_interleaved(L, D, dst_dtype) ? D / 2 : 0;
   if (src_dtype == MILB200_F32 && dst_dtype == MILB200_F32)
     k_pack_gate<float, float><<<blocks, 256, 0, st>>>((const float*)Wv, (const float*)Wu, (const float*)bv,
-                                                      (const float*)bu, L, D, (float*)Wcat, bcat);
+                                                      (const float*)bu, L, D, (float*)Wcat, bcat, dh);
   else if (src_dtype == MILB200_F32 && dst_dtype == MILB200_BF16)
     k_pack_gate<float, __nv_bfloat16><<<blocks, 256, 0, st>>>((const float*)Wv, (const float*)Wu, (const float*)bv,
-                                                              (const float*)bu, L, D, (__nv_bfloat16*)Wcat, bcat);
+                                                              (const float*)bu, L, D, (__nv_bfloat16*)Wcat, bcat, dh);
   else if (src_dtype == MILB200_BF16 && dst_dtype == MILB200_BF16)
     k_pack_gate<__nv_bfloat16, __nv_bfloat16><<<blocks, 256, 0, st>>>(
         (const __nv_bfloat16*)Wv, (const __nv_bfloat16*)Wu, (const __nv_bfloat16*)bv, (const __nv_bfloat16*)bu, L, D,
-        (__nv_bfloat16*)Wcat, bcat);
+        (__nv_bfloat16*)Wcat, bcat, dh);
   else
     MIL_CHECK_ARG(false, MILB200_EUNSUPPORTED, "pack_gate_weights: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
   MIL_LAUNCH_CHECK();

@@ -9,6 +9,7 @@
 namespace milb200 {
 
 bool force_simt();
+int splitk_reduce_gate(const float* part, int splits, int D, int L, int dh, float* out, cudaStream_t st);
 int transpose2d(const void* in, void* out, int rows, int cols, int dtype, cudaStream_t st);
 
 constexpr int64_t SIMT_ROW_CHUNK = 32768;
@@ -82,12 +83,16 @@ k_gate_bwd(float* __restrict__ Z, const float* __restrict__ ww, const float* __r
   if (lane == 0) atomicAdd(dbw, sds);
 }
 
+// records: [ncta][8 epilogue warps e = half*4 + q][stride]; column d of each kind was produced by the warps whose
+// half == (d % (D/2)) / (D/4); the sum(ds) slot by the half-0 warps.
 __global__ void k_colsum_finalize(const float* __restrict__ ws, int nrec, int stride, float* __restrict__ dbcat,
                                   float* __restrict__ dww, float* __restrict__ dbw, int D) {
   int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c > 3 * D) return;
+  const int half = (c < 3 * D) ? ((c % D) % (D / 2)) / (D / 4) : 0;
   float a = 0.f;
-  for (int r = 0; r < nrec; ++r) a += ws[static_cast<int64_t>(r) * stride + c];
+  for (int r = 0; r < nrec; r += 8)
+    for (int q = 0; q < 4; ++q) a += ws[static_cast<int64_t>(r + half * 4 + q) * stride + c];
   if (c < 2 * D) dbcat[c] = a;
   else if (c < 3 * D) dww[c - 2 * D] = a;
   else dbw[0] = a;
@@ -130,6 +135,9 @@ static size_t simt_splits(int64_t K) {
 static bool tc_gate_ok(int L, int D, int dtype) {
   return dtype == MILB200_BF16 && D == tc::GATE_D && L >= 64 && L % 8 == 0 && !force_simt();
 }
+// The tensor-core gate kernels want the packed weight rows in interleaved-halves order (see tc_gemm.cu);
+// milb200_pack_gate_weights asks here so that packer and consumer always agree.
+bool gate_layout_interleaved(int L, int D, int dtype) { return tc_gate_ok(L, D, dtype); }
 
 // ---- workspace layouts ---------------------------------------------------------------------------
 struct GateWs {
@@ -324,7 +332,7 @@ int milb200_gated_score_bwd(const void* X, const void* Wcat, const float* bcat, 
     rc = tc::gemm_tn_splitk(dZ, 2 * D, X, L, total_n, 2 * D, L, part, &splits, st);
     if (rc) return rc;
     prof_mark(st);
-    rc = splitk_reduce(part, splits, static_cast<int64_t>(2) * D * L, dWcat, 0, st);
+    rc = splitk_reduce_gate(part, splits, D, L, D / 2, dWcat, st);
     if (rc) return rc;
     prof_mark(st);
     if (dX) {

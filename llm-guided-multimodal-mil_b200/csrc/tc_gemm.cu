@@ -20,8 +20,11 @@ namespace tc {
 constexpr int BM = 128;      // rows per tile = TMEM lanes
 constexpr int BK = 64;       // bf16 per 128-byte swizzle span
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 256;
-constexpr int EPI_WARP0 = 4;
+constexpr int EPI_WARP0 = 4;                 // warps 0-3: TMA producer, MMA issuer, TMEM allocator, spare
+constexpr int EPI_WARPS = 8;                 // two warps per TMEM lane quarter, each takes half of the columns
+constexpr int NUM_THREADS = (EPI_WARP0 + EPI_WARPS) * 32;
+constexpr int GATE_DH = GATE_D / 2;          // gate tiles: [V half | U half] = 192 accumulator columns
+constexpr int GATE_BN = 2 * GATE_DH;
 
 template <int BN>
 struct TileCfg {
@@ -32,7 +35,7 @@ struct TileCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (196608 / STAGE_BYTES) > 8 ? 8 : (196608 / STAGE_BYTES);
+  static constexpr int STAGES = (204800 / STAGE_BYTES) > 8 ? 8 : (204800 / STAGE_BYTES);
   static_assert(UMMA_N % 16 == 0 && UMMA_N <= 256, "invalid UMMA N");
   static_assert((UMMA_N * 128) % 1024 == 0, "B boxes must start on a swizzle-atom boundary");
 };
@@ -45,8 +48,15 @@ constexpr size_t kmajor_smem_bytes() {
          sizeof(float) * Epi::SMEM_FLOATS;
 }
 
+// sub-CTA barrier for the two epilogue warps that share a TMEM lane quarter
+__device__ __forceinline__ void quarter_sync(int q) {
+  asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
-// epilogues
+// epilogues.  tile<BN>(...) is called by each of the 8 epilogue warps: `q` = TMEM lane quarter (rows
+// 32q..32q+31 of the tile), `half` = which half of the tile's columns this warp owns, `nt`/`n_tiles`
+// = position in the row tile's sweep over N, `iter` = per-CTA row-tile counter.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == MILB200_ACT_TANH) return tanh_fast(v);
@@ -54,6 +64,12 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == MILB200_ACT_SIGMOID) return sigmoid_fast(v);
   return v;
 }
+
+struct EpiCtx {
+  int64_t row, M;
+  int n0, N, nt, n_tiles, q, half, lane;
+  int64_t iter;
+};
 
 struct EpiStore {
   struct Params {
@@ -71,9 +87,10 @@ struct EpiStore {
   __device__ static void prologue(const Params&, float*, int) {}
   __device__ EpiStore() {}
   template <int BN>
-  __device__ __forceinline__ void tile(const Params& p, float*, uint32_t tacc, int64_t row, int64_t M, int n0, int N,
-                                       int lane) {
-    const bool row_ok = row < M;
+  __device__ __forceinline__ void tile(const Params& p, float*, uint32_t tacc, const EpiCtx& cx) {
+    const int64_t row = cx.row;
+    const int n0 = cx.n0, N = cx.N;
+    const bool row_ok = row < cx.M;
     float a = 0.f;
     const float* dmrow = nullptr;
     if (p.attn && row_ok) {
@@ -81,7 +98,7 @@ struct EpiStore {
       dmrow = p.dM + static_cast<int64_t>(find_bag(p.offsets, p.nbags, row)) * p.ldo;
     }
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
+    for (int c = cx.half * (BN / 2); c < (cx.half + 1) * (BN / 2); c += 32) {
       if (n0 + c >= N) break;  // warp-uniform
       uint32_t r[32];
       tmem_ld32(tacc + c, r);
@@ -116,42 +133,61 @@ struct EpiStore {
   __device__ void finish(const Params&, int, int) {}
 };
 
+// Gate tiles.  The packed weight rows (and bcat) are ordered [V 0..95 | U 0..95 | V 96..191 | U 96..191], so
+// N tile h = 0/1 holds the matching (V, U) pairs of gate units d = 96h .. 96h+95 in its 192 columns and the
+// accumulator is double-buffered in TMEM (2 x 192 columns): the epilogue of one half overlaps the MMAs of
+// the next.  Warp (q, half) owns pairs [48 half, 48 half + 48) of rows [32q, 32q+32).
+constexpr int GATE_PW = GATE_DH / 2;  // pairs per warp per tile = 48
+
 struct EpiScore {
   struct Params {
-    const float* bcat;  // [384] = [bv | bu]
-    const float* ww;    // [192]
+    const float* bcat;  // [384] packed order
+    const float* ww;    // [192] natural order
     const float* bw;    // [1]
     float* scores;
   };
-  static constexpr int SMEM_FLOATS = 3 * GATE_D;
+  // bias[384] | w[192] | partial[2 parities][4 (h, half)][128 rows]
+  static constexpr int SMEM_FLOATS = 3 * GATE_D + 2 * 4 * BM;
   __device__ static void prologue(const Params& p, float* esm, int tid) {
     for (int i = tid; i < 2 * GATE_D; i += NUM_THREADS) esm[i] = __ldg(p.bcat + i);
     for (int i = tid; i < GATE_D; i += NUM_THREADS) esm[2 * GATE_D + i] = __ldg(p.ww + i);
   }
   __device__ EpiScore() {}
   template <int BN>
-  __device__ __forceinline__ void tile(const Params& p, float* esm, uint32_t tacc, int64_t row, int64_t M, int, int,
-                                       int) {
-    static_assert(BN == 2 * GATE_D, "score epilogue expects the [V | U] 384-column tile");
+  __device__ __forceinline__ void tile(const Params& p, float* esm, uint32_t tacc, const EpiCtx& cx) {
+    static_assert(BN == GATE_BN, "score epilogue expects the [V half | U half] 192-column tile");
+    const int h = cx.nt;
+    const float* bV = esm + h * GATE_BN + cx.half * GATE_PW;
+    const float* bU = bV + GATE_DH;
+    const float* wv = esm + 2 * GATE_D + h * GATE_DH + cx.half * GATE_PW;
     float part = 0.f;
-#pragma unroll 1
-    for (int c = 0; c < GATE_D; c += 16) {
+#pragma unroll
+    for (int c = 0; c < GATE_PW; c += 16) {
       uint32_t v[16], u[16];
-      tmem_ld16(tacc + c, v);
-      tmem_ld16(tacc + GATE_D + c, u);
+      tmem_ld16(tacc + cx.half * GATE_PW + c, v);
+      tmem_ld16(tacc + GATE_DH + cx.half * GATE_PW + c, u);
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
-        float4 bv = *reinterpret_cast<const float4*>(esm + c + j);
-        float4 bu = *reinterpret_cast<const float4*>(esm + GATE_D + c + j);
-        float4 w = *reinterpret_cast<const float4*>(esm + 2 * GATE_D + c + j);
+        float4 bv = *reinterpret_cast<const float4*>(bV + c + j);
+        float4 bu = *reinterpret_cast<const float4*>(bU + c + j);
+        float4 w = *reinterpret_cast<const float4*>(wv + c + j);
         part = fmaf(tanh_fast(__uint_as_float(v[j]) + bv.x) * sigmoid_fast(__uint_as_float(u[j]) + bu.x), w.x, part);
         part = fmaf(tanh_fast(__uint_as_float(v[j + 1]) + bv.y) * sigmoid_fast(__uint_as_float(u[j + 1]) + bu.y), w.y, part);
         part = fmaf(tanh_fast(__uint_as_float(v[j + 2]) + bv.z) * sigmoid_fast(__uint_as_float(u[j + 2]) + bu.z), w.z, part);
         part = fmaf(tanh_fast(__uint_as_float(v[j + 3]) + bv.w) * sigmoid_fast(__uint_as_float(u[j + 3]) + bu.w), w.w, part);
       }
     }
-    if (row < M) p.scores[row] = part + __ldg(p.bw);
+    // the four (h, half) partial sums of a row meet in shared memory; parity double-buffering keeps the next
+    // row tile's writes away from this row tile's reads
+    float* ps = esm + 3 * GATE_D + static_cast<int>(cx.iter & 1) * 4 * BM;
+    const int r = cx.q * 32 + cx.lane;
+    ps[(h * 2 + cx.half) * BM + r] = part;
+    if (h == cx.n_tiles - 1) {
+      quarter_sync(cx.q);
+      if (cx.half == 0 && cx.row < cx.M)
+        p.scores[cx.row] = ((ps[r] + ps[BM + r]) + (ps[2 * BM + r] + ps[3 * BM + r])) + __ldg(p.bw);
+    }
   }
   __device__ void finish(const Params&, int, int) {}
 };
@@ -186,45 +222,52 @@ __device__ __forceinline__ float colsum16(float* v, int lane) {
 
 struct EpiDz {
   struct Params {
-    const float* bcat;
+    const float* bcat;  // packed order
     const float* ww;
     const float* dscores;
-    __nv_bfloat16* dZ;  // [M, 384]
-    float* colsum_ws;   // [gridDim.x * 4][CS_STRIDE]
+    __nv_bfloat16* dZ;  // [M, 384], packed column order (same as the weight rows)
+    float* colsum_ws;   // [gridDim.x * EPI_WARPS][CS_STRIDE], natural order: dVpre[192] | dUpre[192] | ds*V*U[192] | sum ds
   };
   static constexpr int SMEM_FLOATS = 3 * GATE_D;
   __device__ static void prologue(const Params& p, float* esm, int tid) {
     for (int i = tid; i < 2 * GATE_D; i += NUM_THREADS) esm[i] = __ldg(p.bcat + i);
     for (int i = tid; i < GATE_D; i += NUM_THREADS) esm[2 * GATE_D + i] = __ldg(p.ww + i);
   }
-  float colacc[3 * GATE_D / 16];  // [0,12) dVpre, [12,24) dUpre, [24,36) ds*V*U; column (lane>>1) of each chunk
+  static constexpr int NCH = GATE_PW / 16;  // 16-pair chunks per warp per tile = 3
+  float colacc[2][3][NCH];                  // [h][dVpre, dUpre, ds*V*U][chunk]; column (lane>>1) of each chunk
   float ds_acc;
   __device__ EpiDz() {
 #pragma unroll
-    for (int i = 0; i < 3 * GATE_D / 16; ++i) colacc[i] = 0.f;
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) colacc[h][k][c] = 0.f;
     ds_acc = 0.f;
   }
-  template <int BN>
-  __device__ __forceinline__ void tile(const Params& p, float* esm, uint32_t tacc, int64_t row, int64_t M, int, int,
-                                       int lane) {
-    static_assert(BN == 2 * GATE_D, "dz epilogue expects the [V | U] 384-column tile");
-    const bool row_ok = row < M;
-    const float ds = row_ok ? __ldg(p.dscores + row) : 0.f;
-    ds_acc += ds;
-    __nv_bfloat16* zrow = p.dZ + row * (2 * GATE_D);
+  template <int H>
+  __device__ __forceinline__ void half_tile(const Params& p, float* esm, uint32_t tacc, const EpiCtx& cx) {
+    const bool row_ok = cx.row < cx.M;
+    const float ds = row_ok ? __ldg(p.dscores + cx.row) : 0.f;
+    if (H == 0 && cx.half == 0) ds_acc += ds;
+    const int pbase = cx.half * GATE_PW;  // first pair of this warp inside the tile
+    const float* bV = esm + H * GATE_BN + pbase;
+    const float* bU = bV + GATE_DH;
+    const float* wv = esm + 2 * GATE_D + H * GATE_DH + pbase;
+    __nv_bfloat16* zrow = p.dZ + cx.row * (2 * GATE_D) + H * GATE_BN + pbase;
 #pragma unroll
-    for (int ci = 0; ci < GATE_D / 16; ++ci) {
+    for (int ci = 0; ci < NCH; ++ci) {
       const int c = ci * 16;
       uint32_t v[16], u[16];
-      tmem_ld16(tacc + c, v);
-      tmem_ld16(tacc + GATE_D + c, u);
+      tmem_ld16(tacc + pbase + c, v);
+      tmem_ld16(tacc + GATE_DH + pbase + c, u);
       tmem_ld_wait();
       float dv[16], du[16], vu[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        float V = tanh_fast(__uint_as_float(v[j]) + esm[c + j]);
-        float U = sigmoid_fast(__uint_as_float(u[j]) + esm[GATE_D + c + j]);
-        float g = ds * esm[2 * GATE_D + c + j];
+        float V = tanh_fast(__uint_as_float(v[j]) + bV[c + j]);
+        float U = sigmoid_fast(__uint_as_float(u[j]) + bU[c + j]);
+        float g = ds * wv[c + j];
         float gu = g * U;
         dv[j] = gu * (1.f - V * V);
         du[j] = gu * V * (1.f - U);
@@ -233,19 +276,31 @@ struct EpiDz {
       if (row_ok) {
         *reinterpret_cast<uint4*>(zrow + c) = Vec16<__nv_bfloat16>::pack(dv);
         *reinterpret_cast<uint4*>(zrow + c + 8) = Vec16<__nv_bfloat16>::pack(dv + 8);
-        *reinterpret_cast<uint4*>(zrow + GATE_D + c) = Vec16<__nv_bfloat16>::pack(du);
-        *reinterpret_cast<uint4*>(zrow + GATE_D + c + 8) = Vec16<__nv_bfloat16>::pack(du + 8);
+        *reinterpret_cast<uint4*>(zrow + GATE_DH + c) = Vec16<__nv_bfloat16>::pack(du);
+        *reinterpret_cast<uint4*>(zrow + GATE_DH + c + 8) = Vec16<__nv_bfloat16>::pack(du + 8);
       }
-      colacc[ci] += colsum16(dv, lane);
-      colacc[GATE_D / 16 + ci] += colsum16(du, lane);
-      colacc[2 * GATE_D / 16 + ci] += colsum16(vu, lane);
+      colacc[H][0][ci] += colsum16(dv, cx.lane);
+      colacc[H][1][ci] += colsum16(du, cx.lane);
+      colacc[H][2][ci] += colsum16(vu, cx.lane);
     }
   }
-  __device__ void finish(const Params& p, int q, int lane) {
-    float* rec = p.colsum_ws + (static_cast<int64_t>(blockIdx.x) * 4 + q) * CS_STRIDE;
+  template <int BN>
+  __device__ __forceinline__ void tile(const Params& p, float* esm, uint32_t tacc, const EpiCtx& cx) {
+    static_assert(BN == GATE_BN, "dz epilogue expects the [V half | U half] 192-column tile");
+    if (cx.nt == 0) half_tile<0>(p, esm, tacc, cx);
+    else half_tile<1>(p, esm, tacc, cx);
+  }
+  __device__ void finish(const Params& p, int e, int lane) {
+    const int half = e / 4;
+    float* rec = p.colsum_ws + (static_cast<int64_t>(blockIdx.x) * EPI_WARPS + e) * CS_STRIDE;
     if ((lane & 1) == 0) {
 #pragma unroll
-      for (int i = 0; i < 3 * GATE_D / 16; ++i) rec[i * 16 + (lane >> 1)] = colacc[i];
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+          for (int c = 0; c < NCH; ++c)
+            rec[k * GATE_D + h * GATE_DH + half * GATE_PW + c * 16 + (lane >> 1)] = colacc[h][k][c];
     }
     float s = warp_sum(ds_acc);
     if (lane == 0) rec[3 * GATE_D] = s;
@@ -253,7 +308,8 @@ struct EpiDz {
 };
 
 // ---------------------------------------------------------------------------------------------
-// K-major persistent GEMM
+// K-major persistent GEMM.  A CTA owns row tiles mt = blockIdx.x, blockIdx.x + gridDim.x, ... and sweeps
+// the N tiles of each (the A tile's second pass comes from L2).
 // ---------------------------------------------------------------------------------------------
 template <int BN, class Epi>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -275,7 +331,6 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m_tiles = (M + BM - 1) / BM;
   const int n_tiles = (N + BN - 1) / BN;
-  const int64_t tiles = m_tiles * n_tiles;
   const int num_kb = (K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -289,7 +344,7 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar + a, 1);
-      mbar_init(tempty_bar + a, 128);
+      mbar_init(tempty_bar + a, EPI_WARPS * 32);
     }
     fence_barrier_init();
   }
@@ -306,19 +361,21 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       int s = 0;
       uint32_t ph = 0;
       const uint32_t stage_tx = Cfg::A_BYTES + Cfg::N_MMA * b_box_bytes;
-      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int64_t mt = tile / n_tiles;
-        const int nt = static_cast<int>(tile % n_tiles);
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(empty_bar + s, ph ^ 1);
-          uint8_t* sa = stage_base + s * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_BYTES;
-          mbar_arrive_expect_tx(full_bar + s, stage_tx);
-          tma_load_2d(sa, &tmA, full_bar + s, kb * BK, static_cast<int32_t>(mt * BM), kEvictFirst);
+      for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+        for (int nt = 0; nt < n_tiles; ++nt) {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(empty_bar + s, ph ^ 1);
+            uint8_t* sa = stage_base + s * Cfg::STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            mbar_arrive_expect_tx(full_bar + s, stage_tx);
+            // the A tile is read n_tiles times back to back: keep it in L2 until the last sweep
+            tma_load_2d(sa, &tmA, full_bar + s, kb * BK, static_cast<int32_t>(mt * BM),
+                        nt == n_tiles - 1 ? kEvictFirst : kEvictNormal);
 #pragma unroll
-          for (int j = 0; j < Cfg::N_MMA; ++j)
-            tma_load_2d(sb + j * Cfg::UMMA_N * 128, &tmB, full_bar + s, kb * BK, nt * BN + j * Cfg::UMMA_N, kEvictLast);
-          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+            for (int j = 0; j < Cfg::N_MMA; ++j)
+              tma_load_2d(sb + j * Cfg::UMMA_N * 128, &tmB, full_bar + s, kb * BK, nt * BN + j * Cfg::UMMA_N, kEvictLast);
+            if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+          }
         }
       }
     }
@@ -329,50 +386,58 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       int s = 0;
       uint32_t ph = 0;
       int64_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-        const int acc = static_cast<int>(it % Cfg::ACC_STAGES);
-        const uint32_t acc_ph = static_cast<uint32_t>((it / Cfg::ACC_STAGES) & 1);
-        mbar_wait(tempty_bar + acc, acc_ph ^ 1);
-        tc_fence_after();
-        const uint32_t tacc = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(full_bar + s, ph);
+      for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+        for (int nt = 0; nt < n_tiles; ++nt, ++it) {
+          const int acc = static_cast<int>(it % Cfg::ACC_STAGES);
+          const uint32_t acc_ph = static_cast<uint32_t>((it / Cfg::ACC_STAGES) & 1);
+          mbar_wait(tempty_bar + acc, acc_ph ^ 1);
           tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + s * Cfg::STAGE_BYTES);
-          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint32_t tacc = tmem_base + acc * BN;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(full_bar + s, ph);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(stage_base + s * Cfg::STAGE_BYTES);
+            const uint32_t sb = sa + Cfg::A_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            const uint64_t da = umma_desc_sw128(sa + k * UMMA_K * 2, 16, 1024);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = umma_desc_sw128(sa + k * UMMA_K * 2, 16, 1024);
 #pragma unroll
-            for (int j = 0; j < Cfg::N_MMA; ++j) {
-              const uint64_t db = umma_desc_sw128(sb + j * Cfg::UMMA_N * 128 + k * UMMA_K * 2, 16, 1024);
-              umma_bf16(tacc + j * Cfg::UMMA_N, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              for (int j = 0; j < Cfg::N_MMA; ++j) {
+                const uint64_t db = umma_desc_sw128(sb + j * Cfg::UMMA_N * 128 + k * UMMA_K * 2, 16, 1024);
+                umma_bf16(tacc + j * Cfg::UMMA_N, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+              }
             }
+            tc_commit(empty_bar + s);  // frees the smem stage once these MMAs have read it
+            if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
           }
-          tc_commit(empty_bar + s);  // frees the smem stage once these MMAs have read it
-          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+          tc_commit(tfull_bar + acc);  // accumulator complete -> epilogue
         }
-        tc_commit(tfull_bar + acc);  // accumulator complete -> epilogue
       }
     }
   } else if (warp >= EPI_WARP0) {
-    // ===== epilogue warps: warp q may touch TMEM lanes [32q, 32q+32) =====
-    const int q = warp - EPI_WARP0;
+    // ===== epilogue warps: warp e may touch TMEM lanes [32 (e%4), 32 (e%4) + 32) =====
+    const int e = warp - EPI_WARP0;
     Epi epi;
+    EpiCtx cx;
+    cx.M = M; cx.N = N; cx.n_tiles = n_tiles; cx.q = e & 3; cx.half = e >> 2; cx.lane = lane;
     int64_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-      const int64_t mt = tile / n_tiles;
-      const int nt = static_cast<int>(tile % n_tiles);
-      const int acc = static_cast<int>(it % Cfg::ACC_STAGES);
-      const uint32_t acc_ph = static_cast<uint32_t>((it / Cfg::ACC_STAGES) & 1);
-      mbar_wait(tfull_bar + acc, acc_ph);
-      tc_fence_after();
-      const uint32_t tacc = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-      epi.template tile<BN>(ep, esm, tacc, mt * BM + q * 32 + lane, M, nt * BN, N, lane);
-      tc_fence_before();
-      mbar_arrive(tempty_bar + acc);
+    cx.iter = 0;
+    for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++cx.iter) {
+      cx.row = mt * BM + cx.q * 32 + lane;
+      for (int nt = 0; nt < n_tiles; ++nt, ++it) {
+        const int acc = static_cast<int>(it % Cfg::ACC_STAGES);
+        const uint32_t acc_ph = static_cast<uint32_t>((it / Cfg::ACC_STAGES) & 1);
+        mbar_wait(tfull_bar + acc, acc_ph);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + acc * BN + (static_cast<uint32_t>(cx.q * 32) << 16);
+        cx.nt = nt;
+        cx.n0 = nt * BN;
+        epi.template tile<BN>(ep, esm, tacc, cx);
+        tc_fence_before();
+        mbar_arrive(tempty_bar + acc);
+      }
     }
-    epi.finish(ep, q, lane);
+    epi.finish(ep, e, lane);
   }
 
   tc_fence_before();
@@ -397,8 +462,8 @@ static int launch_kmajor(const void* A, int64_t M, int K, int64_t lda, const voi
   constexpr size_t smem = kmajor_smem_bytes<BN, Epi>();
   static_assert(smem <= 232448, "shared memory budget exceeded");
   MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const int64_t tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
+  const int64_t m_tiles = (M + BM - 1) / BM;
+  const int grid = static_cast<int>(m_tiles < sm_count() ? m_tiles : sm_count());
   if (grid_out) *grid_out = grid;
   kern<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, M, N, K, box_rows * 128u, ep);
   MIL_LAUNCH_CHECK();
@@ -422,17 +487,17 @@ int gemm_store(const void* A, int64_t M, int K, int64_t lda, const void* W, int 
 int gated_score(const void* X, int64_t n, int L, const void* Wcat, const float* bcat, const float* ww,
                 const float* bw, float* scores, cudaStream_t st) {
   EpiScore::Params ep{bcat, ww, bw, scores};
-  return launch_kmajor<2 * GATE_D, EpiScore>(X, n, L, L, Wcat, 2 * GATE_D, L, ep, nullptr, st);
+  return launch_kmajor<GATE_BN, EpiScore>(X, n, L, L, Wcat, 2 * GATE_D, L, ep, nullptr, st);
 }
 
-int gated_dz_max_records() { return sm_count() * 4; }
+int gated_dz_max_records() { return sm_count() * EPI_WARPS; }
 
 int gated_dz(const void* X, int64_t n, int L, const void* Wcat, const float* bcat, const float* ww,
              const float* dscores, void* dZ, float* colsum_ws, int* nrec, cudaStream_t st) {
   EpiDz::Params ep{bcat, ww, dscores, static_cast<__nv_bfloat16*>(dZ), colsum_ws};
   int grid = 0;
-  int rc = launch_kmajor<2 * GATE_D, EpiDz>(X, n, L, L, Wcat, 2 * GATE_D, L, ep, &grid, st);
-  if (nrec) *nrec = grid * 4;
+  int rc = launch_kmajor<GATE_BN, EpiDz>(X, n, L, L, Wcat, 2 * GATE_D, L, ep, &grid, st);
+  if (nrec) *nrec = grid * EPI_WARPS;
   return rc;
 }
 
@@ -534,7 +599,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       tc_commit(tfull_bar);
     }
   } else if (warp >= EPI_WARP0) {
-    const int q = warp - EPI_WARP0;
+    const int q = (warp - EPI_WARP0) & 3, half = (warp - EPI_WARP0) >> 2;
     const int m = mt * BM + q * 32 + lane;
     float* prow = part + (static_cast<int64_t>(split) * Mo + m) * No + nt * TN_BNO;
     if (nkb > 0) {
@@ -543,7 +608,7 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     }
     const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-    for (int c = 0; c < TN_BNO; c += 32) {
+    for (int c = half * (TN_BNO / 2); c < (half + 1) * (TN_BNO / 2); c += 32) {
       if (nt * TN_BNO + c >= No) break;
       uint32_t r[32];
       if (nkb > 0) {

@@ -31,8 +31,8 @@ class AbmilTrainer:
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.step_count = 0
-        self._wcat_lp = (torch.empty((2 * D, L_feat), dtype=compute_dtype, device=self.device)
-                         if compute_dtype != torch.float32 else None)
+        self._wcat_c = torch.empty((2 * D, L_feat), dtype=compute_dtype, device=self.device)
+        self._bcat_c = torch.empty((2 * D,), dtype=torch.float32, device=self.device)
 
     # ---- views into the flat buffers -----------------------------------------------------------
     def _views(self, flat):
@@ -77,20 +77,21 @@ class AbmilTrainer:
         """Forward + backward of the pool over one packed CSR batch.  Upstream gradient dM defaults to ones
         (loss = sum of the pooled vectors).  Returns (M fp32 [B, L], dX or None)."""
         v = self._views(self.params)
-        if self._wcat_lp is not None:
-            L.check(L.lib().milb200_cast(L.ptr(v["Wcat"]), L.F32, L.ptr(self._wcat_lp), L.BF16,
-                                         v["Wcat"].numel(), L.stream_ptr()), "cast")
-            Wcat = self._wcat_lp
-        else:
-            Wcat = v["Wcat"]
-        s = F.gated_scores(X, Wcat, v["bcat"], v["ww"], v["bw"])
+        # fp32 master -> compute-dtype operand in the row order the kernels expect (one tiny kernel)
+        D = self.D
+        L.check(L.lib().milb200_pack_gate_weights(L.ptr(v["Wcat"][:D]), L.ptr(v["Wcat"][D:]), L.ptr(v["bcat"][:D]),
+                                                  L.ptr(v["bcat"][D:]), L.F32, self.L, D, L.ptr(self._wcat_c),
+                                                  L.dtype_code(self._wcat_c), L.ptr(self._bcat_c), L.stream_ptr()),
+                "pack_gate_weights")
+        Wcat, bcat = self._wcat_c, self._bcat_c
+        s = F.gated_scores(X, Wcat, bcat, v["ww"], v["bw"])
         M, _, am, _ = F.segment_softmax_pool(X, s, offsets)
         if dM is None:
             if getattr(self, "_ones", None) is None or self._ones.shape != M.shape:
                 self._ones = torch.ones_like(M)
             dM = self._ones
         ds, attn = F.segment_softmax_pool_bwd(X, s, offsets, dM, M, want_attn=self.need_input_grad)
-        dX, *_ = F.gated_scores_bwd(X, Wcat, v["bcat"], v["ww"], v["bw"], ds, attn, dM, offsets,
+        dX, *_ = F.gated_scores_bwd(X, Wcat, bcat, v["ww"], v["bw"], ds, attn, dM, offsets,
                                     self.need_input_grad, grad_out=self.grads)
         self.last_argmax, self.last_scores = am, s
         return M, dX
