@@ -67,18 +67,20 @@ static EncodeTiledFn get_encoder() {
 }
 
 static int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int esz, const void* base, uint64_t rows,
-                     uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+                     uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols, bool swizzle128 = true) {
   EncodeTiledFn enc = get_encoder();
   MIL_CHECK_ARG(enc != nullptr, MILB200_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
   MIL_CHECK_ARG(aligned16(base) && (ld * esz) % 16 == 0, MILB200_EALIGN,
                 "TMA operand needs a 16-byte aligned base and row pitch (ld=%llu)", (unsigned long long)ld);
-  MIL_CHECK_ARG(box_rows >= 1 && box_rows <= 256 && box_cols * esz <= 128, MILB200_EINVAL, "bad TMA box");
+  MIL_CHECK_ARG(box_rows >= 1 && box_rows <= 256 && box_cols >= 1 && box_cols <= 256 &&
+                    (!swizzle128 || box_cols * esz <= 128) && (box_cols * esz) % 16 == 0,
+                MILB200_EINVAL, "bad TMA box");
   cuuint64_t dims[2] = {cols, rows};
   cuuint64_t strides[1] = {ld * esz};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MIL_CHECK_ARG(r == CUDA_SUCCESS, MILB200_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u",
                 (int)r, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
@@ -87,6 +89,10 @@ static int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int esz, const vo
 int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                       uint32_t box_rows, uint32_t box_cols) {
   return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, ld, box_rows, box_cols);
+}
+int make_tmap_bf16_2d_linear(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                             uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, ld, box_rows, box_cols, false);
 }
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                      uint32_t box_rows, uint32_t box_cols) {

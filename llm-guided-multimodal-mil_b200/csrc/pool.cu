@@ -117,20 +117,23 @@ k_pool_fwd(const T* __restrict__ X, const float* __restrict__ scores, const int3
 #pragma unroll
       for (int k = 0; k < VN; ++k) acc[j][k] = 0.f;
     if (active) {
+      // software-pipelined: the next batch of UNR rows is in flight while the current one is consumed
       constexpr int UNR = (VPT == 1) ? 4 : 2;
-      int i = rg;
-      for (; i + (UNR - 1) * R < nseg; i += UNR * R) {
-        uint4 v[UNR][VPT];
+      auto load_batch = [&](uint4 (&v)[UNR][VPT], int i0) {
 #pragma unroll
         for (int u = 0; u < UNR; ++u)
 #pragma unroll
           for (int j = 0; j < VPT; ++j) {
             int vec = vt + j * TPR;
-            v[u][j] = (vec < V) ? ldg_stream(Xv + (s0 + i + u * R) * rowvecs + vec) : make_uint4(0, 0, 0, 0);
+            int row = i0 + u * R;
+            v[u][j] = (vec < V && row < nseg) ? ldg_stream(Xv + (s0 + row) * rowvecs + vec) : make_uint4(0, 0, 0, 0);
           }
+      };
+      auto consume = [&](const uint4 (&v)[UNR][VPT], int i0) {
 #pragma unroll
         for (int u = 0; u < UNR; ++u) {
-          float w = e_s[i + u * R];
+          int row = i0 + u * R;
+          float w = row < nseg ? e_s[row] : 0.f;
 #pragma unroll
           for (int j = 0; j < VPT; ++j) {
             float f[VN];
@@ -139,19 +142,20 @@ k_pool_fwd(const T* __restrict__ X, const float* __restrict__ scores, const int3
             for (int k = 0; k < VN; ++k) acc[j][k] = fmaf(w, f[k], acc[j][k]);
           }
         }
-      }
-      for (; i < nseg; i += R) {
-        float w = e_s[i];
-#pragma unroll
-        for (int j = 0; j < VPT; ++j) {
-          int vec = vt + j * TPR;
-          if (vec < V) {
-            float f[VN];
-            Vec16<T>::unpack(ldg_stream(Xv + (s0 + i) * rowvecs + vec), f);
-#pragma unroll
-            for (int k = 0; k < VN; ++k) acc[j][k] = fmaf(w, f[k], acc[j][k]);
-          }
-        }
+      };
+      uint4 bufA[UNR][VPT], bufB[UNR][VPT];
+      int i = rg;
+      if (i < nseg) load_batch(bufA, i);
+      while (i < nseg) {
+        const int inext = i + UNR * R;
+        if (inext < nseg) load_batch(bufB, inext);
+        consume(bufA, i);
+        i = inext;
+        if (i >= nseg) break;
+        const int inext2 = i + UNR * R;
+        if (inext2 < nseg) load_batch(bufA, inext2);
+        consume(bufB, i);
+        i = inext2;
       }
 #pragma unroll
       for (int j = 0; j < VPT; ++j) {

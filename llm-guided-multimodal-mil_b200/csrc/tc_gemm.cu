@@ -35,17 +35,25 @@ struct TileCfg {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (204800 / STAGE_BYTES) > 8 ? 8 : (204800 / STAGE_BYTES);
   static_assert(UMMA_N % 16 == 0 && UMMA_N <= 256, "invalid UMMA N");
   static_assert((UMMA_N * 128) % 1024 == 0, "B boxes must start on a swizzle-atom boundary");
 };
 
 constexpr int BAR_BYTES = 256;
+constexpr int SMEM_BUDGET = 232448;  // 227 KB opt-in maximum per CTA
 
+// shared-memory image: [stages][barriers 256 B][epilogue staging (TMA-store source)][epilogue floats]
+template <int BN, class Epi>
+__host__ __device__ constexpr int epi_bytes() { return Epi::STAGING_BYTES + static_cast<int>(sizeof(float)) * Epi::SMEM_FLOATS; }
+template <int BN, class Epi>
+__host__ __device__ constexpr int kmajor_stages() {
+  int s = (SMEM_BUDGET - 1024 - BAR_BYTES - epi_bytes<BN, Epi>()) / TileCfg<BN>::STAGE_BYTES;
+  return s > 8 ? 8 : s;
+}
 template <int BN, class Epi>
 constexpr size_t kmajor_smem_bytes() {
-  return 1024 + static_cast<size_t>(TileCfg<BN>::STAGES) * TileCfg<BN>::STAGE_BYTES + BAR_BYTES +
-         sizeof(float) * Epi::SMEM_FLOATS;
+  return 1024 + static_cast<size_t>(kmajor_stages<BN, Epi>()) * TileCfg<BN>::STAGE_BYTES + BAR_BYTES +
+         epi_bytes<BN, Epi>();
 }
 
 // sub-CTA barrier for the two epilogue warps that share a TMEM lane quarter
@@ -84,10 +92,11 @@ struct EpiStore {
     int nbags;
   };
   static constexpr int SMEM_FLOATS = 0;
+  static constexpr int STAGING_BYTES = 0;
   __device__ static void prologue(const Params&, float*, int) {}
   __device__ EpiStore() {}
   template <int BN>
-  __device__ __forceinline__ void tile(const Params& p, float*, uint32_t tacc, const EpiCtx& cx) {
+  __device__ __forceinline__ void tile(const Params& p, float*, uint8_t*, uint32_t tacc, const EpiCtx& cx) {
     const int64_t row = cx.row;
     const int n0 = cx.n0, N = cx.N;
     const bool row_ok = row < cx.M;
@@ -148,13 +157,14 @@ struct EpiScore {
   };
   // bias[384] | w[192] | partial[2 parities][4 (h, half)][128 rows]
   static constexpr int SMEM_FLOATS = 3 * GATE_D + 2 * 4 * BM;
+  static constexpr int STAGING_BYTES = 0;
   __device__ static void prologue(const Params& p, float* esm, int tid) {
     for (int i = tid; i < 2 * GATE_D; i += NUM_THREADS) esm[i] = __ldg(p.bcat + i);
     for (int i = tid; i < GATE_D; i += NUM_THREADS) esm[2 * GATE_D + i] = __ldg(p.ww + i);
   }
   __device__ EpiScore() {}
   template <int BN>
-  __device__ __forceinline__ void tile(const Params& p, float* esm, uint32_t tacc, const EpiCtx& cx) {
+  __device__ __forceinline__ void tile(const Params& p, float* esm, uint8_t*, uint32_t tacc, const EpiCtx& cx) {
     static_assert(BN == GATE_BN, "score epilogue expects the [V half | U half] 192-column tile");
     const int h = cx.nt;
     const float* bV = esm + h * GATE_BN + cx.half * GATE_PW;
@@ -225,10 +235,12 @@ struct EpiDz {
     const float* bcat;  // packed order
     const float* ww;
     const float* dscores;
-    __nv_bfloat16* dZ;  // [M, 384], packed column order (same as the weight rows)
+    CUtensorMap tmZ;    // dZ [M, 384] bf16, packed column order (same as the weight rows); box [32 rows x 48 cols]
     float* colsum_ws;   // [gridDim.x * EPI_WARPS][CS_STRIDE], natural order: dVpre[192] | dUpre[192] | ds*V*U[192] | sum ds
   };
   static constexpr int SMEM_FLOATS = 3 * GATE_D;
+  static constexpr int BOX_BYTES = 32 * GATE_PW * 2;              // one [32 rows x 48 bf16] TMA-store box
+  static constexpr int STAGING_BYTES = EPI_WARPS * 2 * BOX_BYTES;  // per warp: dVpre box | dUpre box
   __device__ static void prologue(const Params& p, float* esm, int tid) {
     for (int i = tid; i < 2 * GATE_D; i += NUM_THREADS) esm[i] = __ldg(p.bcat + i);
     for (int i = tid; i < GATE_D; i += NUM_THREADS) esm[2 * GATE_D + i] = __ldg(p.ww + i);
@@ -246,15 +258,22 @@ struct EpiDz {
     ds_acc = 0.f;
   }
   template <int H>
-  __device__ __forceinline__ void half_tile(const Params& p, float* esm, uint32_t tacc, const EpiCtx& cx) {
+  __device__ __forceinline__ void half_tile(const Params& p, float* esm, uint8_t* staging, uint32_t tacc,
+                                            const EpiCtx& cx) {
     const bool row_ok = cx.row < cx.M;
     const float ds = row_ok ? __ldg(p.dscores + cx.row) : 0.f;
+    // this warp's staging boxes: thread (lane) owns row `lane` of each [32 x 48] box (96 B per row)
+    uint8_t* boxV = staging + (cx.half * 4 + cx.q) * 2 * BOX_BYTES;
+    uint8_t* boxU = boxV + BOX_BYTES;
+    if (cx.lane == 0) tma_store_wait_read<0>();  // the previous half tile's boxes have been read out
+    __syncwarp();
     if (H == 0 && cx.half == 0) ds_acc += ds;
     const int pbase = cx.half * GATE_PW;  // first pair of this warp inside the tile
     const float* bV = esm + H * GATE_BN + pbase;
     const float* bU = bV + GATE_DH;
     const float* wv = esm + 2 * GATE_D + H * GATE_DH + pbase;
-    __nv_bfloat16* zrow = p.dZ + cx.row * (2 * GATE_D) + H * GATE_BN + pbase;
+    uint8_t* rowV = boxV + cx.lane * (GATE_PW * 2);
+    uint8_t* rowU = boxU + cx.lane * (GATE_PW * 2);
 #pragma unroll
     for (int ci = 0; ci < NCH; ++ci) {
       const int c = ci * 16;
@@ -273,24 +292,33 @@ struct EpiDz {
         du[j] = gu * V * (1.f - U);
         vu[j] = ds * V * U;
       }
-      if (row_ok) {
-        *reinterpret_cast<uint4*>(zrow + c) = Vec16<__nv_bfloat16>::pack(dv);
-        *reinterpret_cast<uint4*>(zrow + c + 8) = Vec16<__nv_bfloat16>::pack(dv + 8);
-        *reinterpret_cast<uint4*>(zrow + GATE_DH + c) = Vec16<__nv_bfloat16>::pack(du);
-        *reinterpret_cast<uint4*>(zrow + GATE_DH + c + 8) = Vec16<__nv_bfloat16>::pack(du + 8);
-      }
+      *reinterpret_cast<uint4*>(rowV + c * 2) = Vec16<__nv_bfloat16>::pack(dv);
+      *reinterpret_cast<uint4*>(rowV + c * 2 + 16) = Vec16<__nv_bfloat16>::pack(dv + 8);
+      *reinterpret_cast<uint4*>(rowU + c * 2) = Vec16<__nv_bfloat16>::pack(du);
+      *reinterpret_cast<uint4*>(rowU + c * 2 + 16) = Vec16<__nv_bfloat16>::pack(du + 8);
       colacc[H][0][ci] += colsum16(dv, cx.lane);
       colacc[H][1][ci] += colsum16(du, cx.lane);
       colacc[H][2][ci] += colsum16(vu, cx.lane);
     }
+    // hand the two boxes to the TMA engine: rows beyond M are clipped by the tensor map
+    fence_proxy_async();
+    __syncwarp();
+    if (cx.lane == 0) {
+      const int32_t r0 = static_cast<int32_t>(cx.row);  // lane 0 holds the first row of this warp's quarter
+      tma_store_2d(&p.tmZ, boxV, H * GATE_BN + pbase, r0);
+      tma_store_2d(&p.tmZ, boxU, H * GATE_BN + GATE_DH + pbase, r0);
+      tma_store_commit();
+    }
   }
   template <int BN>
-  __device__ __forceinline__ void tile(const Params& p, float* esm, uint32_t tacc, const EpiCtx& cx) {
+  __device__ __forceinline__ void tile(const Params& p, float* esm, uint8_t* staging, uint32_t tacc,
+                                       const EpiCtx& cx) {
     static_assert(BN == GATE_BN, "dz epilogue expects the [V half | U half] 192-column tile");
-    if (cx.nt == 0) half_tile<0>(p, esm, tacc, cx);
-    else half_tile<1>(p, esm, tacc, cx);
+    if (cx.nt == 0) half_tile<0>(p, esm, staging, tacc, cx);
+    else half_tile<1>(p, esm, staging, tacc, cx);
   }
   __device__ void finish(const Params& p, int e, int lane) {
+    if (lane == 0) tma_store_wait<0>();  // all dZ boxes are globally visible before the kernel ends
     const int half = e / 4;
     float* rec = p.colsum_ws + (static_cast<int64_t>(blockIdx.x) * EPI_WARPS + e) * CS_STRIDE;
     if ((lane & 1) == 0) {
@@ -314,19 +342,23 @@ struct EpiDz {
 template <int BN, class Epi>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int64_t M, int N, int K,
-              uint32_t b_box_bytes, typename Epi::Params ep) {
+              uint32_t b_box_bytes, const __grid_constant__ typename Epi::Params ep) {
   using Cfg = TileCfg<BN>;
+  constexpr int STAGES = kmajor_stages<BN, Epi>();
+  static_assert(STAGES >= 3, "pipeline too shallow");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
-  uint64_t* full_bar = bars;                       // [STAGES]
-  uint64_t* empty_bar = bars + Cfg::STAGES;        // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * Cfg::STAGES;    // [2]
-  uint64_t* tempty_bar = bars + 2 * Cfg::STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * Cfg::STAGES + 4);
-  float* esm = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + BAR_BYTES);
-  static_assert((2 * Cfg::STAGES + 4) * 8 + 8 <= BAR_BYTES, "barrier block overflow");
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full_bar = bars;                   // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;         // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;     // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint8_t* staging = smem + STAGES * Cfg::STAGE_BYTES + BAR_BYTES;
+  float* esm = reinterpret_cast<float*>(staging + Epi::STAGING_BYTES);
+  static_assert((2 * STAGES + 4) * 8 + 8 <= BAR_BYTES, "barrier block overflow");
+  static_assert(Epi::STAGING_BYTES % 128 == 0, "TMA-store staging must stay 128-byte aligned");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m_tiles = (M + BM - 1) / BM;
@@ -338,7 +370,7 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     prefetch_tmap(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) {
+    for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
     }
@@ -374,7 +406,7 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < Cfg::N_MMA; ++j)
               tma_load_2d(sb + j * Cfg::UMMA_N * 128, &tmB, full_bar + s, kb * BK, nt * BN + j * Cfg::UMMA_N, kEvictLast);
-            if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+            if (++s == STAGES) { s = 0; ph ^= 1; }
           }
         }
       }
@@ -408,7 +440,7 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               }
             }
             tc_commit(empty_bar + s);  // frees the smem stage once these MMAs have read it
-            if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+            if (++s == STAGES) { s = 0; ph ^= 1; }
           }
           tc_commit(tfull_bar + acc);  // accumulator complete -> epilogue
         }
@@ -432,7 +464,7 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const uint32_t tacc = tmem_base + acc * BN + (static_cast<uint32_t>(cx.q * 32) << 16);
         cx.nt = nt;
         cx.n0 = nt * BN;
-        epi.template tile<BN>(ep, esm, tacc, cx);
+        epi.template tile<BN>(ep, esm, staging, tacc, cx);
         tc_fence_before();
         mbar_arrive(tempty_bar + acc);
       }
@@ -494,7 +526,10 @@ int gated_dz_max_records() { return sm_count() * EPI_WARPS; }
 
 int gated_dz(const void* X, int64_t n, int L, const void* Wcat, const float* bcat, const float* ww,
              const float* dscores, void* dZ, float* colsum_ws, int* nrec, cudaStream_t st) {
-  EpiDz::Params ep{bcat, ww, dscores, static_cast<__nv_bfloat16*>(dZ), colsum_ws};
+  EpiDz::Params ep;
+  ep.bcat = bcat; ep.ww = ww; ep.dscores = dscores; ep.colsum_ws = colsum_ws;
+  int rc0 = make_tmap_bf16_2d_linear(&ep.tmZ, dZ, static_cast<uint64_t>(n), 2 * GATE_D, 2 * GATE_D, 32, GATE_PW);
+  if (rc0) return rc0;
   int grid = 0;
   int rc = launch_kmajor<GATE_BN, EpiDz>(X, n, L, L, Wcat, 2 * GATE_D, L, ep, &grid, st);
   if (nrec) *nrec = grid * EPI_WARPS;

@@ -96,7 +96,7 @@ def stage_gate(dtype, with_dx=True, Ls=(1024, 512, 768), n_list=(1, 300, 5000)):
             Wcat, bcat = F.pack_gate_weights(Wv, bv, Wu, bu, dtype)
             s = F.gated_scores(X, Wcat, bcat, ww.reshape(-1).contiguous(), bw)
             torch.cuda.synchronize()
-            Wvq, Wuq = Wcat[:D].float(), Wcat[D:].float()
+            Wvq, Wuq = Wv.to(dtype).float(), Wu.to(dtype).float()
             sr, V, U = ref_gate(X, Wvq, bv, Wuq, bu, ww, bw)
             e_s = rel(s, sr)
             ds = torch.randn(n, device="cuda") / n ** 0.5
@@ -141,7 +141,7 @@ def stage_tc_score():
             Wcat, bcat = F.pack_gate_weights(Wv, bv, Wu, bu, torch.bfloat16)
             s = F.gated_scores(X, Wcat, bcat, ww.reshape(-1).contiguous(), bw)
             torch.cuda.synchronize()
-            sr, V, U = ref_gate(X, Wcat[:D].float(), bv, Wcat[D:].float(), bu, ww, bw)
+            sr, V, U = ref_gate(X, Wv.bfloat16().float(), bv, Wu.bfloat16().float(), bu, ww, bw)
             print(f"tc_score L={L} n={n}: s rel {rel(s, sr):.2e}  (s[0..3]={s[:3].tolist()} ref={sr[:3].tolist()})", flush=True)
 
 
