@@ -412,37 +412,41 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer (one thread) =====
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, Cfg::UMMA_N, 0, 0);
-      int s = 0;
-      uint32_t ph = 0;
-      int64_t it = 0;
-      for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
-        for (int nt = 0; nt < n_tiles; ++nt, ++it) {
-          const int acc = static_cast<int>(it % Cfg::ACC_STAGES);
-          const uint32_t acc_ph = static_cast<uint32_t>((it / Cfg::ACC_STAGES) & 1);
-          mbar_wait(tempty_bar + acc, acc_ph ^ 1);
+    // ===== MMA issuer: the whole warp walks the loop (so addresses stay in uniform registers); one elected
+    // lane issues tcgen05.mma / tcgen05.commit =====
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, Cfg::UMMA_N, 0, 0);
+    const uint64_t desc0 = umma_desc_sw128(smem_u32(stage_base), 16, 1024);
+    const uint32_t d_hi = static_cast<uint32_t>(desc0 >> 32);
+    const uint32_t a_lo0 = static_cast<uint32_t>(desc0);
+    const uint32_t b_lo0 = a_lo0 + (Cfg::A_BYTES >> 4);
+    int s = 0;
+    uint32_t ph = 0;
+    int64_t it = 0;
+    for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+      for (int nt = 0; nt < n_tiles; ++nt, ++it) {
+        const int acc = static_cast<int>(it % Cfg::ACC_STAGES);
+        const uint32_t acc_ph = static_cast<uint32_t>((it / Cfg::ACC_STAGES) & 1);
+        mbar_wait(tempty_bar + acc, acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + s, ph);
           tc_fence_after();
-          const uint32_t tacc = tmem_base + acc * BN;
-          for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(full_bar + s, ph);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(stage_base + s * Cfg::STAGE_BYTES);
-            const uint32_t sb = sa + Cfg::A_BYTES;
+          if (elect_one()) {
+            const uint32_t so = static_cast<uint32_t>(s) * (Cfg::STAGE_BYTES >> 4);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
-              const uint64_t da = umma_desc_sw128(sa + k * UMMA_K * 2, 16, 1024);
 #pragma unroll
-              for (int j = 0; j < Cfg::N_MMA; ++j) {
-                const uint64_t db = umma_desc_sw128(sb + j * Cfg::UMMA_N * 128 + k * UMMA_K * 2, 16, 1024);
-                umma_bf16(tacc + j * Cfg::UMMA_N, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-              }
+              for (int j = 0; j < Cfg::N_MMA; ++j)
+                umma_bf16_lohi(tacc + j * Cfg::UMMA_N, a_lo0 + so + k * (UMMA_K * 2 >> 4), d_hi,
+                               b_lo0 + so + ((j * Cfg::UMMA_N * 128) >> 4) + k * (UMMA_K * 2 >> 4), d_hi, idesc,
+                               (kb | k) != 0 ? 1u : 0u);
             }
             tc_commit(empty_bar + s);  // frees the smem stage once these MMAs have read it
-            if (++s == STAGES) { s = 0; ph ^= 1; }
+            if (kb == num_kb - 1) tc_commit(tfull_bar + acc);  // accumulator complete -> epilogue
           }
-          tc_commit(tfull_bar + acc);  // accumulator complete -> epilogue
+          __syncwarp();
+          if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
     }
@@ -608,30 +612,35 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && nkb > 0) {
+    if (nkb > 0) {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, 256, 1, 1);
+      // MN-major, 128-byte swizzle: 8 k-rows x 128 B per atom; next 8 k-rows at SBO = 1024 B, next 64 m/n
+      // elements at LBO = one box
+      const uint64_t desc0 = umma_desc_sw128(smem_u32(smem), TN_BOX_BYTES, 1024);
+      const uint32_t d_hi = static_cast<uint32_t>(desc0 >> 32);
+      const uint32_t a_lo0 = static_cast<uint32_t>(desc0);
+      const uint32_t b_lo0 = a_lo0 + (TN_A_BYTES >> 4);
       int s = 0;
       uint32_t ph = 0;
       for (int i = 0; i < nkb; ++i) {
         mbar_wait(full_bar + s, ph);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * TN_STAGE_BYTES);
-        const uint32_t sb = sa + TN_A_BYTES;
+        if (elect_one()) {
+          const uint32_t so = static_cast<uint32_t>(s) * (TN_STAGE_BYTES >> 4);
 #pragma unroll
-        for (int k = 0; k < TN_BK / UMMA_K; ++k) {
-          // MN-major, 128-byte swizzle: 8 k-rows x 128 B per atom; next 8 k-rows at SBO = 1024 B,
-          // next 64 m/n elements at LBO = one box
-          const uint64_t da = umma_desc_sw128(sa + k * 2048, TN_BOX_BYTES, 1024);
+          for (int k = 0; k < TN_BK / UMMA_K; ++k) {
 #pragma unroll
-          for (int h = 0; h < TN_BNO / 256; ++h) {
-            const uint64_t db = umma_desc_sw128(sb + h * 4 * TN_BOX_BYTES + k * 2048, TN_BOX_BYTES, 1024);
-            umma_bf16(tmem_base + h * 256, da, db, idesc, (i | k) != 0 ? 1u : 0u);
+            for (int h = 0; h < TN_BNO / 256; ++h)
+              umma_bf16_lohi(tmem_base + h * 256, a_lo0 + so + k * (2048 >> 4), d_hi,
+                             b_lo0 + so + ((h * 4 * TN_BOX_BYTES) >> 4) + k * (2048 >> 4), d_hi, idesc,
+                             (i | k) != 0 ? 1u : 0u);
           }
+          tc_commit(empty_bar + s);
+          if (i == nkb - 1) tc_commit(tfull_bar);
         }
-        tc_commit(empty_bar + s);
+        __syncwarp();
         if (++s == TN_STAGES) { s = 0; ph ^= 1; }
       }
-      tc_commit(tfull_bar);
     }
   } else if (warp >= EPI_WARP0) {
     const int q = (warp - EPI_WARP0) & 3, half = (warp - EPI_WARP0) >> 2;
