@@ -147,14 +147,21 @@ int milb200_attention_bwd(const void* Q, const void* K, const void* V, const voi
 int milb200_clip_logits_fwd(const void* I, const void* T, const float* logit_scale, float* logits,
                             float* inv_norm_i, float* inv_norm_t, int bi, int bt, int d, int dtype,
                             void* stream);
+/* Backward: upstream gradients of logits_per_image ([bi,bt]) and/or logits_per_text ([bt,bi]) — either may be
+ * NULL.  dI/dT in `dtype` (may be NULL), dscale[1] = d/d logit_scale (may be NULL).                      */
 int milb200_clip_logits_bwd(const void* I, const void* T, const float* logit_scale, const float* logits,
-                            const float* inv_norm_i, const float* inv_norm_t, const float* dlogits,
-                            void* dI, void* dT, float* dscale, int bi, int bt, int d, int dtype,
-                            void* stream);
+                            const float* inv_norm_i, const float* inv_norm_t, const float* dlogits_per_image,
+                            const float* dlogits_per_text, void* dI, void* dT, float* dscale, int bi, int bt,
+                            int d, int dtype, void* stream);
 /* utils.py:277-282 (CLIPloss_v1): logits[i] = out @ feat[:,i,:]^T ([I,b,b]), CE over dim 1 against the
- * identity, mean over I*b.  out[b,d] (dtype), feat[b,I,d] (dtype, frozen).  loss[1], dout[b,d] fp32.  */
-int milb200_cliploss_fwd_bwd(const void* out, const void* feat, float* logits, float* loss, float* dout,
-                             int b, int n_info, int d, int dtype, void* stream);
+ * identity, mean over I*b.  out[b,d] (dtype), feat[b,I,d] (dtype, frozen).  logits fp32 [I,b,b];
+ * lse_ws fp32 [2*I*b] scratch; loss[1]; dout[b,d] fp32 (may be NULL).                                     */
+int milb200_cliploss_fwd_bwd(const void* out, const void* feat, float* logits, float* lse_ws, float* loss,
+                             float* dout, int b, int n_info, int d, int dtype, void* stream);
+/* nn.CosineEmbeddingLoss(a, b, target=+1) (train_ddp.py:102,326): loss[1] = mean_i(1 - cos(a_i, b_i)) and its
+ * gradients da, db ([n,d] in dtype, may be NULL).  loss_rows_ws fp32 [n] scratch.                          */
+int milb200_cosine_embedding_fwd_bwd(const void* a, const void* b, float* loss, float* loss_rows_ws, void* da,
+                                     void* db, int n, int d, int dtype, void* stream);
 /* sigmoid + BCELoss(mean) of aggregator.py:200 / train_ddp.py:99,319: prob = sigmoid(z),
  * loss = mean BCE(prob, target), dz = (prob - target)/numel.  z,target,prob,dz fp32[n].             */
 int milb200_sigmoid_bce_fwd_bwd(const float* z, const float* target, float* prob, float* loss, float* dz,

@@ -206,3 +206,350 @@ class _DenseSumPool(torch.autograd.Function):
 
 def dense_sum_pool(x):
     return _DenseSumPool.apply(x)
+
+
+# --------------------------------------------------------------------------------------------------
+# dense layers, LayerNorm, attention core                    (reference: model/sam/transformer.py)
+# --------------------------------------------------------------------------------------------------
+_ACT = {None: L.ACT_NONE, "none": L.ACT_NONE, "tanh": L.ACT_TANH, "relu": L.ACT_RELU, "sigmoid": L.ACT_SIGMOID}
+
+
+def cast(t, dtype):
+    """dtype conversion through the library's cast kernel (fp32 <-> bf16)."""
+    if t.dtype == dtype:
+        return t
+    t = t.contiguous()
+    out = torch.empty_like(t, dtype=dtype)
+    L.check(L.lib().milb200_cast(L.ptr(t), L.dtype_code(t), L.ptr(out), L.dtype_code(out), t.numel(),
+                                 L.stream_ptr()), "cast")
+    return out
+
+
+class _Linear(torch.autograd.Function):
+    """y = act((x [+ add]) W^T + b): nn.Linear (+Tanh/ReLU) sites of aggregator.py:44,47,66 and
+    transformer.py:430-432,448 / common.py:26.  `add` fuses the `keys + key_pe` / `queries + query_pe` sums."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, act, add):
+        shp = x.shape
+        k = shp[-1]
+        n = W.shape[0]
+        x2 = x.contiguous().view(-1, k)
+        a2 = add.contiguous().view(-1, k) if add is not None else None
+        if a2 is not None and a2.shape != x2.shape:
+            raise L.MilB200Error("linear: `add` must have the shape of x")
+        m = x2.shape[0]
+        Wc = cast(W, x2.dtype)
+        bf = _f32(b).contiguous() if b is not None else None
+        y = torch.empty((m, n), dtype=x2.dtype, device=x2.device)
+        code = L.dtype_code(x2)
+        nb = L.lib().milb200_linear_workspace_bytes(m, n, k, code, 0)
+        ws = L.workspace(nb, x2.device)
+        L.check(L.lib().milb200_linear_fwd(L.ptr(x2), L.ptr(a2), L.ptr(Wc), L.ptr(bf), L.ptr(y), m, n, k, act, code,
+                                           L.ptr(ws), ws.numel(), L.stream_ptr()), "linear_fwd")
+        ctx.save_for_backward(x2, a2, Wc, y)
+        ctx.meta = (shp, m, n, k, act, W.dtype, b.dtype if b is not None else None, add is not None,
+                    add.shape if add is not None else None)
+        return y.view(*shp[:-1], n)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, a2, Wc, y = ctx.saved_tensors
+        shp, m, n, k, act, wdt, bdt, has_add, ashp = ctx.meta
+        need_dx = ctx.needs_input_grad[0] or (has_add and ctx.needs_input_grad[4])
+        need_dw = ctx.needs_input_grad[1]
+        need_db = bdt is not None and ctx.needs_input_grad[2]
+        dy2 = dy.contiguous().view(m, n)
+        if dy2.dtype != x2.dtype:
+            dy2 = cast(dy2, x2.dtype)
+        dX = torch.empty_like(x2) if need_dx else None
+        dW = torch.empty((n, k), dtype=torch.float32, device=x2.device) if need_dw else None
+        db = torch.empty((n,), dtype=torch.float32, device=x2.device) if need_db else None
+        code = L.dtype_code(x2)
+        nb = L.lib().milb200_linear_workspace_bytes(m, n, k, code, 1)
+        ws = L.workspace(nb, x2.device)
+        L.check(L.lib().milb200_linear_bwd(L.ptr(x2), L.ptr(a2), L.ptr(Wc), L.ptr(y), L.ptr(dy2), L.ptr(dX), L.ptr(dW),
+                                           L.ptr(db), m, n, k, act, code, 0, L.ptr(ws), ws.numel(), L.stream_ptr()),
+                "linear_bwd")
+        gx = dX.view(shp) if (dX is not None and ctx.needs_input_grad[0]) else None
+        ga = dX.view(ashp) if (dX is not None and has_add and ctx.needs_input_grad[4]) else None
+        gw = cast(dW, wdt) if dW is not None else None
+        gb = cast(db, bdt) if db is not None else None
+        return gx, gw, gb, None, ga
+
+
+def linear(x, W, b=None, act=None, add=None):
+    return _Linear.apply(x, W, b, _ACT[act] if not isinstance(act, int) else act, add)
+
+
+class _LayerNorm(torch.autograd.Function):
+    """y = LayerNorm(x [+ r]) * gamma + beta, eps 1e-5 (transformer.py:288,295,300,307,118; the residual adds of
+    :286,294,299,306 are fused in)."""
+
+    @staticmethod
+    def forward(ctx, x, r, gamma, beta):
+        shp = x.shape
+        n = shp[-1]
+        x2 = x.contiguous().view(-1, n)
+        r2 = r.contiguous().view(-1, n) if r is not None else None
+        m = x2.shape[0]
+        g, b = _f32(gamma).contiguous(), _f32(beta).contiguous()
+        y = torch.empty_like(x2)
+        mean = torch.empty((m,), dtype=torch.float32, device=x2.device)
+        rstd = torch.empty((m,), dtype=torch.float32, device=x2.device)
+        L.check(L.lib().milb200_layernorm_fwd(L.ptr(x2), L.ptr(r2), L.ptr(g), L.ptr(b), L.ptr(y), L.ptr(mean),
+                                              L.ptr(rstd), m, n, L.dtype_code(x2), L.stream_ptr()), "layernorm_fwd")
+        ctx.save_for_backward(x2, r2, g, mean, rstd)
+        ctx.meta = (shp, m, n, gamma.dtype, beta.dtype, r is not None)
+        return y.view(shp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, r2, g, mean, rstd = ctx.saved_tensors
+        shp, m, n, gdt, bdt, has_r = ctx.meta
+        dy2 = dy.contiguous().view(m, n)
+        if dy2.dtype != x2.dtype:
+            dy2 = cast(dy2, x2.dtype)
+        dxr = torch.empty_like(x2)
+        dg = torch.empty((n,), dtype=torch.float32, device=x2.device)
+        db = torch.empty((n,), dtype=torch.float32, device=x2.device)
+        nb = L.lib().milb200_layernorm_workspace_bytes(m, n)
+        ws = L.workspace(nb, x2.device)
+        L.check(L.lib().milb200_layernorm_bwd(L.ptr(x2), L.ptr(r2), L.ptr(g), L.ptr(mean), L.ptr(rstd), L.ptr(dy2),
+                                              L.ptr(dxr), L.ptr(dg), L.ptr(db), m, n, L.dtype_code(x2), 0, L.ptr(ws),
+                                              ws.numel(), L.stream_ptr()), "layernorm_bwd")
+        gx = dxr.view(shp)
+        return gx, (gx if has_r else None), cast(dg, gdt), cast(db, bdt)
+
+
+def layernorm(x, gamma, beta, residual=None):
+    return _LayerNorm.apply(x, residual, gamma, beta)
+
+
+class _AttentionCore(torch.autograd.Function):
+    """O = softmax(Q K^T / sqrt(c)) V per head (transformer.py:434-446). q [nq, H*c], k/v [nk, H*c]."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, heads):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        nq, C = q.shape
+        nk = k.shape[0]
+        c = C // heads
+        o = torch.empty_like(q)
+        lse = torch.empty((heads, nq), dtype=torch.float32, device=q.device)
+        nb = L.lib().milb200_attention_workspace_bytes(nq, nk, heads, c, 0)
+        ws = L.workspace(nb, q.device)
+        L.check(L.lib().milb200_attention_fwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(o), L.ptr(lse), nq, nk, heads, c,
+                                              L.dtype_code(q), L.ptr(ws), ws.numel(), L.stream_ptr()), "attention_fwd")
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.heads = heads
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o, lse = ctx.saved_tensors
+        heads = ctx.heads
+        nq, C = q.shape
+        nk = k.shape[0]
+        c = C // heads
+        do = do.contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        nb = L.lib().milb200_attention_workspace_bytes(nq, nk, heads, c, 1)
+        ws = L.workspace(nb, q.device)
+        L.check(L.lib().milb200_attention_bwd(L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(o), L.ptr(lse), L.ptr(do), L.ptr(dq),
+                                              L.ptr(dk), L.ptr(dv), nq, nk, heads, c, L.dtype_code(q), L.ptr(ws),
+                                              ws.numel(), L.stream_ptr()), "attention_bwd")
+        return dq, dk, dv, None
+
+
+def attention_core(q, k, v, heads):
+    return _AttentionCore.apply(q, k, v, heads)
+
+
+class _Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        out = torch.empty_like(a)
+        L.check(L.lib().milb200_add(L.ptr(a), L.ptr(b), L.ptr(out), a.numel(), L.dtype_code(a), L.stream_ptr()), "add")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add(a, b):
+    """a + b for same-shape tensors through the library's vectorised add kernel."""
+    if a.shape != b.shape or a.dtype != b.dtype:
+        raise L.MilB200Error("add: operands must share shape and dtype")
+    return _Add.apply(a, b)
+
+
+class _CtTokens(torch.autograd.Function):
+    """(1, C, T, h, w) CT feature map -> (1, T, C) tokens: mean over (h, w) then permute (transformer.py:93)."""
+
+    @staticmethod
+    def forward(ctx, fmap):
+        b, c, t, h, w = fmap.shape
+        if b != 1:
+            raise L.MilB200Error("ct_tokens: the reference runs one bag per call (batch 1)")
+        fmap = fmap.contiguous()
+        out = torch.empty((1, t, c), dtype=fmap.dtype, device=fmap.device)
+        L.check(L.lib().milb200_ct_tokens_fwd(L.ptr(fmap), L.ptr(out), c, t, h * w, L.dtype_code(fmap), L.stream_ptr()),
+                "ct_tokens_fwd")
+        ctx.shape = (b, c, t, h, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        b, c, t, h, w = ctx.shape
+        g = g.contiguous()
+        out = torch.empty((b, c, t, h, w), dtype=g.dtype, device=g.device)
+        L.check(L.lib().milb200_ct_tokens_bwd(L.ptr(g), L.ptr(out), c, t, h * w, L.dtype_code(g), L.stream_ptr()),
+                "ct_tokens_bwd")
+        return out
+
+
+def ct_tokens(fmap):
+    return _CtTokens.apply(fmap)
+
+
+def sinusoid_pe(n_pos, dim, dtype, device):
+    """On-device sinusoidal table (aggregator.py:99-106), shape (1, n_pos, dim)."""
+    pe = torch.empty((1, n_pos, dim), dtype=dtype, device=device)
+    L.check(L.lib().milb200_sinusoid_pe(L.ptr(pe), n_pos, dim, L.dtype_code(pe), L.stream_ptr()), "sinusoid_pe")
+    return pe
+
+
+# --------------------------------------------------------------------------------------------------
+# CLIP logits and the small losses
+# --------------------------------------------------------------------------------------------------
+class _ClipLogits(torch.autograd.Function):
+    """clip/model.py:359-368: (logits_per_image, logits_per_text) = exp(logit_scale) * cos(I, T) and transpose."""
+
+    @staticmethod
+    def forward(ctx, img, txt, logit_scale):
+        img, txt = img.contiguous(), txt.contiguous()
+        bi, d = img.shape
+        bt = txt.shape[0]
+        ls = _f32(logit_scale).reshape(1).contiguous()
+        li = torch.empty((bi, bt), dtype=torch.float32, device=img.device)
+        ni = torch.empty((bi,), dtype=torch.float32, device=img.device)
+        nt = torch.empty((bt,), dtype=torch.float32, device=img.device)
+        L.check(L.lib().milb200_clip_logits_fwd(L.ptr(img), L.ptr(txt), L.ptr(ls), L.ptr(li), L.ptr(ni), L.ptr(nt), bi,
+                                                bt, d, L.dtype_code(img), L.stream_ptr()), "clip_logits_fwd")
+        lt = torch.empty((bt, bi), dtype=torch.float32, device=img.device)
+        L.check(L.lib().milb200_transpose(L.ptr(li), L.ptr(lt), bi, bt, L.F32, L.stream_ptr()), "transpose")
+        ctx.save_for_backward(img, txt, ls, li, ni, nt)
+        ctx.ls_meta = (logit_scale.dtype, logit_scale.shape)
+        return li, lt
+
+    @staticmethod
+    def backward(ctx, dli, dlt):
+        img, txt, ls, li, ni, nt = ctx.saved_tensors
+        bi, d = img.shape
+        bt = txt.shape[0]
+        dli = _f32(dli).contiguous() if dli is not None else None
+        dlt = _f32(dlt).contiguous() if dlt is not None else None
+        dI = torch.empty_like(img) if ctx.needs_input_grad[0] else None
+        dT = torch.empty_like(txt) if ctx.needs_input_grad[1] else None
+        dsc = torch.empty((1,), dtype=torch.float32, device=img.device) if ctx.needs_input_grad[2] else None
+        L.check(L.lib().milb200_clip_logits_bwd(L.ptr(img), L.ptr(txt), L.ptr(ls), L.ptr(li), L.ptr(ni), L.ptr(nt),
+                                                L.ptr(dli), L.ptr(dlt), L.ptr(dI), L.ptr(dT), L.ptr(dsc), bi, bt, d,
+                                                L.dtype_code(img), L.stream_ptr()), "clip_logits_bwd")
+        if dsc is not None:
+            dt, shp = ctx.ls_meta
+            dsc = cast(dsc, dt).view(shp)
+        return dI, dT, dsc
+
+
+def clip_logits(image_features, text_features, logit_scale):
+    return _ClipLogits.apply(image_features, text_features, logit_scale)
+
+
+class _ClipLossV1(torch.autograd.Function):
+    """utils.py:277-282 given the frozen text features feat [b, I, d]: returns (loss, logits [I,b,b])."""
+
+    @staticmethod
+    def forward(ctx, out, feat):
+        out, feat = out.contiguous(), feat.contiguous()
+        b, d = out.shape
+        n_info = feat.shape[1]
+        if feat.dtype != out.dtype:
+            feat = cast(feat, out.dtype)
+        logits = torch.empty((n_info, b, b), dtype=torch.float32, device=out.device)
+        wsb = torch.empty((2 * n_info * b,), dtype=torch.float32, device=out.device)
+        loss = torch.empty((1,), dtype=torch.float32, device=out.device)
+        dout = torch.empty((b, d), dtype=torch.float32, device=out.device)
+        L.check(L.lib().milb200_cliploss_fwd_bwd(L.ptr(out), L.ptr(feat), L.ptr(logits), L.ptr(wsb), L.ptr(loss),
+                                                 L.ptr(dout), b, n_info, d, L.dtype_code(out), L.stream_ptr()),
+                "cliploss_fwd_bwd")
+        ctx.save_for_backward(dout)
+        ctx.odt = out.dtype
+        ctx.mark_non_differentiable(logits)
+        return loss.view(()), logits
+
+    @staticmethod
+    def backward(ctx, g, _gl):
+        (dout,) = ctx.saved_tensors
+        return cast((dout * g).contiguous(), ctx.odt) if dout.dtype != ctx.odt else dout * g, None
+
+
+def cliploss_v1(output, text_features):
+    return _ClipLossV1.apply(output, text_features)
+
+
+class _SigmoidBCE(torch.autograd.Function):
+    """prob = sigmoid(z); loss = BCELoss(prob, target) (mean) — aggregator.py:200 + train_ddp.py:99,319."""
+
+    @staticmethod
+    def forward(ctx, z, target):
+        zf, tf = _f32(z).contiguous(), _f32(target).contiguous()
+        n = zf.numel()
+        prob = torch.empty_like(zf)
+        loss = torch.empty((1,), dtype=torch.float32, device=z.device)
+        dz = torch.empty_like(zf)
+        L.check(L.lib().milb200_sigmoid_bce_fwd_bwd(L.ptr(zf), L.ptr(tf), L.ptr(prob), L.ptr(loss), L.ptr(dz), n,
+                                                    L.stream_ptr()), "sigmoid_bce")
+        ctx.save_for_backward(dz)
+        ctx.zdt = z.dtype
+        ctx.mark_non_differentiable(prob)
+        return loss.view(()), prob
+
+    @staticmethod
+    def backward(ctx, g, _gp):
+        (dz,) = ctx.saved_tensors
+        out = dz * g
+        return (out if ctx.zdt == torch.float32 else cast(out.contiguous(), ctx.zdt)), None
+
+
+def sigmoid_bce(logits, target):
+    """Returns (loss, prob)."""
+    return _SigmoidBCE.apply(logits, target)
+
+
+class _CosineEmbeddingLoss(torch.autograd.Function):
+    """nn.CosineEmbeddingLoss(a, b, target=+1) = mean(1 - cos(a_i, b_i)) (train_ddp.py:102,326)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        n, d = a.shape
+        loss = torch.empty((1,), dtype=torch.float32, device=a.device)
+        rows = torch.empty((n,), dtype=torch.float32, device=a.device)
+        da, db = torch.empty_like(a), torch.empty_like(b)
+        L.check(L.lib().milb200_cosine_embedding_fwd_bwd(L.ptr(a), L.ptr(b), L.ptr(loss), L.ptr(rows), L.ptr(da),
+                                                         L.ptr(db), n, d, L.dtype_code(a), L.stream_ptr()),
+                "cosine_embedding")
+        ctx.save_for_backward(da, db)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        da, db = ctx.saved_tensors
+        return da * g.to(da.dtype), db * g.to(db.dtype)
+
+
+def cosine_embedding_loss(a, b):
+    return _CosineEmbeddingLoss.apply(a, b)
