@@ -105,8 +105,8 @@ int milb200_segment_softmax_pool_bwd(const void* X, const float* scores, const i
  * fc_CI2CT/fc_CI2Pth (model/aggregator.py:44,47,66), q/k/v/out projections
  * (model/sam/transformer.py:430-432,448) and MLPBlock (model/sam/common.py:26).
  * X, W, Y share `dtype`; bias fp32 (may be NULL).  If `add` != NULL the input is (X + add) — the
- * `keys + key_pe` / `queries + query_pe` sums of transformer.py:291-292,303-304 fused into the load
- * (fp32 path only; the bf16 path needs it pre-added).                                               */
+ * `keys + key_pe` / `queries + query_pe` sums of transformer.py:291-292,303-304 (the sum is staged in
+ * the workspace, so query milb200_linear_workspace_bytes for the forward too).                      */
 size_t milb200_linear_workspace_bytes(int64_t m, int n, int k, int dtype, int backward);
 
 int milb200_linear_fwd(const void* X, const void* add, const void* W, const float* bias, void* Y,
@@ -188,6 +188,10 @@ int milb200_cast(const void* in, int src_dtype, void* out, int dst_dtype, int64_
 int milb200_transpose(const void* in, void* out, int rows, int cols, int dtype, void* stream);
 /* out = a + b (broadcast none); any of the three dtypes per `dtype`. (keys + key_pe, residual adds)   */
 int milb200_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream);
+/* out = alpha * a + beta * b (b may be NULL: out = alpha * a) — (x_CT + x_pathology) / 2 of
+ * model/aggregator_clip.py:94 and gradient scaling.                                                  */
+int milb200_axpby(const void* a, const void* b, void* out, int64_t n, float alpha, float beta, int dtype,
+                  void* stream);
 /* on-device sinusoidal table pe[n_pos, dim] (model/aggregator.py:99-106), written in `dtype`.         */
 int milb200_sinusoid_pe(void* pe, int64_t n_pos, int dim, int dtype, void* stream);
 /* (B,C,T,H*W) -> (T,C) mean over the trailing axis then transpose (transformer.py:93), fwd and bwd.    */

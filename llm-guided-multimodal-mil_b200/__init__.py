@@ -7,5 +7,12 @@ from . import _lib
 from ._lib import MilB200Error, launch_count, lib
 from . import functional
 from .abmil import ABMIL, ABMIL_v2
+from . import model
+from . import clip_loss
+from .clip_loss import CLIPLogits, CLIPloss_v1
+from .model.sam.transformer import Attention, TwoWayAttentionBlock, TwoWayTransformer
+from .model.sam.common import MLPBlock
+from .model.utils import get_model
 
-__all__ = ["ABMIL", "ABMIL_v2", "functional", "lib", "launch_count", "MilB200Error"]
+__all__ = ["ABMIL", "ABMIL_v2", "Attention", "TwoWayAttentionBlock", "TwoWayTransformer", "MLPBlock", "CLIPLogits",
+           "CLIPloss_v1", "get_model", "model", "clip_loss", "functional", "lib", "launch_count", "MilB200Error"]

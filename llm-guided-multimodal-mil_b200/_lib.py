@@ -53,6 +53,7 @@ SIGNATURES = {
     "milb200_cliploss_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "milb200_cosine_embedding_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "milb200_add": (_i, [_p, _p, _p, _i64, _i, _p]),
+    "milb200_axpby": (_i, [_p, _p, _p, _i64, _f, _f, _i, _p]),
     "milb200_sinusoid_pe": (_i, [_p, _i64, _i, _i, _p]),
     "milb200_ct_tokens_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "milb200_ct_tokens_bwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),

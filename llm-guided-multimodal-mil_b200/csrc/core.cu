@@ -155,21 +155,23 @@ int splitk_reduce_gate(const float* part, int splits, int D, int L, int dh, floa
 
 // ---- elementwise glue ----------------------------------------------------------------------------
 template <typename T>
-__global__ void k_add(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t n) {
+__global__ void k_add(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out, int64_t n, float alpha,
+                      float beta) {
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   constexpr int V = Vec16<T>::N;
   int64_t nv = n / V;
   for (int64_t v = i; v < nv; v += stride) {
-    uint4 ua = reinterpret_cast<const uint4*>(a)[v], ub = reinterpret_cast<const uint4*>(b)[v];
+    uint4 ua = reinterpret_cast<const uint4*>(a)[v], ub = b ? reinterpret_cast<const uint4*>(b)[v] : make_uint4(0, 0, 0, 0);
     float fa[V], fb[V];
     Vec16<T>::unpack(ua, fa);
     Vec16<T>::unpack(ub, fb);
 #pragma unroll
-    for (int j = 0; j < V; ++j) fa[j] += fb[j];
+    for (int j = 0; j < V; ++j) fa[j] = alpha * fa[j] + beta * fb[j];
     reinterpret_cast<uint4*>(out)[v] = Vec16<T>::pack(fa);
   }
-  for (int64_t e = nv * V + i; e < n; e += stride) out[e] = from_f32<T>(to_f32<T>(a[e]) + to_f32<T>(b[e]));
+  for (int64_t e = nv * V + i; e < n; e += stride)
+    out[e] = from_f32<T>(alpha * to_f32<T>(a[e]) + (b ? beta * to_f32<T>(b[e]) : 0.f));
 }
 
 template <typename T>
@@ -415,18 +417,24 @@ int milb200_transpose(const void* in, void* out, int rows, int cols, int dtype, 
   return transpose2d(in, out, rows, cols, dtype, static_cast<cudaStream_t>(stream));
 }
 
-int milb200_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream) {
-  MIL_CHECK_ARG(a && b && out && n >= 0, MILB200_EINVAL, "add: null pointer");
-  MIL_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(out), MILB200_EALIGN, "add: pointers must be 16-byte aligned");
+int milb200_axpby(const void* a, const void* b, void* out, int64_t n, float alpha, float beta, int dtype, void* stream) {
+  MIL_CHECK_ARG(a && out && n >= 0, MILB200_EINVAL, "axpby: null pointer");
+  MIL_CHECK_ARG(aligned16(a) && aligned16(b) && aligned16(out), MILB200_EALIGN, "axpby: pointers must be 16-byte aligned");
   if (n == 0) return MILB200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n / 4 + 255) / 256 + 1, 148 * 8));
   if (dtype == MILB200_BF16)
-    k_add<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)out, n);
+    k_add<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, (__nv_bfloat16*)out, n,
+                                                 alpha, beta);
   else
-    k_add<float><<<blocks, 256, 0, st>>>((const float*)a, (const float*)b, (float*)out, n);
+    k_add<float><<<blocks, 256, 0, st>>>((const float*)a, (const float*)b, (float*)out, n, alpha, beta);
   MIL_LAUNCH_CHECK();
   return MILB200_OK;
+}
+
+int milb200_add(const void* a, const void* b, void* out, int64_t n, int dtype, void* stream) {
+  MIL_CHECK_ARG(b, MILB200_EINVAL, "add: null pointer");
+  return milb200_axpby(a, b, out, n, 1.f, 1.f, dtype, stream);
 }
 
 int milb200_sinusoid_pe(void* pe, int64_t n_pos, int dim, int dtype, void* stream) {

@@ -291,7 +291,7 @@ k_cliploss_dout(const T* __restrict__ feat, const float* __restrict__ logits, co
   }
 }
 
-// CosineEmbeddingLoss(a, b, target=+1) = mean_i (1 - cos_i), cos = a.b / sqrt((a.a + eps)(b.b + eps)), eps = 1e-8
+// CosineEmbeddingLoss(a, b, target=+1) = mean_i (1 - cos_i), cos = a.b / sqrt((a.a + eps)(b.b + eps)), eps = 1e-12 (ATen Loss.cpp EPSILON)
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_cosine_loss(const T* __restrict__ A, const T* __restrict__ Bm, int n, int d, float* __restrict__ loss_rows,
@@ -304,7 +304,7 @@ k_cosine_loss(const T* __restrict__ A, const T* __restrict__ Bm, int n, int d, f
     float a = to_f32<T>(A[static_cast<int64_t>(row) * d + c]), b = to_f32<T>(Bm[static_cast<int64_t>(row) * d + c]);
     ab = fmaf(a, b, ab); aa = fmaf(a, a, aa); bb = fmaf(b, b, bb);
   }
-  ab = warp_sum(ab); aa = warp_sum(aa) + 1e-8f; bb = warp_sum(bb) + 1e-8f;
+  ab = warp_sum(ab); aa = warp_sum(aa) + 1e-12f; bb = warp_sum(bb) + 1e-12f;
   const float inv = rsqrtf(aa * bb);
   const float cs = ab * inv;
   if (lane == 0) loss_rows[row] = 1.f - cs;

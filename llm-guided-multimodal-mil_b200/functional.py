@@ -386,6 +386,33 @@ def add(a, b):
     return _Add.apply(a, b)
 
 
+class _Axpby(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, alpha, beta):
+        a = a.contiguous()
+        b = b.contiguous() if b is not None else None
+        out = torch.empty_like(a)
+        L.check(L.lib().milb200_axpby(L.ptr(a), L.ptr(b), L.ptr(out), a.numel(), float(alpha), float(beta),
+                                      L.dtype_code(a), L.stream_ptr()), "axpby")
+        ctx.ab = (float(alpha), float(beta), b is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        alpha, beta, has_b = ctx.ab
+        g = g.contiguous()
+        ga = _Axpby.apply(g, None, alpha, 0.0) if ctx.needs_input_grad[0] else None
+        gb = _Axpby.apply(g, None, beta, 0.0) if (has_b and ctx.needs_input_grad[1]) else None
+        return ga, gb, None, None
+
+
+def axpby(a, b, alpha, beta):
+    """alpha * a + beta * b (b may be None) — e.g. (x_CT + x_pathology) / 2 of aggregator_clip.py:94."""
+    if b is not None and (a.shape != b.shape or a.dtype != b.dtype):
+        raise L.MilB200Error("axpby: operands must share shape and dtype")
+    return _Axpby.apply(a, b, alpha, beta)
+
+
 class _CtTokens(torch.autograd.Function):
     """(1, C, T, h, w) CT feature map -> (1, T, C) tokens: mean over (h, w) then permute (transformer.py:93)."""
 

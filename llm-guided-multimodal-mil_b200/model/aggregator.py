@@ -1,0 +1,146 @@
+"""Multimodal aggregator — drop-in for model/aggregator.py:9-209 (``aggregator(args).forward(x_list, x_CI)``).
+
+Same ``args`` fields, forward signature, outputs and ``state_dict`` keys (``fc_pathology.0``, ``fc_CI2CT.0``,
+``fc_CI2Pth.0``, ``fc_CI.0``, ``TwoWayTransformer_{CT,Pth,Both}``, ``extractor_pathology``, ``aggregator``,
+``prompt_embedding``, ``fc.1``).  Differences, all outside the hot path:
+  * the CT encoders (model/dim3) and the clinical-text encoder (model/dim1/CLIP.py, simpleFCs) are upstream,
+    frozen or cuDNN-bound components that this library does not rebuild: by default ``x_list[0]`` is the CT
+    encoder's OUTPUT feature map (1, 512, c, h, w) and ``x_CI`` the text encoder's OUTPUT (1, T, 512); real
+    encoders can be injected through the constructor;
+  * ``pe`` is generated on the device by a kernel and cached, instead of a 205 MB host table copied
+    host->device on every forward; the attribute ``pe`` is kept, shape (1, 100000, 512);
+  * TransMIL aggregators raise: upstream they return a tuple that ``self.fc`` cannot consume.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from .. import functional as F
+from .._lib import MilB200Error
+from ..abmil import ABMIL, ABMIL_v2
+from .encoders import PrecomputedFeatures
+from .sam.transformer import TwoWayTransformer
+
+_CT_MODELS = ("resnet2plus1d_18", "resnetMC3_18", "medicalNet", "SwinUNETR", "MViT")
+_CI_MODELS = ("simpleFCs_v1", "simpleFCs_v1d", "simpleFCs_v2", "simpleFCs_v2d", "CLIP")
+
+
+def _make_pool(kind, args, L, where):
+    if kind == "ABMIL":
+        return ABMIL(args, L=L)
+    if kind == "ABMIL_v2":
+        # upstream calls ABMIL_v2(args, L=...) which raises TypeError; keep that behaviour explicit
+        raise TypeError(f"{where}: ABMIL_v2.__init__() got an unexpected keyword argument 'L' (as upstream)")
+    if kind in ("TransMIL", "TransMIL_seperate"):
+        raise NotImplementedError(f"{where}='{kind}': Nystrom-attention TransMIL is outside the hot path "
+                                  "(needs the un-vendored nystrom_attention package; SURVEY F5)")
+    return None
+
+
+class aggregator(nn.Module):
+    def __init__(self, args, extractor_CT: nn.Module = None, clinic_extractor: nn.Module = None):
+        super().__init__()
+        self.args = args
+        embedding_dim = 512
+        self.max_seq_len = 100000
+        self.embedding_dim = embedding_dim
+        tw = dict(args=args, depth=2, embedding_dim=embedding_dim, num_heads=8, mlp_dim=2048)
+
+        if "CT" in args.modality:                                                     # aggregator.py:17-42
+            self.extractor_CT = extractor_CT if extractor_CT is not None else PrecomputedFeatures()
+            self.TwoWayTransformer_CT = TwoWayTransformer(**tw)
+        self.fc_CI2CT = nn.Sequential(nn.Linear(embedding_dim, embedding_dim), nn.Tanh())           # :44
+        if "pathology" in args.modality:                                              # :46-64
+            self.fc_pathology = nn.Sequential(nn.Linear(768, embedding_dim), nn.Tanh())
+            pool = _make_pool(getattr(args, "model_pathology", None), args, embedding_dim, "model_pathology")
+            if pool is not None:
+                self.extractor_pathology = pool                                       # built but unused upstream too
+            self.TwoWayTransformer_Pth = TwoWayTransformer(**tw)
+        self.fc_CI2Pth = nn.Sequential(nn.Linear(embedding_dim, embedding_dim), nn.Tanh())          # :66
+        self.fc_CI = nn.Sequential(nn.Linear(embedding_dim, embedding_dim), nn.Tanh())              # :68
+        self.TwoWayTransformer_Both = TwoWayTransformer(**tw)                                       # :70-76
+        pool = _make_pool(getattr(args, "aggregator", None), args, embedding_dim, "aggregator")     # :79-96
+        if pool is not None:
+            self.aggregator = pool
+        self.clinic_extractor = clinic_extractor if clinic_extractor is not None else PrecomputedFeatures()  # :108-122
+        self.prompt_embedding = nn.Parameter(torch.randn(1, embedding_dim))           # :124 (unused, kept for the ABI)
+        self.fc = nn.Sequential(nn.Dropout(0.25), nn.Linear(embedding_dim, args.num_classes))      # :128-131
+        self._pe_cache = {}
+
+    # ---- sinusoidal position table (aggregator.py:99-106), device resident -----------------------------
+    def _pe(self, n, like):
+        key = (like.device, like.dtype)
+        tab = self._pe_cache.get(key)
+        if tab is None or tab.shape[1] < n:
+            rows = min(self.max_seq_len, max(int(n), 4096 if tab is None else 2 * tab.shape[1]))
+            if n > self.max_seq_len:
+                raise MilB200Error(f"bag of {n} instances exceeds the position table ({self.max_seq_len}, aggregator.py:99)")
+            tab = F.sinusoid_pe(rows, self.embedding_dim, like.dtype, like.device)
+            self._pe_cache[key] = tab
+        return tab[:, :n]
+
+    @property
+    def pe(self):
+        """(1, 100000, 512) fp32, like the upstream attribute (generated on first access, on the device)."""
+        dev = self.fc[1].weight.device
+        return self._pe(self.max_seq_len, torch.empty(0, dtype=torch.float32, device=dev))
+
+    # ---- small fused pieces ------------------------------------------------------------------------------
+    @staticmethod
+    def _fc_tanh(seq, x):
+        return F.linear(x, seq[0].weight, seq[0].bias, act="tanh")
+
+    def _head(self, x0):
+        if self.training and self.fc[0].p > 0:
+            x0 = F.dropout(x0, self.fc[0].p)
+        return F.linear(x0, self.fc[1].weight, self.fc[1].bias, act="sigmoid")      # torch.sigmoid(self.fc(x0)), :200
+
+    def _fuse(self, transformer, x_img, text_tokens):
+        if x_img.dim() == 5:
+            b, t, c, h, w = x_img.shape                                               # :156 (t = 512 channels, c = slices)
+            n = c * h * w if getattr(self.args, "model_CT", None) == "medicalNet" else c
+        else:
+            n = x_img.shape[1]
+        return transformer(x_img, self._pe(n, text_tokens), text_tokens)
+
+    def forward(self, x_list, x_CI):
+        mod = self.args.modality
+        has_ct, has_path = "CT" in mod, "pathology" in mod
+        x_input_CT = x_input_pathology = None
+        if has_ct:
+            x_input_CT = self.extractor_CT(x_list[0])                                 # :140,146
+        if has_path:
+            x_input_pathology = self._fc_tanh(self.fc_pathology, x_list[1 if has_ct else 0])      # :141,149
+        x_CI_prompted = self.clinic_extractor(x_CI)                                   # :151 -> (1, T, 512)
+
+        if has_ct and has_path:
+            x_CT2CI, x_CI2CT = self._fuse(self.TwoWayTransformer_Both, x_input_CT,
+                                          self._fc_tanh(self.fc_CI2CT, x_CI_prompted))            # :160
+            x_Pth2CI, x_CI2Pth = self._fuse(self.TwoWayTransformer_Both, x_input_pathology,
+                                            self._fc_tanh(self.fc_CI2Pth, x_CI_prompted))         # :168
+            x0 = torch.cat([x_CT2CI, x_CI2CT, x_Pth2CI, x_CI2Pth], dim=1)             # :173 the multi-modal bag
+        elif has_ct:
+            # upstream reads an undefined name here; this is the evident intent
+            x_CT2CI, x_CI2CT = self._fuse(self.TwoWayTransformer_CT, x_input_CT,
+                                          self._fc_tanh(self.fc_CI2CT, x_CI_prompted))            # :179
+            x0 = torch.cat([x_CT2CI, x_CI2CT], dim=1)
+        elif has_path:
+            x_Pth2CI, x_CI2Pth = self._fuse(self.TwoWayTransformer_Pth, x_input_pathology,
+                                            self._fc_tanh(self.fc_CI2Pth, x_CI_prompted))         # :190
+            x0 = torch.cat([x_Pth2CI, x_CI2Pth], dim=1)
+        elif "CI" in mod:
+            x0 = self._fc_tanh(self.fc_CI, x_CI_prompted)                             # :195
+        else:
+            raise MilB200Error(f"aggregator: unsupported modality {mod}")
+
+        if getattr(self.args, "aggregator", "-") != "-":
+            x0 = self.aggregator(x0)                                                  # :199 gated-attention MIL pool
+        x = self._head(x0)                                                            # :200
+        if has_ct and has_path:
+            return x, x_CT2CI, x_Pth2CI
+        if has_ct:
+            return x, x_CT2CI
+        if has_path:
+            return x, x_Pth2CI
+        return x

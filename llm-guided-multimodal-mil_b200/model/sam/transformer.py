@@ -1,0 +1,137 @@
+"""Cross-modal fusion modules — drop-ins for model/sam/transformer.py (TwoWayTransformer,
+TwoWayAttentionBlock, Attention).
+
+Same constructor arguments, forward signatures, outputs and ``state_dict`` keys as upstream
+(``layers.{i}.self_attn.q_proj.weight`` ...).  The ``nn.Linear`` / ``nn.LayerNorm`` children are parameter
+containers only; every forward/backward runs in libmilb200:
+
+  * q/k/v/out projections and the MLP      -> ``milb200_linear_fwd/bwd`` (tcgen05 GEMM for bf16 image-side
+    rows, FFMA for fp32), with the ``x + pe`` sums of transformer.py:291-292,303-304 folded into the call;
+  * softmax(QK^T/sqrt(c))V per head        -> ``milb200_attention_fwd/bwd`` (one side is always the <=16
+    text tokens: token->image streams K,V once with an online softmax, image->token keeps K,V in smem);
+  * residual + LayerNorm                   -> ``milb200_layernorm_fwd/bwd`` (one kernel, residual fused).
+
+The reference runs one bag per call (batch 1, train_ddp.py:75); a leading batch B>1 is looped.
+"""
+from __future__ import annotations
+
+from typing import Tuple, Type
+
+import torch
+from torch import Tensor, nn
+
+from ... import functional as F
+from ..._lib import MilB200Error
+from .common import MLPBlock
+
+
+class Attention(nn.Module):
+    """model/sam/transformer.py:395-450."""
+
+    def __init__(self, embedding_dim: int, num_heads: int, downsample_rate: int = 1) -> None:
+        super().__init__()
+        self.embedding_dim = embedding_dim
+        self.internal_dim = embedding_dim // downsample_rate
+        self.num_heads = num_heads
+        assert self.internal_dim % num_heads == 0, "num_heads must divide embedding_dim."
+        self.q_proj = nn.Linear(embedding_dim, self.internal_dim)
+        self.k_proj = nn.Linear(embedding_dim, self.internal_dim)
+        self.v_proj = nn.Linear(embedding_dim, self.internal_dim)
+        self.out_proj = nn.Linear(self.internal_dim, embedding_dim)
+
+    def forward(self, q: Tensor, k: Tensor, v: Tensor, q_add: Tensor = None, k_add: Tensor = None) -> Tensor:
+        """``q_add`` / ``k_add`` (extension, optional): positional terms added to q / k inside the projection
+        kernels, so callers need not materialise ``queries + query_pe`` / ``keys + key_pe``."""
+        if q.dim() != 3 or k.dim() != 3 or v.dim() != 3:
+            raise MilB200Error("Attention.forward expects (B, N_tokens, C) tensors")
+        qp = F.linear(q, self.q_proj.weight, self.q_proj.bias, add=q_add)          # transformer.py:430
+        kp = F.linear(k, self.k_proj.weight, self.k_proj.bias, add=k_add)          # :431
+        vp = F.linear(v, self.v_proj.weight, self.v_proj.bias)                     # :432
+        outs = [F.attention_core(qp[b], kp[b], vp[b], self.num_heads) for b in range(q.shape[0])]   # :434-446
+        o = outs[0].unsqueeze(0) if len(outs) == 1 else torch.stack(outs, dim=0)
+        return F.linear(o, self.out_proj.weight, self.out_proj.bias)               # :448
+
+
+class TwoWayAttentionBlock(nn.Module):
+    """model/sam/transformer.py:236-309."""
+
+    def __init__(self, embedding_dim: int, num_heads: int, mlp_dim: int = 2048,
+                 activation: Type[nn.Module] = nn.ReLU, attention_downsample_rate: int = 2,
+                 skip_first_layer_pe: bool = False) -> None:
+        super().__init__()
+        self.self_attn = Attention(embedding_dim, num_heads)
+        self.norm1 = nn.LayerNorm(embedding_dim)
+        self.cross_attn_token_to_image = Attention(embedding_dim, num_heads, downsample_rate=attention_downsample_rate)
+        self.norm2 = nn.LayerNorm(embedding_dim)
+        self.mlp = MLPBlock(embedding_dim, mlp_dim, activation)
+        self.norm3 = nn.LayerNorm(embedding_dim)
+        self.norm4 = nn.LayerNorm(embedding_dim)
+        self.cross_attn_image_to_token = Attention(embedding_dim, num_heads, downsample_rate=attention_downsample_rate)
+        self.skip_first_layer_pe = skip_first_layer_pe
+
+    @staticmethod
+    def _ln(norm, x, residual=None):
+        if abs(norm.eps - 1e-5) > 1e-12:
+            raise MilB200Error("layernorm kernels are built for eps = 1e-5 (nn.LayerNorm default)")
+        return F.layernorm(x, norm.weight, norm.bias, residual=residual)
+
+    def forward(self, queries: Tensor, keys: Tensor, query_pe: Tensor, key_pe: Tensor) -> Tuple[Tensor, Tensor]:
+        # (1) token self-attention (:281-288)
+        if self.skip_first_layer_pe:
+            queries = self._ln(self.norm1, self.self_attn(q=queries, k=queries, v=queries))
+        else:
+            attn_out = self.self_attn(q=queries, k=queries, v=queries, q_add=query_pe, k_add=query_pe)
+            queries = self._ln(self.norm1, queries, residual=attn_out)
+        # (2) tokens attend to the image bag (:290-295)
+        attn_out = self.cross_attn_token_to_image(q=queries, k=keys, v=keys, q_add=query_pe, k_add=key_pe)
+        queries = self._ln(self.norm2, queries, residual=attn_out)
+        # (3) MLP on the tokens (:297-300)
+        queries = self._ln(self.norm3, queries, residual=self.mlp(queries))
+        # (4) the image bag attends to the tokens (:302-307)
+        attn_out = self.cross_attn_image_to_token(q=keys, k=queries, v=queries, q_add=key_pe, k_add=query_pe)
+        keys = self._ln(self.norm4, keys, residual=attn_out)
+        return queries, keys
+
+
+class TwoWayTransformer(nn.Module):
+    """model/sam/transformer.py:10-120.  ``args`` supplies ``alignment_base`` and ``model_CT`` like upstream."""
+
+    def __init__(self, args, depth: int, embedding_dim: int, num_heads: int, mlp_dim: int,
+                 activation: Type[nn.Module] = nn.ReLU, attention_downsample_rate: int = 2) -> None:
+        super().__init__()
+        self.args = args
+        self.depth = depth
+        self.embedding_dim = embedding_dim
+        self.num_heads = num_heads
+        self.mlp_dim = mlp_dim
+        self.layers = nn.ModuleList()
+        for i in range(depth):
+            self.layers.append(TwoWayAttentionBlock(embedding_dim=embedding_dim, num_heads=num_heads, mlp_dim=mlp_dim,
+                                                    activation=activation,
+                                                    attention_downsample_rate=attention_downsample_rate,
+                                                    skip_first_layer_pe=(i == 0)))
+        self.final_attn_token_to_image = Attention(embedding_dim, num_heads, downsample_rate=attention_downsample_rate)
+        self.norm_final_attn = nn.LayerNorm(embedding_dim)
+
+    def _ct_to_tokens(self, x: Tensor) -> Tensor:
+        """(B, C, T, h, w) CT feature map -> (B, tokens, C)  (transformer.py:79-95)."""
+        model_ct = getattr(self.args, "model_CT", None)
+        if model_ct == "resnetMC3_18":
+            return F.ct_tokens(x)                                   # mean over (h, w), permute: one kernel
+        if model_ct == "medicalNet":
+            return x.flatten(2).permute(0, 2, 1).contiguous()       # pure data movement
+        return x                                                     # upstream leaves other encoders untouched
+
+    def forward(self, image_embedding: Tensor, image_pe: Tensor, point_embedding: Tensor) -> Tuple[Tensor, Tensor]:
+        if getattr(self.args, "alignment_base", None) == "CT":
+            if point_embedding.dim() == 5:
+                point_embedding = self._ct_to_tokens(point_embedding)
+        elif image_embedding.dim() == 5:
+            image_embedding = self._ct_to_tokens(image_embedding)
+        queries, keys = point_embedding, image_embedding
+        for layer in self.layers:                                                     # :105-111
+            queries, keys = layer(queries=queries, keys=keys, query_pe=point_embedding, key_pe=image_pe)
+        attn_out = self.final_attn_token_to_image(q=queries, k=keys, v=keys, q_add=point_embedding,
+                                                  k_add=image_pe)                     # :114-116
+        queries = TwoWayAttentionBlock._ln(self.norm_final_attn, queries, residual=attn_out)   # :117-118
+        return queries, keys

@@ -252,7 +252,7 @@ def sigmoid_head_bce(x, W, b, target):
 def cosine_embedding_loss_pos(a, b):
     """CosineEmbeddingLoss(a, b, target=+1) = mean(1 - cos(a_i, b_i))  (train_ddp.py:102,326)."""
     a, b = _f(a), _f(b)
-    eps = 1e-8
+    eps = 1e-12   # ATen cosine_embedding_loss EPSILON
     cos = (a * b).sum(-1) / np.sqrt(((a * a).sum(-1) + eps) * ((b * b).sum(-1) + eps))
     return float((1.0 - cos).mean())
 

@@ -43,10 +43,10 @@ def test_abmil_fp32_vs_reference_golden(name):
     (M * dM).sum().backward()
     torch.cuda.synchronize()
     assert rel_err(M.detach().cpu().numpy(), fx["M"]) <= TOL_F32
-    assert rel_err(m.last_scores.cpu().numpy(), fx["s"]) <= TOL_F32
+    assert rel_err(m.last_scores.detach().cpu().numpy(), fx["s"]) <= TOL_F32
     assert int(m.last_argmax.item()) == int(fx["argmax"])                 # bit-exact index
-    g = mo.abmil_backward(p, x.detach().cpu().numpy()[0], dM.cpu().numpy())
-    assert rel_err(x.grad.cpu().numpy()[0], g["x"]) <= TOL_F32
+    g = mo.abmil_backward(p, x.detach().cpu().numpy()[0], dM.detach().cpu().numpy())
+    assert rel_err(x.grad.detach().cpu().numpy()[0], g["x"]) <= TOL_F32
     if N == 1:
         # a one-instance bag has softmax weight exactly 1: every attention gradient is exactly 0 in exact
         # arithmetic (the reference stores 0); the kernels may leave float noise from g_i - dM.M
@@ -80,10 +80,10 @@ def test_abmil_csr_ragged_vs_oracle(dtype, L, tol):
     Mr, sr, amr = mo.abmil_forward_csr(pq, Xq, off)
     assert mo.score_margin(sr, off) > 1e-4, "seed gives a near-tie; argmax would not be well-posed"
     gr = mo.abmil_backward_csr(pq, Xq, off, dM)
-    assert np.array_equal(offt.cpu().numpy(), off)                         # offsets untouched, bit-exact
-    assert m.last_argmax.cpu().numpy().tolist() == amr.tolist()            # bit-exact argmax
+    assert np.array_equal(offt.detach().cpu().numpy(), off)                         # offsets untouched, bit-exact
+    assert m.last_argmax.detach().cpu().numpy().tolist() == amr.tolist()            # bit-exact argmax
     assert rel_err(M.detach().float().cpu().numpy(), Mr) <= tol
-    assert rel_err(m.last_scores.cpu().numpy(), sr) <= tol
+    assert rel_err(m.last_scores.detach().cpu().numpy(), sr) <= tol
     assert rel_err(Xt.grad.float().cpu().numpy(), gr["x"]) <= tol
     g = _grads(m)
     for k in p:
@@ -117,7 +117,7 @@ def test_abmil_v2_matches_reference_golden():
     x = torch.from_numpy(rnd(seed + 100, 1, N, 768)).cuda()
     out = m(x, torch.tensor([[1.0]]).cuda())
     assert tuple(out.shape) == (1, 769)
-    assert rel_err(out.cpu().numpy(), fx["M"]) <= TOL_F32
+    assert rel_err(out.detach().cpu().numpy(), fx["M"]) <= TOL_F32
 
 
 def test_masked_padded_bags_equal_unpadded_reference():
@@ -130,7 +130,7 @@ def test_masked_padded_bags_equal_unpadded_reference():
     Mr = mo.abmil_forward_masked(p, Xpad, lens)
     packed = np.concatenate([Xpad[b, :int(n)] for b, n in enumerate(lens)])
     M = m.forward_csr(torch.from_numpy(packed).cuda(), torch.from_numpy(mo.offsets_from_lengths(lens)).cuda())
-    assert rel_err(M.cpu().numpy(), Mr) <= TOL_F32
+    assert rel_err(M.detach().cpu().numpy(), Mr) <= TOL_F32
 
 
 def test_train_mode_dropout_is_statistical_and_regenerated():
@@ -165,8 +165,8 @@ lens = mo.ragged_lengths(7, 50, 3000, 9); off = mo.offsets_from_lengths(lens)
 X = torch.from_numpy(np.random.RandomState(1).standard_normal((int(off[-1]), 1024)).astype(np.float32)).cuda().bfloat16()
 X.requires_grad_(True)
 M = m.forward_csr(X, torch.from_numpy(off).cuda()); M.float().sum().backward(); torch.cuda.synchronize()
-np.savez(sys.argv[1], M=M.detach().float().cpu().numpy(), s=m.last_scores.cpu().numpy(), dX=X.grad.float().cpu().numpy(),
-         dW=m.attention_V[0].weight.grad.cpu().numpy(), am=m.last_argmax.cpu().numpy())
+np.savez(sys.argv[1], M=M.detach().float().cpu().numpy(), s=m.last_scores.detach().cpu().numpy(), dX=X.grad.float().cpu().numpy(),
+         dW=m.attention_V[0].weight.grad.detach().cpu().numpy(), am=m.last_argmax.detach().cpu().numpy())
 """
     import tempfile
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

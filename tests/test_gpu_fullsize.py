@@ -28,9 +28,9 @@ def big():
 def test_fullsize_sampled_bags_match_oracle(big):
     m, p, X, off, lens = big
     offt = torch.from_numpy(off).cuda()
-    M = m.forward_csr(X, offt).float().cpu().numpy()
-    s = m.last_scores.cpu().numpy()
-    am = m.last_argmax.cpu().numpy()
+    M = m.forward_csr(X, offt).detach().float().cpu().numpy()
+    s = m.last_scores.detach().cpu().numpy()
+    am = m.last_argmax.detach().cpu().numpy()
     pq = {k: (torch.from_numpy(v).bfloat16().float().numpy() if k.endswith("0.weight") else v) for k, v in p.items()}
     for b in (0, 17, 63, int(np.argmin(lens)), int(np.argmax(lens))):
         xb = X[off[b]:off[b + 1]].float().cpu().numpy()
@@ -59,7 +59,7 @@ def test_fullsize_properties(big):
     assert torch.allclose(lse2 - lse1, torch.full_like(lse1, 3.0), atol=1e-4)
     assert torch.equal(am1, am2)
     # (3) argmax indexes the largest score of its bag
-    sc = s.cpu().numpy()
+    sc = s.detach().cpu().numpy()
     for b in (0, 5, 31, 63):
         seg = sc[off[b]:off[b + 1]]
         assert seg[int(am1[b])] == seg.max()
@@ -74,7 +74,7 @@ def test_fullsize_properties(big):
     dsA, _ = F.segment_softmax_pool_bwd(X, s, offt, dA, Mf, False)
     dsB, _ = F.segment_softmax_pool_bwd(X, s, offt, dB, Mf, False)
     dsAB, _ = F.segment_softmax_pool_bwd(X, s, offt, dA + dB, Mf, False)
-    assert rel_err((dsA + dsB).cpu().numpy(), dsAB.cpu().numpy()) <= 1e-4
+    assert rel_err((dsA + dsB).detach().cpu().numpy(), dsAB.detach().cpu().numpy()) <= 1e-4
     # (6) d(scores) sums to zero inside every bag (softmax Jacobian annihilates constants)
     tot = torch.zeros(64, device="cuda", dtype=torch.float64)
     bag = torch.bucketize(torch.arange(X.shape[0], device="cuda"), offt[1:].long(), right=True)
@@ -96,7 +96,7 @@ def test_fullsize_trainer_step_matches_module_autograd(big):
     tr.load_from(m)
     Mt, _ = tr.forward_backward(X, offt)
     gv = tr.grad_views()
-    assert rel_err(Mt.cpu().numpy(), M.detach().float().cpu().numpy()) <= 1e-2
-    assert rel_err(gv["Wcat"][:192].cpu().numpy(), m.attention_V[0].weight.grad.cpu().numpy()) <= 1e-4
-    assert rel_err(gv["Wcat"][192:].cpu().numpy(), m.attention_U[0].weight.grad.cpu().numpy()) <= 1e-4
-    assert rel_err(gv["ww"].cpu().numpy(), m.attention_weights.weight.grad.cpu().numpy().reshape(-1)) <= 1e-4
+    assert rel_err(Mt.detach().cpu().numpy(), M.detach().float().cpu().numpy()) <= 1e-2
+    assert rel_err(gv["Wcat"][:192].detach().cpu().numpy(), m.attention_V[0].weight.grad.detach().cpu().numpy()) <= 1e-4
+    assert rel_err(gv["Wcat"][192:].detach().cpu().numpy(), m.attention_U[0].weight.grad.detach().cpu().numpy()) <= 1e-4
+    assert rel_err(gv["ww"].detach().cpu().numpy(), m.attention_weights.weight.grad.detach().cpu().numpy().reshape(-1)) <= 1e-4

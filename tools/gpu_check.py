@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 STAGES = ["pool_f32", "pool_bf16", "gate_f32", "gate_bf16_simt", "tc_score", "tc_linear", "tc_gate_bwd",
-          "tc_linear_bwd", "abmil"]
+          "tc_linear_bwd", "abmil", "attention", "layernorm", "clip", "fusion"]
 
 
 def rel(a, b):
@@ -228,6 +228,189 @@ def stage_abmil():
         print(f"abmil {dtype} L={L} tol={tol}: " + " ".join(out), flush=True)
 
 
+def stage_attention():
+    import torch
+    from mil_b200 import functional as F
+    for dtype in (torch.float32, torch.bfloat16):
+        for (nq, nk, H, c) in [(10, 5000, 8, 32), (1, 160, 8, 32), (1, 20000, 8, 32), (16, 333, 8, 32), (5000, 10, 8, 32),
+                               (160, 1, 8, 32), (20000, 1, 8, 32), (10, 10, 8, 64), (1, 1, 8, 64), (3, 3, 8, 64), (7, 17, 8, 32)]:
+            g = torch.Generator(device="cuda").manual_seed(nq * 31 + nk)
+            q = torch.randn(nq, H * c, device="cuda", generator=g).to(dtype).requires_grad_(True)
+            k = torch.randn(nk, H * c, device="cuda", generator=g).to(dtype).requires_grad_(True)
+            v = torch.randn(nk, H * c, device="cuda", generator=g).to(dtype).requires_grad_(True)
+            do = torch.randn(nq, H * c, device="cuda", generator=g).to(dtype)
+            o = F.attention_core(q, k, v, H)
+            (o.float() * do.float()).sum().backward()
+            torch.cuda.synchronize()
+            qd, kd, vd = (t.detach().double().requires_grad_(True) for t in (q, k, v))
+            qh = qd.view(nq, H, c).transpose(0, 1); kh = kd.view(nk, H, c).transpose(0, 1); vh = vd.view(nk, H, c).transpose(0, 1)
+            a = torch.softmax(qh @ kh.transpose(1, 2) / c ** 0.5, -1)
+            orf = (a @ vh).transpose(0, 1).reshape(nq, H * c)
+            (orf * do.double()).sum().backward()
+            print(f"attention {dtype} nq={nq} nk={nk} c={c}: O {rel(o, orf):.2e} dQ {rel(q.grad, qd.grad):.2e} "
+                  f"dK {rel(k.grad, kd.grad):.2e} dV {rel(v.grad, vd.grad):.2e}", flush=True)
+
+
+def stage_layernorm():
+    import torch
+    from mil_b200 import functional as F
+    for dtype in (torch.float32, torch.bfloat16):
+        for (m, n, res) in [(1, 512, False), (10, 512, True), (5000, 512, True), (20000, 512, False), (77, 64, True), (3, 768, True)]:
+            g = torch.Generator(device="cuda").manual_seed(m + n)
+            x = torch.randn(m, n, device="cuda", generator=g).to(dtype).requires_grad_(True)
+            r = torch.randn(m, n, device="cuda", generator=g).to(dtype).requires_grad_(True) if res else None
+            ga = (torch.rand(n, device="cuda", generator=g) + 0.5).requires_grad_(True)
+            be = torch.randn(n, device="cuda", generator=g).requires_grad_(True)
+            dy = torch.randn(m, n, device="cuda", generator=g).to(dtype)
+            y = F.layernorm(x, ga, be, residual=r)
+            (y.float() * dy.float()).sum().backward()
+            torch.cuda.synchronize()
+            xd = x.detach().double().requires_grad_(True)
+            rd = r.detach().double().requires_grad_(True) if res else None
+            gd, bd = ga.detach().double().requires_grad_(True), be.detach().double().requires_grad_(True)
+            yr = torch.nn.functional.layer_norm(xd + (rd if res else 0), (n,), gd, bd, 1e-5)
+            (yr * dy.double()).sum().backward()
+            msg = f"layernorm {dtype} m={m} n={n} res={res}: Y {rel(y, yr):.2e} dX {rel(x.grad, xd.grad):.2e} dg {rel(ga.grad, gd.grad):.2e} db {rel(be.grad, bd.grad):.2e}"
+            if res:
+                msg += f" dR {rel(r.grad, rd.grad):.2e}"
+            print(msg, flush=True)
+
+
+def stage_clip():
+    import math
+    import numpy as np
+    import torch
+    from mil_b200 import functional as F
+    from oracle import mil_oracle as mo
+    for dtype in (torch.float32, torch.bfloat16):
+        for (bi, bt, d) in [(24, 24, 512), (64, 64, 512), (5, 9, 512), (1, 1, 512), (300, 300, 512)]:
+            g = torch.Generator(device="cuda").manual_seed(bi)
+            img = torch.randn(bi, d, device="cuda", generator=g).to(dtype).requires_grad_(True)
+            txt = torch.randn(bt, d, device="cuda", generator=g).to(dtype).requires_grad_(True)
+            ls = torch.tensor(math.log(1 / 0.07), device="cuda", requires_grad=True)
+            dli = torch.randn(bi, bt, device="cuda", generator=g)
+            dlt = torch.randn(bt, bi, device="cuda", generator=g)
+            li, lt = F.clip_logits(img, txt, ls)
+            ((li * dli).sum() + (lt * dlt).sum()).backward()
+            torch.cuda.synchronize()
+            i_np, t_np = img.detach().float().cpu().numpy(), txt.detach().float().cpu().numpy()
+            lir, ltr = mo.clip_cosine_logits(i_np, t_np, float(ls))
+            gi, gt, gs = mo.clip_cosine_logits_bwd(i_np, t_np, float(ls), dli.cpu().numpy(), dlt.cpu().numpy())
+            r = lambda a, b: float(np.abs(np.asarray(a.detach().float().cpu().numpy(), dtype=np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+            print(f"clip_logits {dtype} bi={bi} bt={bt}: li {r(li, lir):.2e} lt {r(lt, ltr):.2e} dI {r(img.grad, gi):.2e} dT {r(txt.grad, gt):.2e} "
+                  f"dscale {abs(float(ls.grad) - gs) / max(abs(gs), 1e-30):.2e}", flush=True)
+        for (b, I, d) in [(6, 9, 512), (64, 9, 512), (1, 9, 512), (200, 3, 512)]:
+            g = torch.Generator(device="cuda").manual_seed(b)
+            out = (torch.randn(b, d, device="cuda", generator=g) * 0.3).to(dtype).requires_grad_(True)
+            feat = (torch.randn(b, I, d, device="cuda", generator=g) * 0.3).to(dtype)
+            loss, logits = F.cliploss_v1(out, feat)
+            (loss * 1.7).backward()
+            torch.cuda.synchronize()
+            o_np, f_np = out.detach().float().cpu().numpy(), feat.float().cpu().numpy()
+            lr_, lg = mo.cliploss_v1(o_np, f_np)
+            dr = mo.cliploss_v1_bwd(o_np, f_np)
+            print(f"cliploss {dtype} b={b} I={I}: loss {abs(float(loss) - lr_) / max(abs(lr_), 1e-30):.2e} logits "
+                  f"{float(np.abs(logits.cpu().numpy() - lg).max() / max(np.abs(lg).max(), 1e-30)):.2e} dout "
+                  f"{float(np.abs(out.grad.float().cpu().numpy() / 1.7 - dr).max() / max(np.abs(dr).max(), 1e-30)):.2e}", flush=True)
+        for (n, d) in [(1, 512), (10, 512), (64, 512)]:
+            g = torch.Generator(device="cuda").manual_seed(n)
+            a = torch.randn(n, d, device="cuda", generator=g).to(dtype).requires_grad_(True)
+            b = torch.randn(n, d, device="cuda", generator=g).to(dtype).requires_grad_(True)
+            loss = F.cosine_embedding_loss(a, b)
+            loss.backward()
+            ad, bd = a.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+            lr_ = torch.nn.CosineEmbeddingLoss()(ad, bd, torch.ones(n, device="cuda", dtype=torch.float64))
+            lr_.backward()
+            print(f"cosine {dtype} n={n}: loss {abs(float(loss) - float(lr_)):.2e} da {rel(a.grad, ad.grad):.2e} db {rel(b.grad, bd.grad):.2e}", flush=True)
+    z = torch.randn(7, 2, device="cuda", requires_grad=True)
+    t = torch.randint(0, 2, (7, 2), device="cuda").float()
+    loss, prob = F.sigmoid_bce(z, t)
+    loss.backward()
+    zd = z.detach().double().requires_grad_(True)
+    lr_ = torch.nn.BCELoss()(torch.sigmoid(zd), t.double())
+    lr_.backward()
+    print(f"bce: loss {abs(float(loss) - float(lr_)):.2e} dz {rel(z.grad, zd.grad):.2e} prob {rel(prob, torch.sigmoid(zd)):.2e}", flush=True)
+
+
+def _sd_np(module):
+    return {k: v.detach().float().cpu().numpy() for k, v in module.state_dict().items()}
+
+
+def stage_fusion():
+    """Module level: TwoWayAttentionBlock / TwoWayTransformer / aggregator at the real dims vs the float64 oracle."""
+    import numpy as np
+    import torch
+    import mil_b200
+    from argparse import Namespace
+    from oracle import fusion_oracle as fo
+    from oracle import mil_oracle as mo
+    from tests.test_oracle_golden import aggregator_shapes, transformer_shapes
+    args = Namespace(modality=["CT", "pathology"], model_CT="resnetMC3_18", model_pathology="ABMIL", model_CI="none",
+                     aggregator="ABMIL", num_classes=2, alignment_base="none", clinical_features=list("abcdefghi"))
+    for dtype in (torch.float32, torch.bfloat16):
+        for T, N in ((1, 300), (10, 1000), (3, 5000)):
+            sdn = mo.procedural_state(transformer_shapes(512, 2048), 7)
+            m = mil_b200.TwoWayTransformer(args=args, depth=2, embedding_dim=512, num_heads=8, mlp_dim=2048).cuda()
+            m.load_state_dict({k: torch.from_numpy(v) for k, v in sdn.items()})
+            g = torch.Generator(device="cuda").manual_seed(T * 1000 + N)
+            img = torch.randn(1, N, 512, device="cuda", generator=g).to(dtype).requires_grad_(True)
+            pe = torch.randn(1, N, 512, device="cuda", generator=g).to(dtype)
+            pt = (torch.randn(1, T, 512, device="cuda", generator=g) * 0.5).to(dtype).requires_grad_(True)
+            dq = torch.randn(1, T, 512, device="cuda", generator=g)
+            dk = torch.randn(1, N, 512, device="cuda", generator=g)
+            oq, ok = m(img, pe, pt)
+            ((oq.float() * dq).sum() + (ok.float() * dk).sum()).backward()
+            torch.cuda.synchronize()
+            quant = (lambda a: torch.from_numpy(a).to(dtype).double()) if dtype != torch.float32 else (lambda a: torch.from_numpy(a).double())
+            sd = {k: (quant(v) if v.ndim == 2 else torch.from_numpy(v).double()).requires_grad_(True) for k, v in sdn.items()}
+            sd = {"t." + k: v for k, v in sd.items()}
+            imgd = img.detach().double().cpu().requires_grad_(True)
+            ptd = pt.detach().double().cpu().requires_grad_(True)
+            roq, rok = fo.two_way_transformer(sd, "t", imgd, pe.double().cpu(), ptd)
+            ((roq * dq.double().cpu()).sum() + (rok * dk.double().cpu()).sum()).backward()
+            worst, wname = 0.0, ""
+            for k_, p_ in m.named_parameters():
+                rg = sd["t." + k_].grad
+                if rg is None or p_.grad is None:
+                    continue
+                if k_.endswith("k_proj.bias"):
+                    continue
+                e = rel(p_.grad.cpu(), rg)
+                if e > worst:
+                    worst, wname = e, k_
+            print(f"twoway {dtype} T={T} N={N}: oq {rel(oq.cpu(), roq):.2e} ok {rel(ok.cpu(), rok):.2e} dimg {rel(img.grad.cpu(), imgd.grad):.2e} "
+                  f"dpt {rel(pt.grad.cpu(), ptd.grad):.2e} worst param grad {worst:.2e} ({wname})", flush=True)
+    # full aggregator vs the reference fixtures
+    from tests.helpers import load_golden, rnd, digest
+    for name in ("aggregator_T1_N70", "aggregator_T10_N45"):
+        fx = load_golden(name)
+        seed, T, N = int(fx["seed"]), int(fx["T"]), int(fx["N"])
+        m = mil_b200.get_model(args).cuda().eval()
+        sdn = mo.procedural_state(aggregator_shapes(), seed)
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in sdn.items()})
+        x_ct = torch.from_numpy(rnd(seed + 100, 1, 512, 160, 1, 2)).cuda().requires_grad_(True)
+        x_p = torch.from_numpy(rnd(seed + 200, 1, N, 768)).cuda().requires_grad_(True)
+        x_t = torch.from_numpy(rnd(seed + 300, 1, T, 512, scale=0.05)).cuda()
+        prob, ct2ci, pth2ci = m([x_ct, x_p], x_t)
+        label = torch.tensor([[0.0, 1.0]], device="cuda")
+        loss = torch.nn.BCELoss()(prob, label) + mil_b200.clip_loss.cosine_embedding_loss(ct2ci.squeeze(0), pth2ci.squeeze(0))
+        loss.backward()
+        torch.cuda.synchronize()
+        r = lambda a, b: float(np.abs(a.detach().cpu().numpy().astype(np.float64) - b).max() / max(np.abs(b).max(), 1e-30))
+        worst, wname = 0.0, ""
+        for k_, p_ in m.named_parameters():
+            ref = fx.get("g:" + k_)
+            if ref is None or p_.grad is None or k_.endswith("k_proj.bias") or k_.endswith("attention_weights.bias"):
+                continue
+            d = digest(p_.grad.cpu().numpy())
+            e = abs(d[1] - ref[1]) / max(ref[1], 1e-30)
+            if e > worst:
+                worst, wname = e, k_
+        print(f"{name}: prob {r(prob, fx['prob']):.2e} ct2ci {r(ct2ci, fx['ct2ci']):.2e} pth2ci {r(pth2ci, fx['pth2ci']):.2e} "
+              f"loss {abs(float(loss) - float(fx['loss'])):.2e} worst sumsq-digest rel {worst:.2e} ({wname}) "
+              f"dx_p sumsq {abs(digest(x_p.grad.cpu().numpy())[1] - fx['dx_p'][1]) / fx['dx_p'][1]:.2e}", flush=True)
+
+
 def run_stage(name):
     import torch
     if name == "pool_f32":
@@ -250,6 +433,14 @@ def run_stage(name):
         stage_linear(torch.float32, True)
     elif name == "abmil":
         stage_abmil()
+    elif name == "attention":
+        stage_attention()
+    elif name == "layernorm":
+        stage_layernorm()
+    elif name == "clip":
+        stage_clip()
+    elif name == "fusion":
+        stage_fusion()
 
 
 if __name__ == "__main__":
