@@ -15,6 +15,32 @@ from . import _lib as L
 from . import functional as F
 
 
+def shard_bags(lengths, rank, world, balance=True):
+    """Indices of the bags rank `rank` owns.  balance=False is DistributedSampler's stride (train_ddp.py:191:
+    rank, rank+world, ...).  balance=True assigns bags longest-first to the rank with the fewest instances so far
+    (bag sizes span 200x, so equal bag COUNTS would leave ranks idle at the all-reduce); ties go to the lowest rank,
+    which makes the assignment a pure function of `lengths` — every rank computes the same partition locally."""
+    n = len(lengths)
+    if not balance:
+        return list(range(rank, n, world))
+    order = sorted(range(n), key=lambda i: (-int(lengths[i]), i))
+    load = [0] * world
+    owner = [0] * n
+    for i in order:
+        r = min(range(world), key=lambda q: (load[q], q))
+        owner[i] = r
+        load[r] += int(lengths[i])
+    return [i for i in range(n) if owner[i] == rank]
+
+
+def flat_layout(L_feat, D):
+    """Element ranges of the flat fp32 parameter/gradient buffer, keyed by the reference's state_dict names."""
+    o = 2 * D * L_feat
+    return {"attention_V.0.weight": (0, D * L_feat), "attention_U.0.weight": (D * L_feat, o),
+            "attention_V.0.bias": (o, o + D), "attention_U.0.bias": (o + D, o + 2 * D),
+            "attention_weights.weight": (o + 2 * D, o + 3 * D), "attention_weights.bias": (o + 3 * D, o + 3 * D + 1)}
+
+
 class AbmilTrainer:
     def __init__(self, L_feat=1024, D=192, compute_dtype=torch.bfloat16, lr=1e-5, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=1e-7, device="cuda", process_group=None, world_size=1, need_input_grad=False):
@@ -96,10 +122,14 @@ class AbmilTrainer:
         self.last_argmax, self.last_scores = am, s
         return M, dX
 
-    def reduce_and_update(self):
-        """all-reduce(sum) of the flat gradient over NCCL, then fused Adam with grad_scale = 1/world."""
+    def allreduce_grads(self):
+        """The path's only exchange: ONE all-reduce(sum) of the flat gradient buffer (NCCL on GPUs; any backend)."""
         if self.world > 1:
             torch.distributed.all_reduce(self.grads, group=self.pg)
+
+    def reduce_and_update(self):
+        """all-reduce(sum) of the flat gradient over NCCL, then fused Adam with grad_scale = 1/world."""
+        self.allreduce_grads()
         self.step_count += 1
         L.check(L.lib().milb200_adam_step(L.ptr(self.params), L.ptr(self.grads), L.ptr(self.exp_avg),
                                           L.ptr(self.exp_avg_sq), self.numel, self.lr, self.betas[0], self.betas[1],
