@@ -2,11 +2,11 @@
 // forward and backward (replaces F.softmax(A, dim=1) and torch.matmul(A, x), model/dim1/ABMIL.py:56-59,
 // and their autograd).  Bandwidth-bound: X is streamed exactly once per pass with 128-bit loads.
 //
-// Forward = ONE kernel.  The packed rows are cut into fixed chunks of `ch` rows; a CTA owns one chunk
-// and walks the bag pieces inside it.  For every piece it computes a local (max, sum, weighted
-// accumulator) online-softmax partial; a bag that lies inside one chunk is finished on the spot, a bag
-// that spans chunks is finished by whichever CTA publishes its last piece (per-bag arrival counter),
-// which folds the partials in piece order, so the result is deterministic.
+// Forward = ONE persistent kernel: two CTAs per SM, each owning a contiguous slab of the packed rows and
+// walking the bag pieces inside it.  For every piece it computes a local (max, sum, weighted accumulator)
+// softmax partial; a bag that lies inside one slab is finished on the spot, a bag that spans slabs is
+// finished by whichever CTA publishes its last piece (per-bag arrival counter), which folds the partials
+// in piece order, so the result is deterministic.
 #include <algorithm>
 #include <cfloat>
 
@@ -15,54 +15,43 @@
 namespace milb200 {
 
 constexpr int POOL_THREADS = 256;
-constexpr int POOL_MAX_CH = 128;
-
-struct PoolLayout {  // how the 256 threads of a CTA tile one row of V 16-byte vectors
-  int V, TPR, R, VPT;
-};
-static PoolLayout pool_layout(int L, int esz) {
-  PoolLayout p;
-  p.V = L * esz / 16;
-  p.VPT = (p.V + POOL_THREADS - 1) / POOL_THREADS;
-  int per = (p.V + p.VPT - 1) / p.VPT;
-  p.TPR = per;
-  p.R = POOL_THREADS / p.TPR;
-  if (p.R < 1) p.R = 1;
-  return p;
-}
+constexpr int POOL_WARPS = POOL_THREADS / 32;
+constexpr int POOL_BLK = 16;         // rows a warp owns at a time (one score per lane 0..15)
+constexpr int POOL_MIN_SLAB = 256;   // rows per CTA at least (512 KB of bf16 x 1024)
 
 template <typename T> __device__ __forceinline__ float exp_t(float x);
 template <> __device__ __forceinline__ float exp_t<float>(float x) { return expf(x); }
 template <> __device__ __forceinline__ float exp_t<__nv_bfloat16>(float x) { return __expf(x); }
 
-struct PiecePartial {  // published per (chunk, bag) piece
+struct PiecePartial {  // published per (CTA, bag) piece
   float m, l;
   int argmax;  // index within the bag
   int pad;
 };
 
-template <typename T, int VPT>
+// Persistent layout: CTA c owns the contiguous row slab [c*slab, (c+1)*slab) and walks the bag pieces inside it.
+// Per piece: (1) block max/argmax of the piece's scores, (2) every warp streams 16-row blocks of the piece — lane j
+// owns the 16-byte vectors j, j+32, ... of a row, two rows in flight — accumulating exp(s_i - max) * x_i in registers,
+// (3) one shared-memory fold across the 8 warps.  A bag inside one slab is finished on the spot; a bag spanning
+// slabs is finished by the CTA that publishes its last piece, folding the partials in piece order (deterministic).
+template <typename T, int NV>
 __global__ void __launch_bounds__(POOL_THREADS)
 k_pool_fwd(const T* __restrict__ X, const float* __restrict__ scores, const int32_t* __restrict__ offsets, int B,
-           int64_t total_n, int L, int ch, int V, int TPR, int R, float* __restrict__ M, T* __restrict__ M_lowp,
+           int64_t total_n, int L, int V, int64_t slab, float* __restrict__ M, T* __restrict__ M_lowp,
            int32_t* __restrict__ argmax_out, float* __restrict__ lse_out, float* __restrict__ ws_acc,
            PiecePartial* __restrict__ ws_ml, unsigned int* __restrict__ counters, int normalize) {
   constexpr int VN = Vec16<T>::N;
-  extern __shared__ __align__(16) float smem[];
-  float* e_s = smem;                    // [POOL_MAX_CH] exp(s - m_piece)
-  float* red = smem + POOL_MAX_CH;      // [R][L] cross-row-group reduction, then the piece accumulator
-  __shared__ float wred_v[8];
-  __shared__ int wred_i[8];
+  extern __shared__ __align__(16) float red[];  // [POOL_WARPS][L]
+  __shared__ float wred_v[POOL_WARPS];
+  __shared__ int wred_i[POOL_WARPS];
   __shared__ float piece_m, piece_l;
   __shared__ int piece_arg, is_last;
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int64_t chunk = blockIdx.x;
-  const int64_t r0 = chunk * ch;
-  const int64_t r1 = (r0 + ch < total_n) ? r0 + ch : total_n;
-  const int rg = t / TPR, vt = t % TPR;
-  const bool active = rg < R;
-  const int64_t rowvecs = static_cast<int64_t>(V);
+  const int64_t cta = blockIdx.x;
+  const int64_t r0 = cta * slab;
+  if (r0 >= total_n) return;
+  const int64_t r1 = (r0 + slab < total_n) ? r0 + slab : total_n;
   const uint4* Xv = reinterpret_cast<const uint4*>(X);
 
   int b = find_bag(offsets, B, r0);
@@ -73,12 +62,15 @@ k_pool_fwd(const T* __restrict__ X, const float* __restrict__ scores, const int3
     const int nseg = static_cast<int>(s1 - s0);
     if (nseg <= 0) continue;  // empty bag: nothing to pool (contract: bags are non-empty)
 
-    // ---- piece max / first argmax ----
-    float sv = (t < nseg) ? (scores ? __ldg(scores + s0 + t) : 0.f) : -FLT_MAX;
-    int si = (t < nseg) ? t : 0x7fffffff;
-    {
-      float mv = sv;
-      int mi = si;
+    // ---- (1) piece max and first argmax ----
+    float pm = 0.f;
+    if (scores) {
+      float mv = -FLT_MAX;
+      int mi = 0x7fffffff;
+      for (int i = t; i < nseg; i += POOL_THREADS) {
+        float v = __ldg(scores + s0 + i);
+        if (v > mv) { mv = v; mi = i; }  // i ascends: the first maximum is kept
+      }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         float ov = __shfl_xor_sync(0xffffffffu, mv, o);
@@ -86,96 +78,99 @@ k_pool_fwd(const T* __restrict__ X, const float* __restrict__ scores, const int3
         if (ov > mv || (ov == mv && oi < mi)) { mv = ov; mi = oi; }
       }
       if (lane == 0) { wred_v[warp] = mv; wred_i[warp] = mi; }
-    }
-    __syncthreads();
-    if (t == 0) {
-      float mv = wred_v[0];
-      int mi = wred_i[0];
-      for (int w = 1; w < POOL_THREADS / 32; ++w)
-        if (wred_v[w] > mv || (wred_v[w] == mv && wred_i[w] < mi)) { mv = wred_v[w]; mi = wred_i[w]; }
-      piece_m = mv;
-      piece_arg = mi + static_cast<int>(s0 - ob);
-    }
-    __syncthreads();
-    const float pm = piece_m;
-    float ev = (t < nseg) ? exp_t<T>(sv - pm) : 0.f;
-    if (t < nseg) e_s[t] = ev;
-    ev = warp_sum(ev);
-    __syncthreads();  // e_s visible; wred_v reads above are done
-    if (lane == 0) wred_v[warp] = ev;
-    __syncthreads();
-    if (t == 0) {
-      float l = 0.f;
-      for (int w = 0; w < POOL_THREADS / 32; ++w) l += wred_v[w];
-      piece_l = l;
+      __syncthreads();
+      if (t == 0) {
+        float bv = wred_v[0];
+        int bi = wred_i[0];
+        for (int w = 1; w < POOL_WARPS; ++w)
+          if (wred_v[w] > bv || (wred_v[w] == bv && wred_i[w] < bi)) { bv = wred_v[w]; bi = wred_i[w]; }
+        piece_m = bv;
+        piece_arg = bi + static_cast<int>(s0 - ob);
+      }
+      __syncthreads();
+      pm = piece_m;
+    } else if (t == 0) {
+      piece_m = 0.f;
+      piece_arg = 0;
     }
 
-    // ---- weighted row sum: thread (rg, vt) owns vectors vt + j*TPR of rows rg, rg+R, ... ----
-    float acc[VPT][VN];
+    // ---- (2) stream the piece ----
+    float acc[NV][VN];
 #pragma unroll
-    for (int j = 0; j < VPT; ++j)
+    for (int j = 0; j < NV; ++j)
 #pragma unroll
       for (int k = 0; k < VN; ++k) acc[j][k] = 0.f;
-    if (active) {
-      // software-pipelined: the next batch of UNR rows is in flight while the current one is consumed
-      constexpr int UNR = (VPT == 1) ? 4 : 2;
-      auto load_batch = [&](uint4 (&v)[UNR][VPT], int i0) {
+    float lsum = 0.f;
+    const int nblk = (nseg + POOL_BLK - 1) / POOL_BLK;
+    for (int blk = warp; blk < nblk; blk += POOL_WARPS) {
+      const int64_t rb = s0 + static_cast<int64_t>(blk) * POOL_BLK;
+      const int nr = (nseg - blk * POOL_BLK < POOL_BLK) ? nseg - blk * POOL_BLK : POOL_BLK;
+      float e = 0.f;
+      if (lane < nr) e = scores ? exp_t<T>(__ldg(scores + rb + lane) - pm) : 1.f;
+      lsum += e;
+      int i = 0;
+      for (; i + 1 < nr; i += 2) {
+        uint4 v0[NV], v1[NV];
 #pragma unroll
-        for (int u = 0; u < UNR; ++u)
-#pragma unroll
-          for (int j = 0; j < VPT; ++j) {
-            int vec = vt + j * TPR;
-            int row = i0 + u * R;
-            v[u][j] = (vec < V && row < nseg) ? ldg_stream(Xv + (s0 + row) * rowvecs + vec) : make_uint4(0, 0, 0, 0);
-          }
-      };
-      auto consume = [&](const uint4 (&v)[UNR][VPT], int i0) {
-#pragma unroll
-        for (int u = 0; u < UNR; ++u) {
-          int row = i0 + u * R;
-          float w = row < nseg ? e_s[row] : 0.f;
-#pragma unroll
-          for (int j = 0; j < VPT; ++j) {
-            float f[VN];
-            Vec16<T>::unpack(v[u][j], f);
-#pragma unroll
-            for (int k = 0; k < VN; ++k) acc[j][k] = fmaf(w, f[k], acc[j][k]);
-          }
+        for (int j = 0; j < NV; ++j) {
+          const int vec = lane + j * 32;
+          v0[j] = (vec < V) ? ldg_stream(Xv + (rb + i) * V + vec) : make_uint4(0, 0, 0, 0);
+          v1[j] = (vec < V) ? ldg_stream(Xv + (rb + i + 1) * V + vec) : make_uint4(0, 0, 0, 0);
         }
-      };
-      uint4 bufA[UNR][VPT], bufB[UNR][VPT];
-      int i = rg;
-      if (i < nseg) load_batch(bufA, i);
-      while (i < nseg) {
-        const int inext = i + UNR * R;
-        if (inext < nseg) load_batch(bufB, inext);
-        consume(bufA, i);
-        i = inext;
-        if (i >= nseg) break;
-        const int inext2 = i + UNR * R;
-        if (inext2 < nseg) load_batch(bufA, inext2);
-        consume(bufB, i);
-        i = inext2;
+        const float w0 = __shfl_sync(0xffffffffu, e, i), w1 = __shfl_sync(0xffffffffu, e, i + 1);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          float f[VN];
+          Vec16<T>::unpack(v0[j], f);
+#pragma unroll
+          for (int k = 0; k < VN; ++k) acc[j][k] = fmaf(w0, f[k], acc[j][k]);
+          Vec16<T>::unpack(v1[j], f);
+#pragma unroll
+          for (int k = 0; k < VN; ++k) acc[j][k] = fmaf(w1, f[k], acc[j][k]);
+        }
       }
+      if (i < nr) {
+        const float w0 = __shfl_sync(0xffffffffu, e, i);
 #pragma unroll
-      for (int j = 0; j < VPT; ++j) {
-        int vec = vt + j * TPR;
-        if (vec < V) {
+        for (int j = 0; j < NV; ++j) {
+          const int vec = lane + j * 32;
+          if (vec < V) {
+            float f[VN];
+            Vec16<T>::unpack(ldg_stream(Xv + (rb + i) * V + vec), f);
 #pragma unroll
-          for (int k = 0; k < VN; ++k) red[static_cast<int64_t>(rg) * L + vec * VN + k] = acc[j][k];
+            for (int k = 0; k < VN; ++k) acc[j][k] = fmaf(w0, f[k], acc[j][k]);
+          }
         }
       }
     }
+    lsum = warp_sum(lsum);
+
+    // ---- (3) fold the 8 warps in fixed order ----
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int vec = lane + j * 32;
+      if (vec < V) {
+        float* dst = red + static_cast<int64_t>(warp) * L + vec * VN;
+#pragma unroll
+        for (int k = 0; k < VN; k += 4) *reinterpret_cast<float4*>(dst + k) = make_float4(acc[j][k], acc[j][k + 1], acc[j][k + 2], acc[j][k + 3]);
+      }
+    }
+    if (lane == 0) wred_v[warp] = lsum;
     __syncthreads();
-    // fold row groups in fixed order into red[0][:]
     for (int c = t; c < L; c += POOL_THREADS) {
       float a = red[c];
-      for (int g = 1; g < R; ++g) a += red[static_cast<int64_t>(g) * L + c];
+#pragma unroll
+      for (int g = 1; g < POOL_WARPS; ++g) a += red[static_cast<int64_t>(g) * L + c];
       red[c] = a;
+    }
+    if (t == 0) {
+      float l = 0.f;
+      for (int w = 0; w < POOL_WARPS; ++w) l += wred_v[w];
+      piece_l = l;
     }
     __syncthreads();
 
-    const int64_t c_first = ob / ch, c_last = (oe - 1) / ch;
+    const int64_t c_first = ob / slab, c_last = (oe - 1) / slab;
     const int pieces = static_cast<int>(c_last - c_first + 1);
     if (pieces == 1) {
       const float inv = normalize ? 1.f / piece_l : 1.f;
@@ -189,7 +184,7 @@ k_pool_fwd(const T* __restrict__ X, const float* __restrict__ scores, const int3
         if (lse_out) lse_out[b] = piece_m + logf(piece_l);
       }
     } else {
-      const int64_t slot = chunk + b;  // unique per (chunk, bag) piece, monotone along the row order
+      const int64_t slot = cta + b;  // unique per (CTA, bag) piece, consecutive along the row order
       for (int c = t; c < L; c += POOL_THREADS) ws_acc[slot * L + c] = red[c];
       if (t == 0) {
         PiecePartial pp;
@@ -220,10 +215,16 @@ k_pool_fwd(const T* __restrict__ X, const float* __restrict__ scores, const int3
         const float inv = normalize ? 1.f / gl : 1.f;
         for (int c = t; c < L; c += POOL_THREADS) {
           float a = 0.f;
-          for (int p = 0; p < pieces; ++p) {
-            float sc = exp_t<T>(ws_ml[slot0 + p].m - gm);
-            a = fmaf(sc, __ldcg(ws_acc + (slot0 + p) * L + c), a);
+          int p = 0;
+          for (; p + 4 <= pieces; p += 4) {  // four independent loads in flight; the fold order stays p ascending
+            float x0 = __ldcg(ws_acc + (slot0 + p) * L + c), x1 = __ldcg(ws_acc + (slot0 + p + 1) * L + c);
+            float x2 = __ldcg(ws_acc + (slot0 + p + 2) * L + c), x3 = __ldcg(ws_acc + (slot0 + p + 3) * L + c);
+            a = fmaf(exp_t<T>(ws_ml[slot0 + p].m - gm), x0, a);
+            a = fmaf(exp_t<T>(ws_ml[slot0 + p + 1].m - gm), x1, a);
+            a = fmaf(exp_t<T>(ws_ml[slot0 + p + 2].m - gm), x2, a);
+            a = fmaf(exp_t<T>(ws_ml[slot0 + p + 3].m - gm), x3, a);
           }
+          for (; p < pieces; ++p) a = fmaf(exp_t<T>(ws_ml[slot0 + p].m - gm), __ldcg(ws_acc + (slot0 + p) * L + c), a);
           float mval = a * inv;
           M[static_cast<int64_t>(b) * L + c] = mval;
           if (M_lowp) M_lowp[static_cast<int64_t>(b) * L + c] = from_f32<T>(mval);
@@ -234,7 +235,7 @@ k_pool_fwd(const T* __restrict__ X, const float* __restrict__ scores, const int3
         }
       }
     }
-    __syncthreads();  // smem (e_s, red, piece_*) is reused by the next piece
+    __syncthreads();  // smem (red, wred_*, piece_*) is reused by the next piece
   }
 }
 
@@ -400,11 +401,12 @@ k_bag_broadcast(const float* __restrict__ src, const float* __restrict__ w, cons
   }
 }
 
-static int pool_chunk_rows(int64_t total_n) {
-  int64_t target = static_cast<int64_t>(sm_count()) * 4;
-  if (total_n >= target * 128) return 128;
-  if (total_n >= target * 64) return 64;
-  return 32;
+// rows per CTA: persistent slabs, two CTAs per SM, never below POOL_MIN_SLAB rows
+static int64_t pool_slab_rows(int64_t total_n) {
+  int64_t ctas = static_cast<int64_t>(sm_count()) * 2;
+  int64_t slab = (total_n + ctas - 1) / ctas;
+  if (slab < POOL_MIN_SLAB) slab = POOL_MIN_SLAB;
+  return (slab + POOL_BLK - 1) / POOL_BLK * POOL_BLK;
 }
 
 struct PoolWs {
@@ -415,8 +417,8 @@ struct PoolWs {
   size_t bytes;
 };
 static PoolWs pool_ws(void* base, int64_t total_n, int B, int L) {
-  // sized for the smallest chunk (32 rows): slots <= ceil(total_n/32) + B
-  int64_t slots = (total_n + 31) / 32 + B + 1;
+  const int64_t slab = pool_slab_rows(total_n);
+  const int64_t slots = (total_n + slab - 1) / slab + B + 1;  // (CTA, bag) pieces: slot = cta + bag
   size_t off = 0;
   PoolWs w;
   char* p = static_cast<char*>(base);
@@ -427,11 +429,7 @@ static PoolWs pool_ws(void* base, int64_t total_n, int B, int L) {
   w.ml = reinterpret_cast<PiecePartial*>(p + off);
   off = align_up(off + sizeof(PiecePartial) * static_cast<size_t>(slots), 256);
   w.acc = reinterpret_cast<float*>(p + off);
-  // partial accumulators are only written for bags that span chunks; with the chunk size picked by
-  // pool_chunk_rows the slot count is bounded by ceil(total_n / ch) + B
-  int ch = pool_chunk_rows(total_n);
-  int64_t acc_slots = (total_n + ch - 1) / ch + B + 1;
-  off = align_up(off + sizeof(float) * static_cast<size_t>(acc_slots) * L, 256);
+  off = align_up(off + sizeof(float) * static_cast<size_t>(slots) * L, 256);
   w.bytes = off;
   return w;
 }
@@ -440,26 +438,29 @@ template <typename T>
 static int pool_fwd_t(const T* X, const float* scores, const int32_t* offsets, int B, int64_t total_n, int L, float* M,
                       T* M_lowp, int32_t* argmax, float* lse, void* workspace, size_t ws_bytes, cudaStream_t st,
                       int normalize = 1) {
-  PoolLayout pl = pool_layout(L, sizeof(T));
-  MIL_CHECK_ARG(pl.VPT <= 4, MILB200_EUNSUPPORTED, "pool: row of %d bytes exceeds the 16 KB limit", L * (int)sizeof(T));
+  const int V = L * static_cast<int>(sizeof(T)) / 16;
+  const int nv = (V + 31) / 32;
+  MIL_CHECK_ARG(nv <= 16, MILB200_EUNSUPPORTED, "pool: row of %d bytes exceeds the 8 KB limit", L * (int)sizeof(T));
   PoolWs w = pool_ws(workspace, total_n, B, L);
   MIL_CHECK_ARG(workspace && ws_bytes >= w.bytes, MILB200_EWORKSPACE, "pool_fwd: workspace %zu < %zu", ws_bytes, w.bytes);
   MIL_CUDA(cudaMemsetAsync(w.counters, 0, sizeof(unsigned int) * static_cast<size_t>(B), st));
-  int ch = pool_chunk_rows(total_n);
-  int64_t chunks = (total_n + ch - 1) / ch;
-  size_t smem = sizeof(float) * (POOL_MAX_CH + static_cast<size_t>(pl.R) * L);
+  const int64_t slab = pool_slab_rows(total_n);
+  const int64_t ctas = (total_n + slab - 1) / slab;
+  const size_t smem = sizeof(float) * static_cast<size_t>(POOL_WARPS) * L;
   auto launch = [&](auto kern) -> int {
     if (smem > 48 * 1024) MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<static_cast<unsigned>(chunks), POOL_THREADS, smem, st>>>(X, scores, offsets, B, total_n, L, ch, pl.V, pl.TPR,
-                                                                   pl.R, M, M_lowp, argmax, lse, w.acc, w.ml, w.counters, normalize);
+    kern<<<static_cast<unsigned>(ctas), POOL_THREADS, smem, st>>>(X, scores, offsets, B, total_n, L, V, slab, M, M_lowp,
+                                                                 argmax, lse, w.acc, w.ml, w.counters, normalize);
     MIL_LAUNCH_CHECK();
     return MILB200_OK;
   };
-  switch (pl.VPT) {
-    case 1: return launch(k_pool_fwd<T, 1>);
-    case 2: return launch(k_pool_fwd<T, 2>);
-    default: return launch(k_pool_fwd<T, 4>);
-  }
+  if (nv <= 1) return launch(k_pool_fwd<T, 1>);
+  if (nv == 2) return launch(k_pool_fwd<T, 2>);
+  if (nv == 3) return launch(k_pool_fwd<T, 3>);
+  if (nv == 4) return launch(k_pool_fwd<T, 4>);
+  if (nv <= 6) return launch(k_pool_fwd<T, 6>);
+  if (nv <= 8) return launch(k_pool_fwd<T, 8>);
+  return launch(k_pool_fwd<T, 16>);
 }
 
 template <typename T>
