@@ -152,6 +152,8 @@ def main():
     ap.add_argument("--bags", type=int, default=64, help="bags per rank per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--input-grad", action="store_true", help="also produce dX (instances are trainable upstream)")
+    ap.add_argument("--recompute-gate", action="store_true",
+                    help="backward re-runs the gate GEMM instead of reading the V,U activations saved by the forward")
     args = ap.parse_args()
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -165,6 +167,7 @@ def main():
               "bags_per_rank": args.bags, "L": L_FEAT, "D": D_GATE, "parallelism": f"dp{world}",
               "input_grad": bool(args.input_grad),
               "cache": "inputs (~1.3 GB/rank) exceed the 126 MB L2, no flush needed",
+              "gate_backward": "recompute GEMM" if args.recompute_gate else "saved V,U (bf16, 768 B/instance)",
               "mode": "eval-mode semantics (no dropout), dM = ones, optimizer = fused Adam in the timed region"}
 
     if args.impl == "reference":
@@ -209,7 +212,7 @@ def main():
     torch.manual_seed(1234)
     module = mil_b200.ABMIL(None, L=L_FEAT, D=D_GATE).to(dev)
     tr = AbmilTrainer(L_FEAT, D_GATE, torch.bfloat16, lr=1e-5, weight_decay=1e-7, device=dev, process_group=pg,
-                      world_size=world, need_input_grad=args.input_grad)
+                      world_size=world, need_input_grad=args.input_grad, save_gate=not args.recompute_gate)
     tr.load_from(module)
     tr.broadcast_params()
 
@@ -284,7 +287,7 @@ def main():
         Wcat, bcat_c = tr._wcat_c, tr._bcat_c
         hbm_peak = float(peaks.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"]))
         tf_peak = float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"]))
-        s = F.gated_scores(X, Wcat, bcat_c, v["ww"], v["bw"])
+        s, act = F.gated_scores(X, Wcat, bcat_c, v["ww"], v["bw"], save=True)
         M, _, _, _ = F.segment_softmax_pool(X, s, offsets)
         dM = torch.ones_like(M)
         ds, _ = F.segment_softmax_pool_bwd(X, s, offsets, dM, M, False)
@@ -303,10 +306,13 @@ def main():
 
         n, Lf, D, B = total_n, L_FEAT, D_GATE, args.bags
         gemm_flops = 2.0 * n * Lf * 2 * D
-        t_score = timeit(lambda: F.gated_scores(X, Wcat, bcat_c, v["ww"], v["bw"]))
-        kernels.append({"name": "gated_score_fwd (k_gemm_kmajor<384,EpiScore>)", "ms": t_score, "bound": "tensor",
+        save = tr.save_gate and act is not None
+        t_score = timeit(lambda: F.gated_scores(X, Wcat, bcat_c, v["ww"], v["bw"], save=save))
+        kernels.append({"name": "gated_score_fwd (k_gemm_kmajor<192x2,EpiScore%s>)" % ("+save V,U" if save else ""),
+                        "ms": t_score, "bound": "tensor",
                         "achieved": gemm_flops / t_score / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
-                        "algorithmic": "2*n*L*2D flop", "hbm_gbs": (n * Lf * 2 + n * 4) / t_score / 1e6})
+                        "algorithmic": "2*n*L*2D flop",
+                        "hbm_gbs": (n * Lf * 2 + n * 4 + (n * 2 * D * 2 if save else 0)) / t_score / 1e6})
         t_pool = timeit(lambda: F.segment_softmax_pool(X, s, offsets))
         pool_bytes = n * (Lf * 2 + 4) + B * Lf * 4 + (B + 1) * 4
         kernels.append({"name": "segment_softmax_pool_fwd (k_pool_fwd)", "ms": t_pool, "bound": "hbm",
@@ -321,16 +327,23 @@ def main():
         acc = [0.0] * 4
         reps = 10
         for i in range(reps + 3):
-            F.gated_scores_bwd(X, Wcat, bcat_c, v["ww"], v["bw"], ds, None, dM, offsets, False, grad_out=tr.grads)
+            F.gated_scores_bwd(X, Wcat, bcat_c, v["ww"], v["bw"], ds, None, dM, offsets, False, grad_out=tr.grads,
+                               gate_act=act if save else None)
             buf = (ctypes.c_float * 8)()
             k = Lb.lib().milb200_profile_read(buf, 8)
             if i >= 3:
                 for j in range(min(k, 4)):
                     acc[j] += buf[j] / reps
         Lb.lib().milb200_profile_enable(0)
-        kernels.append({"name": "gate_bwd dZ recompute (k_gemm_kmajor<384,EpiDz>)", "ms": acc[0], "bound": "tensor",
-                        "achieved": gemm_flops / acc[0] / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
-                        "algorithmic": "2*n*L*2D flop", "hbm_gbs": (n * Lf * 2 + n * 2 * D * 2) / acc[0] / 1e6})
+        if save:
+            dz_bytes = n * (2 * 2 * D * 2 + 4)
+            kernels.append({"name": "gate_bwd dZ from saved V,U (k_gate_dz_saved)", "ms": acc[0], "bound": "hbm",
+                            "achieved": dz_bytes / acc[0] / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                            "algorithmic": "n*(2*2D*2 + 4) bytes"})
+        else:
+            kernels.append({"name": "gate_bwd dZ recompute (k_gemm_kmajor<192x2,EpiDz>)", "ms": acc[0], "bound": "tensor",
+                            "achieved": gemm_flops / acc[0] / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
+                            "algorithmic": "2*n*L*2D flop", "hbm_gbs": (n * Lf * 2 + n * 2 * D * 2) / acc[0] / 1e6})
         kernels.append({"name": "gate_bwd dW split-K (k_gemm_tn)", "ms": acc[1], "bound": "tensor",
                         "achieved": gemm_flops / acc[1] / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
                         "algorithmic": "2*n*L*2D flop", "hbm_gbs": (n * Lf * 2 + n * 2 * D * 2) / acc[1] / 1e6})

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MILB200_VERSION 100
+#define MILB200_VERSION 101
 
 enum { MILB200_F32 = 0, MILB200_BF16 = 1 };
 
@@ -59,23 +59,29 @@ int milb200_pack_gate_weights(const void* Wv, const void* Wu, const void* bv, co
 
 size_t milb200_gated_score_workspace_bytes(int64_t total_n, int L, int D, int dtype, int backward);
 
+/* gate_act (optional, may be NULL): receives the gate activations [total_n, 2D] in X's dtype (V = tanh(.), U =
+ * sigmoid(.), column order of Wcat's packed rows) for the backward.  Only the tensor-core path writes it
+ * (milb200_gated_score_saves_activations() == 1); passing it to milb200_gated_score_bwd replaces the recompute
+ * GEMM by an elementwise pass (+0.77 KB/instance of memory for -35 % of the backward time at L = 1024).      */
+int milb200_gated_score_saves_activations(int L, int D, int dtype);
 int milb200_gated_score_fwd(const void* X, const void* Wcat, const float* bcat, const float* ww,
-                            const float* bw, float* scores, int64_t total_n, int L, int D, int dtype,
-                            void* workspace, size_t ws_bytes, void* stream);
+                            const float* bw, float* scores, void* gate_act, int64_t total_n, int L, int D,
+                            int dtype, void* workspace, size_t ws_bytes, void* stream);
 
 /* Backward of the line above (autograd of ABMIL.py:52-54).  dscores[total_n] is dL/ds.
- * Recomputes V,U from X (nothing but s is kept from forward).  Outputs (fp32, overwritten):
+ * gate_act == NULL: recomputes V,U from X (nothing but s is kept from forward); otherwise uses the activations
+ * the forward saved.  Outputs (fp32, overwritten):
  * dWcat[2D,L], dbcat[2D], dww[D], dbw[1].  If dX != NULL it receives
  *   dX_i = attn_i * dM[bag(i)] + dVpre_i Wv + dUpre_i Wu      (dtype of X)
  * where attn/dM/offsets describe the pooling term (pass attn=NULL to get the GEMM term only).       */
 int milb200_gated_score_bwd(const void* X, const void* Wcat, const float* bcat, const float* ww,
-                            const float* bw, const float* dscores, const float* attn,
+                            const float* bw, const float* dscores, const void* gate_act, const float* attn,
                             const float* dM, const int32_t* offsets, int B, int64_t total_n, int L,
                             int D, int dtype, float* dWcat, float* dbcat, float* dww, float* dbw,
                             void* dX, void* workspace, size_t ws_bytes, void* stream);
 
 /* Bench hook: with profiling enabled the bf16 path of milb200_gated_score_bwd records CUDA events between its
- * sub-kernels (dz recompute | dW split-K GEMM | split-K reduce | optional dX GEMM); profile_read waits for the
+ * sub-kernels (dZ pass: recompute GEMM or elementwise | dW split-K GEMM | split-K reduce | optional dX GEMM); profile_read waits for the
  * last one and returns up to max_intervals durations in milliseconds (return value = count).              */
 void milb200_profile_enable(int on);
 int milb200_profile_read(float* ms, int max_intervals);

@@ -98,6 +98,95 @@ __global__ void k_colsum_finalize(const float* __restrict__ ws, int nrec, int st
   else dbw[0] = a;
 }
 
+// ---- dZ from SAVED gate activations (tensor-core path, forward ran with gate_act != NULL) -------------------
+// VU [n, 384] bf16 in the packed column order [V 0..95 | U 0..95 | V 96..191 | U 96..191] (see tc_gemm.cu).
+// dZ (same layout) = [ds w U (1 - V^2) | ds w V U (1 - U)].  Elementwise and HBM-bound: 768 B read + 768 B written
+// per instance, instead of re-running the X . Wcat^T GEMM.  Block = 16 row groups x 24 (V vector, U vector) pairs;
+// column sums (-> dbcat, dww, dbw) are kept in registers, folded in fixed order and written one record per block.
+constexpr int DZS_THREADS = 384;
+constexpr int DZS_PAIRS = 24;
+constexpr int DZS_RG = DZS_THREADS / DZS_PAIRS;  // 16
+__global__ void __launch_bounds__(DZS_THREADS, 2)
+k_gate_dz_saved(const __nv_bfloat16* __restrict__ VU, const float* __restrict__ ww, const float* __restrict__ dscores,
+                int64_t n, int64_t rows_per_block, __nv_bfloat16* __restrict__ dZ, float* __restrict__ rec_ws, int stride) {
+  constexpr int D = tc::GATE_D, DH = D / 2;
+  __shared__ float red[DZS_RG][DZS_PAIRS][25];
+  __shared__ float red_ds[DZS_RG];
+  const int t = threadIdx.x, p = t % DZS_PAIRS, rg = t / DZS_PAIRS;
+  const int h = p / 12, j = p % 12;
+  const int colV = h * (2 * DH) + j * 8;  // element offset of this thread's V vector inside a packed row
+  const int colU = colV + DH;
+  const int d0 = h * DH + j * 8;          // natural gate index of the first of the 8 columns
+  float w[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) w[e] = __ldg(ww + d0 + e);
+  float sdv[8], sdu[8], svu[8], sds = 0.f;
+#pragma unroll
+  for (int e = 0; e < 8; ++e) sdv[e] = sdu[e] = svu[e] = 0.f;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_block;
+  const int64_t r1 = (r0 + rows_per_block < n) ? r0 + rows_per_block : n;
+  auto body = [&](const uint4& qv, const uint4& qu, float ds, int64_t r) {
+    float V[8], U[8], dv[8], du[8];
+    Vec16<__nv_bfloat16>::unpack(qv, V);
+    Vec16<__nv_bfloat16>::unpack(qu, U);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const float gu = ds * w[e] * U[e];
+      dv[e] = gu * (1.f - V[e] * V[e]);
+      du[e] = gu * V[e] * (1.f - U[e]);
+      sdv[e] += dv[e];
+      sdu[e] += du[e];
+      svu[e] = fmaf(ds * V[e], U[e], svu[e]);
+    }
+    *reinterpret_cast<uint4*>(dZ + r * (2 * D) + colV) = Vec16<__nv_bfloat16>::pack(dv);
+    *reinterpret_cast<uint4*>(dZ + r * (2 * D) + colU) = Vec16<__nv_bfloat16>::pack(du);
+  };
+  int64_t r = r0 + rg;
+  for (; r + DZS_RG < r1; r += 2 * DZS_RG) {  // two rows in flight per thread
+    const uint4 qv0 = ldg_stream(VU + r * (2 * D) + colV), qu0 = ldg_stream(VU + r * (2 * D) + colU);
+    const uint4 qv1 = ldg_stream(VU + (r + DZS_RG) * (2 * D) + colV), qu1 = ldg_stream(VU + (r + DZS_RG) * (2 * D) + colU);
+    const float ds0 = __ldg(dscores + r), ds1 = __ldg(dscores + r + DZS_RG);
+    if (p == 0) sds += ds0 + ds1;
+    body(qv0, qu0, ds0, r);
+    body(qv1, qu1, ds1, r + DZS_RG);
+  }
+  if (r < r1) {
+    const uint4 qv0 = ldg_stream(VU + r * (2 * D) + colV), qu0 = ldg_stream(VU + r * (2 * D) + colU);
+    const float ds0 = __ldg(dscores + r);
+    if (p == 0) sds += ds0;
+    body(qv0, qu0, ds0, r);
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { red[rg][p][e] = sdv[e]; red[rg][p][8 + e] = sdu[e]; red[rg][p][16 + e] = svu[e]; }
+  if (p == 0) red_ds[rg] = sds;
+  __syncthreads();
+  float* rec = rec_ws + static_cast<int64_t>(blockIdx.x) * stride;
+  for (int i = t; i < 3 * D; i += DZS_THREADS) {  // record: dVpre[192] | dUpre[192] | ds*V*U[192] | sum ds (natural order)
+    const int k = i / D, d = i % D;
+    const int pp = (d / DH) * 12 + (d % DH) / 8, e = d % 8;
+    float a = 0.f;
+#pragma unroll
+    for (int g = 0; g < DZS_RG; ++g) a += red[g][pp][k * 8 + e];
+    rec[i] = a;
+  }
+  if (t == 0) {
+    float a = 0.f;
+    for (int g = 0; g < DZS_RG; ++g) a += red_ds[g];
+    rec[3 * D] = a;
+  }
+}
+// fold the per-block records in block order
+__global__ void k_colsum_finalize_flat(const float* __restrict__ ws, int nrec, int stride, float* __restrict__ dbcat,
+                                       float* __restrict__ dww, float* __restrict__ dbw, int D) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > 3 * D) return;
+  float a = 0.f;
+  for (int r = 0; r < nrec; ++r) a += ws[static_cast<int64_t>(r) * stride + c];
+  if (c < 2 * D) dbcat[c] = a;
+  else if (c < 3 * D) dww[c - 2 * D] = a;
+  else dbw[0] = a;
+}
+
 // dYpre = dY * act'(Y)   (Y is the activation OUTPUT)
 template <typename T>
 __global__ void k_act_bwd(const T* __restrict__ Y, const T* __restrict__ dY, T* __restrict__ out, int64_t n, int act) {
@@ -280,9 +369,11 @@ size_t milb200_gated_score_workspace_bytes(int64_t total_n, int L, int D, int dt
   return gate_ws(total_n, L, D, dtype, backward).total;
 }
 
+int milb200_gated_score_saves_activations(int L, int D, int dtype) { return tc_gate_ok(L, D, dtype) ? 1 : 0; }
+
 int milb200_gated_score_fwd(const void* X, const void* Wcat, const float* bcat, const float* ww, const float* bw,
-                            float* scores, int64_t total_n, int L, int D, int dtype, void* workspace, size_t ws_bytes,
-                            void* stream) {
+                            float* scores, void* gate_act, int64_t total_n, int L, int D, int dtype, void* workspace,
+                            size_t ws_bytes, void* stream) {
   MIL_CHECK_ARG(X && Wcat && bcat && ww && bw && scores, MILB200_EINVAL, "gated_score_fwd: null pointer");
   MIL_CHECK_ARG(total_n > 0 && L > 0 && D > 0, MILB200_EINVAL, "gated_score_fwd: total_n=%lld L=%d D=%d must be positive",
                 (long long)total_n, L, D);
@@ -290,7 +381,11 @@ int milb200_gated_score_fwd(const void* X, const void* Wcat, const float* bcat, 
   MIL_CHECK_ARG(aligned16(X) && aligned16(Wcat) && (L * elem_size(dtype)) % 16 == 0, MILB200_EALIGN,
                 "gated_score_fwd: X/Wcat must be 16-byte aligned with a 16-byte multiple row pitch");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (tc_gate_ok(L, D, dtype)) return tc::gated_score(X, total_n, L, Wcat, bcat, ww, bw, scores, st);
+  if (tc_gate_ok(L, D, dtype)) {
+    MIL_CHECK_ARG(gate_act == nullptr || aligned16(gate_act), MILB200_EALIGN, "gated_score_fwd: gate_act must be 16-byte aligned");
+    return tc::gated_score(X, total_n, L, Wcat, bcat, ww, bw, scores, gate_act, st);
+  }
+  // FFMA path: nothing is saved (its backward recomputes the pre-activations chunk by chunk)
   GateWs w = gate_ws(total_n, L, D, dtype, 0);
   MIL_CHECK_ARG(workspace && ws_bytes >= w.total, MILB200_EWORKSPACE, "gated_score_fwd: workspace %zu < %zu", ws_bytes, w.total);
   char* ws = static_cast<char*>(workspace);
@@ -301,7 +396,8 @@ int milb200_gated_score_fwd(const void* X, const void* Wcat, const float* bcat, 
 }
 
 int milb200_gated_score_bwd(const void* X, const void* Wcat, const float* bcat, const float* ww, const float* bw,
-                            const float* dscores, const float* attn, const float* dM, const int32_t* offsets, int B,
+                            const float* dscores, const void* gate_act, const float* attn, const float* dM,
+                            const int32_t* offsets, int B,
                             int64_t total_n, int L, int D, int dtype, float* dWcat, float* dbcat, float* dww, float* dbw,
                             void* dX, void* workspace, size_t ws_bytes, void* stream) {
   (void)bw;
@@ -324,10 +420,25 @@ int milb200_gated_score_bwd(const void* X, const void* Wcat, const float* bcat, 
     int nrec = 0, splits = 0;
     g_prof_n = 0;
     prof_mark(st);
-    int rc = tc::gated_dz(X, total_n, L, Wcat, bcat, ww, dscores, dZ, colsum, &nrec, st);
-    if (rc) return rc;
-    k_colsum_finalize<<<(3 * D + 1 + 255) / 256, 256, 0, st>>>(colsum, nrec, tc::CS_STRIDE, dbcat, dww, dbw, D);
-    MIL_LAUNCH_CHECK();
+    int rc;
+    if (gate_act) {
+      // saved V,U: dZ is an elementwise pass (1.5 KB of traffic per instance instead of the recompute GEMM)
+      MIL_CHECK_ARG(aligned16(gate_act), MILB200_EALIGN, "gated_score_bwd: gate_act must be 16-byte aligned");
+      int64_t blocks = std::min<int64_t>((total_n + 63) / 64, static_cast<int64_t>(sm_count()) * 2);
+      int64_t rpb = (total_n + blocks - 1) / blocks;
+      rpb = (rpb + DZS_RG - 1) / DZS_RG * DZS_RG;
+      nrec = static_cast<int>((total_n + rpb - 1) / rpb);
+      k_gate_dz_saved<<<nrec, DZS_THREADS, 0, st>>>((const __nv_bfloat16*)gate_act, ww, dscores, total_n, rpb,
+                                                    (__nv_bfloat16*)dZ, colsum, tc::CS_STRIDE);
+      MIL_LAUNCH_CHECK();
+      k_colsum_finalize_flat<<<(3 * D + 1 + 255) / 256, 256, 0, st>>>(colsum, nrec, tc::CS_STRIDE, dbcat, dww, dbw, D);
+      MIL_LAUNCH_CHECK();
+    } else {
+      rc = tc::gated_dz(X, total_n, L, Wcat, bcat, ww, dscores, dZ, colsum, &nrec, st);
+      if (rc) return rc;
+      k_colsum_finalize<<<(3 * D + 1 + 255) / 256, 256, 0, st>>>(colsum, nrec, tc::CS_STRIDE, dbcat, dww, dbw, D);
+      MIL_LAUNCH_CHECK();
+    }
     prof_mark(st);
     rc = tc::gemm_tn_splitk(dZ, 2 * D, X, L, total_n, 2 * D, L, part, &splits, st);
     if (rc) return rc;

@@ -148,28 +148,44 @@ struct EpiStore {
 // the next.  Warp (q, half) owns pairs [48 half, 48 half + 48) of rows [32q, 32q+32).
 constexpr int GATE_PW = GATE_DH / 2;  // pairs per warp per tile = 48
 
-struct EpiScore {
+// SAVE: additionally write the gate activations V = tanh(.), U = sigmoid(.) as bf16 [M, 384] in the packed column
+// order of the weight rows ([V 0..95 | U 0..95 | V 96..191 | U 96..191]) so that the backward can form dZ with an
+// elementwise pass instead of re-running this GEMM (one box pair per warp per half tile, TMA store).
+template <bool SAVE>
+struct EpiScoreT {
   struct Params {
     const float* bcat;  // [384] packed order
     const float* ww;    // [192] natural order
     const float* bw;    // [1]
     float* scores;
+    CUtensorMap tmS;    // SAVE: gate activations [M, 384] bf16; box [32 rows x 48 cols]
   };
   // bias[384] | w[192] | partial[2 parities][4 (h, half)][128 rows]
   static constexpr int SMEM_FLOATS = 3 * GATE_D + 2 * 4 * BM;
-  static constexpr int STAGING_BYTES = 0;
+  static constexpr int BOX_BYTES = 32 * GATE_PW * 2;
+  static constexpr int STAGING_BYTES = SAVE ? EPI_WARPS * 2 * BOX_BYTES : 0;
   __device__ static void prologue(const Params& p, float* esm, int tid) {
     for (int i = tid; i < 2 * GATE_D; i += NUM_THREADS) esm[i] = __ldg(p.bcat + i);
     for (int i = tid; i < GATE_D; i += NUM_THREADS) esm[2 * GATE_D + i] = __ldg(p.ww + i);
   }
-  __device__ EpiScore() {}
+  __device__ EpiScoreT() {}
   template <int BN>
-  __device__ __forceinline__ void tile(const Params& p, float* esm, uint8_t*, uint32_t tacc, const EpiCtx& cx) {
+  __device__ __forceinline__ void tile(const Params& p, float* esm, uint8_t* staging, uint32_t tacc, const EpiCtx& cx) {
     static_assert(BN == GATE_BN, "score epilogue expects the [V half | U half] 192-column tile");
     const int h = cx.nt;
     const float* bV = esm + h * GATE_BN + cx.half * GATE_PW;
     const float* bU = bV + GATE_DH;
     const float* wv = esm + 2 * GATE_D + h * GATE_DH + cx.half * GATE_PW;
+    uint8_t* rowV = nullptr;
+    uint8_t* rowU = nullptr;
+    uint8_t* boxV = nullptr;
+    if (SAVE) {
+      boxV = staging + (cx.half * 4 + cx.q) * 2 * BOX_BYTES;
+      rowV = boxV + cx.lane * (GATE_PW * 2);
+      rowU = rowV + BOX_BYTES;
+      if (cx.lane == 0) tma_store_wait_read<0>();  // the previous half tile's boxes have been read out
+      __syncwarp();
+    }
     float part = 0.f;
 #pragma unroll
     for (int c = 0; c < GATE_PW; c += 16) {
@@ -177,15 +193,36 @@ struct EpiScore {
       tmem_ld16(tacc + cx.half * GATE_PW + c, v);
       tmem_ld16(tacc + GATE_DH + cx.half * GATE_PW + c, u);
       tmem_ld_wait();
+      float fv[16], fu[16];
 #pragma unroll
       for (int j = 0; j < 16; j += 4) {
         float4 bv = *reinterpret_cast<const float4*>(bV + c + j);
         float4 bu = *reinterpret_cast<const float4*>(bU + c + j);
         float4 w = *reinterpret_cast<const float4*>(wv + c + j);
-        part = fmaf(tanh_fast(__uint_as_float(v[j]) + bv.x) * sigmoid_fast(__uint_as_float(u[j]) + bu.x), w.x, part);
-        part = fmaf(tanh_fast(__uint_as_float(v[j + 1]) + bv.y) * sigmoid_fast(__uint_as_float(u[j + 1]) + bu.y), w.y, part);
-        part = fmaf(tanh_fast(__uint_as_float(v[j + 2]) + bv.z) * sigmoid_fast(__uint_as_float(u[j + 2]) + bu.z), w.z, part);
-        part = fmaf(tanh_fast(__uint_as_float(v[j + 3]) + bv.w) * sigmoid_fast(__uint_as_float(u[j + 3]) + bu.w), w.w, part);
+        fv[j] = tanh_fast(__uint_as_float(v[j]) + bv.x); fu[j] = sigmoid_fast(__uint_as_float(u[j]) + bu.x);
+        fv[j + 1] = tanh_fast(__uint_as_float(v[j + 1]) + bv.y); fu[j + 1] = sigmoid_fast(__uint_as_float(u[j + 1]) + bu.y);
+        fv[j + 2] = tanh_fast(__uint_as_float(v[j + 2]) + bv.z); fu[j + 2] = sigmoid_fast(__uint_as_float(u[j + 2]) + bu.z);
+        fv[j + 3] = tanh_fast(__uint_as_float(v[j + 3]) + bv.w); fu[j + 3] = sigmoid_fast(__uint_as_float(u[j + 3]) + bu.w);
+        part = fmaf(fv[j] * fu[j], w.x, part);
+        part = fmaf(fv[j + 1] * fu[j + 1], w.y, part);
+        part = fmaf(fv[j + 2] * fu[j + 2], w.z, part);
+        part = fmaf(fv[j + 3] * fu[j + 3], w.w, part);
+      }
+      if (SAVE) {
+        *reinterpret_cast<uint4*>(rowV + c * 2) = Vec16<__nv_bfloat16>::pack(fv);
+        *reinterpret_cast<uint4*>(rowV + c * 2 + 16) = Vec16<__nv_bfloat16>::pack(fv + 8);
+        *reinterpret_cast<uint4*>(rowU + c * 2) = Vec16<__nv_bfloat16>::pack(fu);
+        *reinterpret_cast<uint4*>(rowU + c * 2 + 16) = Vec16<__nv_bfloat16>::pack(fu + 8);
+      }
+    }
+    if (SAVE) {
+      fence_proxy_async();
+      __syncwarp();
+      if (cx.lane == 0) {
+        const int32_t r0 = static_cast<int32_t>(cx.row);  // lane 0 holds the first row of this warp's quarter
+        tma_store_2d(&p.tmS, boxV, h * GATE_BN + cx.half * GATE_PW, r0);
+        tma_store_2d(&p.tmS, boxV + BOX_BYTES, h * GATE_BN + GATE_DH + cx.half * GATE_PW, r0);
+        tma_store_commit();
       }
     }
     // the four (h, half) partial sums of a row meet in shared memory; parity double-buffering keeps the next
@@ -199,7 +236,9 @@ struct EpiScore {
         p.scores[cx.row] = ((ps[r] + ps[BM + r]) + (ps[2 * BM + r] + ps[3 * BM + r])) + __ldg(p.bw);
     }
   }
-  __device__ void finish(const Params&, int, int) {}
+  __device__ void finish(const Params&, int, int lane) {
+    if (SAVE && lane == 0) tma_store_wait<0>();  // all boxes are globally visible before the kernel ends
+  }
 };
 
 // sum over the 32 lanes of a warp of 16 per-lane columns; lanes 2c and 2c+1 both return column c's total
@@ -521,9 +560,17 @@ int gemm_store(const void* A, int64_t M, int K, int64_t lda, const void* W, int 
 }
 
 int gated_score(const void* X, int64_t n, int L, const void* Wcat, const float* bcat, const float* ww,
-                const float* bw, float* scores, cudaStream_t st) {
-  EpiScore::Params ep{bcat, ww, bw, scores};
-  return launch_kmajor<GATE_BN, EpiScore>(X, n, L, L, Wcat, 2 * GATE_D, L, ep, nullptr, st);
+                const float* bw, float* scores, void* gate_act, cudaStream_t st) {
+  if (gate_act) {
+    EpiScoreT<true>::Params ep;
+    ep.bcat = bcat; ep.ww = ww; ep.bw = bw; ep.scores = scores;
+    int rc0 = make_tmap_bf16_2d_linear(&ep.tmS, gate_act, static_cast<uint64_t>(n), 2 * GATE_D, 2 * GATE_D, 32, GATE_PW);
+    if (rc0) return rc0;
+    return launch_kmajor<GATE_BN, EpiScoreT<true>>(X, n, L, L, Wcat, 2 * GATE_D, L, ep, nullptr, st);
+  }
+  EpiScoreT<false>::Params ep;
+  ep.bcat = bcat; ep.ww = ww; ep.bw = bw; ep.scores = scores;
+  return launch_kmajor<GATE_BN, EpiScoreT<false>>(X, n, L, L, Wcat, 2 * GATE_D, L, ep, nullptr, st);
 }
 
 int gated_dz_max_records() { return sm_count() * EPI_WARPS; }

@@ -17,8 +17,9 @@ int gemm_store(const void* A, int64_t M, int K, int64_t lda, const void* W, int 
 bool gemm_store_supported(int64_t M, int N, int K);
 
 // s[i] = sum_d tanh(x_i.Wv_d + bv_d) * sigmoid(x_i.Wu_d + bu_d) * ww_d + bw     (D = 192)
+// gate_act (optional): bf16 [n, 384] gate activations V|U in the packed column order, saved for the backward.
 int gated_score(const void* X, int64_t n, int L, const void* Wcat, const float* bcat, const float* ww,
-                const float* bw, float* scores, cudaStream_t st);
+                const float* bw, float* scores, void* gate_act, cudaStream_t st);
 
 // Recompute V,U and emit dZ[n, 384] = [dL/dVpre | dL/dUpre] (bf16) for upstream dscores; per-warp column sums
 // (-> dbcat, dww, dbw) are written to colsum_ws[nrec][CS_STRIDE]; *nrec receives the record count.

@@ -43,13 +43,15 @@ def flat_layout(L_feat, D):
 
 class AbmilTrainer:
     def __init__(self, L_feat=1024, D=192, compute_dtype=torch.bfloat16, lr=1e-5, betas=(0.9, 0.999), eps=1e-8,
-                 weight_decay=1e-7, device="cuda", process_group=None, world_size=1, need_input_grad=False):
+                 weight_decay=1e-7, device="cuda", process_group=None, world_size=1, need_input_grad=False,
+                 save_gate=True):
         self.L, self.D = L_feat, D
         self.dtype = compute_dtype
         self.device = torch.device(device)
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.pg, self.world = process_group, world_size
         self.need_input_grad = need_input_grad
+        self.save_gate = save_gate     # keep V,U from the forward (memory) instead of re-running the GEMM (time)
         n = 2 * D * L_feat + 3 * D + 1
         self.numel = n
         self.params = torch.zeros(n, dtype=torch.float32, device=self.device)
@@ -110,7 +112,10 @@ class AbmilTrainer:
                                                   L.dtype_code(self._wcat_c), L.ptr(self._bcat_c), L.stream_ptr()),
                 "pack_gate_weights")
         Wcat, bcat = self._wcat_c, self._bcat_c
-        s = F.gated_scores(X, Wcat, bcat, v["ww"], v["bw"])
+        if self.save_gate:
+            s, act = F.gated_scores(X, Wcat, bcat, v["ww"], v["bw"], save=True)
+        else:
+            s, act = F.gated_scores(X, Wcat, bcat, v["ww"], v["bw"]), None
         M, _, am, _ = F.segment_softmax_pool(X, s, offsets)
         if dM is None:
             if getattr(self, "_ones", None) is None or self._ones.shape != M.shape:
@@ -118,7 +123,7 @@ class AbmilTrainer:
             dM = self._ones
         ds, attn = F.segment_softmax_pool_bwd(X, s, offsets, dM, M, want_attn=self.need_input_grad)
         dX, *_ = F.gated_scores_bwd(X, Wcat, bcat, v["ww"], v["bw"], ds, attn, dM, offsets,
-                                    self.need_input_grad, grad_out=self.grads)
+                                    self.need_input_grad, grad_out=self.grads, gate_act=act)
         self.last_argmax, self.last_scores = am, s
         return M, dX
 

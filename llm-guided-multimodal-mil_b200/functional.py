@@ -16,6 +16,11 @@ def _f32(t):
     return t if t.dtype == torch.float32 else t.float()
 
 
+def _recompute_gate():
+    import os
+    return os.environ.get("MILB200_RECOMPUTE_GATE", "0") == "1"
+
+
 def pack_gate_weights(Wv, bv, Wu, bu, dtype):
     """[Wv; Wu] -> Wcat (2D, L) in `dtype`, [bv; bu] -> bcat fp32 (one kernel)."""
     D, Lf = Wv.shape
@@ -30,18 +35,23 @@ def pack_gate_weights(Wv, bv, Wu, bu, dtype):
     return Wcat, bcat
 
 
-def gated_scores(X, Wcat, bcat, ww, bw):
-    """s[i] = (tanh(x_i Wv^T + bv) * sigmoid(x_i Wu^T + bu)) . ww + bw   -> fp32 [total_n]."""
+def gated_scores(X, Wcat, bcat, ww, bw, save=False):
+    """s[i] = (tanh(x_i Wv^T + bv) * sigmoid(x_i Wu^T + bu)) . ww + bw   -> fp32 [total_n].
+    save=True additionally returns the gate activations [total_n, 2D] (or None when the kernel path in use recomputes
+    them in backward anyway) to hand to gated_scores_bwd."""
     n, Lf = X.shape
     D = Wcat.shape[0] // 2
     s = torch.empty((n,), dtype=torch.float32, device=X.device)
     code = L.dtype_code(X)
+    act = None
+    if save and L.lib().milb200_gated_score_saves_activations(Lf, D, code):
+        act = torch.empty((n, 2 * D), dtype=X.dtype, device=X.device)
     nb = L.lib().milb200_gated_score_workspace_bytes(n, Lf, D, code, 0)
     ws = L.workspace(nb, X.device)
     L.check(L.lib().milb200_gated_score_fwd(L.ptr(X), L.ptr(Wcat), L.ptr(bcat), L.ptr(ww), L.ptr(bw), L.ptr(s),
-                                            n, Lf, D, code, L.ptr(ws), ws.numel(), L.stream_ptr()),
+                                            L.ptr(act), n, Lf, D, code, L.ptr(ws), ws.numel(), L.stream_ptr()),
             "gated_score_fwd")
-    return s
+    return (s, act) if save else s
 
 
 def segment_softmax_pool(X, s, offsets, want_lowp=False):
@@ -76,7 +86,7 @@ def segment_softmax_pool_bwd(X, s, offsets, dM, M, want_attn):
     return ds, attn
 
 
-def gated_scores_bwd(X, Wcat, bcat, ww, bw, ds, attn, dM, offsets, need_dx, grad_out=None):
+def gated_scores_bwd(X, Wcat, bcat, ww, bw, ds, attn, dM, offsets, need_dx, grad_out=None, gate_act=None):
     """Backward of gated_scores (+ the pooling term of dX).  `grad_out`, if given, is a flat fp32 buffer of
     2D*L + 2D + D + 1 elements (laid out dWcat | dbcat | dww | dbw) that the kernels write in place — the
     data-parallel trainer passes a slice of its flat gradient buffer."""
@@ -97,7 +107,7 @@ def gated_scores_bwd(X, Wcat, bcat, ww, bw, ds, attn, dM, offsets, need_dx, grad
     nb = L.lib().milb200_gated_score_workspace_bytes(n, Lf, D, code, 1)
     ws = L.workspace(nb, X.device)
     L.check(L.lib().milb200_gated_score_bwd(L.ptr(X), L.ptr(Wcat), L.ptr(bcat), L.ptr(ww), L.ptr(bw), L.ptr(ds),
-                                            L.ptr(attn) if need_dx else None, L.ptr(dM) if need_dx else None,
+                                            L.ptr(gate_act), L.ptr(attn) if need_dx else None, L.ptr(dM) if need_dx else None,
                                             L.ptr(offsets), B, n, Lf, D, code, L.ptr(dWcat), L.ptr(dbcat),
                                             L.ptr(dww), L.ptr(dbw), L.ptr(dX), L.ptr(ws), ws.numel(),
                                             L.stream_ptr()), "gated_score_bwd")
@@ -114,9 +124,12 @@ class _AbmilPoolCSR(torch.autograd.Function):
         Wcat, bcat = pack_gate_weights(Wv, bv, Wu, bu, X.dtype)
         wwf = _f32(ww).reshape(-1).contiguous()
         bwf = _f32(bw).reshape(-1).contiguous()
-        s = gated_scores(X, Wcat, bcat, wwf, bwf)
+        # training: keep the gate activations (0.77 KB/instance in bf16) so that backward skips the recompute GEMM;
+        # MILB200_RECOMPUTE_GATE=1 trades that memory back for time
+        need_grad = any(ctx.needs_input_grad) and not _recompute_gate()
+        s, act = gated_scores(X, Wcat, bcat, wwf, bwf, save=True) if need_grad else (gated_scores(X, Wcat, bcat, wwf, bwf), None)
         M, Ml, am, lse = segment_softmax_pool(X, s, offsets, want_lowp=X.dtype != torch.float32)
-        ctx.save_for_backward(X, offsets, Wcat, bcat, wwf, bwf, s, M)
+        ctx.save_for_backward(X, offsets, Wcat, bcat, wwf, bwf, s, M, act)
         ctx.param_dtypes = (Wv.dtype, bv.dtype, Wu.dtype, bu.dtype, ww.dtype, bw.dtype)
         ctx.D = Wv.shape[0]
         ctx.mark_non_differentiable(am, s)
@@ -124,12 +137,13 @@ class _AbmilPoolCSR(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dM_out, _dam, _ds):
-        X, offsets, Wcat, bcat, wwf, bwf, s, M = ctx.saved_tensors
+        X, offsets, Wcat, bcat, wwf, bwf, s, M, act = ctx.saved_tensors
         D = ctx.D
         need_dx = ctx.needs_input_grad[0]
         dM = _f32(dM_out).contiguous()
         ds, attn = segment_softmax_pool_bwd(X, s, offsets, dM, M, want_attn=need_dx)
-        dX, dWcat, dbcat, dww, dbw = gated_scores_bwd(X, Wcat, bcat, wwf, bwf, ds, attn, dM, offsets, need_dx)
+        dX, dWcat, dbcat, dww, dbw = gated_scores_bwd(X, Wcat, bcat, wwf, bwf, ds, attn, dM, offsets, need_dx,
+                                                      gate_act=act)
         dt = ctx.param_dtypes
         return (dX, None, dWcat[:D].to(dt[0]), dbcat[:D].to(dt[1]), dWcat[D:].to(dt[2]), dbcat[D:].to(dt[3]),
                 dww.view(1, D).to(dt[4]), dbw.view(1).to(dt[5]))

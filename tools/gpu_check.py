@@ -94,8 +94,10 @@ def stage_gate(dtype, with_dx=True, Ls=(1024, 512, 768), n_list=(1, 300, 5000)):
             ww = (torch.rand(1, D, device="cuda", generator=g) * 2 - 1) / D ** 0.5
             bw = torch.rand(1, device="cuda", generator=g)
             Wcat, bcat = F.pack_gate_weights(Wv, bv, Wu, bu, dtype)
-            s = F.gated_scores(X, Wcat, bcat, ww.reshape(-1).contiguous(), bw)
+            s, act = F.gated_scores(X, Wcat, bcat, ww.reshape(-1).contiguous(), bw, save=True)
+            s2 = F.gated_scores(X, Wcat, bcat, ww.reshape(-1).contiguous(), bw)
             torch.cuda.synchronize()
+            assert torch.equal(s, s2), "saving the gate activations changed the scores"
             Wvq, Wuq = Wv.to(dtype).float(), Wu.to(dtype).float()
             sr, V, U = ref_gate(X, Wvq, bv, Wuq, bu, ww, bw)
             e_s = rel(s, sr)
@@ -105,6 +107,14 @@ def stage_gate(dtype, with_dx=True, Ls=(1024, 512, 768), n_list=(1, 300, 5000)):
             dX, dWcat, dbcat, dww, dbw = F.gated_scores_bwd(X, Wcat, bcat, ww.reshape(-1).contiguous(), bw, ds, attn,
                                                             dM, off, with_dx)
             torch.cuda.synchronize()
+            if act is not None:   # saved-activation backward vs the recompute backward
+                dX2, dW2, db2, dww2, dbw2 = (t.clone() if t is not None else None for t in
+                                              F.gated_scores_bwd(X, Wcat, bcat, ww.reshape(-1).contiguous(), bw, ds, attn,
+                                                                 dM, off, with_dx, gate_act=act))
+                torch.cuda.synchronize()
+                print(f"   saved-vs-recompute: dW {rel(dW2, dWcat):.2e} db {rel(db2, dbcat):.2e} dww {rel(dww2, dww):.2e} "
+                      f"dbw {abs(float(dbw2) - float(dbw)):.1e} dX {rel(dX2, dX) if with_dx else -1:.2e}", flush=True)
+                dX, dWcat, dbcat, dww, dbw = dX2, dW2, db2, dww2, dbw2
             dG = ds.double()[:, None] * ww.double().reshape(1, -1)
             dVp = dG * U * (1 - V * V)
             dUp = dG * V * U * (1 - U)
