@@ -247,28 +247,49 @@ def main():
     total_bags = args.bags * world * args.steps
     value = total_bags / (ms_max / 1e3)
 
-    # ---- end to end: host (pinned) inputs, H2D + D2H inside the timed region ----
+    # ---- end to end: host (pinned) inputs, H2D + D2H inside the timed region -----------------------------------
+    # Every step copies ITS bags host->device (pinned memory, copy stream), runs the public step and reads the pooled
+    # vectors back.  Two device buffers: the copy of step k+1 overlaps the kernels of step k (the copy engine and the
+    # SMs are independent), and the host consumes the result of step k-1 while step k runs.
     X_h = torch.empty((total_n, L_FEAT), dtype=torch.bfloat16).pin_memory()
     X_h.copy_(X)
     off_pin = offsets_h.pin_memory()
-    M_h = torch.empty((args.bags, L_FEAT), dtype=torch.float32).pin_memory()
-    X_d = torch.empty_like(X)
-    off_d = torch.empty_like(offsets)
+    M_h = [torch.empty((args.bags, L_FEAT), dtype=torch.float32).pin_memory() for _ in range(2)]
+    X_d = [torch.empty_like(X) for _ in range(2)]
+    off_d = [torch.empty_like(offsets) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream()
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    read_back = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_step():
-        X_d.copy_(X_h, non_blocking=True)
-        off_d.copy_(off_pin, non_blocking=True)
-        M = tr.step(X_d, off_d)
-        M_h.copy_(M, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the caller consumes the pooled vectors
+    def e2e_run(n_steps):
+        checksum = 0.0
+        for k in range(n_steps):
+            b = k & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[b])            # the kernels that read this buffer two steps ago are done
+                X_d[b].copy_(X_h, non_blocking=True)
+                off_d[b].copy_(off_pin, non_blocking=True)
+                copied[b].record(copy_stream)
+            main_stream.wait_event(copied[b])
+            M = tr.step(X_d[b], off_d[b])
+            consumed[b].record(main_stream)
+            M_h[b].copy_(M, non_blocking=True)
+            read_back[b].record(main_stream)
+            if k > 0:                                          # the caller consumes step k-1's pooled vectors
+                read_back[b ^ 1].synchronize()
+                checksum += float(M_h[b ^ 1][0, 0])
+        read_back[(n_steps - 1) & 1].synchronize()
+        return checksum + float(M_h[(n_steps - 1) & 1][0, 0])
 
+    for ev in consumed:
+        ev.record(main_stream)
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step()
+    e2e_run(2)
     barrier()
     e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
+    e2e_run(e2e_steps)
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -277,7 +298,8 @@ def main():
     e2e_ms = float(t.item())
     e2e_value = args.bags * world * e2e_steps / (e2e_ms / 1e3)
     h2d = X_h.numel() * 2 + off_pin.numel() * 4
-    d2h = M_h.numel() * 4
+    d2h = M_h[0].numel() * 4
+    del X_d
 
     # ---- per-kernel roofline (timed alone, CUDA events on the launch stream, same inputs) ----
     kernels = []
@@ -349,8 +371,24 @@ def main():
                         "algorithmic": "2*n*L*2D flop", "hbm_gbs": (n * Lf * 2 + n * 2 * D * 2) / acc[1] / 1e6})
         kernels.append({"name": "split-K reduce (k_splitk_reduce)", "ms": acc[2], "bound": "hbm", "achieved": None,
                         "peak": hbm_peak, "unit": "GB/s"})
+        # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full
+        # capture of this same workload (tools/ncu_summary.py -> profiles/kernel_traffic.json); null if absent
+        try:
+            ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
+        except Exception:
+            ncu_traffic = {}
+        ncu_keys = {"gated_score_fwd": "k_gemm_kmajor<192, tc::EpiScoreT<%d>>" % (1 if save else 0),
+                    "segment_softmax_pool_fwd": "k_pool_fwd<__nv_bfloat16, 4>",
+                    "segment_softmax_pool_bwd": "k_pool_bwd<__nv_bfloat16, 4>",
+                    "gate_bwd dZ from saved": "k_gate_dz_saved", "gate_bwd dZ recompute": "k_gemm_kmajor<192, tc::EpiDz>",
+                    "gate_bwd dW": "k_gemm_tn"}
         for kinfo in kernels:
             kinfo["frac"] = (kinfo["achieved"] / kinfo["peak"]) if kinfo.get("achieved") else None
+            kinfo["traffic"] = None
+            for prefix, key in ncu_keys.items():
+                if kinfo["name"].startswith(prefix) and key in ncu_traffic:
+                    kinfo["traffic"] = ncu_traffic[key]["dram_bytes"]
+                    kinfo["traffic_source"] = ncu_traffic[key].get("source")
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -360,7 +398,8 @@ def main():
     if rank == 0:
         dom = max(kernels, key=lambda k: k["ms"])
         roof = {"kernel": dom["name"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
-                "unit": dom["unit"], "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                "unit": dom["unit"], "frac": dom["frac"], "traffic": dom.get("traffic"),
+                "traffic_source": dom.get("traffic_source"), "peak_source": peak_src,
                 "ms_per_launch": dom["ms"], "algorithmic": dom.get("algorithmic")}
         line = {"metric": "bags/sec fwd+bwd", "value": value, "unit": "bags/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
