@@ -143,7 +143,17 @@ def cpu_reference(lengths, steps, warmup, budget_s=20.0):
             "ms_per_step": 1e3 * total / len(times), "steps": len(times), "bags_per_step": per_step}
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner to stdout) must not add
+    to it: point fd 1 at stderr for the whole run and return a writer on the original stdout for the final line."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(keep, "w")
+
+
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -181,7 +191,8 @@ def main():
                 "config": config,
                 "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
                 "e2e": {"value": cb["value"], "unit": "bags/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        out.write(json.dumps(line) + "\n")
+        out.flush()
         return 0
 
     import torch
@@ -408,7 +419,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "bags/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
                 "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_base, "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        out.write(json.dumps(line) + "\n")
+        out.flush()
     if world > 1:
         dist.destroy_process_group()
     return 0
