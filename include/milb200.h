@@ -204,6 +204,47 @@ int milb200_sinusoid_pe(void* pe, int64_t n_pos, int dim, int dtype, void* strea
 int milb200_ct_tokens_fwd(const void* fmap, void* tokens, int c, int t, int hw, int dtype, void* stream);
 int milb200_ct_tokens_bwd(const void* dtokens, void* dfmap, int c, int t, int hw, int dtype, void* stream);
 
+/* ---- static operator programs ("tapes") ------------------------------------------------------------------
+ * The cross-modal fusion path (model/sam/transformer.py:58-120,278-309 as called by model/aggregator.py:160,168) is
+ * ~130 launches forward / ~370 backward per bag; driven op by op from the host language it is launch-bound.  A tape
+ * is that forward written down once as ops over numbered tensor slots; milb200_tape_forward runs it in ONE call and
+ * keeps every activation in `arena`; milb200_tape_backward runs the reverse program (reverse-mode accumulation over
+ * the slots, parameter gradients accumulated into one flat fp32 buffer).
+ *   slots   [rows, cols] matrices in `dtype`; external = 1: the caller supplies the pointer (program inputs, and
+ *           outputs it wants written in place, e.g. straight into the packed multi-modal bag of aggregator.py:173)
+ *   params  ranges of two flat buffers with identical element offsets: w_compute (weights in `dtype`) and p_f32
+ *           (fp32: biases, LayerNorm gamma/beta); gradients go to g_f32 (fp32, same offsets; zero-fill it first)
+ *   ops     LINEAR    out = act((in0 [+ in1]) W^T + b)      p0 = W [out.cols, in0.cols], p1 = bias or -1, a0 = act
+ *           ATTENTION out = softmax(Q K^T / sqrt(c)) V      in0/in1/in2 = Q/K/V (distinct slots), a0 = heads
+ *           LAYERNORM out = LN(in0 [+ in1]) * gamma + beta  p0 = gamma, p1 = beta (eps 1e-5)
+ * Backward: seed_ptrs[s] != NULL gives dL/d(slot s) for program outputs; ext_grad_ptrs[s] != NULL asks for the
+ * gradient of external input s (written there); internal slots' gradients live in the workspace.                  */
+enum { MILB200_OP_LINEAR = 1, MILB200_OP_ATTENTION = 2, MILB200_OP_LAYERNORM = 3 };
+typedef struct milb200_tape_op {
+  int32_t kind, in0, in1, in2, out, p0, p1, a0;
+} milb200_tape_op;
+typedef struct milb200_tape_slot {
+  int64_t rows;
+  int32_t cols, external;
+} milb200_tape_slot;
+typedef struct milb200_tape_param {
+  int64_t offset; /* elements from the start of the flat buffers; multiple of 8 */
+  int32_t rows, cols;
+} milb200_tape_param;
+size_t milb200_tape_arena_bytes(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
+                                int dtype);
+size_t milb200_tape_workspace_bytes(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
+                                    int dtype, int backward);
+int milb200_tape_forward(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
+                         const milb200_tape_param* params, int n_params, void* const* ext_ptrs, const void* w_compute,
+                         const float* p_f32, void* arena, size_t arena_bytes, void* workspace, size_t ws_bytes,
+                         int dtype, void* stream);
+int milb200_tape_backward(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
+                          const milb200_tape_param* params, int n_params, void* const* ext_ptrs,
+                          void* const* ext_grad_ptrs, const void* const* seed_ptrs, const void* w_compute,
+                          const float* p_f32, float* g_f32, const void* arena, size_t arena_bytes, void* workspace,
+                          size_t ws_bytes, int dtype, void* stream);
+
 /* ---- optimiser (train_ddp.py:111-118): fused Adam over one flat fp32 buffer -----------------------
  * g is first scaled by grad_scale (1/world after the NCCL sum = DDP's average).                      */
 int milb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,

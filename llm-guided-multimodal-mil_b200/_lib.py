@@ -58,9 +58,29 @@ SIGNATURES = {
     "milb200_sinusoid_pe": (_i, [_p, _i64, _i, _i, _p]),
     "milb200_ct_tokens_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "milb200_ct_tokens_bwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "milb200_tape_arena_bytes": (_sz, [_p, _i, _p, _i, _i]),
+    "milb200_tape_workspace_bytes": (_sz, [_p, _i, _p, _i, _i, _i]),
+    "milb200_tape_forward": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _sz, _p, _sz, _i, _p]),
+    "milb200_tape_backward": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p, _sz, _i, _p]),
     "milb200_adam_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _i, _p]),
     "milb200_sigmoid_bce_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _i, _p]),
 }
+
+
+
+class TapeOp(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("kind", "in0", "in1", "in2", "out", "p0", "p1", "a0")]
+
+
+class TapeSlot(C.Structure):
+    _fields_ = [("rows", C.c_int64), ("cols", C.c_int32), ("external", C.c_int32)]
+
+
+class TapeParam(C.Structure):
+    _fields_ = [("offset", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32)]
+
+
+OP_LINEAR, OP_ATTENTION, OP_LAYERNORM = 1, 2, 3
 
 _lib = None
 _lock = threading.Lock()

@@ -9,6 +9,12 @@
 namespace milb200 {
 
 bool force_simt();
+// smallm.cu: weight-streaming kernels for m <= 16 rows (token side, heads)
+bool smallm_ok(int64_t m, int n, int k, int dtype);
+int smallm_fwd(const void* X, const void* add, const void* W, const float* bias, void* Y, int64_t m, int n, int k, int act,
+               int dtype, cudaStream_t st);
+int smallm_bwd(const void* X, const void* add, const void* W, const void* Y, const void* dY, void* dX, float* dW,
+               float* dbias, int64_t m, int n, int k, int act, int dtype, int accumulate, cudaStream_t st);
 int splitk_reduce_gate(const float* part, int splits, int D, int L, int dh, float* out, cudaStream_t st);
 int transpose2d(const void* in, void* out, int rows, int cols, int dtype, cudaStream_t st);
 
@@ -492,6 +498,8 @@ int milb200_linear_fwd(const void* X, const void* add, const void* W, const floa
   if (rc) return rc;
   MIL_CHECK_ARG(Y != nullptr, MILB200_EINVAL, "linear_fwd: Y is null");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (smallm_ok(m, n, k, dtype) && aligned16(X) && aligned16(W) && (!add || aligned16(add)))
+    return smallm_fwd(X, add, W, bias, Y, m, n, k, act, dtype, st);
   const void* xin = X;
   if (add) {
     LinWs w = linear_ws(m, n, k, dtype, 0, 1);
@@ -569,6 +577,11 @@ int milb200_linear_bwd(const void* X, const void* add, const void* W, const void
   if (rc) return rc;
   MIL_CHECK_ARG(dY != nullptr, MILB200_EINVAL, "linear_bwd: dY is null");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (smallm_ok(m, n, k, dtype) && aligned16(X) && aligned16(W) && (!add || aligned16(add)) && aligned16(dW)) {
+    MIL_CHECK_ARG(act == MILB200_ACT_NONE || Y != nullptr, MILB200_EINVAL, "linear_bwd: the forward output Y is required for act=%d", act);
+    MIL_CHECK_ARG(dW != nullptr || dbias == nullptr, MILB200_EINVAL, "linear_bwd: dbias without dW");
+    return smallm_bwd(X, add, W, Y, dY, dX, dW, dbias, m, n, k, act, dtype, accumulate, st);
+  }
   LinWs w = linear_ws(m, n, k, dtype, 1, add != nullptr);
   MIL_CHECK_ARG(workspace && ws_bytes >= w.total, MILB200_EWORKSPACE, "linear_bwd: workspace %zu < %zu", ws_bytes, w.total);
   char* ws = static_cast<char*>(workspace);

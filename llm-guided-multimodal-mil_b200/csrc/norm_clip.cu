@@ -104,18 +104,30 @@ k_ln_bwd(const T* __restrict__ X, const T* __restrict__ R, const float* __restri
   }
 }
 
-__global__ void k_ln_reduce(const float* __restrict__ part, int parts, int n, float* __restrict__ dgamma,
-                            float* __restrict__ dbeta, int accumulate) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * n) return;
+// block = 32 columns x 8 part-lanes; the 8 lanes' sums are folded in fixed order
+__global__ void __launch_bounds__(256)
+k_ln_reduce(const float* __restrict__ part, int parts, int n, float* __restrict__ dgamma, float* __restrict__ dbeta,
+            int accumulate) {
+  __shared__ float red[8][33];
+  const int c = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + c;
   float a = 0.f;
-  for (int s = 0; s < parts; ++s) a += part[static_cast<int64_t>(s) * 2 * n + i];
-  float* dst = (i < n) ? dgamma + i : dbeta + (i - n);
-  *dst = accumulate ? *dst + a : a;
+  if (i < 2 * n)
+    for (int s = w; s < parts; s += 8) a += part[static_cast<int64_t>(s) * 2 * n + i];
+  red[w][c] = a;
+  __syncthreads();
+  if (w == 0 && i < 2 * n) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][c];
+    float* dst = (i < n) ? dgamma + i : dbeta + (i - n);
+    *dst = accumulate ? *dst + t : t;
+  }
 }
 
+// one row per warp up to 4 CTAs per SM; beyond that the CTAs walk more rows
 static int ln_ctas(int64_t m) {
-  int64_t c = std::min<int64_t>((m + 63) / 64, static_cast<int64_t>(sm_count()) * 2);
+  int64_t c = std::min<int64_t>((m + 7) / 8, static_cast<int64_t>(sm_count()) * 4);
   return static_cast<int>(c < 1 ? 1 : c);
 }
 
@@ -373,7 +385,7 @@ int milb200_layernorm_bwd(const void* X, const void* R, const float* gamma, cons
                                   n, rows_per_cta);
   }
   MIL_LAUNCH_CHECK();
-  k_ln_reduce<<<(2 * n + 255) / 256, 256, 0, st>>>(part, ctas, n, dgamma, dbeta, accumulate);
+  k_ln_reduce<<<(2 * n + 31) / 32, 256, 0, st>>>(part, ctas, n, dgamma, dbeta, accumulate);
   MIL_LAUNCH_CHECK();
   return MILB200_OK;
 }

@@ -1,0 +1,339 @@
+// tape.cu — native executor for static operator programs ("tapes") over the library's own kernels.
+//
+// Why: the cross-modal fusion path (model/sam/transformer.py:58-120,278-309 inside model/aggregator.py:134-203) is
+// ~130 kernel launches forward and ~370 backward per bag.  Driven op by op from Python (one autograd node, several
+// allocations and a ctypes call per launch) it is host-bound at ~25 us per launch; the reference has the same shape
+// of problem (eager PyTorch, ~120 launches per TwoWayTransformer call).  Here the host side of the whole
+// program is ONE call: the Python module describes its forward once as a list of ops over numbered tensor slots,
+// this file runs it, keeps the activations in a caller-provided arena, and runs the reverse program for the
+// backward (a small reverse-mode engine: per-slot gradient buffers, first-write/accumulate tracking, parameter
+// gradients accumulated into one flat fp32 buffer).  No allocation, no synchronisation, everything on `stream`.
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace milb200 {
+
+struct TapePlan {
+  std::vector<size_t> slot_off;   // arena offset of every internal slot (SIZE_MAX for external ones)
+  std::vector<size_t> aux_off;    // arena offset of every op's saved statistics (lse / mean,rstd)
+  size_t arena_bytes = 0;
+  size_t max_slot_bytes = 0;
+  size_t scratch_fwd = 0, scratch_bwd = 0;
+};
+
+static inline size_t slot_bytes(const milb200_tape_slot& s, int dtype) {
+  return static_cast<size_t>(s.rows) * static_cast<size_t>(s.cols) * elem_size(dtype);
+}
+
+static int tape_validate(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
+                         const milb200_tape_param* params, int n_params) {
+  MIL_CHECK_ARG(ops && slots && n_ops > 0 && n_slots > 0, MILB200_EINVAL, "tape: empty program");
+  auto ok_slot = [&](int s, bool optional) { return (optional && s < 0) || (s >= 0 && s < n_slots); };
+  for (int i = 0; i < n_slots; ++i)
+    MIL_CHECK_ARG(slots[i].rows > 0 && slots[i].cols > 0, MILB200_EINVAL, "tape: slot %d has shape %lld x %d", i,
+                  (long long)slots[i].rows, slots[i].cols);
+  for (int i = 0; i < n_ops; ++i) {
+    const milb200_tape_op& o = ops[i];
+    MIL_CHECK_ARG(ok_slot(o.out, false) && ok_slot(o.in0, false), MILB200_EINVAL, "tape: op %d has a bad slot id", i);
+    const milb200_tape_slot& so = slots[o.out];
+    const milb200_tape_slot& s0 = slots[o.in0];
+    switch (o.kind) {
+      case MILB200_OP_LINEAR: {
+        MIL_CHECK_ARG(ok_slot(o.in1, true), MILB200_EINVAL, "tape: op %d has a bad `add` slot", i);
+        MIL_CHECK_ARG(params && o.p0 >= 0 && o.p0 < n_params && o.p1 < n_params, MILB200_EINVAL, "tape: op %d bad param id", i);
+        const milb200_tape_param& w = params[o.p0];
+        MIL_CHECK_ARG(w.rows == so.cols && w.cols == s0.cols && so.rows == s0.rows, MILB200_EINVAL,
+                      "tape: op %d linear shape mismatch: x %lld x %d, W %d x %d, y %lld x %d", i, (long long)s0.rows, s0.cols,
+                      w.rows, w.cols, (long long)so.rows, so.cols);
+        MIL_CHECK_ARG(o.in1 < 0 || (o.in1 != o.in0 && slots[o.in1].rows == s0.rows && slots[o.in1].cols == s0.cols),
+                      MILB200_EINVAL, "tape: op %d `add` slot must differ from x and share its shape", i);
+        MIL_CHECK_ARG(o.p1 < 0 || params[o.p1].rows * params[o.p1].cols == so.cols, MILB200_EINVAL, "tape: op %d bias size", i);
+        break;
+      }
+      case MILB200_OP_ATTENTION: {
+        MIL_CHECK_ARG(ok_slot(o.in1, false) && ok_slot(o.in2, false), MILB200_EINVAL, "tape: op %d bad k/v slot", i);
+        MIL_CHECK_ARG(o.in0 != o.in1 && o.in0 != o.in2 && o.in1 != o.in2, MILB200_EINVAL,
+                      "tape: op %d attention operands must be distinct slots", i);
+        const milb200_tape_slot& sk = slots[o.in1];
+        const milb200_tape_slot& sv = slots[o.in2];
+        MIL_CHECK_ARG(o.a0 > 0 && s0.cols % o.a0 == 0 && sk.cols == s0.cols && sv.cols == s0.cols && sk.rows == sv.rows &&
+                          so.rows == s0.rows && so.cols == s0.cols,
+                      MILB200_EINVAL, "tape: op %d attention shape mismatch", i);
+        break;
+      }
+      case MILB200_OP_LAYERNORM: {
+        MIL_CHECK_ARG(ok_slot(o.in1, true), MILB200_EINVAL, "tape: op %d bad residual slot", i);
+        MIL_CHECK_ARG(params && o.p0 >= 0 && o.p0 < n_params && o.p1 >= 0 && o.p1 < n_params, MILB200_EINVAL,
+                      "tape: op %d bad param id", i);
+        MIL_CHECK_ARG(so.rows == s0.rows && so.cols == s0.cols &&
+                          (o.in1 < 0 || (o.in1 != o.in0 && slots[o.in1].rows == s0.rows && slots[o.in1].cols == s0.cols)),
+                      MILB200_EINVAL, "tape: op %d layernorm shape mismatch", i);
+        break;
+      }
+      default:
+        MIL_CHECK_ARG(false, MILB200_EINVAL, "tape: op %d has unknown kind %d", i, o.kind);
+    }
+  }
+  return MILB200_OK;
+}
+
+static TapePlan tape_plan(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots, int dtype) {
+  TapePlan p;
+  p.slot_off.assign(n_slots, SIZE_MAX);
+  p.aux_off.assign(n_ops, SIZE_MAX);
+  size_t off = 0;
+  for (int i = 0; i < n_slots; ++i) {
+    const size_t b = slot_bytes(slots[i], dtype);
+    p.max_slot_bytes = std::max(p.max_slot_bytes, b);
+    if (slots[i].external) continue;
+    off = align_up(off, 256);
+    p.slot_off[i] = off;
+    off += b;
+  }
+  for (int i = 0; i < n_ops; ++i) {
+    const milb200_tape_op& o = ops[i];
+    size_t aux = 0;
+    if (o.kind == MILB200_OP_ATTENTION) aux = sizeof(float) * static_cast<size_t>(o.a0) * slots[o.in0].rows;
+    if (o.kind == MILB200_OP_LAYERNORM) aux = sizeof(float) * 2 * static_cast<size_t>(slots[o.in0].rows);
+    if (aux) {
+      off = align_up(off, 256);
+      p.aux_off[i] = off;
+      off += aux;
+    }
+    size_t f = 0, b = 0;
+    if (o.kind == MILB200_OP_LINEAR) {
+      f = milb200_linear_workspace_bytes(slots[o.in0].rows, slots[o.out].cols, slots[o.in0].cols, dtype, 0);
+      b = milb200_linear_workspace_bytes(slots[o.in0].rows, slots[o.out].cols, slots[o.in0].cols, dtype, 1);
+    } else if (o.kind == MILB200_OP_ATTENTION) {
+      const int c = slots[o.in0].cols / o.a0;
+      f = milb200_attention_workspace_bytes(slots[o.in0].rows, slots[o.in1].rows, o.a0, c, 0);
+      b = milb200_attention_workspace_bytes(slots[o.in0].rows, slots[o.in1].rows, o.a0, c, 1);
+    } else if (o.kind == MILB200_OP_LAYERNORM) {
+      b = milb200_layernorm_workspace_bytes(slots[o.in0].rows, slots[o.in0].cols);
+    }
+    p.scratch_fwd = std::max(p.scratch_fwd, f);
+    p.scratch_bwd = std::max(p.scratch_bwd, b);
+  }
+  p.arena_bytes = align_up(off, 256) + 256;
+  p.scratch_fwd = align_up(p.scratch_fwd, 256) + 256;
+  p.scratch_bwd = align_up(p.scratch_bwd, 256) + 256;
+  return p;
+}
+
+// backward workspace image: [kernel scratch][3 temporaries of max_slot_bytes][gradient buffer of every internal slot]
+static size_t tape_bwd_ws_bytes(const TapePlan& p) {
+  return p.scratch_bwd + 3 * align_up(p.max_slot_bytes, 256) + p.arena_bytes;
+}
+
+}  // namespace milb200
+
+using namespace milb200;
+
+extern "C" {
+
+size_t milb200_tape_arena_bytes(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots, int dtype) {
+  if (!ops || !slots || n_ops <= 0 || n_slots <= 0) return 256;
+  return tape_plan(ops, n_ops, slots, n_slots, dtype).arena_bytes;
+}
+
+size_t milb200_tape_workspace_bytes(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
+                                    int dtype, int backward) {
+  if (!ops || !slots || n_ops <= 0 || n_slots <= 0) return 256;
+  TapePlan p = tape_plan(ops, n_ops, slots, n_slots, dtype);
+  return backward ? tape_bwd_ws_bytes(p) : p.scratch_fwd;
+}
+
+int milb200_tape_forward(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
+                         const milb200_tape_param* params, int n_params, void* const* ext_ptrs, const void* w_compute,
+                         const float* p_f32, void* arena, size_t arena_bytes, void* workspace, size_t ws_bytes, int dtype,
+                         void* stream) {
+  int rc = tape_validate(ops, n_ops, slots, n_slots, params, n_params);
+  if (rc) return rc;
+  MIL_CHECK_ARG(dtype == MILB200_F32 || dtype == MILB200_BF16, MILB200_EINVAL, "tape: bad dtype %d", dtype);
+  MIL_CHECK_ARG(ext_ptrs && w_compute && p_f32 && arena, MILB200_EINVAL, "tape_forward: null pointer");
+  TapePlan pl = tape_plan(ops, n_ops, slots, n_slots, dtype);
+  MIL_CHECK_ARG(arena_bytes >= pl.arena_bytes, MILB200_EWORKSPACE, "tape_forward: arena %zu < %zu", arena_bytes, pl.arena_bytes);
+  MIL_CHECK_ARG(workspace && ws_bytes >= pl.scratch_fwd, MILB200_EWORKSPACE, "tape_forward: workspace %zu < %zu", ws_bytes,
+                pl.scratch_fwd);
+  const size_t esz = elem_size(dtype);
+  char* ar = static_cast<char*>(arena);
+  std::vector<void*> ptr(n_slots);
+  for (int i = 0; i < n_slots; ++i) {
+    ptr[i] = slots[i].external ? ext_ptrs[i] : static_cast<void*>(ar + pl.slot_off[i]);
+    MIL_CHECK_ARG(ptr[i] != nullptr && aligned16(ptr[i]), MILB200_EALIGN, "tape_forward: slot %d pointer is null or misaligned", i);
+  }
+  const char* wc = static_cast<const char*>(w_compute);
+  for (int i = 0; i < n_ops; ++i) {
+    const milb200_tape_op& o = ops[i];
+    const milb200_tape_slot& s0 = slots[o.in0];
+    const milb200_tape_slot& so = slots[o.out];
+    switch (o.kind) {
+      case MILB200_OP_LINEAR:
+        rc = milb200_linear_fwd(ptr[o.in0], o.in1 >= 0 ? ptr[o.in1] : nullptr, wc + params[o.p0].offset * esz,
+                                o.p1 >= 0 ? p_f32 + params[o.p1].offset : nullptr, ptr[o.out], s0.rows, so.cols, s0.cols, o.a0,
+                                dtype, workspace, ws_bytes, stream);
+        break;
+      case MILB200_OP_ATTENTION:
+        rc = milb200_attention_fwd(ptr[o.in0], ptr[o.in1], ptr[o.in2], ptr[o.out], reinterpret_cast<float*>(ar + pl.aux_off[i]),
+                                   s0.rows, slots[o.in1].rows, o.a0, s0.cols / o.a0, dtype, workspace, ws_bytes, stream);
+        break;
+      case MILB200_OP_LAYERNORM: {
+        float* mean = reinterpret_cast<float*>(ar + pl.aux_off[i]);
+        rc = milb200_layernorm_fwd(ptr[o.in0], o.in1 >= 0 ? ptr[o.in1] : nullptr, p_f32 + params[o.p0].offset,
+                                   p_f32 + params[o.p1].offset, ptr[o.out], mean, mean + s0.rows, s0.rows, s0.cols, dtype, stream);
+        break;
+      }
+      default:
+        rc = MILB200_EINVAL;
+    }
+    if (rc) return rc;
+  }
+  return MILB200_OK;
+}
+
+int milb200_tape_backward(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
+                          const milb200_tape_param* params, int n_params, void* const* ext_ptrs, void* const* ext_grad_ptrs,
+                          const void* const* seed_ptrs, const void* w_compute, const float* p_f32, float* g_f32,
+                          const void* arena, size_t arena_bytes, void* workspace, size_t ws_bytes, int dtype, void* stream) {
+  int rc = tape_validate(ops, n_ops, slots, n_slots, params, n_params);
+  if (rc) return rc;
+  MIL_CHECK_ARG(dtype == MILB200_F32 || dtype == MILB200_BF16, MILB200_EINVAL, "tape: bad dtype %d", dtype);
+  MIL_CHECK_ARG(ext_ptrs && ext_grad_ptrs && seed_ptrs && w_compute && p_f32 && g_f32 && arena, MILB200_EINVAL,
+                "tape_backward: null pointer");
+  TapePlan pl = tape_plan(ops, n_ops, slots, n_slots, dtype);
+  MIL_CHECK_ARG(arena_bytes >= pl.arena_bytes, MILB200_EWORKSPACE, "tape_backward: arena %zu < %zu", arena_bytes, pl.arena_bytes);
+  const size_t need = tape_bwd_ws_bytes(pl);
+  MIL_CHECK_ARG(workspace && ws_bytes >= need, MILB200_EWORKSPACE, "tape_backward: workspace %zu < %zu", ws_bytes, need);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t esz = elem_size(dtype);
+  const char* ar = static_cast<const char*>(arena);
+  char* ws = static_cast<char*>(workspace);
+  void* scratch = ws;
+  const size_t scratch_bytes = pl.scratch_bwd;
+  const size_t tmp_stride = align_up(pl.max_slot_bytes, 256);
+  char* tmp0 = ws + pl.scratch_bwd;
+  char* gbase = tmp0 + 3 * tmp_stride;
+
+  std::vector<const void*> val(n_slots);
+  std::vector<void*> grad(n_slots);
+  std::vector<char> has(n_slots, 0), needs(n_slots, 1);
+  for (int i = 0; i < n_slots; ++i) {
+    if (slots[i].external) {
+      val[i] = ext_ptrs[i];
+      grad[i] = ext_grad_ptrs[i];
+      needs[i] = grad[i] != nullptr;
+    } else {
+      val[i] = ar + pl.slot_off[i];
+      grad[i] = gbase + pl.slot_off[i];
+    }
+    MIL_CHECK_ARG(val[i] != nullptr, MILB200_EINVAL, "tape_backward: slot %d has no value pointer", i);
+  }
+  // upstream gradients: the first contribution of their slots
+  for (int i = 0; i < n_slots; ++i) {
+    if (!seed_ptrs[i]) continue;
+    MIL_CHECK_ARG(grad[i] != nullptr, MILB200_EINVAL, "tape_backward: seeded slot %d has no gradient buffer", i);
+    MIL_CUDA(cudaMemcpyAsync(grad[i], seed_ptrs[i], slot_bytes(slots[i], dtype), cudaMemcpyDeviceToDevice, st));
+    has[i] = 1;
+  }
+  std::vector<char> ptouched(n_params > 0 ? n_params : 1, 0);
+
+  // where an op should write its gradient w.r.t. slot s: straight into the slot's buffer if nothing is there yet,
+  // else into temporary `t` (folded in by settle())
+  auto target = [&](int s, int t) -> void* {
+    if (s < 0 || !needs[s]) return nullptr;
+    return has[s] ? static_cast<void*>(tmp0 + t * tmp_stride) : grad[s];
+  };
+  auto settle = [&](int s, void* wrote) -> int {
+    if (s < 0 || !needs[s] || !wrote) return MILB200_OK;
+    if (wrote == grad[s]) { has[s] = 1; return MILB200_OK; }
+    const int64_t n = slots[s].rows * slots[s].cols;
+    if (!has[s]) {
+      MIL_CUDA(cudaMemcpyAsync(grad[s], wrote, static_cast<size_t>(n) * esz, cudaMemcpyDeviceToDevice, st));
+      count_launch();
+      has[s] = 1;
+      return MILB200_OK;
+    }
+    return milb200_add(grad[s], wrote, grad[s], n, dtype, stream);
+  };
+
+  for (int i = n_ops - 1; i >= 0; --i) {
+    const milb200_tape_op& o = ops[i];
+    if (!has[o.out]) continue;  // no gradient reaches this op
+    const milb200_tape_slot& s0 = slots[o.in0];
+    const milb200_tape_slot& so = slots[o.out];
+    const void* dY = grad[o.out];
+    switch (o.kind) {
+      case MILB200_OP_LINEAR: {
+        const bool need_dx = needs[o.in0] || (o.in1 >= 0 && needs[o.in1]);
+        void* dX = nullptr;
+        if (need_dx) dX = needs[o.in0] ? target(o.in0, 0) : target(o.in1, 0);
+        const int acc = ptouched[o.p0] ? 1 : 0;
+        rc = milb200_linear_bwd(val[o.in0], o.in1 >= 0 ? val[o.in1] : nullptr,
+                                static_cast<const char*>(w_compute) + params[o.p0].offset * esz, val[o.out], dY, dX,
+                                g_f32 + params[o.p0].offset, o.p1 >= 0 ? g_f32 + params[o.p1].offset : nullptr, s0.rows,
+                                so.cols, s0.cols, o.a0, dtype, acc, scratch, scratch_bytes, stream);
+        if (rc) return rc;
+        ptouched[o.p0] = 1;
+        if (o.p1 >= 0) ptouched[o.p1] = 1;
+        if (need_dx) {
+          if (needs[o.in0]) {
+            rc = settle(o.in0, dX);
+            if (rc) return rc;
+            // after settle, the complete contribution lives in dX (direct or temporary); the `add` operand gets the same
+            if (o.in1 >= 0) rc = settle(o.in1, dX);
+          } else {
+            rc = settle(o.in1, dX);
+          }
+          if (rc) return rc;
+        }
+        break;
+      }
+      case MILB200_OP_ATTENTION: {
+        void* dQ = target(o.in0, 0);
+        void* dK = target(o.in1, 1);
+        void* dV = target(o.in2, 2);
+        // the kernels always produce all three; route unwanted ones to the temporaries
+        void* dQw = dQ ? dQ : static_cast<void*>(tmp0);
+        void* dKw = dK ? dK : static_cast<void*>(tmp0 + tmp_stride);
+        void* dVw = dV ? dV : static_cast<void*>(tmp0 + 2 * tmp_stride);
+        rc = milb200_attention_bwd(val[o.in0], val[o.in1], val[o.in2], val[o.out],
+                                   reinterpret_cast<const float*>(ar + pl.aux_off[i]), dY, dQw, dKw, dVw, s0.rows,
+                                   slots[o.in1].rows, o.a0, s0.cols / o.a0, dtype, scratch, scratch_bytes, stream);
+        if (rc) return rc;
+        if ((rc = settle(o.in0, dQ))) return rc;
+        if ((rc = settle(o.in1, dK))) return rc;
+        if ((rc = settle(o.in2, dV))) return rc;
+        break;
+      }
+      case MILB200_OP_LAYERNORM: {
+        const float* mean = reinterpret_cast<const float*>(ar + pl.aux_off[i]);
+        const bool need_dx = needs[o.in0] || (o.in1 >= 0 && needs[o.in1]);
+        void* dX = needs[o.in0] ? target(o.in0, 0) : (o.in1 >= 0 ? target(o.in1, 0) : nullptr);
+        if (!need_dx) dX = tmp0;  // the kernel always writes dXR
+        const int acc = ptouched[o.p0] ? 1 : 0;
+        rc = milb200_layernorm_bwd(val[o.in0], o.in1 >= 0 ? val[o.in1] : nullptr, p_f32 + params[o.p0].offset, mean,
+                                   mean + s0.rows, dY, dX, g_f32 + params[o.p0].offset, g_f32 + params[o.p1].offset, s0.rows,
+                                   s0.cols, dtype, acc, scratch, scratch_bytes, stream);
+        if (rc) return rc;
+        ptouched[o.p0] = ptouched[o.p1] = 1;
+        if (need_dx) {
+          if (needs[o.in0]) {
+            if ((rc = settle(o.in0, dX))) return rc;
+            if (o.in1 >= 0 && (rc = settle(o.in1, dX))) return rc;
+          } else if ((rc = settle(o.in1, dX))) {
+            return rc;
+          }
+        }
+        break;
+      }
+      default:
+        return MILB200_EINVAL;
+    }
+  }
+  // parameters no gradient reached keep whatever the caller put in g_f32 (the caller zero-fills it)
+  return MILB200_OK;
+}
+
+}  // extern "C"

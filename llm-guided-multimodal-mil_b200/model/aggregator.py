@@ -20,7 +20,8 @@ from .. import functional as F
 from .._lib import MilB200Error
 from ..abmil import ABMIL, ABMIL_v2
 from .encoders import PrecomputedFeatures
-from .sam.transformer import TwoWayTransformer
+from .sam.transformer import TwoWayTransformer, _use_tape
+from ..tape import Tape
 
 _CT_MODELS = ("resnet2plus1d_18", "resnetMC3_18", "medicalNet", "SwinUNETR", "MViT")
 _CI_MODELS = ("simpleFCs_v1", "simpleFCs_v1d", "simpleFCs_v2", "simpleFCs_v2d", "CLIP")
@@ -104,10 +105,48 @@ class aggregator(nn.Module):
             n = x_img.shape[1]
         return transformer(x_img, self._pe(n, text_tokens), text_tokens)
 
+    # ---- CT + pathology branch as ONE native program (csrc/tape.cu) ----------------------------------------
+    def _fusion_tape(self):
+        """aggregator.py:141,160,168,173 on a tape: fc_pathology, fc_CI2CT / fc_CI2Pth, both TwoWayTransformer_Both
+        calls, and the four results written in place into the packed multi-modal bag (no torch.cat copy)."""
+        t = getattr(self, "_tape_cache", None)
+        if t is None:
+            t = Tape()
+            E = self.embedding_dim
+            ct, pe_ct = t.input("Nc", E), t.input("Nc", E)
+            xp, pe_p = t.input("Np", 768), t.input("Np", E)
+            txt = t.input("T", E)
+            xin_p = t.linear(xp, self.fc_pathology[0], act="tanh")                                   # :141
+            q1, k1 = self.TwoWayTransformer_Both.emit(t, ct, pe_ct, t.linear(txt, self.fc_CI2CT[0], act="tanh"))   # :160
+            q2, k2 = self.TwoWayTransformer_Both.emit(t, xin_p, pe_p, t.linear(txt, self.fc_CI2Pth[0], act="tanh"))  # :168
+            bag = t.buffer(lambda r: 2 * r["T"] + r["Nc"] + r["Np"], E)                             # :173 row order
+            t.output(q1, bag, lambda r: 0)
+            t.output(k1, bag, lambda r: r["T"])
+            t.output(q2, bag, lambda r: r["T"] + r["Nc"])
+            t.output(k2, bag, lambda r: 2 * r["T"] + r["Nc"])
+            object.__setattr__(self, "_tape_cache", t)
+        return t
+
+    def _forward_fused(self, x_ct_tokens, x_path, x_text):
+        T, Nc, Np = x_text.shape[1], x_ct_tokens.shape[1], x_path.shape[1]
+        like = x_text
+        (bag,) = self._fusion_tape().run({"T": T, "Nc": Nc, "Np": Np},
+                                         [x_ct_tokens[0], self._pe(Nc, like)[0], x_path[0], self._pe(Np, like)[0], x_text[0]])
+        x0 = bag.unsqueeze(0)
+        return x0, x0[:, :T], x0[:, T + Nc:2 * T + Nc]
+
     def forward(self, x_list, x_CI):
         mod = self.args.modality
         has_ct, has_path = "CT" in mod, "pathology" in mod
         x_input_CT = x_input_pathology = None
+        if (has_ct and has_path and _use_tape() and getattr(self.args, "model_CT", None) == "resnetMC3_18"
+                and getattr(self.args, "alignment_base", None) != "CT" and getattr(self.args, "aggregator", "-") != "-"):
+            x_ct = self.extractor_CT(x_list[0])
+            x_text = self.clinic_extractor(x_CI)
+            if x_ct.dim() == 5 and x_ct.shape[0] == 1 and x_list[1].dim() == 3 and x_list[1].shape[0] == 1 \
+                    and x_text.dim() == 3 and x_text.shape[0] == 1 and x_ct.dtype == x_list[1].dtype == x_text.dtype:
+                x0, x_CT2CI, x_Pth2CI = self._forward_fused(F.ct_tokens(x_ct), x_list[1], x_text)
+                return self._head(self.aggregator(x0)), x_CT2CI, x_Pth2CI
         if has_ct:
             x_input_CT = self.extractor_CT(x_list[0])                                 # :140,146
         if has_path:

@@ -19,11 +19,17 @@ class MLPBlock(nn.Module):
         self.lin2 = nn.Linear(mlp_dim, embedding_dim)
         self.act = act()
 
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
+    def _act_name(self):
         kind = type(self.act)
         if kind not in _ACT_NAMES:
             # TwoWayTransformer always passes nn.ReLU (transformer.py:18,268); GELU is upstream's unused default
             raise MilB200Error(f"MLPBlock: activation {kind.__name__} has no fused epilogue in libmilb200 "
                                "(built: ReLU, Tanh, Sigmoid, Identity)")
-        h = F.linear(x, self.lin1.weight, self.lin1.bias, act=_ACT_NAMES[kind])     # common.py:26, act fused
+        return _ACT_NAMES[kind]
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        h = F.linear(x, self.lin1.weight, self.lin1.bias, act=self._act_name())     # common.py:26, act fused
         return F.linear(h, self.lin2.weight, self.lin2.bias)
+
+    def emit(self, tape, x: int) -> int:
+        return tape.linear(tape.linear(x, self.lin1, act=self._act_name()), self.lin2)

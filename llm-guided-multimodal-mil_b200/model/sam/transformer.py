@@ -20,9 +20,18 @@ from typing import Tuple, Type
 import torch
 from torch import Tensor, nn
 
+import os
+
 from ... import functional as F
 from ..._lib import MilB200Error
+from ...tape import Tape
 from .common import MLPBlock
+
+
+def _use_tape():
+    """MILB200_NO_TAPE=1 falls back to one autograd node per operator (same kernels, same numerics; ~8x the host
+    time per bag) — kept for debugging and for the tape-vs-eager equivalence test."""
+    return os.environ.get("MILB200_NO_TAPE", "0") != "1"
 
 
 class Attention(nn.Module):
@@ -50,6 +59,15 @@ class Attention(nn.Module):
         outs = [F.attention_core(qp[b], kp[b], vp[b], self.num_heads) for b in range(q.shape[0])]   # :434-446
         o = outs[0].unsqueeze(0) if len(outs) == 1 else torch.stack(outs, dim=0)
         return F.linear(o, self.out_proj.weight, self.out_proj.bias)               # :448
+
+
+    def emit(self, tape: Tape, q: int, k: int, v: int, q_add: int = None, k_add: int = None) -> int:
+        """The same computation recorded on a tape (slot ids in, slot id out)."""
+        qp = tape.linear(q, self.q_proj, add=q_add)
+        kp = tape.linear(k, self.k_proj, add=k_add)
+        vp = tape.linear(v, self.v_proj)
+        o = tape.attention(qp, kp, vp, self.num_heads)
+        return tape.linear(o, self.out_proj)
 
 
 class TwoWayAttentionBlock(nn.Module):
@@ -93,6 +111,21 @@ class TwoWayAttentionBlock(nn.Module):
         return queries, keys
 
 
+    def emit(self, tape: Tape, queries: int, keys: int, query_pe: int, key_pe: int):
+        """forward() recorded on a tape."""
+        if self.skip_first_layer_pe:
+            queries = tape.layernorm(self.self_attn.emit(tape, queries, queries, queries), self.norm1)
+        else:
+            attn_out = self.self_attn.emit(tape, queries, queries, queries, q_add=query_pe, k_add=query_pe)
+            queries = tape.layernorm(queries, self.norm1, residual=attn_out)
+        attn_out = self.cross_attn_token_to_image.emit(tape, queries, keys, keys, q_add=query_pe, k_add=key_pe)
+        queries = tape.layernorm(queries, self.norm2, residual=attn_out)
+        queries = tape.layernorm(queries, self.norm3, residual=self.mlp.emit(tape, queries))
+        attn_out = self.cross_attn_image_to_token.emit(tape, keys, queries, queries, q_add=key_pe, k_add=query_pe)
+        keys = tape.layernorm(keys, self.norm4, residual=attn_out)
+        return queries, keys
+
+
 class TwoWayTransformer(nn.Module):
     """model/sam/transformer.py:10-120.  ``args`` supplies ``alignment_base`` and ``model_CT`` like upstream."""
 
@@ -122,12 +155,40 @@ class TwoWayTransformer(nn.Module):
             return x.flatten(2).permute(0, 2, 1).contiguous()       # pure data movement
         return x                                                     # upstream leaves other encoders untouched
 
+    def emit(self, tape: Tape, image: int, image_pe: int, points: int):
+        """The token/image program of forward() on a tape: returns (queries slot, keys slot)."""
+        queries, keys = points, image
+        for layer in self.layers:
+            queries, keys = layer.emit(tape, queries, keys, points, image_pe)
+        attn_out = self.final_attn_token_to_image.emit(tape, queries, keys, keys, q_add=points, k_add=image_pe)
+        queries = tape.layernorm(queries, self.norm_final_attn, residual=attn_out)
+        return queries, keys
+
+    def _tape(self):
+        t = getattr(self, "_tape_cache", None)
+        if t is None:
+            t = Tape()
+            E = self.embedding_dim
+            img, pe, pts = t.input("N", E), t.input("N", E), t.input("T", E)
+            q, k = self.emit(t, img, pe, pts)
+            bq, bk = t.buffer(lambda r: r["T"], E), t.buffer(lambda r: r["N"], E)
+            t.output(q, bq, lambda r: 0)
+            t.output(k, bk, lambda r: 0)
+            object.__setattr__(self, "_tape_cache", t)      # not a submodule / parameter: keep it out of nn.Module state
+        return t
+
     def forward(self, image_embedding: Tensor, image_pe: Tensor, point_embedding: Tensor) -> Tuple[Tensor, Tensor]:
         if getattr(self.args, "alignment_base", None) == "CT":
             if point_embedding.dim() == 5:
                 point_embedding = self._ct_to_tokens(point_embedding)
         elif image_embedding.dim() == 5:
             image_embedding = self._ct_to_tokens(image_embedding)
+        if (_use_tape() and image_embedding.dim() == 3 and image_embedding.shape[0] == 1 and point_embedding.shape[0] == 1
+                and image_pe.shape == image_embedding.shape):
+            # one bag per call (train_ddp.py:75): the whole program is a single native call each way
+            n, t_ = image_embedding.shape[1], point_embedding.shape[1]
+            q, k = self._tape().run({"N": n, "T": t_}, [image_embedding[0], image_pe[0], point_embedding[0]])
+            return q.unsqueeze(0), k.unsqueeze(0)
         queries, keys = point_embedding, image_embedding
         for layer in self.layers:                                                     # :105-111
             queries, keys = layer(queries=queries, keys=keys, query_pe=point_embedding, key_pe=image_pe)

@@ -339,3 +339,39 @@ def test_train_mode_runs_and_is_seeded():
     assert torch.equal(p1, p2) and not torch.equal(p1, p3)
     p3.sum().backward()
     assert m.fc[1].weight.grad is not None and torch.isfinite(m.fc[1].weight.grad).all()
+
+
+def test_tape_program_equals_per_operator_autograd(monkeypatch):
+    """The native tape executor (csrc/tape.cu: one call forward, one call backward) and the per-operator autograd path
+    launch the same kernels; outputs and every gradient must agree to fp32 round-off (accumulation order of multi-use
+    gradients differs)."""
+    import mil_b200
+    torch.manual_seed(5)
+    m = mil_b200.get_model(ARGS).cuda().eval()
+    x_ct = torch.randn(1, 512, 160, 1, 2, device="cuda").requires_grad_(True)
+    x_p = torch.randn(1, 333, 768, device="cuda").requires_grad_(True)
+    x_t = (torch.randn(1, 10, 512, device="cuda") * 0.05).requires_grad_(True)
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("MILB200_NO_TAPE", mode)
+        for t in (x_ct, x_p, x_t):
+            t.grad = None
+        m.zero_grad(set_to_none=True)
+        l0 = mil_b200.launch_count()
+        prob, a, b = m([x_ct, x_p], x_t)
+        (prob[0, 1] + (a * b).sum()).backward()
+        torch.cuda.synchronize()
+        res[mode] = dict(prob=prob.detach().clone(), a=a.detach().clone(), b=b.detach().clone(), dct=x_ct.grad.clone(),
+                         dp=x_p.grad.clone(), dt=x_t.grad.clone(),
+                         g={k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None},
+                         launches=mil_b200.launch_count() - l0)
+    t, e = res["0"], res["1"]
+    for k in ("prob", "a", "b", "dct", "dp", "dt"):
+        assert _rel(t[k], e[k]) <= 2e-6, k
+    live_e = {k for k, v in e["g"].items() if float(v.abs().max()) > 0}
+    assert live_e <= set(t["g"])
+    for k in live_e:
+        if k.endswith("k_proj.bias") or k.endswith("attention_weights.bias"):
+            continue                                   # exactly-zero true gradients: float noise on both sides
+        assert _rel(t["g"][k], e["g"][k]) <= 5e-5, k
+    assert t["launches"] > 0 and e["launches"] > 0
