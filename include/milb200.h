@@ -217,9 +217,10 @@ int milb200_ct_tokens_bwd(const void* dtokens, void* dfmap, int c, int t, int hw
  *   ops     LINEAR    out = act((in0 [+ in1]) W^T + b)      p0 = W [out.cols, in0.cols], p1 = bias or -1, a0 = act
  *           ATTENTION out = softmax(Q K^T / sqrt(c)) V      in0/in1/in2 = Q/K/V (distinct slots), a0 = heads
  *           LAYERNORM out = LN(in0 [+ in1]) * gamma + beta  p0 = gamma, p1 = beta (eps 1e-5)
+ *           ADD       out = in0 + in1                       (a sum several ops share, e.g. keys + key_pe)
  * Backward: seed_ptrs[s] != NULL gives dL/d(slot s) for program outputs; ext_grad_ptrs[s] != NULL asks for the
  * gradient of external input s (written there); internal slots' gradients live in the workspace.                  */
-enum { MILB200_OP_LINEAR = 1, MILB200_OP_ATTENTION = 2, MILB200_OP_LAYERNORM = 3 };
+enum { MILB200_OP_LINEAR = 1, MILB200_OP_ATTENTION = 2, MILB200_OP_LAYERNORM = 3, MILB200_OP_ADD = 4 };
 typedef struct milb200_tape_op {
   int32_t kind, in0, in1, in2, out, p0, p1, a0;
 } milb200_tape_op;

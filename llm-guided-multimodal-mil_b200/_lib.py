@@ -80,7 +80,7 @@ class TapeParam(C.Structure):
     _fields_ = [("offset", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32)]
 
 
-OP_LINEAR, OP_ATTENTION, OP_LAYERNORM = 1, 2, 3
+OP_LINEAR, OP_ATTENTION, OP_LAYERNORM, OP_ADD = 1, 2, 3, 4
 
 _lib = None
 _lock = threading.Lock()

@@ -51,7 +51,7 @@ template <typename T, int C>
 __global__ void __launch_bounds__(256)
 k_t2i_fwd(const T* __restrict__ Q, const T* __restrict__ K, const T* __restrict__ V, int nq, int64_t nk, int H,
           int keys_per_cta, float* __restrict__ part_ml, float* __restrict__ part_acc) {
-  extern __shared__ float sm[];  // q[H][nq][C] fp32 (pre-scaled by 1/sqrt(C))
+  extern __shared__ float sm[];  // q[H][nq][C] fp32 (pre-scaled by 1/sqrt(C)) | per-warp V tile [32][C + 1]
   const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;
   const int HC = H * C;
   const float scale = rsqrtf(static_cast<float>(C));
@@ -62,6 +62,7 @@ k_t2i_fwd(const T* __restrict__ Q, const T* __restrict__ K, const T* __restrict_
   __syncthreads();
   if (h >= H) return;
   const float* qh = sm + static_cast<int64_t>(h) * nq * C;
+  float* vs = sm + static_cast<int64_t>(H) * nq * C + static_cast<int64_t>(h) * 32 * (C + 1);
   const int64_t k0 = static_cast<int64_t>(blockIdx.x) * keys_per_cta;
   const int64_t k1 = imin64(nk, k0 + keys_per_cta);
 
@@ -104,12 +105,25 @@ k_t2i_fwd(const T* __restrict__ Q, const T* __restrict__ K, const T* __restrict_
         for (int u = 0; u < C / 32; ++u) acc[i][u] *= corr;
       }
     }
-    // acc_i[channel = lane + 32u] += sum_j p_ij V[j, channel]
-    const int nv = static_cast<int>(imin64(32, k1 - t0));
-    for (int jj = 0; jj < nv; ++jj) {
+    // acc_i[channel = lane + 32u] += sum_j p_ij V[j, channel]: every lane fetches ITS key's V row with 128-bit
+    // loads and parks it in the warp's shared tile; the channel-major pass then reads it conflict-free
+    {
+      float vf[C];
+      if (ok) load_row_slice<T>(V + j * HC + h * C, C, vf);
+      else {
+#pragma unroll
+        for (int d = 0; d < C; ++d) vf[d] = 0.f;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int d = 0; d < C; ++d) vs[lane * (C + 1) + d] = vf[d];
+      __syncwarp();
+    }
+#pragma unroll 8
+    for (int jj = 0; jj < 32; ++jj) {
       float vv[C / 32];
 #pragma unroll
-      for (int u = 0; u < C / 32; ++u) vv[u] = to_f32<T>(V[(t0 + jj) * HC + h * C + lane + 32 * u]);
+      for (int u = 0; u < C / 32; ++u) vv[u] = vs[jj * (C + 1) + lane + 32 * u];
 #pragma unroll
       for (int i = 0; i < ATT_MAXT; ++i) {
         if (i < nq) {
@@ -133,22 +147,40 @@ k_t2i_fwd(const T* __restrict__ Q, const T* __restrict__ K, const T* __restrict_
   }
 }
 
-// merge the chunk partials in chunk order: O[i, h*C + d], lse[h, i]
-template <typename T>
-__global__ void k_t2i_combine(const float* __restrict__ part_ml, const float* __restrict__ part_acc, int chunks, int nq,
-                              int H, int C, T* __restrict__ O, float* __restrict__ lse) {
-  const int i = blockIdx.x, h = blockIdx.y, d = threadIdx.x;
+// merge the chunk partials: O[i, h*C + d], lse[h, i].  One warp per (query, head): lanes stride the chunks (fixed
+// assignment, fixed fold order => deterministic), then the per-lane partials are folded across the warp.
+template <typename T, int C>
+__global__ void __launch_bounds__(32)
+k_t2i_combine(const float* __restrict__ part_ml, const float* __restrict__ part_acc, int chunks, int nq, int H,
+              T* __restrict__ O, float* __restrict__ lse) {
+  const int i = blockIdx.x, h = blockIdx.y, lane = threadIdx.x;
   float gm = -FLT_MAX;
-  for (int c = 0; c < chunks; ++c) gm = fmaxf(gm, part_ml[((static_cast<int64_t>(c) * H + h) * nq + i) * 2]);
-  float gl = 0.f, a = 0.f;
-  for (int c = 0; c < chunks; ++c) {
-    int64_t rec = (static_cast<int64_t>(c) * H + h) * nq + i;
-    float w = att_exp<T>(part_ml[rec * 2] - gm);
+  for (int c = lane; c < chunks; c += 32) gm = fmaxf(gm, part_ml[((static_cast<int64_t>(c) * H + h) * nq + i) * 2]);
+  gm = warp_max(gm);
+  float gl = 0.f, a[C];
+#pragma unroll
+  for (int d = 0; d < C; ++d) a[d] = 0.f;
+  for (int c = lane; c < chunks; c += 32) {
+    const int64_t rec = (static_cast<int64_t>(c) * H + h) * nq + i;
+    const float w = att_exp<T>(part_ml[rec * 2] - gm);
     gl = fmaf(part_ml[rec * 2 + 1], w, gl);
-    if (d < C) a = fmaf(part_acc[rec * C + d], w, a);
+    const float4* pa = reinterpret_cast<const float4*>(part_acc + rec * C);
+#pragma unroll
+    for (int d = 0; d < C; d += 4) {
+      const float4 v = pa[d / 4];
+      a[d] = fmaf(v.x, w, a[d]); a[d + 1] = fmaf(v.y, w, a[d + 1]);
+      a[d + 2] = fmaf(v.z, w, a[d + 2]); a[d + 3] = fmaf(v.w, w, a[d + 3]);
+    }
   }
-  if (d < C) O[static_cast<int64_t>(i) * H * C + h * C + d] = from_f32<T>(a / gl);
-  if (d == 0 && lse) lse[h * nq + i] = gm + att_log<T>(gl);
+  gl = warp_sum(gl);
+  float mine = 0.f;
+#pragma unroll
+  for (int d = 0; d < C; ++d) {
+    const float t = warp_sum(a[d]);
+    if ((d & 31) == lane) mine = t;   // C == 32: lane d keeps channel d
+  }
+  if (lane < C) O[static_cast<int64_t>(i) * H * C + h * C + lane] = from_f32<T>(mine / gl);
+  if (lane == 0 && lse) lse[h * nq + i] = gm + att_log<T>(gl);
 }
 
 // =====================================================================================================
@@ -160,7 +192,7 @@ k_t2i_bwd(const T* __restrict__ Q, const T* __restrict__ K, const T* __restrict_
           const float* __restrict__ lse, const T* __restrict__ dO, int nq, int64_t nk, int H, int keys_per_cta,
           T* __restrict__ dK, T* __restrict__ dV, float* __restrict__ dq_part) {
   extern __shared__ float sm[];
-  // q[H][nq][C] (scaled) | do[H][nq][C] | delta[H][nq] | lse[H][nq]
+  // q[H][nq][C] (scaled) | do[H][nq][C] | delta[H][nq] | lse[H][nq] | per-warp K tile [32][C + 1]
   const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;
   const int HC = H * C;
   const float scale = rsqrtf(static_cast<float>(C));
@@ -168,6 +200,7 @@ k_t2i_bwd(const T* __restrict__ Q, const T* __restrict__ K, const T* __restrict_
   float* s_do = s_q + H * nq * C;
   float* s_delta = s_do + H * nq * C;
   float* s_lse = s_delta + H * nq;
+  float* ks = s_lse + H * nq + static_cast<int64_t>(h) * 32 * (C + 1);
   for (int i = threadIdx.x; i < nq * HC; i += blockDim.x) {
     int q = i / HC, col = i % HC;
     int dst = (col / C * nq + q) * C + col % C;
@@ -244,12 +277,16 @@ k_t2i_bwd(const T* __restrict__ Q, const T* __restrict__ K, const T* __restrict_
         *reinterpret_cast<uint4*>(dvr + d) = Vec16<T>::pack(dvf + d);
       }
     }
-    // dQ_i[channel] += scale * sum_j ds_ij K[j, channel]
-    const int nv = static_cast<int>(imin64(32, k1 - t0));
-    for (int jj = 0; jj < nv; ++jj) {
+    // dQ_i[channel] += scale * sum_j ds_ij K[j, channel]  (K rows parked in the warp's shared tile; ds = 0 past the end)
+    __syncwarp();
+#pragma unroll
+    for (int d = 0; d < C; ++d) ks[lane * (C + 1) + d] = kf[d];
+    __syncwarp();
+#pragma unroll 8
+    for (int jj = 0; jj < 32; ++jj) {
       float kk[C / 32];
 #pragma unroll
-      for (int u = 0; u < C / 32; ++u) kk[u] = to_f32<T>(K[(t0 + jj) * HC + h * C + lane + 32 * u]);
+      for (int u = 0; u < C / 32; ++u) kk[u] = ks[jj * (C + 1) + lane + 32 * u];
 #pragma unroll
       for (int i = 0; i < ATT_MAXT; ++i) {
         if (i < nq) {
@@ -352,7 +389,7 @@ __global__ void __launch_bounds__(256)
 k_i2t_bwd(const T* __restrict__ Q, const T* __restrict__ K, const T* __restrict__ V, const float* __restrict__ lse,
           const T* __restrict__ dO, int64_t nq, int nk, int H, int rows_per_cta, T* __restrict__ dQ,
           float* __restrict__ dkv_part) {
-  extern __shared__ float sm[];  // k[H][nk][C] (scaled) | v[H][nk][C]
+  extern __shared__ float sm[];  // k[H][nk][C] (scaled) | v[H][nk][C] | per-warp Q tile, dO tile [32][C + 1] each
   const int lane = threadIdx.x & 31, h = threadIdx.x >> 5;
   const int HC = H * C;
   const float scale = rsqrtf(static_cast<float>(C));
@@ -368,6 +405,8 @@ k_i2t_bwd(const T* __restrict__ Q, const T* __restrict__ K, const T* __restrict_
   if (h >= H) return;
   const float* kh = s_k + static_cast<int64_t>(h) * nk * C;
   const float* vh = s_v + static_cast<int64_t>(h) * nk * C;
+  float* qs = sm + 2 * static_cast<int64_t>(H) * nk * C + static_cast<int64_t>(h) * 2 * 32 * (C + 1);
+  float* gs = qs + 32 * (C + 1);
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
   const int64_t r1 = imin64(nq, r0 + rows_per_cta);
   float* out_dk = dkv_part + static_cast<int64_t>(blockIdx.x) * 2 * nk * HC;
@@ -433,14 +472,19 @@ k_i2t_bwd(const T* __restrict__ Q, const T* __restrict__ K, const T* __restrict_
 #pragma unroll
       for (int d = 0; d < C; d += VN) *reinterpret_cast<uint4*>(dqr + d) = Vec16<T>::pack(dqf + d);
     }
-    // token-side sums over this tile's 32 queries: lane = channel, loop queries with shuffles of (ds, p)
-    const int nv = static_cast<int>(imin64(32, r1 - t0));
-    for (int jj = 0; jj < nv; ++jj) {
+    // token-side sums over this tile's 32 queries: lane = channel, loop queries with shuffles of (ds, p); the Q and
+    // dO rows each lane already holds are parked in the warp's shared tiles (rows past the end carry ds = p = 0)
+    __syncwarp();
+#pragma unroll
+    for (int d = 0; d < C; ++d) { qs[lane * (C + 1) + d] = qf[d] * scale; gs[lane * (C + 1) + d] = gf[d]; }
+    __syncwarp();
+#pragma unroll 4
+    for (int jj = 0; jj < 32; ++jj) {
       float qq[C / 32], gg[C / 32];
 #pragma unroll
       for (int u = 0; u < C / 32; ++u) {
-        qq[u] = to_f32<T>(Q[(t0 + jj) * HC + h * C + lane + 32 * u]) * scale;
-        gg[u] = to_f32<T>(dO[(t0 + jj) * HC + h * C + lane + 32 * u]);
+        qq[u] = qs[jj * (C + 1) + lane + 32 * u];
+        gg[u] = gs[jj * (C + 1) + lane + 32 * u];
       }
 #pragma unroll
       for (int t = 0; t < ATT_MAXT; ++t) {
@@ -527,13 +571,13 @@ static int attention_fwd_t(const T* Q, const T* K, const T* V, T* O, float* lse,
     MIL_CHECK_ARG(ws && ws_bytes >= p.ws_bytes, MILB200_EWORKSPACE, "attention_fwd: workspace %zu < %zu", ws_bytes, p.ws_bytes);
     float* part_ml = static_cast<float*>(ws);
     float* part_acc = part_ml + static_cast<size_t>(p.ctas) * heads * nq * 2;
-    size_t smem = sizeof(float) * nq * HC;
+    size_t smem = sizeof(float) * (nq * HC + static_cast<size_t>(heads) * 32 * (C + 1));
     auto kern = k_t2i_fwd<T, C>;
     if (smem > 48 * 1024) MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<p.ctas, heads * 32, smem, st>>>(Q, K, V, static_cast<int>(nq), nk, heads, p.per_cta, part_ml, part_acc);
     MIL_LAUNCH_CHECK();
-    k_t2i_combine<T><<<dim3(static_cast<unsigned>(nq), heads), std::max(32, C), 0, st>>>(part_ml, part_acc, p.ctas,
-                                                                                         static_cast<int>(nq), heads, C, O, lse);
+    k_t2i_combine<T, C><<<dim3(static_cast<unsigned>(nq), heads), 32, 0, st>>>(part_ml, part_acc, p.ctas,
+                                                                               static_cast<int>(nq), heads, O, lse);
     MIL_LAUNCH_CHECK();
    }
   } else {
@@ -557,7 +601,7 @@ static int attention_bwd_t(const T* Q, const T* K, const T* V, const T* O, const
    if constexpr (C != 32) {
     MIL_CHECK_ARG(false, MILB200_EUNSUPPORTED, "attention_bwd: many-key attention is built for head dim 32 only");
    } else {
-    size_t smem = sizeof(float) * (2 * nq * HC + 2 * heads * nq);
+    size_t smem = sizeof(float) * (2 * nq * HC + 2 * heads * nq + static_cast<size_t>(heads) * 32 * (C + 1));
     auto kern = k_t2i_bwd<T, C>;
     if (smem > 48 * 1024) MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<p.ctas, heads * 32, smem, st>>>(Q, K, V, O, lse, dO, static_cast<int>(nq), nk, heads, p.per_cta, dK, dV, part);
@@ -567,7 +611,7 @@ static int attention_bwd_t(const T* Q, const T* K, const T* V, const T* O, const
     MIL_LAUNCH_CHECK();
    }
   } else {
-    size_t smem = sizeof(float) * 2 * nk * HC;
+    size_t smem = sizeof(float) * (2 * nk * HC + static_cast<size_t>(heads) * 2 * 32 * (C + 1));
     auto kern = k_i2t_bwd<T, C>;
     if (smem > 48 * 1024) MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<p.ctas, heads * 32, smem, st>>>(Q, K, V, lse, dO, nq, static_cast<int>(nk), heads, p.per_cta, dQ, part);

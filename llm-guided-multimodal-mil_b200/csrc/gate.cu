@@ -220,6 +220,72 @@ k_colsum(const T* __restrict__ A, int64_t rows, int cols, float* __restrict__ ou
   }
 }
 
+// same result, 128-bit loads: a CTA owns 32 x VN columns and a slab of rows; its 8 warps stride the rows with four
+// independent loads in flight each, fold in shared memory, one atomicAdd per column per CTA
+template <typename T>
+__global__ void __launch_bounds__(256)
+k_colsum_vec(const T* __restrict__ A, int64_t rows, int cols, float* __restrict__ out, int rows_per_block) {
+  constexpr int VN = Vec16<T>::N;
+  __shared__ float red[8][32 * VN + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int vec = blockIdx.x * 32 + lane;           // vector column
+  const int nvec = cols / VN;
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
+  const int64_t r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
+  float acc[VN];
+#pragma unroll
+  for (int e = 0; e < VN; ++e) acc[e] = 0.f;
+  if (vec < nvec) {
+    const uint4* base = reinterpret_cast<const uint4*>(A) + vec;
+    int64_t r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ldg_stream(base + (r + 8 * u) * nvec);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[VN];
+        Vec16<T>::unpack(v[u], f);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) acc[e] += f[e];
+      }
+    }
+    for (; r < r1; r += 8) {
+      float f[VN];
+      Vec16<T>::unpack(ldg_stream(base + r * nvec), f);
+#pragma unroll
+      for (int e = 0; e < VN; ++e) acc[e] += f[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < VN; ++e) red[warp][lane * VN + e] = acc[e];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * VN; c += 256) {
+    const int col = blockIdx.x * 32 * VN + c;
+    if (col >= cols) continue;
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) a += red[w][c];
+    atomicAdd(out + col, a);
+  }
+}
+
+template <typename T>
+static int colsum_launch(const T* A, int64_t rows, int cols, float* out, cudaStream_t st) {
+  constexpr int VN = Vec16<T>::N;
+  if (cols % VN == 0 && aligned16(A)) {
+    int64_t slabs = std::max<int64_t>(1, std::min<int64_t>((rows + 63) / 64, (2 * sm_count() * 32 * VN + cols - 1) / cols));
+    int rpb = static_cast<int>((rows + slabs - 1) / slabs);
+    dim3 grid(static_cast<unsigned>((cols / VN + 31) / 32), static_cast<unsigned>((rows + rpb - 1) / rpb));
+    k_colsum_vec<T><<<grid, 256, 0, st>>>(A, rows, cols, out, rpb);
+  } else {
+    int rpb = 128;
+    k_colsum<T><<<static_cast<unsigned>((rows + rpb - 1) / rpb), 256, 0, st>>>(A, rows, cols, out, rpb);
+  }
+  MIL_LAUNCH_CHECK();
+  return MILB200_OK;
+}
+
 static size_t simt_splits(int64_t K) {
   int64_t s = K / 512;
   if (s < 1) s = 1;
@@ -533,9 +599,8 @@ static int linear_bwd_t(const T* Xin, const T* W, const T* Y, const T* dY, T* dX
   }
   if (dbias) {
     if (!accumulate) MIL_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * n, st));
-    int rpb = 128;
-    k_colsum<T><<<static_cast<unsigned>((m + rpb - 1) / rpb), 256, 0, st>>>(dypre, m, n, dbias, rpb);
-    MIL_LAUNCH_CHECK();
+    int rcs = colsum_launch<T>(dypre, m, n, dbias, st);
+    if (rcs) return rcs;
   }
   float* part = reinterpret_cast<float*>(ws + w.part);
   const bool use_tc = tc_linear_bwd_ok(m, n, k, dtype) && aligned16(dypre) && aligned16(Xin) && aligned16(W);

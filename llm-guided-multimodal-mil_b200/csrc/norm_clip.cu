@@ -14,38 +14,59 @@ namespace milb200 {
 // ---------------------------------------------------------------------------------------------------
 constexpr int LN_MAX_PER_LANE = 32;  // n <= 1024
 
+// Vector layout: lane owns the 16-byte vectors lane, lane + 32, ... of its row (n % VN == 0, rows 16-byte aligned).
+template <typename T> struct LnCfg { static constexpr int VN = Vec16<T>::N; static constexpr int MAXV = 32 * LN_MAX_PER_LANE / (32 * VN); };
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_ln_fwd(const T* __restrict__ X, const T* __restrict__ R, const float* __restrict__ gamma, const float* __restrict__ beta,
          T* __restrict__ Y, float* __restrict__ mean, float* __restrict__ rstd, int64_t m, int n) {
+  constexpr int VN = LnCfg<T>::VN, MAXV = LnCfg<T>::MAXV;
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= m) return;
-  const T* x = X + row * n;
-  const T* r = R ? R + row * n : nullptr;
-  float v[LN_MAX_PER_LANE];
+  const int nvec = n / VN;
+  const uint4* x = reinterpret_cast<const uint4*>(X + row * n);
+  const uint4* r = R ? reinterpret_cast<const uint4*>(R + row * n) : nullptr;
+  float v[MAXV][VN];
   float s = 0.f;
 #pragma unroll
-  for (int j = 0; j < LN_MAX_PER_LANE; ++j) {
-    int c = lane + 32 * j;
-    v[j] = 0.f;
-    if (c < n) {
-      v[j] = to_f32<T>(x[c]) + (r ? to_f32<T>(r[c]) : 0.f);
-      s += v[j];
+  for (int j = 0; j < MAXV; ++j) {
+    const int vec = lane + 32 * j;
+#pragma unroll
+    for (int e = 0; e < VN; ++e) v[j][e] = 0.f;
+    if (vec < nvec) {
+      Vec16<T>::unpack(ldg_stream(x + vec), v[j]);
+      if (r) {
+        float f[VN];
+        Vec16<T>::unpack(ldg_stream(r + vec), f);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) v[j][e] += f[e];
+      }
+#pragma unroll
+      for (int e = 0; e < VN; ++e) s += v[j][e];
     }
   }
   const float mu = warp_sum(s) / static_cast<float>(n);
   float q = 0.f;
 #pragma unroll
-  for (int j = 0; j < LN_MAX_PER_LANE; ++j) {
-    int c = lane + 32 * j;
-    if (c < n) { float d = v[j] - mu; q = fmaf(d, d, q); }
+  for (int j = 0; j < MAXV; ++j) {
+    if (lane + 32 * j < nvec) {
+#pragma unroll
+      for (int e = 0; e < VN; ++e) { const float d = v[j][e] - mu; q = fmaf(d, d, q); }
+    }
   }
   const float rs = rsqrtf(warp_sum(q) / static_cast<float>(n) + 1e-5f);
+  uint4* y = reinterpret_cast<uint4*>(Y + row * n);
 #pragma unroll
-  for (int j = 0; j < LN_MAX_PER_LANE; ++j) {
-    int c = lane + 32 * j;
-    if (c < n) Y[row * n + c] = from_f32<T>((v[j] - mu) * rs * __ldg(gamma + c) + __ldg(beta + c));
+  for (int j = 0; j < MAXV; ++j) {
+    const int vec = lane + 32 * j;
+    if (vec < nvec) {
+      float o[VN];
+#pragma unroll
+      for (int e = 0; e < VN; ++e) o[e] = (v[j][e] - mu) * rs * __ldg(gamma + vec * VN + e) + __ldg(beta + vec * VN + e);
+      y[vec] = Vec16<T>::pack(o);
+    }
   }
   if (lane == 0) { mean[row] = mu; rstd[row] = rs; }
 }
@@ -56,44 +77,79 @@ __global__ void __launch_bounds__(256)
 k_ln_bwd(const T* __restrict__ X, const T* __restrict__ R, const float* __restrict__ gamma, const float* __restrict__ mean,
          const float* __restrict__ rstd, const T* __restrict__ dY, T* __restrict__ dXR, float* __restrict__ part, int64_t m,
          int n, int rows_per_cta) {
+  constexpr int VN = LnCfg<T>::VN, MAXV = LnCfg<T>::MAXV;
   extern __shared__ float sm[];  // [8 warps][2][n]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float dg[LN_MAX_PER_LANE], db[LN_MAX_PER_LANE];
+  const int nvec = n / VN;
+  float dg[MAXV][VN], db[MAXV][VN], gm[MAXV][VN];
 #pragma unroll
-  for (int j = 0; j < LN_MAX_PER_LANE; ++j) dg[j] = db[j] = 0.f;
+  for (int j = 0; j < MAXV; ++j) {
+    const int vec = lane + 32 * j;
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      dg[j][e] = db[j][e] = 0.f;
+      gm[j][e] = (vec < nvec) ? __ldg(gamma + vec * VN + e) : 0.f;
+    }
+  }
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
   const int64_t r1 = (r0 + rows_per_cta < m) ? r0 + rows_per_cta : m;
   for (int64_t row = r0 + warp; row < r1; row += 8) {
     const float mu = mean[row], rs = rstd[row];
-    float xh[LN_MAX_PER_LANE], g[LN_MAX_PER_LANE];
+    const uint4* x = reinterpret_cast<const uint4*>(X + row * n);
+    const uint4* r = R ? reinterpret_cast<const uint4*>(R + row * n) : nullptr;
+    const uint4* dy = reinterpret_cast<const uint4*>(dY + row * n);
+    float xh[MAXV][VN], g[MAXV][VN];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < LN_MAX_PER_LANE; ++j) {
-      int c = lane + 32 * j;
-      xh[j] = g[j] = 0.f;
-      if (c < n) {
-        float xv = to_f32<T>(X[row * n + c]) + (R ? to_f32<T>(R[row * n + c]) : 0.f);
-        float dy = to_f32<T>(dY[row * n + c]);
-        xh[j] = (xv - mu) * rs;
-        g[j] = dy * __ldg(gamma + c);
-        s1 += g[j];
-        s2 = fmaf(g[j], xh[j], s2);
-        dg[j] = fmaf(dy, xh[j], dg[j]);
-        db[j] += dy;
+    for (int j = 0; j < MAXV; ++j) {
+      const int vec = lane + 32 * j;
+#pragma unroll
+      for (int e = 0; e < VN; ++e) xh[j][e] = g[j][e] = 0.f;
+      if (vec < nvec) {
+        float xv[VN], dv[VN];
+        Vec16<T>::unpack(ldg_stream(x + vec), xv);
+        Vec16<T>::unpack(ldg_stream(dy + vec), dv);
+        if (r) {
+          float f[VN];
+          Vec16<T>::unpack(ldg_stream(r + vec), f);
+#pragma unroll
+          for (int e = 0; e < VN; ++e) xv[e] += f[e];
+        }
+#pragma unroll
+        for (int e = 0; e < VN; ++e) {
+          xh[j][e] = (xv[e] - mu) * rs;
+          g[j][e] = dv[e] * gm[j][e];
+          s1 += g[j][e];
+          s2 = fmaf(g[j][e], xh[j][e], s2);
+          dg[j][e] = fmaf(dv[e], xh[j][e], dg[j][e]);
+          db[j][e] += dv[e];
+        }
       }
     }
     s1 = warp_sum(s1) / static_cast<float>(n);
     s2 = warp_sum(s2) / static_cast<float>(n);
+    uint4* dx = reinterpret_cast<uint4*>(dXR + row * n);
 #pragma unroll
-    for (int j = 0; j < LN_MAX_PER_LANE; ++j) {
-      int c = lane + 32 * j;
-      if (c < n) dXR[row * n + c] = from_f32<T>(rs * (g[j] - s1 - xh[j] * s2));
+    for (int j = 0; j < MAXV; ++j) {
+      const int vec = lane + 32 * j;
+      if (vec < nvec) {
+        float o[VN];
+#pragma unroll
+        for (int e = 0; e < VN; ++e) o[e] = rs * (g[j][e] - s1 - xh[j][e] * s2);
+        dx[vec] = Vec16<T>::pack(o);
+      }
     }
   }
 #pragma unroll
-  for (int j = 0; j < LN_MAX_PER_LANE; ++j) {
-    int c = lane + 32 * j;
-    if (c < n) { sm[(warp * 2) * n + c] = dg[j]; sm[(warp * 2 + 1) * n + c] = db[j]; }
+  for (int j = 0; j < MAXV; ++j) {
+    const int vec = lane + 32 * j;
+    if (vec < nvec) {
+#pragma unroll
+      for (int e = 0; e < VN; ++e) {
+        sm[(warp * 2) * n + vec * VN + e] = dg[j][e];
+        sm[(warp * 2 + 1) * n + vec * VN + e] = db[j][e];
+      }
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) {
@@ -350,6 +406,8 @@ int milb200_layernorm_fwd(const void* X, const void* R, const float* gamma, cons
   MIL_CHECK_ARG(X && gamma && beta && Y && mean && rstd, MILB200_EINVAL, "layernorm_fwd: null pointer");
   MIL_CHECK_ARG(m > 0 && n > 0 && n <= 32 * LN_MAX_PER_LANE, MILB200_EUNSUPPORTED, "layernorm_fwd: n=%d not in (0, %d]", n,
                 32 * LN_MAX_PER_LANE);
+  MIL_CHECK_ARG((n * elem_size(dtype)) % 16 == 0 && aligned16(X) && aligned16(Y) && (!R || aligned16(R)), MILB200_EALIGN,
+                "layernorm_fwd: rows must be 16-byte aligned multiples of 16 bytes (n=%d)", n);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned blocks = static_cast<unsigned>((m + 7) / 8);
   if (dtype == MILB200_BF16)
@@ -366,6 +424,8 @@ int milb200_layernorm_bwd(const void* X, const void* R, const float* gamma, cons
                           int accumulate, void* workspace, size_t ws_bytes, void* stream) {
   MIL_CHECK_ARG(X && gamma && mean && rstd && dY && dXR && dgamma && dbeta, MILB200_EINVAL, "layernorm_bwd: null pointer");
   MIL_CHECK_ARG(m > 0 && n > 0 && n <= 32 * LN_MAX_PER_LANE, MILB200_EUNSUPPORTED, "layernorm_bwd: n=%d unsupported", n);
+  MIL_CHECK_ARG((n * elem_size(dtype)) % 16 == 0 && aligned16(X) && aligned16(dY) && aligned16(dXR) && (!R || aligned16(R)),
+                MILB200_EALIGN, "layernorm_bwd: rows must be 16-byte aligned multiples of 16 bytes (n=%d)", n);
   size_t need = milb200_layernorm_workspace_bytes(m, n);
   MIL_CHECK_ARG(workspace && ws_bytes >= need, MILB200_EWORKSPACE, "layernorm_bwd: workspace %zu < %zu", ws_bytes, need);
   cudaStream_t st = static_cast<cudaStream_t>(stream);

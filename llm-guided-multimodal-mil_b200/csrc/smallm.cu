@@ -102,9 +102,9 @@ k_smallm_dx(const T* __restrict__ W, const T* __restrict__ Y, const T* __restric
 #pragma unroll
   for (int i = 0; i < MT; ++i) acc[i][0] = acc[i][1] = 0.f;
   if (kk < k) {
-#pragma unroll 4
-    for (int r = warp; r < n; r += 8) {
-      float w0, w1;
+    // the chain is load-latency bound (a warp touches 128-256 B per row): keep UNR independent rows in flight
+    constexpr int UNR = 16;
+    auto ldw = [&](int r, float& w0, float& w1) {
       if (sizeof(T) == 4) {
         const float2 w2 = __ldg(reinterpret_cast<const float2*>(W + static_cast<int64_t>(r) * k + kk));
         w0 = w2.x; w1 = w2.y;
@@ -112,6 +112,25 @@ k_smallm_dx(const T* __restrict__ W, const T* __restrict__ Y, const T* __restric
         const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(W + static_cast<int64_t>(r) * k + kk));
         w0 = bf16lo(u); w1 = bf16hi(u);
       }
+    };
+    int r = warp;
+    for (; r + 8 * (UNR - 1) < n; r += 8 * UNR) {
+      float w0[UNR], w1[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) ldw(r + 8 * u, w0[u], w1[u]);
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+          const float g = gs[i * n + r + 8 * u];
+          acc[i][0] = fmaf(g, w0[u], acc[i][0]);
+          acc[i][1] = fmaf(g, w1[u], acc[i][1]);
+        }
+      }
+    }
+    for (; r < n; r += 8) {
+      float w0, w1;
+      ldw(r, w0, w1);
 #pragma unroll
       for (int i = 0; i < MT; ++i) {
         const float g = gs[i * n + r];

@@ -72,6 +72,12 @@ static int tape_validate(const milb200_tape_op* ops, int n_ops, const milb200_ta
                       MILB200_EINVAL, "tape: op %d layernorm shape mismatch", i);
         break;
       }
+      case MILB200_OP_ADD: {
+        MIL_CHECK_ARG(ok_slot(o.in1, false) && o.in1 != o.in0, MILB200_EINVAL, "tape: op %d add needs two distinct slots", i);
+        MIL_CHECK_ARG(so.rows == s0.rows && so.cols == s0.cols && slots[o.in1].rows == s0.rows && slots[o.in1].cols == s0.cols,
+                      MILB200_EINVAL, "tape: op %d add shape mismatch", i);
+        break;
+      }
       default:
         MIL_CHECK_ARG(false, MILB200_EINVAL, "tape: op %d has unknown kind %d", i, o.kind);
     }
@@ -185,6 +191,9 @@ int milb200_tape_forward(const milb200_tape_op* ops, int n_ops, const milb200_ta
                                    p_f32 + params[o.p1].offset, ptr[o.out], mean, mean + s0.rows, s0.rows, s0.cols, dtype, stream);
         break;
       }
+      case MILB200_OP_ADD:
+        rc = milb200_add(ptr[o.in0], ptr[o.in1], ptr[o.out], s0.rows * s0.cols, dtype, stream);
+        break;
       default:
         rc = MILB200_EINVAL;
     }
@@ -326,6 +335,12 @@ int milb200_tape_backward(const milb200_tape_op* ops, int n_ops, const milb200_t
             return rc;
           }
         }
+        break;
+      }
+      case MILB200_OP_ADD: {
+        // d(in0) = d(in1) = dY: fold the op's gradient buffer into both operands (no kernel of its own)
+        if ((rc = settle(o.in0, grad[o.out]))) return rc;
+        if ((rc = settle(o.in1, grad[o.out]))) return rc;
         break;
       }
       default:

@@ -118,10 +118,11 @@ class TwoWayAttentionBlock(nn.Module):
         else:
             attn_out = self.self_attn.emit(tape, queries, queries, queries, q_add=query_pe, k_add=query_pe)
             queries = tape.layernorm(queries, self.norm1, residual=attn_out)
-        attn_out = self.cross_attn_token_to_image.emit(tape, queries, keys, keys, q_add=query_pe, k_add=key_pe)
+        keys_pe = tape.add(keys, key_pe)      # transformer.py:292 and :304 are the same tensor: build it once
+        attn_out = self.cross_attn_token_to_image.emit(tape, queries, keys_pe, keys, q_add=query_pe)
         queries = tape.layernorm(queries, self.norm2, residual=attn_out)
         queries = tape.layernorm(queries, self.norm3, residual=self.mlp.emit(tape, queries))
-        attn_out = self.cross_attn_image_to_token.emit(tape, keys, queries, queries, q_add=key_pe, k_add=query_pe)
+        attn_out = self.cross_attn_image_to_token.emit(tape, keys_pe, queries, queries, k_add=query_pe)
         keys = tape.layernorm(keys, self.norm4, residual=attn_out)
         return queries, keys
 

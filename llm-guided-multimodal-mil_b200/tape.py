@@ -72,6 +72,13 @@ class Tape:
                          self.param(ln.bias), 0))
         return out
 
+    def add(self, a, b):
+        """out = a + b as a slot of its own, for sums that several ops consume (keys + key_pe feeds two projections
+        per block: materialise it once instead of once per consumer)."""
+        out = self.slot(self.slot_rows[a], self.slot_cols[a])
+        self.ops.append((L.OP_ADD, a, b, -1, out, -1, -1, 0))
+        return out
+
     def buffer(self, rows_fn, cols):
         self.buffers.append((rows_fn, int(cols)))
         return len(self.buffers) - 1

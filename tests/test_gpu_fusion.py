@@ -373,5 +373,11 @@ def test_tape_program_equals_per_operator_autograd(monkeypatch):
     for k in live_e:
         if k.endswith("k_proj.bias") or k.endswith("attention_weights.bias"):
             continue                                   # exactly-zero true gradients: float noise on both sides
+        if ".q_proj" in k or ".k_proj" in k:
+            # softmax-Jacobian cancellation class (module docstring): ~1e-7-sized gradients, compare on the scale of
+            # the layer's v_proj gradient instead of their own
+            ref_scale = float(e["g"][k.replace(".q_proj", ".v_proj").replace(".k_proj", ".v_proj")].abs().max())
+            assert float((t["g"][k] - e["g"][k]).abs().max()) <= 1e-5 * ref_scale, k
+            continue
         assert _rel(t["g"][k], e["g"][k]) <= 5e-5, k
     assert t["launches"] > 0 and e["launches"] > 0
