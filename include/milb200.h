@@ -84,6 +84,10 @@ int milb200_gated_score_bwd(const void* X, const void* Wcat, const float* bcat, 
  * sub-kernels (dZ pass: recompute GEMM or elementwise | dW split-K GEMM | split-K reduce | optional dX GEMM); profile_read waits for the
  * last one and returns up to max_intervals durations in milliseconds (return value = count).              */
 void milb200_profile_enable(int on);
+/* Developer hook: CTA 0 of the K-major tensor-core GEMM stamps clock64() at its phase boundaries into dev_u64x16
+ * (16 x uint64 on the device; NULL switches it off): 0 entry, 1 prologue done, 2/3 first/last TMA stage issued,
+ * 4/5 first/last stage landed, 6 accumulator ready, 7 epilogue done, 8 all warps done, 9 TMEM released.        */
+int milb200_debug_trace(void* dev_u64x16);
 int milb200_profile_read(float* ms, int max_intervals);
 
 /* ---- ragged segmented softmax + attention-weighted instance sum ---------------------------------

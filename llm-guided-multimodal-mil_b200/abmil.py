@@ -50,7 +50,8 @@ class ABMIL(nn.Module):
     def forward(self, x):
         x = x.squeeze(0)                                                       # ABMIL.py:48
         if x.dim() == 2:
-            off = torch.tensor([0, x.shape[0]], dtype=torch.int32, device=x.device)
+            # CSR offsets [0, n] built on the device (a host list would cost a synchronous pageable H2D copy per bag)
+            off = torch.arange(0, 2, dtype=torch.int32, device=x.device) * x.shape[0]
             return self.forward_csr(x, off)                                    # (K, L) = (1, L)
         if x.dim() == 3:
             # Upstream quirk: with a dense batch B>1 the softmax runs over the size-1 K axis, so

@@ -426,6 +426,7 @@ int milb200_add(const void* a, const void* b, void* out, int64_t n, int dtype, v
 /* Developer/bench hook: when enabled, the tensor-core path of milb200_gated_score_bwd records CUDA events
  * between its sub-kernels (dz recompute | dW split-K GEMM | split-K reduce | dX GEMM);
  * milb200_profile_read synchronises on the last event and returns the interval durations in ms. */
+int milb200_debug_trace(void* dev_u64x16) { return tc::debug_set_trace(dev_u64x16); }
 void milb200_profile_enable(int on) { g_prof_on = on != 0; g_prof_n = 0; }
 int milb200_profile_read(float* ms, int max_intervals) {
   int n = g_prof_n - 1;

@@ -17,6 +17,12 @@
 namespace milb200 {
 namespace tc {
 
+// developer hook (milb200_debug_trace): CTA 0 stamps clock64() at its phase boundaries into a caller buffer
+__device__ unsigned long long* g_trace = nullptr;
+__device__ __forceinline__ void trace(int slot) {
+  if (g_trace != nullptr && blockIdx.x == 0) g_trace[slot] = static_cast<unsigned long long>(clock64());
+}
+
 constexpr int BM = 128;      // rows per tile = TMEM lanes
 constexpr int BK = 64;       // bf16 per 128-byte swizzle span
 constexpr int UMMA_K = 16;
@@ -106,6 +112,7 @@ struct EpiStore {
       a = __ldg(p.attn + row);
       dmrow = p.dM + static_cast<int64_t>(find_bag(p.offsets, p.nbags, row)) * p.ldo;
     }
+    const bool bias_vec = p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15u) == 0;
 #pragma unroll 1
     for (int c = cx.half * (BN / 2); c < (cx.half + 1) * (BN / 2); c += 32) {
       if (n0 + c >= N) break;  // warp-uniform
@@ -113,19 +120,40 @@ struct EpiStore {
       tmem_ld32(tacc + c, r);
       tmem_ld_wait();
       if (!row_ok) continue;
+      const int nvalid = (N - (n0 + c)) < 32 ? (N - (n0 + c)) : 32;  // multiple of 8 (N % 8 == 0)
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        int n = n0 + c + j;
-        float x = __uint_as_float(r[j]);
-        if (n < N) {
-          if (p.bias) x += __ldg(p.bias + n);
-          x = apply_act(x, p.act);
-          if (dmrow) x = fmaf(a, __ldg(dmrow + n), x);
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      // bias: eight independent 128-bit loads (all lanes read the same addresses: one broadcast transaction each)
+      if (bias_vec) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (j < nvalid) {
+            const float4 t = __ldg(b4 + j / 4);
+            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+          }
         }
-        v[j] = x;
+      } else if (p.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) v[j] += __ldg(p.bias + n0 + c + j);
       }
-      const int nvalid = (N - (n0 + c)) < 32 ? (N - (n0 + c)) : 32;  // multiple of 8 (N % 8 == 0)
+      if (p.act == MILB200_ACT_TANH) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = tanh_fast(v[j]);
+      } else if (p.act == MILB200_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (p.act == MILB200_ACT_SIGMOID) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = sigmoid_fast(v[j]);
+      }
+      if (dmrow) {  // rank-1 pooling term of the gated pool's dX: + attn[row] * dM[bag(row), n]
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (j < nvalid) v[j] = fmaf(a, __ldg(dmrow + n0 + c + j), v[j]);
+      }
       if (p.out_bf16) {
         __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + row * p.ldo + n0 + c;
 #pragma unroll
@@ -403,6 +431,7 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int64_t m_tiles = (M + BM - 1) / BM;
   const int n_tiles = (N + BN - 1) / BN;
   const int num_kb = (K + BK - 1) / BK;
+  if (threadIdx.x == 0) trace(0);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -425,6 +454,7 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) trace(1);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -445,6 +475,8 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
             for (int j = 0; j < Cfg::N_MMA; ++j)
               tma_load_2d(sb + j * Cfg::UMMA_N * 128, &tmB, full_bar + s, kb * BK, nt * BN + j * Cfg::UMMA_N, kEvictLast);
+            if (kb == 0 && nt == 0 && mt == blockIdx.x) trace(2);
+            if (kb == num_kb - 1 && nt == 0 && mt == blockIdx.x) trace(3);
             if (++s == STAGES) { s = 0; ph ^= 1; }
           }
         }
@@ -471,6 +503,7 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar + s, ph);
           tc_fence_after();
+          if (it == 0 && lane == 0) { if (kb == 0) trace(4); if (kb == num_kb - 1) trace(5); }
           if (elect_one()) {
             const uint32_t so = static_cast<uint32_t>(s) * (Cfg::STAGE_BYTES >> 4);
 #pragma unroll
@@ -504,12 +537,14 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         const uint32_t acc_ph = static_cast<uint32_t>((it / Cfg::ACC_STAGES) & 1);
         mbar_wait(tfull_bar + acc, acc_ph);
         tc_fence_after();
+        if (it == 0 && e == 0 && lane == 0) trace(6);
         const uint32_t tacc = tmem_base + acc * BN + (static_cast<uint32_t>(cx.q * 32) << 16);
         cx.nt = nt;
         cx.n0 = nt * BN;
         epi.template tile<BN>(ep, esm, staging, tacc, cx);
         tc_fence_before();
         mbar_arrive(tempty_bar + acc);
+        if (it == 0 && e == 0 && lane == 0) trace(7);
       }
     }
     epi.finish(ep, e, lane);
@@ -517,10 +552,18 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) trace(8);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (lane == 0) trace(9);
   }
+}
+
+int debug_set_trace(void* dev_ptr) {
+  unsigned long long* p = static_cast<unsigned long long*>(dev_ptr);
+  MIL_CUDA(cudaMemcpyToSymbol(g_trace, &p, sizeof(p)));
+  return MILB200_OK;
 }
 
 template <int BN, class Epi>

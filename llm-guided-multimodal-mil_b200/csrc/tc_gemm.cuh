@@ -32,6 +32,7 @@ int gated_dz_max_records();
 int gemm_tn_splitk(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t Kr, int Mo, int No, float* part,
                    int* splits, cudaStream_t st);
 int gemm_tn_max_splits(int Mo, int No);
+int debug_set_trace(void* dev_ptr);
 bool gemm_tn_supported(int Mo, int No);
 
 }  // namespace tc

@@ -46,8 +46,10 @@ def main():
             x_t = (torch.randn(1, T, 512, device=dev) * 0.05).to(dtype)
             label = torch.tensor([[0.0, 1.0]], device=dev)
 
+            plist = list(m.parameters())
+
             def step():
-                for p in m.parameters():
+                for p in plist:
                     p.grad = None
                 prob, a, b = m([x_ct, x_p], x_t)
                 loss = torch.nn.functional.binary_cross_entropy(prob.float(), label) + \
