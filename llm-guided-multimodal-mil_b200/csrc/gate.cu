@@ -109,10 +109,11 @@ __global__ void k_colsum_finalize(const float* __restrict__ ws, int nrec, int st
 // dZ (same layout) = [ds w U (1 - V^2) | ds w V U (1 - U)].  Elementwise and HBM-bound: 768 B read + 768 B written
 // per instance, instead of re-running the X . Wcat^T GEMM.  Block = 16 row groups x 24 (V vector, U vector) pairs;
 // column sums (-> dbcat, dww, dbw) are kept in registers, folded in fixed order and written one record per block.
-constexpr int DZS_THREADS = 384;
+constexpr int DZS_THREADS = 192;
 constexpr int DZS_PAIRS = 24;
-constexpr int DZS_RG = DZS_THREADS / DZS_PAIRS;  // 16
-__global__ void __launch_bounds__(DZS_THREADS, 2)
+constexpr int DZS_RG = DZS_THREADS / DZS_PAIRS;  // 8
+constexpr int DZS_UNR = 4;                       // rows in flight per thread (8 x 16-byte loads)
+__global__ void __launch_bounds__(DZS_THREADS, 4)
 k_gate_dz_saved(const __nv_bfloat16* __restrict__ VU, const float* __restrict__ ww, const float* __restrict__ dscores,
                 int64_t n, int64_t rows_per_block, __nv_bfloat16* __restrict__ dZ, float* __restrict__ rec_ws, int stride) {
   constexpr int D = tc::GATE_D, DH = D / 2;
@@ -148,15 +149,22 @@ k_gate_dz_saved(const __nv_bfloat16* __restrict__ VU, const float* __restrict__ 
     *reinterpret_cast<uint4*>(dZ + r * (2 * D) + colU) = Vec16<__nv_bfloat16>::pack(du);
   };
   int64_t r = r0 + rg;
-  for (; r + DZS_RG < r1; r += 2 * DZS_RG) {  // two rows in flight per thread
-    const uint4 qv0 = ldg_stream(VU + r * (2 * D) + colV), qu0 = ldg_stream(VU + r * (2 * D) + colU);
-    const uint4 qv1 = ldg_stream(VU + (r + DZS_RG) * (2 * D) + colV), qu1 = ldg_stream(VU + (r + DZS_RG) * (2 * D) + colU);
-    const float ds0 = __ldg(dscores + r), ds1 = __ldg(dscores + r + DZS_RG);
-    if (p == 0) sds += ds0 + ds1;
-    body(qv0, qu0, ds0, r);
-    body(qv1, qu1, ds1, r + DZS_RG);
+  for (; r + (DZS_UNR - 1) * DZS_RG < r1; r += DZS_UNR * DZS_RG) {
+    uint4 qv[DZS_UNR], qu[DZS_UNR];
+    float dsv[DZS_UNR];
+#pragma unroll
+    for (int u = 0; u < DZS_UNR; ++u) {
+      qv[u] = ldg_stream(VU + (r + u * DZS_RG) * (2 * D) + colV);
+      qu[u] = ldg_stream(VU + (r + u * DZS_RG) * (2 * D) + colU);
+      dsv[u] = __ldg(dscores + r + u * DZS_RG);
+    }
+#pragma unroll
+    for (int u = 0; u < DZS_UNR; ++u) {
+      if (p == 0) sds += dsv[u];
+      body(qv[u], qu[u], dsv[u], r + u * DZS_RG);
+    }
   }
-  if (r < r1) {
+  for (; r < r1; r += DZS_RG) {
     const uint4 qv0 = ldg_stream(VU + r * (2 * D) + colV), qu0 = ldg_stream(VU + r * (2 * D) + colU);
     const float ds0 = __ldg(dscores + r);
     if (p == 0) sds += ds0;
@@ -182,15 +190,25 @@ k_gate_dz_saved(const __nv_bfloat16* __restrict__ VU, const float* __restrict__ 
   }
 }
 // fold the per-block records in block order
-__global__ void k_colsum_finalize_flat(const float* __restrict__ ws, int nrec, int stride, float* __restrict__ dbcat,
-                                       float* __restrict__ dww, float* __restrict__ dbw, int D) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c > 3 * D) return;
+// block = 32 columns x 8 record-lanes; the 8 lanes' sums are folded in fixed order
+__global__ void __launch_bounds__(256)
+k_colsum_finalize_flat(const float* __restrict__ ws, int nrec, int stride, float* __restrict__ dbcat,
+                       float* __restrict__ dww, float* __restrict__ dbw, int D) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   float a = 0.f;
-  for (int r = 0; r < nrec; ++r) a += ws[static_cast<int64_t>(r) * stride + c];
-  if (c < 2 * D) dbcat[c] = a;
-  else if (c < 3 * D) dww[c - 2 * D] = a;
-  else dbw[0] = a;
+  if (c <= 3 * D)
+    for (int r = w; r < nrec; r += 8) a += ws[static_cast<int64_t>(r) * stride + c];
+  red[w][lane] = a;
+  __syncthreads();
+  if (w != 0 || c > 3 * D) return;
+  float t = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) t += red[k][lane];
+  if (c < 2 * D) dbcat[c] = t;
+  else if (c < 3 * D) dww[c - 2 * D] = t;
+  else dbw[0] = t;
 }
 
 // dYpre = dY * act'(Y)   (Y is the activation OUTPUT)
@@ -497,14 +515,14 @@ int milb200_gated_score_bwd(const void* X, const void* Wcat, const float* bcat, 
     if (gate_act) {
       // saved V,U: dZ is an elementwise pass (1.5 KB of traffic per instance instead of the recompute GEMM)
       MIL_CHECK_ARG(aligned16(gate_act), MILB200_EALIGN, "gated_score_bwd: gate_act must be 16-byte aligned");
-      int64_t blocks = std::min<int64_t>((total_n + 63) / 64, static_cast<int64_t>(sm_count()) * 2);
+      int64_t blocks = std::min<int64_t>((total_n + 63) / 64, static_cast<int64_t>(sm_count()) * 4);
       int64_t rpb = (total_n + blocks - 1) / blocks;
       rpb = (rpb + DZS_RG - 1) / DZS_RG * DZS_RG;
       nrec = static_cast<int>((total_n + rpb - 1) / rpb);
       k_gate_dz_saved<<<nrec, DZS_THREADS, 0, st>>>((const __nv_bfloat16*)gate_act, ww, dscores, total_n, rpb,
                                                     (__nv_bfloat16*)dZ, colsum, tc::CS_STRIDE);
       MIL_LAUNCH_CHECK();
-      k_colsum_finalize_flat<<<(3 * D + 1 + 255) / 256, 256, 0, st>>>(colsum, nrec, tc::CS_STRIDE, dbcat, dww, dbw, D);
+      k_colsum_finalize_flat<<<(3 * D + 1 + 31) / 32, 256, 0, st>>>(colsum, nrec, tc::CS_STRIDE, dbcat, dww, dbw, D);
       MIL_LAUNCH_CHECK();
     } else {
       rc = tc::gated_dz(X, total_n, L, Wcat, bcat, ww, dscores, dZ, colsum, &nrec, st);
