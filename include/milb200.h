@@ -217,7 +217,7 @@ int milb200_ct_tokens_bwd(const void* dtokens, void* dfmap, int c, int t, int hw
  *   slots   [rows, cols] matrices in `dtype`; external = 1: the caller supplies the pointer (program inputs, and
  *           outputs it wants written in place, e.g. straight into the packed multi-modal bag of aggregator.py:173)
  *   params  ranges of two flat buffers with identical element offsets: w_compute (weights in `dtype`) and p_f32
- *           (fp32: biases, LayerNorm gamma/beta); gradients go to g_f32 (fp32, same offsets; zero-fill it first)
+ *           (fp32: biases, LayerNorm gamma/beta); gradients go to g_f32 (fp32, same offsets; cleared by the call)
  *   ops     LINEAR    out = act((in0 [+ in1]) W^T + b)      p0 = W [out.cols, in0.cols], p1 = bias or -1, a0 = act
  *           ATTENTION out = softmax(Q K^T / sqrt(c)) V      in0/in1/in2 = Q/K/V (distinct slots), a0 = heads
  *           LAYERNORM out = LN(in0 [+ in1]) * gamma + beta  p0 = gamma, p1 = beta (eps 1e-5)

@@ -151,10 +151,10 @@ size_t milb200_tape_workspace_bytes(const milb200_tape_op* ops, int n_ops, const
   return backward ? tape_bwd_ws_bytes(p) : p.scratch_fwd;
 }
 
-int milb200_tape_forward(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
-                         const milb200_tape_param* params, int n_params, void* const* ext_ptrs, const void* w_compute,
-                         const float* p_f32, void* arena, size_t arena_bytes, void* workspace, size_t ws_bytes, int dtype,
-                         void* stream) {
+static int tape_forward_run(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
+                            const milb200_tape_param* params, int n_params, void* const* ext_ptrs, const void* w_compute,
+                            const float* p_f32, void* arena, size_t arena_bytes, void* workspace, size_t ws_bytes, int dtype,
+                            void* stream) {
   int rc = tape_validate(ops, n_ops, slots, n_slots, params, n_params);
   if (rc) return rc;
   MIL_CHECK_ARG(dtype == MILB200_F32 || dtype == MILB200_BF16, MILB200_EINVAL, "tape: bad dtype %d", dtype);
@@ -202,10 +202,10 @@ int milb200_tape_forward(const milb200_tape_op* ops, int n_ops, const milb200_ta
   return MILB200_OK;
 }
 
-int milb200_tape_backward(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
-                          const milb200_tape_param* params, int n_params, void* const* ext_ptrs, void* const* ext_grad_ptrs,
-                          const void* const* seed_ptrs, const void* w_compute, const float* p_f32, float* g_f32,
-                          const void* arena, size_t arena_bytes, void* workspace, size_t ws_bytes, int dtype, void* stream) {
+static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
+                             const milb200_tape_param* params, int n_params, void* const* ext_ptrs, void* const* ext_grad_ptrs,
+                             const void* const* seed_ptrs, const void* w_compute, const float* p_f32, float* g_f32,
+                             const void* arena, size_t arena_bytes, void* workspace, size_t ws_bytes, int dtype, void* stream) {
   int rc = tape_validate(ops, n_ops, slots, n_slots, params, n_params);
   if (rc) return rc;
   MIL_CHECK_ARG(dtype == MILB200_F32 || dtype == MILB200_BF16, MILB200_EINVAL, "tape: bad dtype %d", dtype);
@@ -247,6 +247,12 @@ int milb200_tape_backward(const milb200_tape_op* ops, int n_ops, const milb200_t
     has[i] = 1;
   }
   std::vector<char> ptouched(n_params > 0 ? n_params : 1, 0);
+  {  // parameters no gradient reaches must read as zero: clear the whole flat gradient range first
+    int64_t total = 0;
+    for (int i = 0; i < n_params; ++i)
+      total = std::max<int64_t>(total, params[i].offset + static_cast<int64_t>(params[i].rows) * params[i].cols);
+    if (total > 0) MIL_CUDA(cudaMemsetAsync(g_f32, 0, sizeof(float) * static_cast<size_t>(total), st));
+  }
 
   // where an op should write its gradient w.r.t. slot s: straight into the slot's buffer if nothing is there yet,
   // else into temporary `t` (folded in by settle())
@@ -347,8 +353,168 @@ int milb200_tape_backward(const milb200_tape_op* ops, int n_ops, const milb200_t
         return MILB200_EINVAL;
     }
   }
-  // parameters no gradient reached keep whatever the caller put in g_f32 (the caller zero-fills it)
   return MILB200_OK;
+}
+
+
+// ---- CUDA-graph replay --------------------------------------------------------------------------------------------
+// A tape call enqueues 100-350 kernels; at ~3 us of launch cost each the HOST is the bottleneck for one-bag-per-step
+// training (train_ddp.py:75).  The program is static, so a call whose shapes and pointers have been seen before is
+// replayed as one CUDA graph: key = hash(program, slot shapes, every pointer, sizes, dtype).  First sight runs
+// eagerly (a one-off bag must not pay for instantiation), second sight captures on a private stream (PyTorch's
+// current stream is usually the legacy default stream, which cannot be captured) and launches on the caller's
+// stream, later sights replay.  MILB200_TAPE_GRAPHS=0 switches it off.
+}  // extern "C" (reopened below)
+
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_set>
+
+namespace milb200 {
+namespace {
+
+struct GraphEntry {
+  uint64_t key;
+  cudaGraphExec_t exec;
+  int nodes;
+  uint64_t last_use;
+};
+std::mutex g_graph_mu;
+std::vector<GraphEntry> g_graph_cache;
+std::unordered_set<uint64_t> g_graph_seen;
+cudaStream_t g_capture_stream = nullptr;
+uint64_t g_graph_tick = 0;
+constexpr size_t GRAPH_CACHE_MAX = 32;
+
+bool graphs_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MILB200_TAPE_GRAPHS");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+struct Hasher {
+  uint64_t h = 1469598103934665603ull;
+  void bytes(const void* p, size_t n) {
+    const unsigned char* b = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+  }
+  template <typename T> void val(const T& v) { bytes(&v, sizeof(T)); }
+};
+
+// run `body(stream)` either eagerly, or as a captured / replayed graph keyed by `key`
+template <class Body>
+int run_keyed(uint64_t key, cudaStream_t user_stream, Body body) {
+  if (!graphs_enabled()) return body(user_stream);
+  std::unique_lock<std::mutex> lock(g_graph_mu);
+  ++g_graph_tick;
+  for (auto& e : g_graph_cache) {
+    if (e.key == key) {
+      e.last_use = g_graph_tick;
+      cudaGraphExec_t exec = e.exec;
+      const int nodes = e.nodes;
+      lock.unlock();
+      MIL_CUDA(cudaGraphLaunch(exec, user_stream));
+      count_launch(nodes);
+      return MILB200_OK;
+    }
+  }
+  if (!g_graph_seen.count(key)) {
+    if (g_graph_seen.size() > 8192) g_graph_seen.clear();
+    g_graph_seen.insert(key);
+    lock.unlock();
+    return body(user_stream);
+  }
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(user_stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    lock.unlock();
+    return body(user_stream);  // the caller is capturing already: just enqueue into its capture
+  }
+  if (!g_capture_stream) MIL_CUDA(cudaStreamCreateWithFlags(&g_capture_stream, cudaStreamNonBlocking));
+  const int64_t before = milb200_launch_count();
+  MIL_CUDA(cudaStreamBeginCapture(g_capture_stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = body(g_capture_stream);
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(g_capture_stream, &graph);
+  count_launch(-static_cast<int>(milb200_launch_count() - before));  // nothing ran yet
+  if (rc != MILB200_OK || ce != cudaSuccess || graph == nullptr) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    lock.unlock();
+    if (rc != MILB200_OK) return rc;
+    return body(user_stream);  // capture refused: run eagerly
+  }
+  size_t nodes = 0;
+  cudaGraphGetNodes(graph, nullptr, &nodes);
+  cudaGraphExec_t exec = nullptr;
+  ce = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess || exec == nullptr) {
+    cudaGetLastError();
+    lock.unlock();
+    return body(user_stream);
+  }
+  if (g_graph_cache.size() >= GRAPH_CACHE_MAX) {
+    size_t victim = 0;
+    for (size_t i = 1; i < g_graph_cache.size(); ++i)
+      if (g_graph_cache[i].last_use < g_graph_cache[victim].last_use) victim = i;
+    cudaGraphExecDestroy(g_graph_cache[victim].exec);  // freed once its last launch has drained
+    g_graph_cache.erase(g_graph_cache.begin() + victim);
+  }
+  g_graph_cache.push_back(GraphEntry{key, exec, static_cast<int>(nodes), g_graph_tick});
+  lock.unlock();
+  MIL_CUDA(cudaGraphLaunch(exec, user_stream));
+  count_launch(static_cast<int>(nodes));
+  return MILB200_OK;
+}
+
+}  // namespace
+}  // namespace milb200
+
+extern "C" {
+
+int milb200_tape_forward(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
+                         const milb200_tape_param* params, int n_params, void* const* ext_ptrs, const void* w_compute,
+                         const float* p_f32, void* arena, size_t arena_bytes, void* workspace, size_t ws_bytes, int dtype,
+                         void* stream) {
+  MIL_CHECK_ARG(ops && slots && n_ops > 0 && n_slots > 0 && ext_ptrs, MILB200_EINVAL, "tape_forward: null pointer");
+  Hasher h;
+  h.val(static_cast<int>(1));
+  h.bytes(ops, sizeof(milb200_tape_op) * n_ops);
+  h.bytes(slots, sizeof(milb200_tape_slot) * n_slots);
+  if (params && n_params > 0) h.bytes(params, sizeof(milb200_tape_param) * n_params);
+  h.bytes(ext_ptrs, sizeof(void*) * n_slots);
+  h.val(w_compute); h.val(p_f32); h.val(arena); h.val(arena_bytes); h.val(workspace); h.val(ws_bytes); h.val(dtype);
+  return run_keyed(h.h, static_cast<cudaStream_t>(stream), [&](cudaStream_t st) {
+    return tape_forward_run(ops, n_ops, slots, n_slots, params, n_params, ext_ptrs, w_compute, p_f32, arena, arena_bytes,
+                            workspace, ws_bytes, dtype, st);
+  });
+}
+
+int milb200_tape_backward(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
+                          const milb200_tape_param* params, int n_params, void* const* ext_ptrs, void* const* ext_grad_ptrs,
+                          const void* const* seed_ptrs, const void* w_compute, const float* p_f32, float* g_f32,
+                          const void* arena, size_t arena_bytes, void* workspace, size_t ws_bytes, int dtype, void* stream) {
+  MIL_CHECK_ARG(ops && slots && n_ops > 0 && n_slots > 0 && ext_ptrs && ext_grad_ptrs && seed_ptrs, MILB200_EINVAL,
+                "tape_backward: null pointer");
+  Hasher h;
+  h.val(static_cast<int>(2));
+  h.bytes(ops, sizeof(milb200_tape_op) * n_ops);
+  h.bytes(slots, sizeof(milb200_tape_slot) * n_slots);
+  if (params && n_params > 0) h.bytes(params, sizeof(milb200_tape_param) * n_params);
+  h.bytes(ext_ptrs, sizeof(void*) * n_slots);
+  h.bytes(ext_grad_ptrs, sizeof(void*) * n_slots);
+  h.bytes(seed_ptrs, sizeof(void*) * n_slots);
+  h.val(w_compute); h.val(p_f32); h.val(g_f32); h.val(arena); h.val(arena_bytes); h.val(workspace); h.val(ws_bytes);
+  h.val(dtype);
+  return run_keyed(h.h, static_cast<cudaStream_t>(stream), [&](cudaStream_t st) {
+    return tape_backward_run(ops, n_ops, slots, n_slots, params, n_params, ext_ptrs, ext_grad_ptrs, seed_ptrs, w_compute,
+                             p_f32, g_f32, arena, arena_bytes, workspace, ws_bytes, dtype, st);
+  });
 }
 
 }  // extern "C"

@@ -7,7 +7,7 @@ ARGS = Namespace(modality=["CT", "pathology"], model_CT="resnetMC3_18", model_pa
 dtype = torch.bfloat16
 m = mil_b200.get_model(ARGS).cuda().to(dtype).train(False)
 x_ct = torch.randn(1, 512, 160, 1, 1, device="cuda", dtype=dtype)
-x_p = torch.randn(1, 1000, 768, device="cuda", dtype=dtype)
+x_p = torch.randn(1, 15592, 768, device="cuda", dtype=dtype)
 x_t = (torch.randn(1, 1, 512, device="cuda") * 0.05).to(dtype)
 def step():
     m.zero_grad(set_to_none=True)
@@ -19,4 +19,4 @@ pr = cProfile.Profile(); pr.enable()
 for _ in range(30): step()
 torch.cuda.synchronize()
 pr.disable()
-s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(28); print(s.getvalue()[:6000])
+s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(45); print(s.getvalue()[:9000])
