@@ -361,14 +361,22 @@ def main():
         reps = 10
         for i in range(reps + 3):
             F.gated_scores_bwd(X, Wcat, bcat_c, v["ww"], v["bw"], ds, None, dM, offsets, False, grad_out=tr.grads,
-                               gate_act=act if save else None)
+                               gate_act=act if save else None)     # need_dx=False here; --input-grad changes the trainer only
             buf = (ctypes.c_float * 8)()
             k = Lb.lib().milb200_profile_read(buf, 8)
             if i >= 3:
                 for j in range(min(k, 4)):
                     acc[j] += buf[j] / reps
         Lb.lib().milb200_profile_enable(0)
-        if save:
+        fused = save
+        if fused:
+            # one kernel: dW = dZ^T X with dZ built on the fly from the saved V,U; interval 1 = column-sum fold + split-K reduce
+            kernels.append({"name": "gate_bwd dW fused (k_gemm_tn_gate: dZ from saved V,U on the fly)", "ms": acc[0],
+                            "bound": "tensor", "achieved": gemm_flops / acc[0] / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
+                            "algorithmic": "2*n*L*2D flop", "hbm_gbs": (n * Lf * 2 + n * 2 * D * 2 + n * 4) / acc[0] / 1e6})
+            kernels.append({"name": "split-K reduce + column-sum fold", "ms": acc[1], "bound": "hbm", "achieved": None,
+                            "peak": hbm_peak, "unit": "GB/s"})
+        elif save:
             dz_bytes = n * (2 * 2 * D * 2 + 4)
             kernels.append({"name": "gate_bwd dZ from saved V,U (k_gate_dz_saved)", "ms": acc[0], "bound": "hbm",
                             "achieved": dz_bytes / acc[0] / 1e6, "peak": hbm_peak, "unit": "GB/s",
@@ -377,11 +385,12 @@ def main():
             kernels.append({"name": "gate_bwd dZ recompute (k_gemm_kmajor<192x2,EpiDz>)", "ms": acc[0], "bound": "tensor",
                             "achieved": gemm_flops / acc[0] / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
                             "algorithmic": "2*n*L*2D flop", "hbm_gbs": (n * Lf * 2 + n * 2 * D * 2) / acc[0] / 1e6})
-        kernels.append({"name": "gate_bwd dW split-K (k_gemm_tn)", "ms": acc[1], "bound": "tensor",
-                        "achieved": gemm_flops / acc[1] / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
-                        "algorithmic": "2*n*L*2D flop", "hbm_gbs": (n * Lf * 2 + n * 2 * D * 2) / acc[1] / 1e6})
-        kernels.append({"name": "split-K reduce (k_splitk_reduce)", "ms": acc[2], "bound": "hbm", "achieved": None,
-                        "peak": hbm_peak, "unit": "GB/s"})
+        if not fused:
+            kernels.append({"name": "gate_bwd dW split-K (k_gemm_tn)", "ms": acc[1], "bound": "tensor",
+                            "achieved": gemm_flops / acc[1] / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
+                            "algorithmic": "2*n*L*2D flop", "hbm_gbs": (n * Lf * 2 + n * 2 * D * 2) / acc[1] / 1e6})
+            kernels.append({"name": "split-K reduce (k_splitk_reduce)", "ms": acc[2], "bound": "hbm", "achieved": None,
+                            "peak": hbm_peak, "unit": "GB/s"})
         # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full
         # capture of this same workload (tools/ncu_summary.py -> profiles/kernel_traffic.json); null if absent
         try:
@@ -392,7 +401,7 @@ def main():
                     "segment_softmax_pool_fwd": "k_pool_fwd<__nv_bfloat16, 4>",
                     "segment_softmax_pool_bwd": "k_pool_bwd<__nv_bfloat16, 4>",
                     "gate_bwd dZ from saved": "k_gate_dz_saved", "gate_bwd dZ recompute": "k_gemm_kmajor<192, tc::EpiDz>",
-                    "gate_bwd dW": "k_gemm_tn"}
+                    "gate_bwd dW fused": "k_gemm_tn_gate", "gate_bwd dW split-K": "k_gemm_tn"}
         for kinfo in kernels:
             kinfo["frac"] = (kinfo["achieved"] / kinfo["peak"]) if kinfo.get("achieved") else None
             kinfo["traffic"] = None

@@ -98,6 +98,10 @@ int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
                      uint32_t box_rows, uint32_t box_cols) {
   return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, rows, cols, ld, box_rows, box_cols);
 }
+int make_tmap_f32_2d_linear(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                            uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, rows, cols, ld, box_rows, box_cols, false);
+}
 }  // namespace tc
 
 // ---- split-K reduction ---------------------------------------------------------------------------
@@ -146,6 +150,30 @@ __global__ void k_splitk_reduce_gate(const float* __restrict__ part, int splits,
   }
   *reinterpret_cast<float4*>(out + i) = a;
 }
+// same for partials whose rows are in the saved activations' tile-64 order (unit d: V row 128 (d/64) + d%64, U 64 on)
+__global__ void k_splitk_reduce_gate64(const float* __restrict__ part, int splits, int D, int L, float* __restrict__ out) {
+  int64_t i = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  const int64_t n = static_cast<int64_t>(2) * D * L;
+  if (i >= n) return;
+  const int r = static_cast<int>(i / L), c = static_cast<int>(i % L);
+  const bool is_u = r >= D;
+  const int d = is_u ? r - D : r;
+  const int pr = 128 * (d / 64) + (is_u ? 64 : 0) + d % 64;
+  const float* src = part + static_cast<int64_t>(pr) * L + c;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int s = 0; s < splits; ++s) {
+    float4 p = *reinterpret_cast<const float4*>(src + static_cast<int64_t>(s) * n);
+    a.x += p.x; a.y += p.y; a.z += p.z; a.w += p.w;
+  }
+  *reinterpret_cast<float4*>(out + i) = a;
+}
+int splitk_reduce_gate64(const float* part, int splits, int D, int L, float* out, cudaStream_t st) {
+  int64_t threads = static_cast<int64_t>(2) * D * L / 4;
+  k_splitk_reduce_gate64<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(part, splits, D, L, out);
+  MIL_LAUNCH_CHECK();
+  return MILB200_OK;
+}
+
 int splitk_reduce_gate(const float* part, int splits, int D, int L, int dh, float* out, cudaStream_t st) {
   int64_t threads = static_cast<int64_t>(2) * D * L / 4;  // L % 8 == 0 on this path
   k_splitk_reduce_gate<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(part, splits, D, L, dh, out);

@@ -16,6 +16,7 @@ int smallm_fwd(const void* X, const void* add, const void* W, const float* bias,
 int smallm_bwd(const void* X, const void* add, const void* W, const void* Y, const void* dY, void* dX, float* dW,
                float* dbias, int64_t m, int n, int k, int act, int dtype, int accumulate, cudaStream_t st);
 int splitk_reduce_gate(const float* part, int splits, int D, int L, int dh, float* out, cudaStream_t st);
+int splitk_reduce_gate64(const float* part, int splits, int D, int L, float* out, cudaStream_t st);
 int transpose2d(const void* in, void* out, int rows, int cols, int dtype, cudaStream_t st);
 
 constexpr int64_t SIMT_ROW_CHUNK = 32768;
@@ -105,8 +106,9 @@ __global__ void k_colsum_finalize(const float* __restrict__ ws, int nrec, int st
 }
 
 // ---- dZ from SAVED gate activations (tensor-core path, forward ran with gate_act != NULL) -------------------
-// VU [n, 384] bf16 in the packed column order [V 0..95 | U 0..95 | V 96..191 | U 96..191] (see tc_gemm.cu).
-// dZ (same layout) = [ds w U (1 - V^2) | ds w V U (1 - U)].  Elementwise and HBM-bound: 768 B read + 768 B written
+// VU [n, 384] bf16 in the forward's tile-64 column order (unit d: V at 128 (d/64) + d%64, U 64 further; tc_gemm.cu).
+// dZ [n, 384] bf16 in the weight rows' packed order [V 0..95 | U 0..95 | V 96..191 | U 96..191] (what the dX GEMM and the
+// split-K dW GEMM of the recompute path consume) = [ds w U (1 - V^2) | ds w V U (1 - U)].  Elementwise and HBM-bound: 768 B read + 768 B written
 // per instance, instead of re-running the X . Wcat^T GEMM.  Block = 16 row groups x 24 (V vector, U vector) pairs;
 // column sums (-> dbcat, dww, dbw) are kept in registers, folded in fixed order and written one record per block.
 constexpr int DZS_THREADS = 192;
@@ -120,10 +122,11 @@ k_gate_dz_saved(const __nv_bfloat16* __restrict__ VU, const float* __restrict__ 
   __shared__ float red[DZS_RG][DZS_PAIRS][25];
   __shared__ float red_ds[DZS_RG];
   const int t = threadIdx.x, p = t % DZS_PAIRS, rg = t / DZS_PAIRS;
-  const int h = p / 12, j = p % 12;
-  const int colV = h * (2 * DH) + j * 8;  // element offset of this thread's V vector inside a packed row
+  const int d0 = p * 8;                                   // natural gate index of the first of this thread's 8 units
+  const int srcV = 128 * (d0 / 64) + d0 % 64;             // where the forward saved them (tile-64 order)
+  const int srcU = srcV + 64;
+  const int colV = (d0 / DH) * (2 * DH) + d0 % DH;        // where dZ wants them (weight-row packed order)
   const int colU = colV + DH;
-  const int d0 = h * DH + j * 8;          // natural gate index of the first of the 8 columns
   float w[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) w[e] = __ldg(ww + d0 + e);
@@ -154,8 +157,8 @@ k_gate_dz_saved(const __nv_bfloat16* __restrict__ VU, const float* __restrict__ 
     float dsv[DZS_UNR];
 #pragma unroll
     for (int u = 0; u < DZS_UNR; ++u) {
-      qv[u] = ldg_stream(VU + (r + u * DZS_RG) * (2 * D) + colV);
-      qu[u] = ldg_stream(VU + (r + u * DZS_RG) * (2 * D) + colU);
+      qv[u] = ldg_stream(VU + (r + u * DZS_RG) * (2 * D) + srcV);
+      qu[u] = ldg_stream(VU + (r + u * DZS_RG) * (2 * D) + srcU);
       dsv[u] = __ldg(dscores + r + u * DZS_RG);
     }
 #pragma unroll
@@ -165,7 +168,7 @@ k_gate_dz_saved(const __nv_bfloat16* __restrict__ VU, const float* __restrict__ 
     }
   }
   for (; r < r1; r += DZS_RG) {
-    const uint4 qv0 = ldg_stream(VU + r * (2 * D) + colV), qu0 = ldg_stream(VU + r * (2 * D) + colU);
+    const uint4 qv0 = ldg_stream(VU + r * (2 * D) + srcV), qu0 = ldg_stream(VU + r * (2 * D) + srcU);
     const float ds0 = __ldg(dscores + r);
     if (p == 0) sds += ds0;
     body(qv0, qu0, ds0, r);
@@ -177,7 +180,7 @@ k_gate_dz_saved(const __nv_bfloat16* __restrict__ VU, const float* __restrict__ 
   float* rec = rec_ws + static_cast<int64_t>(blockIdx.x) * stride;
   for (int i = t; i < 3 * D; i += DZS_THREADS) {  // record: dVpre[192] | dUpre[192] | ds*V*U[192] | sum ds (natural order)
     const int k = i / D, d = i % D;
-    const int pp = (d / DH) * 12 + (d % DH) / 8, e = d % 8;
+    const int pp = d / 8, e = d % 8;
     float a = 0.f;
 #pragma unroll
     for (int g = 0; g < DZS_RG; ++g) a += red[g][pp][k * 8 + e];
@@ -190,6 +193,20 @@ k_gate_dz_saved(const __nv_bfloat16* __restrict__ VU, const float* __restrict__ 
   }
 }
 // fold the per-block records in block order
+// records of the fused dW kernel: [split][m-tile t][dVpre 64 | dUpre 64 | ds*V*U 64 | sum ds], unit d = 64 t + j
+__global__ void k_colsum_finalize_tn(const float* __restrict__ ws, int splits, int rec, float* __restrict__ dbcat,
+                                     float* __restrict__ dww, float* __restrict__ dbw, int D) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > 3 * D) return;
+  const int k = c < 3 * D ? c / D : 0, d = c < 3 * D ? c % D : 0;
+  const int off = c < 3 * D ? (d / 64) * rec + k * 64 + d % 64 : 192;
+  float a = 0.f;
+  for (int s = 0; s < splits; ++s) a += ws[static_cast<int64_t>(s) * (D / 64) * rec + off];
+  if (c < 2 * D) dbcat[c] = a;
+  else if (c < 3 * D) dww[c - 2 * D] = a;
+  else dbw[0] = a;
+}
+
 // block = 32 columns x 8 record-lanes; the 8 lanes' sums are folded in fixed order
 __global__ void __launch_bounds__(256)
 k_colsum_finalize_flat(const float* __restrict__ ws, int nrec, int stride, float* __restrict__ dbcat,
@@ -512,6 +529,20 @@ int milb200_gated_score_bwd(const void* X, const void* Wcat, const float* bcat, 
     g_prof_n = 0;
     prof_mark(st);
     int rc;
+    if (gate_act && !dX) {
+      // saved V,U and no input gradient wanted: dZ is never materialised — the dW GEMM builds its A operand from V,U
+      MIL_CHECK_ARG(aligned16(gate_act), MILB200_EALIGN, "gated_score_bwd: gate_act must be 16-byte aligned");
+      rc = tc::gemm_tn_gate(gate_act, dscores, ww, X, L, total_n, L, part, &splits, colsum, st);
+      if (rc) return rc;
+      prof_mark(st);
+      k_colsum_finalize_tn<<<(3 * D + 1 + 255) / 256, 256, 0, st>>>(colsum, splits, tc::gemm_tn_gate_record_floats(), dbcat,
+                                                                    dww, dbw, D);
+      MIL_LAUNCH_CHECK();
+      rc = splitk_reduce_gate64(part, splits, D, L, dWcat, st);
+      if (rc) return rc;
+      prof_mark(st);
+      return MILB200_OK;
+    }
     if (gate_act) {
       // saved V,U: dZ is an elementwise pass (1.5 KB of traffic per instance instead of the recompute GEMM)
       MIL_CHECK_ARG(aligned16(gate_act), MILB200_EALIGN, "gated_score_bwd: gate_act must be 16-byte aligned");

@@ -24,6 +24,9 @@ int make_tmap_bf16_2d_linear(CUtensorMap* out, const void* base, uint64_t rows, 
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                      uint32_t box_rows, uint32_t box_cols = 32);
 
+int make_tmap_f32_2d_linear(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                            uint32_t box_rows, uint32_t box_cols);
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
 // device: small PTX wrappers

@@ -176,9 +176,10 @@ struct EpiStore {
 // the next.  Warp (q, half) owns pairs [48 half, 48 half + 48) of rows [32q, 32q+32).
 constexpr int GATE_PW = GATE_DH / 2;  // pairs per warp per tile = 48
 
-// SAVE: additionally write the gate activations V = tanh(.), U = sigmoid(.) as bf16 [M, 384] in the packed column
-// order of the weight rows ([V 0..95 | U 0..95 | V 96..191 | U 96..191]) so that the backward can form dZ with an
-// elementwise pass instead of re-running this GEMM (one box pair per warp per half tile, TMA store).
+// SAVE: additionally write the gate activations V = tanh(.), U = sigmoid(.) as bf16 [M, 384] so that the backward can
+// form dZ without re-running this GEMM.  Column order of the saved matrix ("tile-64 order"): gate unit d lives at
+// V -> 128 (d / 64) + d % 64, U -> 128 (d / 64) + 64 + d % 64, i.e. every 128-column tile of the dW GEMM's A operand
+// holds 64 matching (V, U) pairs.  Six [32 rows x 16 cols] TMA-store boxes per warp per half tile.
 template <bool SAVE>
 struct EpiScoreT {
   struct Params {
@@ -208,8 +209,9 @@ struct EpiScoreT {
     uint8_t* rowU = nullptr;
     uint8_t* boxV = nullptr;
     if (SAVE) {
+      // per warp: V sub-boxes 0..2 | U sub-boxes 0..2, each a dense [32 rows][16 bf16] image (1 KB)
       boxV = staging + (cx.half * 4 + cx.q) * 2 * BOX_BYTES;
-      rowV = boxV + cx.lane * (GATE_PW * 2);
+      rowV = boxV + cx.lane * 32;
       rowU = rowV + BOX_BYTES;
       if (cx.lane == 0) tma_store_wait_read<0>();  // the previous half tile's boxes have been read out
       __syncwarp();
@@ -237,10 +239,12 @@ struct EpiScoreT {
         part = fmaf(fv[j + 3] * fu[j + 3], w.w, part);
       }
       if (SAVE) {
-        *reinterpret_cast<uint4*>(rowV + c * 2) = Vec16<__nv_bfloat16>::pack(fv);
-        *reinterpret_cast<uint4*>(rowV + c * 2 + 16) = Vec16<__nv_bfloat16>::pack(fv + 8);
-        *reinterpret_cast<uint4*>(rowU + c * 2) = Vec16<__nv_bfloat16>::pack(fu);
-        *reinterpret_cast<uint4*>(rowU + c * 2 + 16) = Vec16<__nv_bfloat16>::pack(fu + 8);
+        uint8_t* sv = rowV + (c / 16) * 1024;
+        uint8_t* su = rowU + (c / 16) * 1024;
+        *reinterpret_cast<uint4*>(sv) = Vec16<__nv_bfloat16>::pack(fv);
+        *reinterpret_cast<uint4*>(sv + 16) = Vec16<__nv_bfloat16>::pack(fv + 8);
+        *reinterpret_cast<uint4*>(su) = Vec16<__nv_bfloat16>::pack(fu);
+        *reinterpret_cast<uint4*>(su + 16) = Vec16<__nv_bfloat16>::pack(fu + 8);
       }
     }
     if (SAVE) {
@@ -248,8 +252,13 @@ struct EpiScoreT {
       __syncwarp();
       if (cx.lane == 0) {
         const int32_t r0 = static_cast<int32_t>(cx.row);  // lane 0 holds the first row of this warp's quarter
-        tma_store_2d(&p.tmS, boxV, h * GATE_BN + cx.half * GATE_PW, r0);
-        tma_store_2d(&p.tmS, boxV + BOX_BYTES, h * GATE_BN + GATE_DH + cx.half * GATE_PW, r0);
+#pragma unroll
+        for (int sb = 0; sb < GATE_PW / 16; ++sb) {
+          const int d0 = h * GATE_DH + cx.half * GATE_PW + 16 * sb;  // first gate unit of the sub-box (multiple of 16)
+          const int colv = 128 * (d0 / 64) + d0 % 64;
+          tma_store_2d(&p.tmS, boxV + sb * 1024, colv, r0);
+          tma_store_2d(&p.tmS, boxV + BOX_BYTES + sb * 1024, colv + 64, r0);
+        }
         tma_store_commit();
       }
     }
@@ -607,7 +616,7 @@ int gated_score(const void* X, int64_t n, int L, const void* Wcat, const float* 
   if (gate_act) {
     EpiScoreT<true>::Params ep;
     ep.bcat = bcat; ep.ww = ww; ep.bw = bw; ep.scores = scores;
-    int rc0 = make_tmap_bf16_2d_linear(&ep.tmS, gate_act, static_cast<uint64_t>(n), 2 * GATE_D, 2 * GATE_D, 32, GATE_PW);
+    int rc0 = make_tmap_bf16_2d_linear(&ep.tmS, gate_act, static_cast<uint64_t>(n), 2 * GATE_D, 2 * GATE_D, 32, 16);
     if (rc0) return rc0;
     return launch_kmajor<GATE_BN, EpiScoreT<true>>(X, n, L, L, Wcat, 2 * GATE_D, L, ep, nullptr, st);
   }
@@ -769,6 +778,263 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused gate backward: dWcat = dZ^T X with the A operand dZ = ds * [w U (1 - V^2) | w V U (1 - U)] built ON THE FLY from
+// the V,U the forward saved (tile-64 column order, see EpiScoreT) — dZ never touches HBM (saves 1.5 KB of traffic per
+// instance and a kernel).  Same split-K skeleton as k_gemm_tn.  Per stage the TMA producer lands the RAW operands: the
+// [32 x 64] V box and U box of the m-tile exactly where the A tile lives (same 128-byte-swizzled MN-major image),
+// 32 ds values, and the X boxes.  The 8 epilogue warps then turn V,U into dV,dU IN PLACE (thread (r, pc) owns k-row r
+// and the 16-byte chunk pc of both boxes), fence the async proxy and release the stage to the MMA warp.  (Fetching
+// V,U with ordinary loads instead serialises: the proxy fence drains the thread's outstanding global loads.)
+// Column sums (-> dbcat, dww, dbw) ride along in registers; CTAs of n-tile 0 publish them per (split, m-tile).
+// ---------------------------------------------------------------------------------------------
+constexpr int TNG_MT = 2 * GATE_D / BM;   // 3 m-tiles of 128 columns = 64 (V, U) pairs each
+constexpr int TNG_REC = 200;              // record: dVpre[64] | dUpre[64] | ds*V*U[64] | sum ds | pad
+constexpr int TNG_RED_BYTES = static_cast<int>(sizeof(float)) * EPI_WARPS * 8 * 25;   // 6400: keeps ds_s 128-byte aligned
+constexpr size_t TNG_SMEM = TN_SMEM + TNG_RED_BYTES + TN_STAGES * TN_BK * sizeof(float);
+static_assert(TNG_SMEM <= 232448 && TNG_RED_BYTES % 128 == 0, "fused dW kernel smem budget");
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+k_gemm_tn_gate(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmD, const float* __restrict__ ww, int64_t Kr, int No, int n_tiles,
+               int kb_per_split, float* __restrict__ part, float* __restrict__ rec_ws) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TN_STAGES * TN_STAGE_BYTES);
+  uint64_t* full_bar = bars;                       // A tile transformed: MMA may read the stage
+  uint64_t* empty_bar = bars + TN_STAGES;          // MMA done with the stage
+  uint64_t* tfull_bar = bars + 2 * TN_STAGES;
+  uint64_t* raw_bar = bars + 2 * TN_STAGES + 1;    // raw V,U / ds / X boxes have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TN_STAGES + 1);
+  static_assert((3 * TN_STAGES + 1) * 8 + 8 <= BAR_BYTES, "barrier block overflow");
+  float* red = reinterpret_cast<float*>(smem + TN_STAGES * TN_STAGE_BYTES + BAR_BYTES);  // [8 warps][8 pc][25]
+  float* ds_s = reinterpret_cast<float*>(smem + TN_STAGES * TN_STAGE_BYTES + BAR_BYTES + TNG_RED_BYTES);  // [stages][32]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int Mo = 2 * GATE_D;
+  const int tile = blockIdx.x % (TNG_MT * n_tiles);
+  const int split = blockIdx.x / (TNG_MT * n_tiles);
+  const int mt = tile / n_tiles, nt = tile % n_tiles;
+  const int64_t total_kb = (Kr + TN_BK - 1) / TN_BK;
+  const int64_t kb0 = static_cast<int64_t>(split) * kb_per_split;
+  int64_t kb1 = kb0 + kb_per_split;
+  if (kb1 > total_kb) kb1 = total_kb;
+  const int nkb = kb1 > kb0 ? static_cast<int>(kb1 - kb0) : 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    prefetch_tmap(&tmD);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < TN_STAGES; ++s) {
+      mbar_init(full_bar + s, EPI_WARPS / 2);   // one arrival per warp of the group that transforms the stage
+      mbar_init(empty_bar + s, 1);
+      mbar_init(raw_bar + s, 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(empty_bar + s, ph ^ 1);
+        uint8_t* sa = smem + s * TN_STAGE_BYTES;
+        uint8_t* sb = sa + TN_A_BYTES;
+        const int32_t krow = static_cast<int32_t>((kb0 + i) * TN_BK);
+        mbar_arrive_expect_tx(raw_bar + s, TN_STAGE_BYTES + TN_BK * static_cast<uint32_t>(sizeof(float)));
+        tma_load_2d(sa, &tmA, raw_bar + s, Mo / TNG_MT * mt, krow, kEvictFirst);                       // V box
+        tma_load_2d(sa + TN_BOX_BYTES, &tmA, raw_bar + s, Mo / TNG_MT * mt + 64, krow, kEvictFirst);   // U box
+        tma_load_2d(ds_s + s * TN_BK, &tmD, raw_bar + s, krow, 0, kEvictNormal);
+#pragma unroll
+        for (int j = 0; j < TN_BNO / 64; ++j)
+          tma_load_2d(sb + j * TN_BOX_BYTES, &tmB, raw_bar + s, nt * TN_BNO + j * 64, krow, kEvictNormal);
+        if (++s == TN_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (nkb > 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, 256, 1, 1);
+      const uint64_t desc0 = umma_desc_sw128(smem_u32(smem), TN_BOX_BYTES, 1024);
+      const uint32_t d_hi = static_cast<uint32_t>(desc0 >> 32);
+      const uint32_t a_lo0 = static_cast<uint32_t>(desc0);
+      const uint32_t b_lo0 = a_lo0 + (TN_A_BYTES >> 4);
+      int s = 0;
+      uint32_t ph = 0;
+      for (int i = 0; i < nkb; ++i) {
+        mbar_wait(full_bar + s, ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t so = static_cast<uint32_t>(s) * (TN_STAGE_BYTES >> 4);
+#pragma unroll
+          for (int k = 0; k < TN_BK / UMMA_K; ++k) {
+#pragma unroll
+            for (int h = 0; h < TN_BNO / 256; ++h)
+              umma_bf16_lohi(tmem_base + h * 256, a_lo0 + so + k * (2048 >> 4), d_hi,
+                             b_lo0 + so + ((h * 4 * TN_BOX_BYTES) >> 4) + k * (2048 >> 4), d_hi, idesc,
+                             (i | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(empty_bar + s);
+          if (i == nkb - 1) tc_commit(tfull_bar);
+        }
+        __syncwarp();
+        if (++s == TN_STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===== in-place V,U -> dV,dU transform (main loop), then the accumulator epilogue =====
+    // Two groups of four warps alternate stages, so two stages are in transformation at any time and the latency of
+    // the proxy fence overlaps with the other group's work.  Thread (r, pc) of a group owns k-rows r and r + 16.
+    const int tid = threadIdx.x - EPI_WARP0 * 32;
+    const int grp = tid >> 7, tg = tid & 127;
+    const int r = tg >> 3, pc = tg & 7;
+    const int d0 = 64 * mt + 8 * pc;                                    // first of this thread's 8 gate units
+    const uint32_t a_off0 = static_cast<uint32_t>((r >> 3) * 1024 + (r & 7) * 128 + ((pc ^ (r & 7)) << 4));
+    const uint32_t a_off1 = a_off0 + 2 * 1024;                          // k-row r + 16: same swizzle phase, two atoms on
+    float w[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[e] = __ldg(ww + d0 + e);
+    float sdv[8], sdu[8], svu[8], sds = 0.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sdv[e] = sdu[e] = svu[e] = 0.f;
+    for (int i = grp; i < nkb; i += 2) {
+      const int s = i % TN_STAGES;
+      const uint32_t ph = static_cast<uint32_t>((i / TN_STAGES) & 1);
+      mbar_wait(raw_bar + s, ph);
+      uint8_t* sa = smem + s * TN_STAGE_BYTES;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const uint32_t a_off = hh ? a_off1 : a_off0;
+        uint4* pv = reinterpret_cast<uint4*>(sa + a_off);
+        uint4* pu = reinterpret_cast<uint4*>(sa + TN_BOX_BYTES + a_off);
+        const float dsi = ds_s[s * TN_BK + r + 16 * hh];
+        float V[8], U[8], dv[8], du[8];
+        Vec16<__nv_bfloat16>::unpack(*pv, V);
+        Vec16<__nv_bfloat16>::unpack(*pu, U);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float gu = dsi * w[e] * U[e];
+          dv[e] = gu * (1.f - V[e] * V[e]);
+          du[e] = gu * V[e] * (1.f - U[e]);
+          sdv[e] += dv[e];
+          sdu[e] += du[e];
+          svu[e] = fmaf(dsi * V[e], U[e], svu[e]);
+        }
+        if (pc == 0) sds += dsi;
+        *pv = Vec16<__nv_bfloat16>::pack(dv);
+        *pu = Vec16<__nv_bfloat16>::pack(du);
+      }
+      fence_proxy_async();                          // my generic-proxy writes -> visible to the MMA's async proxy
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar + s);
+    }
+    // column sums: fold the 4 k-rows a warp holds per pc with shuffles, then the 8 warps through shared memory
+    if (nt == 0) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        sdv[e] += __shfl_xor_sync(0xffffffffu, sdv[e], 8);  sdv[e] += __shfl_xor_sync(0xffffffffu, sdv[e], 16);
+        sdu[e] += __shfl_xor_sync(0xffffffffu, sdu[e], 8);  sdu[e] += __shfl_xor_sync(0xffffffffu, sdu[e], 16);
+        svu[e] += __shfl_xor_sync(0xffffffffu, svu[e], 8);  svu[e] += __shfl_xor_sync(0xffffffffu, svu[e], 16);
+      }
+      sds += __shfl_xor_sync(0xffffffffu, sds, 8);
+      sds += __shfl_xor_sync(0xffffffffu, sds, 16);
+      const int ew = warp - EPI_WARP0;
+      if (lane < 8) {
+        float* dst = red + (ew * 8 + lane) * 25;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { dst[e] = sdv[e]; dst[8 + e] = sdu[e]; dst[16 + e] = svu[e]; }
+        dst[24] = sds;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      float* rec = rec_ws + (static_cast<int64_t>(split) * TNG_MT + mt) * TNG_REC;
+      if (tid < 192) {
+        const int k = tid / 64, j = tid % 64;
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < EPI_WARPS; ++q) a += red[(q * 8 + j / 8) * 25 + k * 8 + j % 8];
+        rec[tid] = a;
+      } else if (tid == 192) {
+        float a = 0.f;
+#pragma unroll
+        for (int q = 0; q < EPI_WARPS; ++q) a += red[(q * 8) * 25 + 24];
+        rec[192] = a;
+      }
+    }
+    const int q = (warp - EPI_WARP0) & 3, half = (warp - EPI_WARP0) >> 2;
+    const int m = mt * BM + q * 32 + lane;
+    float* prow = part + (static_cast<int64_t>(split) * Mo + m) * No + nt * TN_BNO;
+    if (nkb > 0) {
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+    for (int c = half * (TN_BNO / 2); c < (half + 1) * (TN_BNO / 2); c += 32) {
+      if (nt * TN_BNO + c >= No) break;
+      uint32_t rr[32];
+      if (nkb > 0) {
+        tmem_ld32(tacc + c, rr);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) rr[j] = 0u;
+      }
+      const int nvalid = (No - (nt * TN_BNO + c)) < 32 ? (No - (nt * TN_BNO + c)) : 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        if (j < nvalid)
+          *reinterpret_cast<float4*>(prow + c + j) =
+              make_float4(__uint_as_float(rr[j]), __uint_as_float(rr[j + 1]), __uint_as_float(rr[j + 2]),
+                          __uint_as_float(rr[j + 3]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int gemm_tn_gate_max_records() { return sm_count(); }  // splits * 3 m-tiles <= resident CTAs
+int gemm_tn_gate_record_floats() { return TNG_REC; }
+
+// part[s][384 (tile-64 order)][No] partial dWcat; rec_ws[splits * 3][TNG_REC] column-sum records
+int gemm_tn_gate(const void* VU, const float* ds, const float* ww, const void* X, int64_t ldx, int64_t Kr, int No,
+                 float* part, int* splits_out, float* rec_ws, cudaStream_t st) {
+  constexpr int Mo = 2 * GATE_D;
+  MIL_CHECK_ARG(gemm_tn_supported(Mo, No), MILB200_EUNSUPPORTED, "tc gemm_tn_gate: unsupported No=%d", No);
+  CUtensorMap tmA, tmB, tmD;
+  int rc = make_tmap_bf16_2d(&tmA, VU, static_cast<uint64_t>(Kr), Mo, Mo, TN_BK);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, X, static_cast<uint64_t>(Kr), static_cast<uint64_t>(No), static_cast<uint64_t>(ldx), TN_BK);
+  if (rc) return rc;
+  // ds as one row of Kr floats: [1 x 32] boxes, zero-filled past the end (the row pitch is never used)
+  rc = make_tmap_f32_2d_linear(&tmD, ds, 1, static_cast<uint64_t>(Kr), static_cast<uint64_t>((Kr + 3) / 4 * 4), 1, TN_BK);
+  if (rc) return rc;
+  const int n_tiles = (No + TN_BNO - 1) / TN_BNO;
+  const int64_t total_kb = (Kr + TN_BK - 1) / TN_BK;
+  int splits = gemm_tn_max_splits(Mo, No);
+  if (splits > total_kb) splits = static_cast<int>(total_kb);
+  if (splits < 1) splits = 1;
+  const int kb_per_split = static_cast<int>((total_kb + splits - 1) / splits);
+  splits = static_cast<int>((total_kb + kb_per_split - 1) / kb_per_split);
+  if (splits_out) *splits_out = splits;
+  MIL_CUDA(cudaFuncSetAttribute(k_gemm_tn_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TNG_SMEM)));
+  k_gemm_tn_gate<<<TNG_MT * n_tiles * splits, NUM_THREADS, TNG_SMEM, st>>>(tmA, tmB, tmD, ww, Kr, No, n_tiles, kb_per_split,
+                                                                           part, rec_ws);
+  MIL_LAUNCH_CHECK();
+  return MILB200_OK;
 }
 
 bool gemm_tn_supported(int Mo, int No) { return Mo >= 64 && Mo % 8 == 0 && No >= 64 && No % 8 == 0; }

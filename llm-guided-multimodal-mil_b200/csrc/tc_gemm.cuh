@@ -32,6 +32,12 @@ int gated_dz_max_records();
 int gemm_tn_splitk(const void* A, int64_t lda, const void* B, int64_t ldb, int64_t Kr, int Mo, int No, float* part,
                    int* splits, cudaStream_t st);
 int gemm_tn_max_splits(int Mo, int No);
+// Gate backward without materialising dZ: dWcat partials from the saved V,U (tile-64 column order), ds and ww; see
+// k_gemm_tn_gate.  part rows are in tile-64 order; rec_ws receives splits*3 column-sum records of record_floats().
+int gemm_tn_gate(const void* VU, const float* ds, const float* ww, const void* X, int64_t ldx, int64_t Kr, int No,
+                 float* part, int* splits, float* rec_ws, cudaStream_t st);
+int gemm_tn_gate_max_records();
+int gemm_tn_gate_record_floats();
 int debug_set_trace(void* dev_ptr);
 bool gemm_tn_supported(int Mo, int No);
 

@@ -107,6 +107,12 @@ def stage_gate(dtype, with_dx=True, Ls=(1024, 512, 768), n_list=(1, 300, 5000)):
             dX, dWcat, dbcat, dww, dbw = F.gated_scores_bwd(X, Wcat, bcat, ww.reshape(-1).contiguous(), bw, ds, attn,
                                                             dM, off, with_dx)
             torch.cuda.synchronize()
+            dG = ds.double()[:, None] * ww.double().reshape(1, -1)
+            dVp = dG * U * (1 - V * V)
+            dUp = dG * V * U * (1 - U)
+            dWr = torch.cat([dVp.t() @ X.double(), dUp.t() @ X.double()])
+            dbr = torch.cat([dVp.sum(0), dUp.sum(0)])
+            dwwr = ds.double() @ (V * U)
             if act is not None:   # saved-activation backward vs the recompute backward
                 dX2, dW2, db2, dww2, dbw2 = (t.clone() if t is not None else None for t in
                                               F.gated_scores_bwd(X, Wcat, bcat, ww.reshape(-1).contiguous(), bw, ds, attn,
@@ -114,6 +120,14 @@ def stage_gate(dtype, with_dx=True, Ls=(1024, 512, 768), n_list=(1, 300, 5000)):
                 torch.cuda.synchronize()
                 print(f"   saved-vs-recompute: dW {rel(dW2, dWcat):.2e} db {rel(db2, dbcat):.2e} dww {rel(dww2, dww):.2e} "
                       f"dbw {abs(float(dbw2) - float(dbw)):.1e} dX {rel(dX2, dX) if with_dx else -1:.2e}", flush=True)
+                # no input gradient wanted: the fused dW GEMM builds dZ on the fly (k_gemm_tn_gate)
+                _, dW3, db3, dww3, dbw3 = (t.clone() if t is not None else None for t in
+                                           F.gated_scores_bwd(X, Wcat, bcat, ww.reshape(-1).contiguous(), bw, ds, None, dM,
+                                                              off, False, gate_act=act))
+                torch.cuda.synchronize()
+                print(f"   fused-dW-vs-recompute: dW {rel(dW3, dWcat):.2e} db {rel(db3, dbcat):.2e} dww {rel(dww3, dww):.2e} "
+                      f"dbw {abs(float(dbw3) - float(dbw)):.1e}   vs oracle: dW {rel(dW3, dWr):.2e} db {rel(db3, dbr):.2e} "
+                      f"dww {rel(dww3, dwwr):.2e}", flush=True)
                 dX, dWcat, dbcat, dww, dbw = dX2, dW2, db2, dww2, dbw2
             dG = ds.double()[:, None] * ww.double().reshape(1, -1)
             dVp = dG * U * (1 - V * V)
