@@ -792,8 +792,12 @@ k_gemm_tn(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 // ---------------------------------------------------------------------------------------------
 constexpr int TNG_MT = 2 * GATE_D / BM;   // 3 m-tiles of 128 columns = 64 (V, U) pairs each
 constexpr int TNG_REC = 200;              // record: dVpre[64] | dUpre[64] | ds*V*U[64] | sum ds | pad
+constexpr int TNG_ASTAGES = 8;            // A ring (8 KB per stage): raw V,U land and are transformed well ahead of the MMA
+constexpr int TNG_BSTAGES = 4;            // B ring (32 KB per stage)
+constexpr int TNG_BAR_BYTES = 512;
 constexpr int TNG_RED_BYTES = static_cast<int>(sizeof(float)) * EPI_WARPS * 8 * 25;   // 6400: keeps ds_s 128-byte aligned
-constexpr size_t TNG_SMEM = TN_SMEM + TNG_RED_BYTES + TN_STAGES * TN_BK * sizeof(float);
+constexpr size_t TNG_SMEM = 1024 + static_cast<size_t>(TNG_ASTAGES) * TN_A_BYTES + static_cast<size_t>(TNG_BSTAGES) * TN_B_BYTES +
+                            TNG_BAR_BYTES + TNG_RED_BYTES + TNG_ASTAGES * TN_BK * sizeof(float);
 static_assert(TNG_SMEM <= 232448 && TNG_RED_BYTES % 128 == 0, "fused dW kernel smem budget");
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -802,15 +806,19 @@ k_gemm_tn_gate(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                int kb_per_split, float* __restrict__ part, float* __restrict__ rec_ws) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TN_STAGES * TN_STAGE_BYTES);
-  uint64_t* full_bar = bars;                       // A tile transformed: MMA may read the stage
-  uint64_t* empty_bar = bars + TN_STAGES;          // MMA done with the stage
-  uint64_t* tfull_bar = bars + 2 * TN_STAGES;
-  uint64_t* raw_bar = bars + 2 * TN_STAGES + 1;    // raw V,U / ds / X boxes have landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * TN_STAGES + 1);
-  static_assert((3 * TN_STAGES + 1) * 8 + 8 <= BAR_BYTES, "barrier block overflow");
-  float* red = reinterpret_cast<float*>(smem + TN_STAGES * TN_STAGE_BYTES + BAR_BYTES);  // [8 warps][8 pc][25]
-  float* ds_s = reinterpret_cast<float*>(smem + TN_STAGES * TN_STAGE_BYTES + BAR_BYTES + TNG_RED_BYTES);  // [stages][32]
+  uint8_t* a_ring = smem;                                          // [TNG_ASTAGES][V box | U box]
+  uint8_t* b_ring = smem + TNG_ASTAGES * TN_A_BYTES;               // [TNG_BSTAGES][8 X boxes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_ring + TNG_BSTAGES * TN_B_BYTES);
+  uint64_t* araw_bar = bars;                                       // raw V,U + ds landed
+  uint64_t* afull_bar = bars + TNG_ASTAGES;                        // transformed: the MMA may read the A stage
+  uint64_t* aempty_bar = bars + 2 * TNG_ASTAGES;                   // MMA done with the A stage
+  uint64_t* bfull_bar = bars + 3 * TNG_ASTAGES;
+  uint64_t* bempty_bar = bars + 3 * TNG_ASTAGES + TNG_BSTAGES;
+  uint64_t* tfull_bar = bars + 3 * TNG_ASTAGES + 2 * TNG_BSTAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+  static_assert((3 * TNG_ASTAGES + 2 * TNG_BSTAGES + 1) * 8 + 8 <= TNG_BAR_BYTES, "barrier block overflow");
+  float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + TNG_BAR_BYTES);  // [8 warps][8 pc][25]
+  float* ds_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(red) + TNG_RED_BYTES);   // [TNG_ASTAGES][32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int Mo = 2 * GATE_D;
@@ -829,10 +837,14 @@ k_gemm_tn_gate(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tmap(&tmD);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < TN_STAGES; ++s) {
-      mbar_init(full_bar + s, EPI_WARPS / 2);   // one arrival per warp of the group that transforms the stage
-      mbar_init(empty_bar + s, 1);
-      mbar_init(raw_bar + s, 1);
+    for (int s = 0; s < TNG_ASTAGES; ++s) {
+      mbar_init(araw_bar + s, 1);
+      mbar_init(afull_bar + s, EPI_WARPS / 2);   // one arrival per warp of the group that transforms the stage
+      mbar_init(aempty_bar + s, 1);
+    }
+    for (int s = 0; s < TNG_BSTAGES; ++s) {
+      mbar_init(bfull_bar + s, 1);
+      mbar_init(bempty_bar + s, 1);
     }
     mbar_init(tfull_bar, 1);
     fence_barrier_init();
@@ -844,22 +856,31 @@ k_gemm_tn_gate(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
+    // ===== X (B operand) producer =====
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
       for (int i = 0; i < nkb; ++i) {
-        mbar_wait(empty_bar + s, ph ^ 1);
-        uint8_t* sa = smem + s * TN_STAGE_BYTES;
-        uint8_t* sb = sa + TN_A_BYTES;
+        const int s = i % TNG_BSTAGES;
+        mbar_wait(bempty_bar + s, static_cast<uint32_t>((i / TNG_BSTAGES) & 1) ^ 1);
+        uint8_t* sb = b_ring + s * TN_B_BYTES;
         const int32_t krow = static_cast<int32_t>((kb0 + i) * TN_BK);
-        mbar_arrive_expect_tx(raw_bar + s, TN_STAGE_BYTES + TN_BK * static_cast<uint32_t>(sizeof(float)));
-        tma_load_2d(sa, &tmA, raw_bar + s, Mo / TNG_MT * mt, krow, kEvictFirst);                       // V box
-        tma_load_2d(sa + TN_BOX_BYTES, &tmA, raw_bar + s, Mo / TNG_MT * mt + 64, krow, kEvictFirst);   // U box
-        tma_load_2d(ds_s + s * TN_BK, &tmD, raw_bar + s, krow, 0, kEvictNormal);
+        mbar_arrive_expect_tx(bfull_bar + s, TN_B_BYTES);
 #pragma unroll
         for (int j = 0; j < TN_BNO / 64; ++j)
-          tma_load_2d(sb + j * TN_BOX_BYTES, &tmB, raw_bar + s, nt * TN_BNO + j * 64, krow, kEvictNormal);
-        if (++s == TN_STAGES) { s = 0; ph ^= 1; }
+          tma_load_2d(sb + j * TN_BOX_BYTES, &tmB, bfull_bar + s, nt * TN_BNO + j * 64, krow, kEvictNormal);
+      }
+    }
+  } else if (warp == 3) {
+    // ===== raw V,U / ds producer: runs up to TNG_ASTAGES stages ahead of the MMA =====
+    if (lane == 0) {
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % TNG_ASTAGES;
+        mbar_wait(aempty_bar + s, static_cast<uint32_t>((i / TNG_ASTAGES) & 1) ^ 1);
+        uint8_t* sa = a_ring + s * TN_A_BYTES;
+        const int32_t krow = static_cast<int32_t>((kb0 + i) * TN_BK);
+        mbar_arrive_expect_tx(araw_bar + s, TN_A_BYTES + TN_BK * static_cast<uint32_t>(sizeof(float)));
+        tma_load_2d(sa, &tmA, araw_bar + s, Mo / TNG_MT * mt, krow, kEvictFirst);                       // V box
+        tma_load_2d(sa + TN_BOX_BYTES, &tmA, araw_bar + s, Mo / TNG_MT * mt + 64, krow, kEvictFirst);   // U box
+        tma_load_2d(ds_s + s * TN_BK, &tmD, araw_bar + s, krow, 0, kEvictNormal);
       }
     }
   } else if (warp == 1) {
@@ -868,27 +889,27 @@ k_gemm_tn_gate(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint64_t desc0 = umma_desc_sw128(smem_u32(smem), TN_BOX_BYTES, 1024);
       const uint32_t d_hi = static_cast<uint32_t>(desc0 >> 32);
       const uint32_t a_lo0 = static_cast<uint32_t>(desc0);
-      const uint32_t b_lo0 = a_lo0 + (TN_A_BYTES >> 4);
-      int s = 0;
-      uint32_t ph = 0;
+      const uint32_t b_lo0 = a_lo0 + ((TNG_ASTAGES * TN_A_BYTES) >> 4);
       for (int i = 0; i < nkb; ++i) {
-        mbar_wait(full_bar + s, ph);
+        const int sa = i % TNG_ASTAGES, sb = i % TNG_BSTAGES;
+        mbar_wait(afull_bar + sa, static_cast<uint32_t>((i / TNG_ASTAGES) & 1));
+        mbar_wait(bfull_bar + sb, static_cast<uint32_t>((i / TNG_BSTAGES) & 1));
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t so = static_cast<uint32_t>(s) * (TN_STAGE_BYTES >> 4);
+          const uint32_t ao = a_lo0 + static_cast<uint32_t>(sa) * (TN_A_BYTES >> 4);
+          const uint32_t bo = b_lo0 + static_cast<uint32_t>(sb) * (TN_B_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < TN_BK / UMMA_K; ++k) {
 #pragma unroll
             for (int h = 0; h < TN_BNO / 256; ++h)
-              umma_bf16_lohi(tmem_base + h * 256, a_lo0 + so + k * (2048 >> 4), d_hi,
-                             b_lo0 + so + ((h * 4 * TN_BOX_BYTES) >> 4) + k * (2048 >> 4), d_hi, idesc,
-                             (i | k) != 0 ? 1u : 0u);
+              umma_bf16_lohi(tmem_base + h * 256, ao + k * (2048 >> 4), d_hi,
+                             bo + ((h * 4 * TN_BOX_BYTES) >> 4) + k * (2048 >> 4), d_hi, idesc, (i | k) != 0 ? 1u : 0u);
           }
-          tc_commit(empty_bar + s);
+          tc_commit(aempty_bar + sa);
+          tc_commit(bempty_bar + sb);
           if (i == nkb - 1) tc_commit(tfull_bar);
         }
         __syncwarp();
-        if (++s == TN_STAGES) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp >= EPI_WARP0) {
@@ -908,10 +929,9 @@ k_gemm_tn_gate(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
     for (int e = 0; e < 8; ++e) sdv[e] = sdu[e] = svu[e] = 0.f;
     for (int i = grp; i < nkb; i += 2) {
-      const int s = i % TN_STAGES;
-      const uint32_t ph = static_cast<uint32_t>((i / TN_STAGES) & 1);
-      mbar_wait(raw_bar + s, ph);
-      uint8_t* sa = smem + s * TN_STAGE_BYTES;
+      const int s = i % TNG_ASTAGES;
+      mbar_wait(araw_bar + s, static_cast<uint32_t>((i / TNG_ASTAGES) & 1));
+      uint8_t* sa = a_ring + s * TN_A_BYTES;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         const uint32_t a_off = hh ? a_off1 : a_off0;
@@ -936,7 +956,7 @@ k_gemm_tn_gate(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       fence_proxy_async();                          // my generic-proxy writes -> visible to the MMA's async proxy
       __syncwarp();
-      if (lane == 0) mbar_arrive(full_bar + s);
+      if (lane == 0) mbar_arrive(afull_bar + s);
     }
     // column sums: fold the 4 k-rows a warp holds per pc with shuffles, then the 8 warps through shared memory
     if (nt == 0) {
