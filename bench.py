@@ -143,6 +143,49 @@ def cpu_reference(lengths, steps, warmup, budget_s=20.0):
             "ms_per_step": 1e3 * total / len(times), "steps": len(times), "bags_per_step": per_step}
 
 
+def secondary_fusion(dev):
+    """BASELINE configs[2]: the multimodal aggregator (fc_pathology -> two TwoWayTransformer calls -> packed bag -> gated
+    pool -> head) forward+backward on ONE WSI-scale bag per call, as the reference trains (train_ddp.py:75), bf16, through
+    the public nn.Module; plus the CPU port of the same step on a smaller bag.  Informational."""
+    import torch
+    from argparse import Namespace
+    import mil_b200
+    ns = Namespace(modality=["CT", "pathology"], model_CT="resnetMC3_18", model_pathology="ABMIL", model_CI="none",
+                   aggregator="ABMIL", num_classes=2, alignment_base="none", clinical_features=list("abcdefghi"))
+    torch.manual_seed(1234)
+    m = mil_b200.get_model(ns).to(dev).to(torch.bfloat16).train(False)
+    plist = list(m.parameters())
+    out = []
+    for T, N in ((1, 15592), (10, 15592)):
+        x_ct = torch.randn(1, 512, 160, 1, 1, device=dev, dtype=torch.bfloat16)
+        x_p = torch.randn(1, N, 768, device=dev, dtype=torch.bfloat16)
+        x_t = (torch.randn(1, T, 512, device=dev) * 0.05).to(torch.bfloat16)
+        label = torch.tensor([[0.0, 1.0]], device=dev)
+
+        def step():
+            for p in plist:
+                p.grad = None
+            prob, a, b = m([x_ct, x_p], x_t)
+            loss = torch.nn.functional.binary_cross_entropy(prob.float(), label) + \
+                mil_b200.clip_loss.cosine_embedding_loss(a.squeeze(0), b.squeeze(0)).float()
+            loss.backward()
+
+        for _ in range(4):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = mil_b200.launch_count()
+        e0.record()
+        for _ in range(10):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        out.append({"workload": f"aggregator CT+pathology fwd+bwd, 1 bag, N={N} x 768 + 160 CT tokens, T={T}, bf16",
+                    "ms_per_bag": ms, "bags_per_s": 1e3 / ms, "kernels_per_bag": (mil_b200.launch_count() - l0) / 10})
+    return out
+
+
 def _claim_stdout():
     """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner to stdout) must not add
     to it: point fd 1 at stderr for the whole run and return a writer on the original stdout for the final line."""
@@ -162,6 +205,7 @@ def main():
     ap.add_argument("--bags", type=int, default=64, help="bags per rank per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--input-grad", action="store_true", help="also produce dX (instances are trainable upstream)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the fusion-path (cfg 3) side measurement")
     ap.add_argument("--recompute-gate", action="store_true",
                     help="backward re-runs the gate GEMM instead of reading the V,U activations saved by the forward")
     args = ap.parse_args()
@@ -410,6 +454,14 @@ def main():
                     kinfo["traffic"] = ncu_traffic[key]["dram_bytes"]
                     kinfo["traffic_source"] = ncu_traffic[key].get("source")
 
+    # ---- secondary rows of SURVEY §8 (not the headline metric): the cross-modal fusion path, one bag per call -------------
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        try:
+            secondary = secondary_fusion(dev)
+        except Exception as e:  # never let a secondary measurement break the contract line
+            secondary = {"error": repr(e)[:200]}
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_reference(lengths, steps=3, warmup=1, budget_s=20.0)
@@ -427,7 +479,7 @@ def main():
                 "instances_per_step_per_rank": total_n, "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "bags/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
-                "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_base, "clocks": clocks}
+                "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_base, "clocks": clocks, "secondary": secondary}
         out.write(json.dumps(line) + "\n")
         out.flush()
     if world > 1:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MILB200_VERSION 101
+#define MILB200_VERSION 102
 
 enum { MILB200_F32 = 0, MILB200_BF16 = 1 };
 
@@ -131,14 +131,19 @@ int milb200_linear_bwd(const void* X, const void* add, const void* W, const void
                        int accumulate, void* workspace, size_t ws_bytes, void* stream);
 
 /* ---- LayerNorm over the last dim (nn.LayerNorm, eps 1e-5; transformer.py:288,295,300,307,118) ----
- * Y = LN(X + R) * gamma + beta, R optional residual (may be NULL).  mean/rstd[m] fp32 are saved.    */
+ * Y = LN(X + R) * gamma + beta, R optional residual (may be NULL).  mean/rstd[m] fp32 are saved.
+ * r_broadcast != 0: R is ONE row [n] added to every row of X — with a single text token the image->token attention of
+ * transformer.py:302-307 degenerates to softmax over one key (weights exactly 1), so its output is the
+ * same row for every instance; the gradient of that row is the column sum of dXR (milb200_colsum).      */
 int milb200_layernorm_fwd(const void* X, const void* R, const float* gamma, const float* beta, void* Y,
-                          float* mean, float* rstd, int64_t m, int n, int dtype, void* stream);
+                          float* mean, float* rstd, int64_t m, int n, int dtype, int r_broadcast, void* stream);
 /* dXR = dL/d(X+R) (same for both addends); dgamma/dbeta fp32[n] overwritten (or added to).          */
 int milb200_layernorm_bwd(const void* X, const void* R, const float* gamma, const float* mean,
                           const float* rstd, const void* dY, void* dXR, float* dgamma, float* dbeta,
-                          int64_t m, int n, int dtype, int accumulate, void* workspace, size_t ws_bytes,
-                          void* stream);
+                          int64_t m, int n, int dtype, int accumulate, int r_broadcast, void* workspace,
+                          size_t ws_bytes, void* stream);
+/* out[c] (+)= sum_r A[r, c] (fp32 out): bias gradients and the gradient of a broadcast residual row.        */
+int milb200_colsum(const void* A, int64_t rows, int cols, float* out, int dtype, int accumulate, void* stream);
 size_t milb200_layernorm_workspace_bytes(int64_t m, int n);
 
 /* ---- multi-head attention core (transformer.py:434-446): O = softmax(Q K^T / sqrt(c)) V per head ---

@@ -45,8 +45,9 @@ SIGNATURES = {
     "milb200_linear_fwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p, _sz, _p]),
     "milb200_linear_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p, _sz, _p]),
     "milb200_layernorm_workspace_bytes": (_sz, [_i64, _i]),
-    "milb200_layernorm_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _p]),
-    "milb200_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p, _sz, _p]),
+    "milb200_layernorm_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p]),
+    "milb200_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p, _sz, _p]),
+    "milb200_colsum": (_i, [_p, _i64, _i, _p, _i, _i, _p]),
     "milb200_attention_workspace_bytes": (_sz, [_i64, _i64, _i, _i, _i]),
     "milb200_attention_fwd": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i, _i, _i, _p, _sz, _p]),
     "milb200_attention_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _i, _p, _sz, _p]),

@@ -461,6 +461,14 @@ int milb200_add(const void* a, const void* b, void* out, int64_t n, int dtype, v
 /* Developer/bench hook: when enabled, the tensor-core path of milb200_gated_score_bwd records CUDA events
  * between its sub-kernels (dz recompute | dW split-K GEMM | split-K reduce | dX GEMM);
  * milb200_profile_read synchronises on the last event and returns the interval durations in ms. */
+int milb200_colsum(const void* A, int64_t rows, int cols, float* out, int dtype, int accumulate, void* stream) {
+  MIL_CHECK_ARG(A && out && rows > 0 && cols > 0, MILB200_EINVAL, "colsum: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!accumulate) MIL_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
+  if (dtype == MILB200_BF16) return colsum_launch<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(A), rows, cols, out, st);
+  return colsum_launch<float>(static_cast<const float*>(A), rows, cols, out, st);
+}
+
 int milb200_debug_trace(void* dev_u64x16) { return tc::debug_set_trace(dev_u64x16); }
 void milb200_profile_enable(int on) { g_prof_on = on != 0; g_prof_n = 0; }
 int milb200_profile_read(float* ms, int max_intervals) {

@@ -20,14 +20,14 @@ template <typename T> struct LnCfg { static constexpr int VN = Vec16<T>::N; stat
 template <typename T>
 __global__ void __launch_bounds__(256)
 k_ln_fwd(const T* __restrict__ X, const T* __restrict__ R, const float* __restrict__ gamma, const float* __restrict__ beta,
-         T* __restrict__ Y, float* __restrict__ mean, float* __restrict__ rstd, int64_t m, int n) {
+         T* __restrict__ Y, float* __restrict__ mean, float* __restrict__ rstd, int64_t m, int n, int r_bcast) {
   constexpr int VN = LnCfg<T>::VN, MAXV = LnCfg<T>::MAXV;
   const int lane = threadIdx.x & 31;
   const int64_t row = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= m) return;
   const int nvec = n / VN;
   const uint4* x = reinterpret_cast<const uint4*>(X + row * n);
-  const uint4* r = R ? reinterpret_cast<const uint4*>(R + row * n) : nullptr;
+  const uint4* r = R ? reinterpret_cast<const uint4*>(R + (r_bcast ? 0 : row * n)) : nullptr;   // r_bcast: one row for all
   float v[MAXV][VN];
   float s = 0.f;
 #pragma unroll
@@ -76,7 +76,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_ln_bwd(const T* __restrict__ X, const T* __restrict__ R, const float* __restrict__ gamma, const float* __restrict__ mean,
          const float* __restrict__ rstd, const T* __restrict__ dY, T* __restrict__ dXR, float* __restrict__ part, int64_t m,
-         int n, int rows_per_cta) {
+         int n, int rows_per_cta, int r_bcast) {
   constexpr int VN = LnCfg<T>::VN, MAXV = LnCfg<T>::MAXV;
   extern __shared__ float sm[];  // [8 warps][2][n]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -96,7 +96,7 @@ k_ln_bwd(const T* __restrict__ X, const T* __restrict__ R, const float* __restri
   for (int64_t row = r0 + warp; row < r1; row += 8) {
     const float mu = mean[row], rs = rstd[row];
     const uint4* x = reinterpret_cast<const uint4*>(X + row * n);
-    const uint4* r = R ? reinterpret_cast<const uint4*>(R + row * n) : nullptr;
+    const uint4* r = R ? reinterpret_cast<const uint4*>(R + (r_bcast ? 0 : row * n)) : nullptr;
     const uint4* dy = reinterpret_cast<const uint4*>(dY + row * n);
     float xh[MAXV][VN], g[MAXV][VN];
     float s1 = 0.f, s2 = 0.f;
@@ -402,7 +402,7 @@ size_t milb200_layernorm_workspace_bytes(int64_t m, int n) {
 }
 
 int milb200_layernorm_fwd(const void* X, const void* R, const float* gamma, const float* beta, void* Y, float* mean,
-                          float* rstd, int64_t m, int n, int dtype, void* stream) {
+                          float* rstd, int64_t m, int n, int dtype, int r_broadcast, void* stream) {
   MIL_CHECK_ARG(X && gamma && beta && Y && mean && rstd, MILB200_EINVAL, "layernorm_fwd: null pointer");
   MIL_CHECK_ARG(m > 0 && n > 0 && n <= 32 * LN_MAX_PER_LANE, MILB200_EUNSUPPORTED, "layernorm_fwd: n=%d not in (0, %d]", n,
                 32 * LN_MAX_PER_LANE);
@@ -412,16 +412,17 @@ int milb200_layernorm_fwd(const void* X, const void* R, const float* gamma, cons
   unsigned blocks = static_cast<unsigned>((m + 7) / 8);
   if (dtype == MILB200_BF16)
     k_ln_fwd<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)X, (const __nv_bfloat16*)R, gamma, beta,
-                                                    (__nv_bfloat16*)Y, mean, rstd, m, n);
+                                                    (__nv_bfloat16*)Y, mean, rstd, m, n, r_broadcast);
   else
-    k_ln_fwd<float><<<blocks, 256, 0, st>>>((const float*)X, (const float*)R, gamma, beta, (float*)Y, mean, rstd, m, n);
+    k_ln_fwd<float><<<blocks, 256, 0, st>>>((const float*)X, (const float*)R, gamma, beta, (float*)Y, mean, rstd, m, n,
+                                            r_broadcast);
   MIL_LAUNCH_CHECK();
   return MILB200_OK;
 }
 
 int milb200_layernorm_bwd(const void* X, const void* R, const float* gamma, const float* mean, const float* rstd,
                           const void* dY, void* dXR, float* dgamma, float* dbeta, int64_t m, int n, int dtype,
-                          int accumulate, void* workspace, size_t ws_bytes, void* stream) {
+                          int accumulate, int r_broadcast, void* workspace, size_t ws_bytes, void* stream) {
   MIL_CHECK_ARG(X && gamma && mean && rstd && dY && dXR && dgamma && dbeta, MILB200_EINVAL, "layernorm_bwd: null pointer");
   MIL_CHECK_ARG(m > 0 && n > 0 && n <= 32 * LN_MAX_PER_LANE, MILB200_EUNSUPPORTED, "layernorm_bwd: n=%d unsupported", n);
   MIL_CHECK_ARG((n * elem_size(dtype)) % 16 == 0 && aligned16(X) && aligned16(dY) && aligned16(dXR) && (!R || aligned16(R)),
@@ -437,12 +438,12 @@ int milb200_layernorm_bwd(const void* X, const void* R, const float* gamma, cons
     auto kern = k_ln_bwd<__nv_bfloat16>;
     if (smem > 48 * 1024) MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<ctas, 256, smem, st>>>((const __nv_bfloat16*)X, (const __nv_bfloat16*)R, gamma, mean, rstd,
-                                  (const __nv_bfloat16*)dY, (__nv_bfloat16*)dXR, part, m, n, rows_per_cta);
+                                  (const __nv_bfloat16*)dY, (__nv_bfloat16*)dXR, part, m, n, rows_per_cta, r_broadcast);
   } else {
     auto kern = k_ln_bwd<float>;
     if (smem > 48 * 1024) MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<ctas, 256, smem, st>>>((const float*)X, (const float*)R, gamma, mean, rstd, (const float*)dY, (float*)dXR, part, m,
-                                  n, rows_per_cta);
+                                  n, rows_per_cta, r_broadcast);
   }
   MIL_LAUNCH_CHECK();
   k_ln_reduce<<<(2 * n + 31) / 32, 256, 0, st>>>(part, ctas, n, dgamma, dbeta, accumulate);

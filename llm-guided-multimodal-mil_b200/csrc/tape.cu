@@ -67,8 +67,10 @@ static int tape_validate(const milb200_tape_op* ops, int n_ops, const milb200_ta
         MIL_CHECK_ARG(ok_slot(o.in1, true), MILB200_EINVAL, "tape: op %d bad residual slot", i);
         MIL_CHECK_ARG(params && o.p0 >= 0 && o.p0 < n_params && o.p1 >= 0 && o.p1 < n_params, MILB200_EINVAL,
                       "tape: op %d bad param id", i);
+        // the residual may be a single row that is broadcast over all rows of in0 (T = 1 shortcut)
         MIL_CHECK_ARG(so.rows == s0.rows && so.cols == s0.cols &&
-                          (o.in1 < 0 || (o.in1 != o.in0 && slots[o.in1].rows == s0.rows && slots[o.in1].cols == s0.cols)),
+                          (o.in1 < 0 || (o.in1 != o.in0 && slots[o.in1].cols == s0.cols &&
+                                         (slots[o.in1].rows == s0.rows || slots[o.in1].rows == 1))),
                       MILB200_EINVAL, "tape: op %d layernorm shape mismatch", i);
         break;
       }
@@ -117,7 +119,7 @@ static TapePlan tape_plan(const milb200_tape_op* ops, int n_ops, const milb200_t
       f = milb200_attention_workspace_bytes(slots[o.in0].rows, slots[o.in1].rows, o.a0, c, 0);
       b = milb200_attention_workspace_bytes(slots[o.in0].rows, slots[o.in1].rows, o.a0, c, 1);
     } else if (o.kind == MILB200_OP_LAYERNORM) {
-      b = milb200_layernorm_workspace_bytes(slots[o.in0].rows, slots[o.in0].cols);
+      b = milb200_layernorm_workspace_bytes(slots[o.in0].rows, slots[o.in0].cols) + 256 + sizeof(float) * slots[o.in0].cols;
     }
     p.scratch_fwd = std::max(p.scratch_fwd, f);
     p.scratch_bwd = std::max(p.scratch_bwd, b);
@@ -187,8 +189,10 @@ static int tape_forward_run(const milb200_tape_op* ops, int n_ops, const milb200
         break;
       case MILB200_OP_LAYERNORM: {
         float* mean = reinterpret_cast<float*>(ar + pl.aux_off[i]);
+        const int bcast = (o.in1 >= 0 && slots[o.in1].rows == 1 && s0.rows > 1) ? 1 : 0;
         rc = milb200_layernorm_fwd(ptr[o.in0], o.in1 >= 0 ? ptr[o.in1] : nullptr, p_f32 + params[o.p0].offset,
-                                   p_f32 + params[o.p1].offset, ptr[o.out], mean, mean + s0.rows, s0.rows, s0.cols, dtype, stream);
+                                   p_f32 + params[o.p1].offset, ptr[o.out], mean, mean + s0.rows, s0.rows, s0.cols, dtype,
+                                   bcast, stream);
         break;
       }
       case MILB200_OP_ADD:
@@ -324,21 +328,36 @@ static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb20
       }
       case MILB200_OP_LAYERNORM: {
         const float* mean = reinterpret_cast<const float*>(ar + pl.aux_off[i]);
-        const bool need_dx = needs[o.in0] || (o.in1 >= 0 && needs[o.in1]);
-        void* dX = needs[o.in0] ? target(o.in0, 0) : (o.in1 >= 0 ? target(o.in1, 0) : nullptr);
-        if (!need_dx) dX = tmp0;  // the kernel always writes dXR
+        const int bcast = (o.in1 >= 0 && slots[o.in1].rows == 1 && s0.rows > 1) ? 1 : 0;
+        const bool need_res = o.in1 >= 0 && needs[o.in1];
+        const bool need_dx = needs[o.in0] || need_res;
+        void* dX = needs[o.in0] ? target(o.in0, 0) : ((need_res && !bcast) ? target(o.in1, 0) : nullptr);
+        if (!dX) dX = tmp0;  // the kernel always writes dXR
         const int acc = ptouched[o.p0] ? 1 : 0;
+        const size_t ln_ws = milb200_layernorm_workspace_bytes(s0.rows, s0.cols);
         rc = milb200_layernorm_bwd(val[o.in0], o.in1 >= 0 ? val[o.in1] : nullptr, p_f32 + params[o.p0].offset, mean,
                                    mean + s0.rows, dY, dX, g_f32 + params[o.p0].offset, g_f32 + params[o.p1].offset, s0.rows,
-                                   s0.cols, dtype, acc, scratch, scratch_bytes, stream);
+                                   s0.cols, dtype, acc, bcast, scratch, ln_ws, stream);
         if (rc) return rc;
         ptouched[o.p0] = ptouched[o.p1] = 1;
         if (need_dx) {
+          if (bcast && need_res) {
+            // gradient of the broadcast row = column sums of dXR (fp32), converted to the slot dtype; dX may live in tmp0,
+            // so the converted row goes to temporary 1
+            float* csum = reinterpret_cast<float*>(static_cast<char*>(scratch) + align_up(ln_ws, 256));
+            if ((rc = milb200_colsum(dX, s0.rows, s0.cols, csum, dtype, 0, stream))) return rc;
+            void* row = csum;  // fp32 slots take the sums as they are (consumed in stream order before scratch is reused)
+            if (dtype != MILB200_F32) {
+              row = tmp0 + tmp_stride;
+              if ((rc = milb200_cast(csum, MILB200_F32, row, dtype, s0.cols, stream))) return rc;
+            }
+            if ((rc = settle(o.in1, row))) return rc;
+          }
           if (needs[o.in0]) {
             if ((rc = settle(o.in0, dX))) return rc;
-            if (o.in1 >= 0 && (rc = settle(o.in1, dX))) return rc;
-          } else if ((rc = settle(o.in1, dX))) {
-            return rc;
+            if (!bcast && need_res && (rc = settle(o.in1, dX))) return rc;
+          } else if (!bcast && need_res) {
+            if ((rc = settle(o.in1, dX))) return rc;
           }
         }
         break;

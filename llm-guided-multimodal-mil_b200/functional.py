@@ -312,7 +312,7 @@ class _LayerNorm(torch.autograd.Function):
         mean = torch.empty((m,), dtype=torch.float32, device=x2.device)
         rstd = torch.empty((m,), dtype=torch.float32, device=x2.device)
         L.check(L.lib().milb200_layernorm_fwd(L.ptr(x2), L.ptr(r2), L.ptr(g), L.ptr(b), L.ptr(y), L.ptr(mean),
-                                              L.ptr(rstd), m, n, L.dtype_code(x2), L.stream_ptr()), "layernorm_fwd")
+                                              L.ptr(rstd), m, n, L.dtype_code(x2), 0, L.stream_ptr()), "layernorm_fwd")
         ctx.save_for_backward(x2, r2, g, mean, rstd)
         ctx.meta = (shp, m, n, gamma.dtype, beta.dtype, r is not None)
         return y.view(shp)
@@ -330,7 +330,7 @@ class _LayerNorm(torch.autograd.Function):
         nb = L.lib().milb200_layernorm_workspace_bytes(m, n)
         ws = L.workspace(nb, x2.device)
         L.check(L.lib().milb200_layernorm_bwd(L.ptr(x2), L.ptr(r2), L.ptr(g), L.ptr(mean), L.ptr(rstd), L.ptr(dy2),
-                                              L.ptr(dxr), L.ptr(dg), L.ptr(db), m, n, L.dtype_code(x2), 0, L.ptr(ws),
+                                              L.ptr(dxr), L.ptr(dg), L.ptr(db), m, n, L.dtype_code(x2), 0, 0, L.ptr(ws),
                                               ws.numel(), L.stream_ptr()), "layernorm_bwd")
         gx = dxr.view(shp)
         return gx, (gx if has_r else None), cast(dg, gdt), cast(db, bdt)

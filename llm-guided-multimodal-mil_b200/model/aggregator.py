@@ -106,10 +106,12 @@ class aggregator(nn.Module):
         return transformer(x_img, self._pe(n, text_tokens), text_tokens)
 
     # ---- CT + pathology branch as ONE native program (csrc/tape.cu) ----------------------------------------
-    def _fusion_tape(self):
+    def _fusion_tape(self, single_token=False):
         """aggregator.py:141,160,168,173 on a tape: fc_pathology, fc_CI2CT / fc_CI2Pth, both TwoWayTransformer_Both
-        calls, and the four results written in place into the packed multi-modal bag (no torch.cat copy)."""
-        t = getattr(self, "_tape_cache", None)
+        calls, and the four results written in place into the packed multi-modal bag (no torch.cat copy).
+        single_token: the T = 1 specialisation (exact, see Attention.emit_single_key)."""
+        name = "_tape_cache_t1" if single_token else "_tape_cache"
+        t = getattr(self, name, None)
         if t is None:
             t = Tape()
             E = self.embedding_dim
@@ -117,20 +119,22 @@ class aggregator(nn.Module):
             xp, pe_p = t.input("Np", 768), t.input("Np", E)
             txt = t.input("T", E)
             xin_p = t.linear(xp, self.fc_pathology[0], act="tanh")                                   # :141
-            q1, k1 = self.TwoWayTransformer_Both.emit(t, ct, pe_ct, t.linear(txt, self.fc_CI2CT[0], act="tanh"))   # :160
-            q2, k2 = self.TwoWayTransformer_Both.emit(t, xin_p, pe_p, t.linear(txt, self.fc_CI2Pth[0], act="tanh"))  # :168
+            q1, k1 = self.TwoWayTransformer_Both.emit(t, ct, pe_ct, t.linear(txt, self.fc_CI2CT[0], act="tanh"),
+                                                      single_token=single_token)                    # :160
+            q2, k2 = self.TwoWayTransformer_Both.emit(t, xin_p, pe_p, t.linear(txt, self.fc_CI2Pth[0], act="tanh"),
+                                                      single_token=single_token)                    # :168
             bag = t.buffer(lambda r: 2 * r["T"] + r["Nc"] + r["Np"], E)                             # :173 row order
             t.output(q1, bag, lambda r: 0)
             t.output(k1, bag, lambda r: r["T"])
             t.output(q2, bag, lambda r: r["T"] + r["Nc"])
             t.output(k2, bag, lambda r: 2 * r["T"] + r["Nc"])
-            object.__setattr__(self, "_tape_cache", t)
+            object.__setattr__(self, name, t)
         return t
 
     def _forward_fused(self, x_ct_tokens, x_path, x_text):
         T, Nc, Np = x_text.shape[1], x_ct_tokens.shape[1], x_path.shape[1]
         like = x_text
-        (bag,) = self._fusion_tape().run({"T": T, "Nc": Nc, "Np": Np},
+        (bag,) = self._fusion_tape(single_token=(T == 1 and Nc > 1 and Np > 1)).run({"T": T, "Nc": Nc, "Np": Np},
                                          [x_ct_tokens[0], self._pe(Nc, like)[0], x_path[0], self._pe(Np, like)[0], x_text[0]])
         x0 = bag.unsqueeze(0)
         return x0, x0[:, :T], x0[:, T + Nc:2 * T + Nc]

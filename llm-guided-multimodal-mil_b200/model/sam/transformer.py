@@ -70,6 +70,16 @@ class Attention(nn.Module):
         return tape.linear(o, self.out_proj)
 
 
+    def emit_single_key(self, tape: Tape, v: int) -> int:
+        """Attention over exactly ONE key (a single text token): softmax over one score is 1.0 for every query and head
+        (transformer.py:441-443), so the output row is out_proj(v_proj(v)) for every query and q_proj / k_proj drop out of
+        the computation with exactly-zero gradients, as in the reference.  Returns a 1-row slot."""
+        for lin in (self.q_proj, self.k_proj):      # still parameters of the program: they receive (exactly) zero gradients
+            tape.param(lin.weight)
+            tape.param(lin.bias)
+        return tape.linear(tape.linear(v, self.v_proj), self.out_proj)
+
+
 class TwoWayAttentionBlock(nn.Module):
     """model/sam/transformer.py:236-309."""
 
@@ -111,9 +121,14 @@ class TwoWayAttentionBlock(nn.Module):
         return queries, keys
 
 
-    def emit(self, tape: Tape, queries: int, keys: int, query_pe: int, key_pe: int):
-        """forward() recorded on a tape."""
-        if self.skip_first_layer_pe:
+    def emit(self, tape: Tape, queries: int, keys: int, query_pe: int, key_pe: int, single_token: bool = False):
+        """forward() recorded on a tape.  single_token: the program is specialised for T = 1 (one clinical prompt, the
+        reference's active configuration, dataset.py:479-480): every attention whose KEYS are the tokens has one key."""
+        if single_token:
+            sa = self.self_attn.emit_single_key(tape, queries)
+            queries = tape.layernorm(sa, self.norm1) if self.skip_first_layer_pe else \
+                tape.layernorm(queries, self.norm1, residual=sa)
+        elif self.skip_first_layer_pe:
             queries = tape.layernorm(self.self_attn.emit(tape, queries, queries, queries), self.norm1)
         else:
             attn_out = self.self_attn.emit(tape, queries, queries, queries, q_add=query_pe, k_add=query_pe)
@@ -122,8 +137,13 @@ class TwoWayAttentionBlock(nn.Module):
         attn_out = self.cross_attn_token_to_image.emit(tape, queries, keys_pe, keys, q_add=query_pe)
         queries = tape.layernorm(queries, self.norm2, residual=attn_out)
         queries = tape.layernorm(queries, self.norm3, residual=self.mlp.emit(tape, queries))
-        attn_out = self.cross_attn_image_to_token.emit(tape, keys_pe, queries, queries, k_add=query_pe)
-        keys = tape.layernorm(keys, self.norm4, residual=attn_out)
+        if single_token:
+            # image -> token attention with one key: the same row for every instance, added by the LayerNorm kernel
+            row = self.cross_attn_image_to_token.emit_single_key(tape, queries)
+            keys = tape.layernorm(keys, self.norm4, residual=row)
+        else:
+            attn_out = self.cross_attn_image_to_token.emit(tape, keys_pe, queries, queries, k_add=query_pe)
+            keys = tape.layernorm(keys, self.norm4, residual=attn_out)
         return queries, keys
 
 
@@ -156,26 +176,27 @@ class TwoWayTransformer(nn.Module):
             return x.flatten(2).permute(0, 2, 1).contiguous()       # pure data movement
         return x                                                     # upstream leaves other encoders untouched
 
-    def emit(self, tape: Tape, image: int, image_pe: int, points: int):
+    def emit(self, tape: Tape, image: int, image_pe: int, points: int, single_token: bool = False):
         """The token/image program of forward() on a tape: returns (queries slot, keys slot)."""
         queries, keys = points, image
         for layer in self.layers:
-            queries, keys = layer.emit(tape, queries, keys, points, image_pe)
+            queries, keys = layer.emit(tape, queries, keys, points, image_pe, single_token=single_token)
         attn_out = self.final_attn_token_to_image.emit(tape, queries, keys, keys, q_add=points, k_add=image_pe)
         queries = tape.layernorm(queries, self.norm_final_attn, residual=attn_out)
         return queries, keys
 
-    def _tape(self):
-        t = getattr(self, "_tape_cache", None)
+    def _tape(self, single_token=False):
+        name = "_tape_cache_t1" if single_token else "_tape_cache"
+        t = getattr(self, name, None)
         if t is None:
             t = Tape()
             E = self.embedding_dim
             img, pe, pts = t.input("N", E), t.input("N", E), t.input("T", E)
-            q, k = self.emit(t, img, pe, pts)
+            q, k = self.emit(t, img, pe, pts, single_token=single_token)
             bq, bk = t.buffer(lambda r: r["T"], E), t.buffer(lambda r: r["N"], E)
             t.output(q, bq, lambda r: 0)
             t.output(k, bk, lambda r: 0)
-            object.__setattr__(self, "_tape_cache", t)      # not a submodule / parameter: keep it out of nn.Module state
+            object.__setattr__(self, name, t)      # not a submodule / parameter: keep it out of nn.Module state
         return t
 
     def forward(self, image_embedding: Tensor, image_pe: Tensor, point_embedding: Tensor) -> Tuple[Tensor, Tensor]:
@@ -188,7 +209,8 @@ class TwoWayTransformer(nn.Module):
                 and image_pe.shape == image_embedding.shape):
             # one bag per call (train_ddp.py:75): the whole program is a single native call each way
             n, t_ = image_embedding.shape[1], point_embedding.shape[1]
-            q, k = self._tape().run({"N": n, "T": t_}, [image_embedding[0], image_pe[0], point_embedding[0]])
+            q, k = self._tape(single_token=(t_ == 1 and n > 1)).run({"N": n, "T": t_},
+                                                                    [image_embedding[0], image_pe[0], point_embedding[0]])
             return q.unsqueeze(0), k.unsqueeze(0)
         queries, keys = point_embedding, image_embedding
         for layer in self.layers:                                                     # :105-111

@@ -30,7 +30,7 @@ for dtype in (torch.bfloat16, torch.float32):
     x = torch.randn(1000, 512, device="cuda").to(dtype); g = torch.ones(512, device="cuda"); be = torch.zeros(512, device="cuda")
     y = torch.empty_like(x); mean = torch.empty(1000, device="cuda"); rstd = torch.empty(1000, device="cuda")
     px, pg, pbe, py, pm, pr = (L.ptr(t) for t in (x, g, be, y, mean, rstd))
-    print(f"layernorm_fwd {dtype}: {loop(lambda: lib.milb200_layernorm_fwd(px, None, pg, pbe, py, pm, pr, 1000, 512, code, st)):.1f} us/call", flush=True)
+    print(f"layernorm_fwd {dtype}: {loop(lambda: lib.milb200_layernorm_fwd(px, None, pg, pbe, py, pm, pr, 1000, 512, code, 0, st)):.1f} us/call", flush=True)
     a = torch.randn(1000, 512, device="cuda").to(dtype)
     pa = L.ptr(a)
     print(f"add {dtype}: {loop(lambda: lib.milb200_add(px, pa, py, 1000 * 512, code, st)):.1f} us/call", flush=True)
