@@ -191,8 +191,11 @@ struct EpiScoreT {
   };
   // bias[384] | w[192] | partial[2 parities][4 (h, half)][128 rows]
   static constexpr int SMEM_FLOATS = 3 * GATE_D + 2 * 4 * BM;
-  static constexpr int BOX_BYTES = 32 * GATE_PW * 2;
-  static constexpr int STAGING_BYTES = SAVE ? EPI_WARPS * 2 * BOX_BYTES : 0;
+  // staging: ONE [32 x 16] V sub-box + ONE U sub-box per warp (2 KB), recycled for each of the three 16-unit chunks of a
+  // half tile.  The main loop is bound by operand supply, so shared memory is better spent on a fifth pipeline stage
+  // than on epilogue staging (the epilogue warps wait for the accumulator most of the time anyway).
+  static constexpr int SUB_BYTES = 32 * 16 * 2;
+  static constexpr int STAGING_BYTES = SAVE ? EPI_WARPS * 2 * SUB_BYTES : 0;
   __device__ static void prologue(const Params& p, float* esm, int tid) {
     for (int i = tid; i < 2 * GATE_D; i += NUM_THREADS) esm[i] = __ldg(p.bcat + i);
     for (int i = tid; i < GATE_D; i += NUM_THREADS) esm[2 * GATE_D + i] = __ldg(p.ww + i);
@@ -209,12 +212,10 @@ struct EpiScoreT {
     uint8_t* rowU = nullptr;
     uint8_t* boxV = nullptr;
     if (SAVE) {
-      // per warp: V sub-boxes 0..2 | U sub-boxes 0..2, each a dense [32 rows][16 bf16] image (1 KB)
-      boxV = staging + (cx.half * 4 + cx.q) * 2 * BOX_BYTES;
+      // per warp: one V sub-box | one U sub-box, each a dense [32 rows][16 bf16] image (1 KB)
+      boxV = staging + (cx.half * 4 + cx.q) * 2 * SUB_BYTES;
       rowV = boxV + cx.lane * 32;
-      rowU = rowV + BOX_BYTES;
-      if (cx.lane == 0) tma_store_wait_read<0>();  // the previous half tile's boxes have been read out
-      __syncwarp();
+      rowU = rowV + SUB_BYTES;
     }
     float part = 0.f;
 #pragma unroll
@@ -239,27 +240,22 @@ struct EpiScoreT {
         part = fmaf(fv[j + 3] * fu[j + 3], w.w, part);
       }
       if (SAVE) {
-        uint8_t* sv = rowV + (c / 16) * 1024;
-        uint8_t* su = rowU + (c / 16) * 1024;
-        *reinterpret_cast<uint4*>(sv) = Vec16<__nv_bfloat16>::pack(fv);
-        *reinterpret_cast<uint4*>(sv + 16) = Vec16<__nv_bfloat16>::pack(fv + 8);
-        *reinterpret_cast<uint4*>(su) = Vec16<__nv_bfloat16>::pack(fu);
-        *reinterpret_cast<uint4*>(su + 16) = Vec16<__nv_bfloat16>::pack(fu + 8);
-      }
-    }
-    if (SAVE) {
-      fence_proxy_async();
-      __syncwarp();
-      if (cx.lane == 0) {
-        const int32_t r0 = static_cast<int32_t>(cx.row);  // lane 0 holds the first row of this warp's quarter
-#pragma unroll
-        for (int sb = 0; sb < GATE_PW / 16; ++sb) {
-          const int d0 = h * GATE_DH + cx.half * GATE_PW + 16 * sb;  // first gate unit of the sub-box (multiple of 16)
+        if (cx.lane == 0) tma_store_wait_read<0>();  // the previous chunk's sub-boxes have been read out
+        __syncwarp();
+        *reinterpret_cast<uint4*>(rowV) = Vec16<__nv_bfloat16>::pack(fv);
+        *reinterpret_cast<uint4*>(rowV + 16) = Vec16<__nv_bfloat16>::pack(fv + 8);
+        *reinterpret_cast<uint4*>(rowU) = Vec16<__nv_bfloat16>::pack(fu);
+        *reinterpret_cast<uint4*>(rowU + 16) = Vec16<__nv_bfloat16>::pack(fu + 8);
+        fence_proxy_async();
+        __syncwarp();
+        if (cx.lane == 0) {
+          const int32_t r0 = static_cast<int32_t>(cx.row);  // lane 0 holds the first row of this warp's quarter
+          const int d0 = h * GATE_DH + cx.half * GATE_PW + c;  // first gate unit of the chunk (multiple of 16)
           const int colv = 128 * (d0 / 64) + d0 % 64;
-          tma_store_2d(&p.tmS, boxV + sb * 1024, colv, r0);
-          tma_store_2d(&p.tmS, boxV + BOX_BYTES + sb * 1024, colv + 64, r0);
+          tma_store_2d(&p.tmS, boxV, colv, r0);
+          tma_store_2d(&p.tmS, boxV + SUB_BYTES, colv + 64, r0);
+          tma_store_commit();
         }
-        tma_store_commit();
       }
     }
     // the four (h, half) partial sums of a row meet in shared memory; parity double-buffering keeps the next
