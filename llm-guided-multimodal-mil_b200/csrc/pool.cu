@@ -288,18 +288,17 @@ constexpr int BWD_ROWS_PER_WARP = 16;
 template <typename T, int NV>
 __global__ void __launch_bounds__(256)
 k_pool_bwd(const T* __restrict__ X, const float* __restrict__ scores, const int32_t* __restrict__ offsets, int B,
-           int64_t total_n, int L, int V, const float* __restrict__ dM, const float2* __restrict__ stats,
+           int64_t total_n, int L, int V, int64_t slab, const float* __restrict__ dM, const float2* __restrict__ stats,
            float* __restrict__ dscores, float* __restrict__ attn) {
   constexpr int VN = Vec16<T>::N;
-  const int lane = threadIdx.x & 31;
-  const int64_t gwarp = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int64_t r0 = gwarp * BWD_ROWS_PER_WARP;
-  if (r0 >= total_n) return;
-  const int64_t r1 = (r0 + BWD_ROWS_PER_WARP < total_n) ? r0 + BWD_ROWS_PER_WARP : total_n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // persistent: CTA c owns the row slab [c * slab, (c + 1) * slab); its warps take 16-row blocks round-robin and keep the
+  // bag's dM slice in registers for as long as consecutive blocks stay inside one bag
+  const int64_t slab_r0 = static_cast<int64_t>(blockIdx.x) * slab;
+  const int64_t slab_r1 = (slab_r0 + slab < total_n) ? slab_r0 + slab : total_n;
   const uint4* Xv = reinterpret_cast<const uint4*>(X);
-
-  int b = find_bag(offsets, B, r0);
-  int64_t bag_end = __ldg(offsets + b + 1);
+  int b = -1;
+  int64_t bag_end = -1;
   float dm[NV][VN];
   float lse = 0.f, cdot = 0.f;
   auto load_bag = [&](int bag) {
@@ -313,7 +312,14 @@ k_pool_bwd(const T* __restrict__ X, const float* __restrict__ scores, const int3
       for (int k = 0; k < VN; ++k) dm[j][k] = (vec < V) ? __ldg(dM + static_cast<int64_t>(bag) * L + vec * VN + k) : 0.f;
     }
   };
-  load_bag(b);
+  for (int64_t r0 = slab_r0 + static_cast<int64_t>(warp) * BWD_ROWS_PER_WARP; r0 < slab_r1;
+       r0 += static_cast<int64_t>(blockDim.x >> 5) * BWD_ROWS_PER_WARP) {
+  const int64_t r1 = (r0 + BWD_ROWS_PER_WARP < slab_r1) ? r0 + BWD_ROWS_PER_WARP : slab_r1;
+  if (b < 0 || r0 >= bag_end) {
+    b = find_bag(offsets, B, r0);
+    bag_end = __ldg(offsets + b + 1);
+    load_bag(b);
+  }
 
   int64_t i = r0;
   for (; i + 1 < r1; i += 2) {
@@ -378,6 +384,7 @@ k_pool_bwd(const T* __restrict__ X, const float* __restrict__ scores, const int3
       if (attn) attn[i] = a;
     }
   }
+  }  // 16-row blocks of this warp
 }
 
 // out[i, :] = (w ? w[i] : 1) * src[bag(i), :]   (dX of a plain sum pool; the pooling term of the gated dX)
@@ -474,10 +481,13 @@ static int pool_bwd_t(const T* X, const float* scores, const int32_t* offsets, i
   int V = L * static_cast<int>(sizeof(T)) / 16;
   int nv = (V + 31) / 32;
   MIL_CHECK_ARG(nv <= 16, MILB200_EUNSUPPORTED, "pool_bwd: row too long (L=%d)", L);
-  int64_t warps = (total_n + BWD_ROWS_PER_WARP - 1) / BWD_ROWS_PER_WARP;
-  unsigned blocks = static_cast<unsigned>((warps + 7) / 8);
+  // two CTAs per SM, each a contiguous slab of whole 128-row groups (8 warps x 16 rows)
+  int64_t ctas = static_cast<int64_t>(sm_count()) * 2;
+  int64_t slab = (total_n + ctas - 1) / ctas;
+  slab = (slab + 8 * BWD_ROWS_PER_WARP - 1) / (8 * BWD_ROWS_PER_WARP) * (8 * BWD_ROWS_PER_WARP);
+  unsigned blocks = static_cast<unsigned>((total_n + slab - 1) / slab);
 #define MIL_POOL_BWD(NVV)                                                                                   \
-  k_pool_bwd<T, NVV><<<blocks, 256, 0, st>>>(X, scores, offsets, B, total_n, L, V, dM, w.stats, dscores, attn)
+  k_pool_bwd<T, NVV><<<blocks, 256, 0, st>>>(X, scores, offsets, B, total_n, L, V, slab, dM, w.stats, dscores, attn)
   if (nv <= 1) MIL_POOL_BWD(1);
   else if (nv == 2) MIL_POOL_BWD(2);
   else if (nv == 3) MIL_POOL_BWD(3);
