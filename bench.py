@@ -102,7 +102,7 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------
 # CPU arm: the oracle's torch restatement of ABMIL.forward (fp32, autograd backward), bag at a time
 # ----------------------------------------------------------------------------------------------------
-def cpu_reference(lengths, steps, warmup, budget_s=20.0):
+def cpu_reference(lengths, steps, warmup, budget_s=20.0, per_step=4):
     import torch
     from oracle import fusion_oracle as fo
     from oracle import mil_oracle as mo
@@ -125,7 +125,7 @@ def cpu_reference(lengths, steps, warmup, budget_s=20.0):
     for i in range(min(warmup, 2)):
         one_bag(lens[i % len(lens)])
     # bounded sample: each "step" is a fixed subset of the workload's bags; stop inside the budget
-    per_step = max(1, min(len(lens), 4))
+    per_step = max(1, min(len(lens), per_step))
     times, done_bags, t_begin = [], 0, time.perf_counter()
     for s in range(max(1, steps)):
         t = 0.0
@@ -137,9 +137,9 @@ def cpu_reference(lengths, steps, warmup, budget_s=20.0):
             break
     total = sum(times)
     return {"value": done_bags / total, "unit": "bags/s", "cores": cores, "kind": "port",
-            "sample": f"{done_bags} bags of the same length distribution (first {per_step} lengths per step, "
-                      f"{len(times)} steps), fp32, bag-at-a-time fwd+bwd (M.sum().backward()), "
-                      f"torch {torch.__version__} with {cores} threads",
+            "sample": f"{done_bags} bags cycling through the workload's {len(lens)} bag lengths ({per_step} bags per step, "
+                      f"{len(times)} steps, {total:.1f} s of CPU work), fp32, bag-at-a-time fwd+bwd (M.sum().backward()) as the "
+                      f"reference trains, torch {torch.__version__} with {cores} threads",
             "ms_per_step": 1e3 * total / len(times), "steps": len(times), "bags_per_step": per_step}
 
 
@@ -183,6 +183,65 @@ def secondary_fusion(dev):
         ms = e0.elapsed_time(e1) / 10
         out.append({"workload": f"aggregator CT+pathology fwd+bwd, 1 bag, N={N} x 768 + 160 CT tokens, T={T}, bf16",
                     "ms_per_bag": ms, "bags_per_s": 1e3 / ms, "kernels_per_bag": (mil_b200.launch_count() - l0) / 10})
+
+    def timed(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    # configs[2], second half: aggregator_clip (CT + pathology) on a packed CSR batch + CLIPloss_v1 + CLIP cosine logits
+    ns = Namespace(modality=["CT", "pathology"], model_CT="resnetMC3_18", model_pathology="ABMIL", num_classes=2)
+    mc = mil_b200.model.utils_clip.get_model(ns).to(dev).to(torch.bfloat16).train(False)
+    g = torch.Generator().manual_seed(1234)
+    lens = torch.randint(100, 15593, (64,), generator=g)
+    off = torch.zeros(65, dtype=torch.int32)
+    off[1:] = lens.cumsum(0)
+    X = torch.randn(int(off[-1]), 768, device=dev, dtype=torch.bfloat16)
+    offd = off.to(dev)
+    x_ct = torch.randn(64, 512, device=dev, dtype=torch.bfloat16)
+    feats = (torch.randn(64, 9, 512, device=dev) * 0.3).to(torch.bfloat16)
+    crit = mil_b200.CLIPloss_v1(Namespace(clinical_features=list("abcdefghi")))
+    head = mil_b200.CLIPLogits().to(dev)
+    pl_c = list(mc.parameters())
+
+    def step_clip():
+        for p in pl_c:
+            p.grad = None
+        a, b, prob = mc.forward_csr(x_ct, X, offd)
+        li, lt = head(a, b)
+        (crit(b, feats) + li.diagonal().mean() * 1e-3 + prob.float().mean()).backward()
+
+    ms = timed(step_clip)
+    out.append({"workload": "aggregator_clip forward_csr (64 ragged bags 100..15592 x 768) + CLIPloss_v1 (I=9) + CLIP logits, "
+                            "fwd+bwd, bf16", "ms_per_step": ms, "bags_per_s": 64e3 / ms, "instances": int(off[-1])})
+
+    # configs[3]: masked MIL over padded CT-slice bags (B, 160, 768) with valid lengths + late-fusion head + BCE, fwd+bwd
+    ns = Namespace(modality=["CT", "pathology"], model_CT="resnetMC3_18_wMask", model_pathology="ABMIL", num_classes=2,
+                   clinical_features=list("abcdefghi"))
+    mw = mil_b200.get_model(ns).to(dev).to(torch.bfloat16).train(False)
+    Bw = 32
+    xpad = torch.randn(Bw, 160, 768, device=dev, dtype=torch.bfloat16)
+    lw = torch.randint(40, 161, (Bw,), generator=g).to(dev)
+    pfeat = torch.randn(Bw, 768, device=dev, dtype=torch.bfloat16)
+    tgt = torch.randint(0, 2, (Bw, 2), generator=g).float().to(dev)
+    pl_w = list(mw.parameters())
+
+    def step_wmask():
+        for p in pl_w:
+            p.grad = None
+        prob = mw.forward_padded(mw.extractor_pathology, xpad, lw, other_feats=(pfeat,))
+        torch.nn.functional.binary_cross_entropy(prob.float(), tgt).backward()
+
+    ms = timed(step_wmask)
+    out.append({"workload": "aggregator_wMask masked MIL: 32 padded CT bags (160 x 768, valid 40..160) + head + BCE, fwd+bwd, bf16",
+                "ms_per_step": ms, "bags_per_s": Bw * 1e3 / ms})
     return out
 
 
@@ -228,7 +287,7 @@ def main():
         if rank != 0:
             return 0
         lengths = bag_lengths(args.bags, 1234)
-        cb = cpu_reference(lengths, args.steps, args.warmup, budget_s=60.0)
+        cb = cpu_reference(lengths, args.steps, args.warmup, budget_s=60.0, per_step=16)
         line = {"impl": "reference", "metric": "bags/sec fwd+bwd", "value": cb["value"], "unit": "bags/s",
                 "n_gpus": args.gpus, "steps": cb["steps"], "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -464,7 +523,7 @@ def main():
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu_base = cpu_reference(lengths, steps=3, warmup=1, budget_s=20.0)
+        cpu_base = cpu_reference(lengths, steps=10 ** 6, warmup=1, budget_s=12.0)   # ~12 s of CPU work over the same bags
         cpu_base = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
