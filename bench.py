@@ -62,7 +62,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -353,7 +353,6 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     launches = mil_b200.launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -414,6 +413,7 @@ def main():
     h2d = X_h.numel() * 2 + off_pin.numel() * 4
     d2h = M_h[0].numel() * 4
     del X_d
+    clocks = sampler.stop() if rank == 0 else None     # sampled across both timed regions (device-resident and end-to-end)
 
     # ---- per-kernel roofline (timed alone, CUDA events on the launch stream, same inputs) ----
     kernels = []
