@@ -14,7 +14,8 @@ bool smallm_ok(int64_t m, int n, int k, int dtype);
 int smallm_fwd(const void* X, const void* add, const void* W, const float* bias, void* Y, int64_t m, int n, int k, int act,
                int dtype, cudaStream_t st);
 int smallm_bwd(const void* X, const void* add, const void* W, const void* Y, const void* dY, void* dX, float* dW,
-               float* dbias, int64_t m, int n, int k, int act, int dtype, int accumulate, cudaStream_t st);
+               float* dbias, int64_t m, int n, int k, int act, int dtype, int accumulate, float* ws, cudaStream_t st);
+size_t smallm_ws_bytes(int64_t m, int k);
 int splitk_reduce_gate(const float* part, int splits, int D, int L, int dh, float* out, cudaStream_t st);
 int splitk_reduce_gate64(const float* part, int splits, int D, int L, float* out, cudaStream_t st);
 int transpose2d(const void* in, void* out, int rows, int cols, int dtype, cudaStream_t st);
@@ -421,7 +422,7 @@ static int gate_bwd_simt(const T* X, const T* Wcat, const float* bcat, const flo
 
 // ---- linear workspace ------------------------------------------------------------------------------
 struct LinWs {
-  size_t xin, dypre, wT, part, total;
+  size_t xin, dypre, wT, part, smallm, total;
 };
 static bool tc_linear_ok(int64_t m, int n, int k, int dtype) {
   return dtype == MILB200_BF16 && !force_simt() && tc::gemm_store_supported(m, n, k);
@@ -445,6 +446,7 @@ static LinWs linear_ws(int64_t m, int n, int k, int dtype, int backward, int has
     w.wT = take(static_cast<size_t>(n) * k * e);
     size_t splits = tc_linear_bwd_ok(m, n, k, dtype) ? static_cast<size_t>(tc::gemm_tn_max_splits(n, k)) : simt_splits(m);
     w.part = take(sizeof(float) * splits * n * k);
+    if (smallm_ok(m, n, k, dtype)) w.smallm = take(smallm_ws_bytes(m, k));
   }
   w.total = align_up(off, 256) + 256;
   return w;
@@ -703,7 +705,10 @@ int milb200_linear_bwd(const void* X, const void* add, const void* W, const void
   if (smallm_ok(m, n, k, dtype) && aligned16(X) && aligned16(W) && (!add || aligned16(add)) && aligned16(dW)) {
     MIL_CHECK_ARG(act == MILB200_ACT_NONE || Y != nullptr, MILB200_EINVAL, "linear_bwd: the forward output Y is required for act=%d", act);
     MIL_CHECK_ARG(dW != nullptr || dbias == nullptr, MILB200_EINVAL, "linear_bwd: dbias without dW");
-    return smallm_bwd(X, add, W, Y, dY, dX, dW, dbias, m, n, k, act, dtype, accumulate, st);
+    LinWs ws_ = linear_ws(m, n, k, dtype, 1, add != nullptr);
+    MIL_CHECK_ARG(workspace && ws_bytes >= ws_.total, MILB200_EWORKSPACE, "linear_bwd: workspace %zu < %zu", ws_bytes, ws_.total);
+    return smallm_bwd(X, add, W, Y, dY, dX, dW, dbias, m, n, k, act, dtype, accumulate,
+                      reinterpret_cast<float*>(static_cast<char*>(workspace) + ws_.smallm), st);
   }
   LinWs w = linear_ws(m, n, k, dtype, 1, add != nullptr);
   MIL_CHECK_ARG(workspace && ws_bytes >= w.total, MILB200_EWORKSPACE, "linear_bwd: workspace %zu < %zu", ws_bytes, w.total);

@@ -81,20 +81,29 @@ k_smallm_fwd(const T* __restrict__ X, const T* __restrict__ add, const T* __rest
   }
 }
 
-// dX[i, kk] = sum_n g[i,n] W[n,kk], g = dY * act'(Y).  CTA = 64 input columns (2 per lane); warps split n.
+// dX[i, kk] = sum_n g[i,n] W[n,kk], g = dY * act'(Y).  CTA (x, y) = 64 input columns (2 per lane) x the y-th slice of the
+// output rows n; its 8 warps split the slice and fold in shared memory; slices are folded by k_smallm_dx_reduce in fixed
+// order.  (One CTA per 64 columns alone leaves 140 SMs idle and serialises 0.25-1 MB of weight reads behind 16 KB in flight.)
+constexpr int SMALLM_NSPLIT_MAX = 16;
 template <typename T, int MT>
 __global__ void __launch_bounds__(256)
-k_smallm_dx(const T* __restrict__ W, const T* __restrict__ Y, const T* __restrict__ dY, T* __restrict__ dX, int m, int n,
-            int k, int act) {
-  extern __shared__ __align__(16) float sm[];  // g[MT][n] | red[8][MT][64]
+k_smallm_dx(const T* __restrict__ W, const T* __restrict__ Y, const T* __restrict__ dY, float* __restrict__ part, int m, int n,
+            int k, int act, int rows_per_split) {
+  extern __shared__ __align__(16) float sm[];  // g[MT][rows_per_split] | red[8][MT][64]
+  const int n0 = blockIdx.y * rows_per_split;
+  const int n1 = min(n, n0 + rows_per_split);
+  const int ns = n1 - n0;
   float* gs = sm;
-  float* red = sm + MT * n;
+  float* red = sm + MT * rows_per_split;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  for (int i = t; i < MT * n; i += 256) {
-    const int r = i / n;
+  for (int i = t; i < MT * ns; i += 256) {
+    const int r = i / ns, c = i % ns;
     float v = 0.f;
-    if (r < m) v = act_grad<T>(to_f32<T>(dY[i]), act != MILB200_ACT_NONE ? to_f32<T>(Y[i]) : 0.f, act);
-    gs[i] = v;
+    if (r < m) {
+      const int64_t yo = static_cast<int64_t>(r) * n + n0 + c;
+      v = act_grad<T>(to_f32<T>(dY[yo]), act != MILB200_ACT_NONE ? to_f32<T>(Y[yo]) : 0.f, act);
+    }
+    gs[r * rows_per_split + c] = v;
   }
   __syncthreads();
   const int kk = blockIdx.x * 64 + lane * 2;
@@ -102,19 +111,18 @@ k_smallm_dx(const T* __restrict__ W, const T* __restrict__ Y, const T* __restric
 #pragma unroll
   for (int i = 0; i < MT; ++i) acc[i][0] = acc[i][1] = 0.f;
   if (kk < k) {
-    // the chain is load-latency bound (a warp touches 128-256 B per row): keep UNR independent rows in flight
-    constexpr int UNR = 16;
+    constexpr int UNR = 8;
     auto ldw = [&](int r, float& w0, float& w1) {
       if (sizeof(T) == 4) {
-        const float2 w2 = __ldg(reinterpret_cast<const float2*>(W + static_cast<int64_t>(r) * k + kk));
+        const float2 w2 = __ldg(reinterpret_cast<const float2*>(W + static_cast<int64_t>(n0 + r) * k + kk));
         w0 = w2.x; w1 = w2.y;
       } else {
-        const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(W + static_cast<int64_t>(r) * k + kk));
+        const uint32_t u = __ldg(reinterpret_cast<const uint32_t*>(W + static_cast<int64_t>(n0 + r) * k + kk));
         w0 = bf16lo(u); w1 = bf16hi(u);
       }
     };
     int r = warp;
-    for (; r + 8 * (UNR - 1) < n; r += 8 * UNR) {
+    for (; r + 8 * (UNR - 1) < ns; r += 8 * UNR) {
       float w0[UNR], w1[UNR];
 #pragma unroll
       for (int u = 0; u < UNR; ++u) ldw(r + 8 * u, w0[u], w1[u]);
@@ -122,18 +130,18 @@ k_smallm_dx(const T* __restrict__ W, const T* __restrict__ Y, const T* __restric
       for (int u = 0; u < UNR; ++u) {
 #pragma unroll
         for (int i = 0; i < MT; ++i) {
-          const float g = gs[i * n + r + 8 * u];
+          const float g = gs[i * rows_per_split + r + 8 * u];
           acc[i][0] = fmaf(g, w0[u], acc[i][0]);
           acc[i][1] = fmaf(g, w1[u], acc[i][1]);
         }
       }
     }
-    for (; r < n; r += 8) {
+    for (; r < ns; r += 8) {
       float w0, w1;
       ldw(r, w0, w1);
 #pragma unroll
       for (int i = 0; i < MT; ++i) {
-        const float g = gs[i * n + r];
+        const float g = gs[i * rows_per_split + r];
         acc[i][0] = fmaf(g, w0, acc[i][0]);
         acc[i][1] = fmaf(g, w1, acc[i][1]);
       }
@@ -145,6 +153,7 @@ k_smallm_dx(const T* __restrict__ W, const T* __restrict__ Y, const T* __restric
     red[(warp * MT + i) * 64 + lane * 2 + 1] = acc[i][1];
   }
   __syncthreads();
+  float* out = part + static_cast<int64_t>(blockIdx.y) * m * k;
   for (int e = t; e < m * 64; e += 256) {
     const int i = e / 64, c = e % 64;
     const int col = blockIdx.x * 64 + c;
@@ -152,8 +161,16 @@ k_smallm_dx(const T* __restrict__ W, const T* __restrict__ Y, const T* __restric
     float a = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) a += red[(w * MT + i) * 64 + c];
-    dX[static_cast<int64_t>(i) * k + col] = from_f32<T>(a);
+    out[static_cast<int64_t>(i) * k + col] = a;
   }
+}
+template <typename T>
+__global__ void k_smallm_dx_reduce(const float* __restrict__ part, int splits, int64_t mk, T* __restrict__ dX) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= mk) return;
+  float a = 0.f;
+  for (int s = 0; s < splits; ++s) a += part[static_cast<int64_t>(s) * mk + i];
+  dX[i] = from_f32<T>(a);
 }
 
 // dW[n, kk..kk+3] (+)= sum_i g[i,n] (X[i,kk..] + add[i,kk..]);  dbias[n] (+)= sum_i g[i,n]
@@ -219,18 +236,26 @@ static int smallm_fwd_t(const T* X, const T* add, const T* W, const float* bias,
   return MILB200_OK;
 }
 
+size_t smallm_ws_bytes(int64_t m, int k) { return sizeof(float) * SMALLM_NSPLIT_MAX * static_cast<size_t>(m) * k; }
+
 template <typename T>
 static int smallm_bwd_t(const T* X, const T* add, const T* W, const T* Y, const T* dY, T* dX, float* dW, float* dbias, int m,
-                        int n, int k, int act, int accumulate, cudaStream_t st) {
+                        int n, int k, int act, int accumulate, float* ws, cudaStream_t st) {
   const int mt = pad_rows(m);
   if (dX) {
-    const unsigned grid = static_cast<unsigned>((k + 63) / 64);
-    const size_t smem = sizeof(float) * (static_cast<size_t>(mt) * n + 8 * static_cast<size_t>(mt) * 64);
+    // enough (column block, row slice) CTAs to cover the SMs; at least 8 rows of W per warp
+    const int colblocks = (k + 63) / 64;
+    int splits = std::min(SMALLM_NSPLIT_MAX, std::max(1, (2 * sm_count() + colblocks - 1) / colblocks));
+    splits = std::min(splits, std::max(1, n / 64));
+    const int rps = (n + splits - 1) / splits;
+    splits = (n + rps - 1) / rps;
+    const dim3 grid(static_cast<unsigned>(colblocks), static_cast<unsigned>(splits));
+    const size_t smem = sizeof(float) * (static_cast<size_t>(mt) * rps + 8 * static_cast<size_t>(mt) * 64);
 #define MIL_SMALLM_DX(MT)                                                                                       \
   {                                                                                                             \
     auto kern = k_smallm_dx<T, MT>;                                                                             \
     if (smem > 48 * 1024) MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    kern<<<grid, 256, smem, st>>>(W, Y, dY, dX, m, n, k, act);                                                  \
+    kern<<<grid, 256, smem, st>>>(W, Y, dY, ws, m, n, k, act, rps);                                             \
   }
     switch (mt) {
       case 1: MIL_SMALLM_DX(1) break;
@@ -240,6 +265,9 @@ static int smallm_bwd_t(const T* X, const T* add, const T* W, const T* Y, const 
       default: MIL_SMALLM_DX(16) break;
     }
 #undef MIL_SMALLM_DX
+    MIL_LAUNCH_CHECK();
+    const int64_t mk = static_cast<int64_t>(m) * k;
+    k_smallm_dx_reduce<T><<<static_cast<unsigned>((mk + 255) / 256), 256, 0, st>>>(ws, splits, mk, dX);
     MIL_LAUNCH_CHECK();
   }
   if (dW) {
@@ -260,13 +288,13 @@ int smallm_fwd(const void* X, const void* add, const void* W, const float* bias,
 }
 
 int smallm_bwd(const void* X, const void* add, const void* W, const void* Y, const void* dY, void* dX, float* dW,
-               float* dbias, int64_t m, int n, int k, int act, int dtype, int accumulate, cudaStream_t st) {
+               float* dbias, int64_t m, int n, int k, int act, int dtype, int accumulate, float* ws, cudaStream_t st) {
   if (dtype == MILB200_BF16)
     return smallm_bwd_t<__nv_bfloat16>((const __nv_bfloat16*)X, (const __nv_bfloat16*)add, (const __nv_bfloat16*)W,
                                        (const __nv_bfloat16*)Y, (const __nv_bfloat16*)dY, (__nv_bfloat16*)dX, dW, dbias,
-                                       (int)m, n, k, act, accumulate, st);
+                                       (int)m, n, k, act, accumulate, ws, st);
   return smallm_bwd_t<float>((const float*)X, (const float*)add, (const float*)W, (const float*)Y, (const float*)dY,
-                             (float*)dX, dW, dbias, (int)m, n, k, act, accumulate, st);
+                             (float*)dX, dW, dbias, (int)m, n, k, act, accumulate, ws, st);
 }
 
 }  // namespace milb200
