@@ -11,6 +11,8 @@
 //                              EpiDz      its backward: recompute V,U, emit dZ + column sums
 //   k_gemm_tn                split-K  D[128 x 512] = sum_k A[k, m] B[k, n]  (both operands MN-major):
 //                            dW = dZ^T X of the gate / linear backward.
+#include <cstdlib>
+
 #include "tc_common.cuh"
 #include "tc_gemm.cuh"
 
@@ -565,6 +567,201 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): the two CTAs of a cluster own two adjacent 128-row tiles and share every B
+// (weight) tile — each loads HALF of it and the pair's MMA (M = 256, issued by the even CTA) reads both halves.  Per CTA
+// that halves the weight traffic from L2 (the main loop of the 1-SM kernel is bound by operand supply, not by the tensor
+// pipe) and shrinks a stage from 40 KB to 28 KB, i.e. more stages in flight.  Barriers: both CTAs' TMA loads credit the
+// leader's full barrier; the leader's MMA commits multicast to both CTAs' empty / accumulator-full barriers; both CTAs'
+// epilogue warps arrive on the leader's accumulator-empty barrier.
+// ---------------------------------------------------------------------------------------------
+template <int BN, class Epi>
+__host__ __device__ constexpr int kmajor2_stage_bytes() { return TileCfg<BN>::A_BYTES + TileCfg<BN>::B_BYTES / 2; }
+template <int BN, class Epi>
+__host__ __device__ constexpr int kmajor2_stages() {
+  int s = (SMEM_BUDGET - 1024 - BAR_BYTES - epi_bytes<BN, Epi>()) / kmajor2_stage_bytes<BN, Epi>();
+  return s > 8 ? 8 : s;
+}
+template <int BN, class Epi>
+constexpr size_t kmajor2_smem_bytes() {
+  return 1024 + static_cast<size_t>(kmajor2_stages<BN, Epi>()) * kmajor2_stage_bytes<BN, Epi>() + BAR_BYTES + epi_bytes<BN, Epi>();
+}
+
+template <int BN, class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+k_gemm_kmajor_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int64_t M, int N, int K,
+                  const __grid_constant__ typename Epi::Params ep) {
+  using Cfg = TileCfg<BN>;
+  static_assert(Cfg::N_MMA == 1 && BN % 32 == 0, "pair kernel: one UMMA per k step, B split in two 8-row-aligned halves");
+  constexpr int STAGES = kmajor2_stages<BN, Epi>();
+  constexpr int STAGE_BYTES = kmajor2_stage_bytes<BN, Epi>();
+  static_assert(STAGES >= 3 && STAGE_BYTES % 1024 == 0, "pair kernel pipeline");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;                   // [STAGES]  (the leader's are the ones in use)
+  uint64_t* empty_bar = bars + STAGES;         // [STAGES]  per CTA
+  uint64_t* tfull_bar = bars + 2 * STAGES;     // [2]       per CTA
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]     leader's
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint8_t* staging = smem + STAGES * STAGE_BYTES + BAR_BYTES;
+  float* esm = reinterpret_cast<float*>(staging + Epi::STAGING_BYTES);
+  static_assert((2 * STAGES + 4) * 8 + 8 <= BAR_BYTES, "barrier block overflow");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int64_t m_tiles = (M + BM - 1) / BM;
+  const int64_t p_tiles = (m_tiles + 1) / 2;                 // pairs of row tiles
+  const int64_t pair0 = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int n_tiles = (N + BN - 1) / BN;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + s, 1);
+      mbar_init(empty_bar + s, 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar + a, 1);
+      mbar_init(tempty_bar + a, 2 * EPI_WARPS);     // one arrival per epilogue warp of BOTH CTAs
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, Cfg::TMEM_COLS);
+  Epi::prologue(ep, esm, threadIdx.x);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                                          // the peer's barriers exist before anything signals them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): my A tile, my half of the B tile =====
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t pt = pair0; pt < p_tiles; pt += n_pairs) {
+        const int64_t mt = 2 * pt + rank;
+        for (int nt = 0; nt < n_tiles; ++nt) {
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(empty_bar + s, ph ^ 1);
+            uint8_t* sa = stage_base + s * STAGE_BYTES;
+            uint8_t* sb = sa + Cfg::A_BYTES;
+            if (rank == 0) mbar_arrive_expect_tx(full_bar + s, 2 * STAGE_BYTES);   // both CTAs' bytes land on my barrier
+            tma_load_2d_2sm(sa, &tmA, full_bar + s, kb * BK, static_cast<int32_t>(mt * BM),
+                            nt == n_tiles - 1 ? kEvictFirst : kEvictNormal);
+            tma_load_2d_2sm(sb, &tmB, full_bar + s, kb * BK, nt * BN + static_cast<int>(rank) * (BN / 2), kEvictLast);
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: the leader CTA only =====
+    if (rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
+      const uint64_t desc0 = umma_desc_sw128(smem_u32(stage_base), 16, 1024);
+      const uint32_t d_hi = static_cast<uint32_t>(desc0 >> 32);
+      const uint32_t a_lo0 = static_cast<uint32_t>(desc0);
+      const uint32_t b_lo0 = a_lo0 + (Cfg::A_BYTES >> 4);
+      int s = 0;
+      uint32_t ph = 0;
+      int64_t it = 0;
+      for (int64_t pt = pair0; pt < p_tiles; pt += n_pairs) {
+        for (int nt = 0; nt < n_tiles; ++nt, ++it) {
+          const int acc = static_cast<int>(it % Cfg::ACC_STAGES);
+          const uint32_t acc_ph = static_cast<uint32_t>((it / Cfg::ACC_STAGES) & 1);
+          mbar_wait(tempty_bar + acc, acc_ph ^ 1);
+          tc_fence_after();
+          const uint32_t tacc = tmem_base + acc * BN;
+          for (int kb = 0; kb < num_kb; ++kb) {
+            mbar_wait(full_bar + s, ph);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t so = static_cast<uint32_t>(s) * (STAGE_BYTES >> 4);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k)
+                umma_bf16_lohi_2sm(tacc, a_lo0 + so + k * (UMMA_K * 2 >> 4), d_hi, b_lo0 + so + k * (UMMA_K * 2 >> 4), d_hi,
+                                   idesc, (kb | k) != 0 ? 1u : 0u);
+              tc_commit_2sm(empty_bar + s);                              // frees the stage in BOTH CTAs
+              if (kb == num_kb - 1) tc_commit_2sm(tfull_bar + acc);      // accumulators complete in BOTH CTAs
+            }
+            __syncwarp();
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===== epilogue warps (both CTAs): my 128 rows of the pair's accumulator live in MY tensor memory =====
+    const int e = warp - EPI_WARP0;
+    Epi epi;
+    EpiCtx cx;
+    cx.M = M; cx.N = N; cx.n_tiles = n_tiles; cx.q = e & 3; cx.half = e >> 2; cx.lane = lane;
+    int64_t it = 0;
+    cx.iter = 0;
+    for (int64_t pt = pair0; pt < p_tiles; pt += n_pairs, ++cx.iter) {
+      const int64_t mt = 2 * pt + rank;
+      cx.row = mt * BM + cx.q * 32 + lane;
+      for (int nt = 0; nt < n_tiles; ++nt, ++it) {
+        const int acc = static_cast<int>(it % Cfg::ACC_STAGES);
+        const uint32_t acc_ph = static_cast<uint32_t>((it / Cfg::ACC_STAGES) & 1);
+        mbar_wait(tfull_bar + acc, acc_ph);
+        tc_fence_after();
+        const uint32_t tacc = tmem_base + acc * BN + (static_cast<uint32_t>(cx.q * 32) << 16);
+        cx.nt = nt;
+        cx.n0 = nt * BN;
+        epi.template tile<BN>(ep, esm, staging, tacc, cx);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(tempty_bar + acc);
+      }
+    }
+    epi.finish(ep, e, lane);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                     // neither CTA leaves (or frees tensor memory) while the pair is still working
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+template <int BN, class Epi>
+static int launch_kmajor_2sm(const void* A, int64_t M, int K, int64_t lda, const void* B, int N, int64_t ldb,
+                             typename Epi::Params ep, cudaStream_t st) {
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap_bf16_2d(&tmA, A, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmB, B, static_cast<uint64_t>(N), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), BN / 2);
+  if (rc) return rc;
+  auto kern = k_gemm_kmajor_2sm<BN, Epi>;
+  constexpr size_t smem = kmajor2_smem_bytes<BN, Epi>();
+  static_assert(smem <= 232448, "shared memory budget exceeded");
+  MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int64_t p_tiles = ((M + BM - 1) / BM + 1) / 2;
+  const int pairs = static_cast<int>(p_tiles < sm_count() / 2 ? p_tiles : sm_count() / 2);
+  kern<<<2 * pairs, NUM_THREADS, smem, st>>>(tmA, tmB, M, N, K, ep);
+  MIL_LAUNCH_CHECK();
+  return MILB200_OK;
+}
+
+static bool gate_2sm() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MILB200_GATE_2SM");      // default on; =0 selects the single-SM kernel
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 int debug_set_trace(void* dev_ptr) {
   unsigned long long* p = static_cast<unsigned long long*>(dev_ptr);
   MIL_CUDA(cudaMemcpyToSymbol(g_trace, &p, sizeof(p)));
@@ -614,10 +811,12 @@ int gated_score(const void* X, int64_t n, int L, const void* Wcat, const float* 
     ep.bcat = bcat; ep.ww = ww; ep.bw = bw; ep.scores = scores;
     int rc0 = make_tmap_bf16_2d_linear(&ep.tmS, gate_act, static_cast<uint64_t>(n), 2 * GATE_D, 2 * GATE_D, 32, 16);
     if (rc0) return rc0;
+    if (gate_2sm()) return launch_kmajor_2sm<GATE_BN, EpiScoreT<true>>(X, n, L, L, Wcat, 2 * GATE_D, L, ep, st);
     return launch_kmajor<GATE_BN, EpiScoreT<true>>(X, n, L, L, Wcat, 2 * GATE_D, L, ep, nullptr, st);
   }
   EpiScoreT<false>::Params ep;
   ep.bcat = bcat; ep.ww = ww; ep.bw = bw; ep.scores = scores;
+  if (gate_2sm()) return launch_kmajor_2sm<GATE_BN, EpiScoreT<false>>(X, n, L, L, Wcat, 2 * GATE_D, L, ep, st);
   return launch_kmajor<GATE_BN, EpiScoreT<false>>(X, n, L, L, Wcat, 2 * GATE_D, L, ep, nullptr, st);
 }
 
