@@ -444,7 +444,7 @@ def main():
         gemm_flops = 2.0 * n * Lf * 2 * D
         save = tr.save_gate and act is not None
         t_score = timeit(lambda: F.gated_scores(X, Wcat, bcat_c, v["ww"], v["bw"], save=save))
-        kernels.append({"name": "gated_score_fwd (k_gemm_kmajor<192x2,EpiScore%s>)" % ("+save V,U" if save else ""),
+        kernels.append({"name": "gated_score_fwd (k_gemm_kmajor_2sm<192x2,EpiScore%s>, CTA pairs)" % ("+save V,U" if save else ""),
                         "ms": t_score, "bound": "tensor",
                         "achieved": gemm_flops / t_score / 1e9, "peak": tf_peak, "unit": "TFLOP/s",
                         "algorithmic": "2*n*L*2D flop",
@@ -500,7 +500,7 @@ def main():
             ncu_traffic = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
         except Exception:
             ncu_traffic = {}
-        ncu_keys = {"gated_score_fwd": "k_gemm_kmajor<192, tc::EpiScoreT<%d>>" % (1 if save else 0),
+        ncu_keys = {"gated_score_fwd": "k_gemm_kmajor_2sm<192, tc::EpiScoreT<%d>>" % (1 if save else 0),
                     "segment_softmax_pool_fwd": "k_pool_fwd<__nv_bfloat16, 4>",
                     "segment_softmax_pool_bwd": "k_pool_bwd<__nv_bfloat16, 4>",
                     "gate_bwd dZ from saved": "k_gate_dz_saved", "gate_bwd dZ recompute": "k_gemm_kmajor<192, tc::EpiDz>",
