@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MILB200_VERSION 102
+#define MILB200_VERSION 103
 
 enum { MILB200_F32 = 0, MILB200_BF16 = 1 };
 
@@ -260,6 +260,10 @@ int milb200_tape_backward(const milb200_tape_op* ops, int n_ops, const milb200_t
 int milb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                       float lr, float beta1, float beta2, float eps, float weight_decay,
                       float grad_scale, int step, void* stream);
+/* torch.optim.SGD(lr, weight_decay) as the learnable-prompt configuration builds it (train_ddp.py:103-108; no
+ * momentum): p -= lr * (grad_scale * g + weight_decay * p).                                          */
+int milb200_sgd_step(float* param, const float* grad, int64_t n, float lr, float weight_decay, float grad_scale,
+                     void* stream);
 
 #ifdef __cplusplus
 }

@@ -254,6 +254,15 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
   }
 }
 
+__global__ void k_sgd(float* __restrict__ p, const float* __restrict__ g, int64_t n, float lr, float wd, float gscale) {
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) {
+    float pi = p[i];
+    p[i] = pi - lr * fmaf(wd, pi, g[i] * gscale);  // torch SGD: d_p = grad + weight_decay * param
+  }
+}
+
 // sigmoid + BCELoss(mean) fwd + bwd (n is tiny: B x num_classes)
 __global__ void k_sigmoid_bce(const float* __restrict__ z, const float* __restrict__ target, float* __restrict__ prob,
                               float* __restrict__ loss, float* __restrict__ dz, int n) {
@@ -513,6 +522,16 @@ int milb200_adam_step(float* param, const float* grad, float* exp_avg, float* ex
   unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 148 * 8));
   k_adam<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
                                                                 eps, weight_decay, grad_scale, bc1, bc2);
+  MIL_LAUNCH_CHECK();
+  return MILB200_OK;
+}
+
+int milb200_sgd_step(float* param, const float* grad, int64_t n, float lr, float weight_decay, float grad_scale,
+                     void* stream) {
+  MIL_CHECK_ARG(param && grad && n >= 0, MILB200_EINVAL, "sgd_step: bad arguments");
+  if (n == 0) return MILB200_OK;
+  unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 148 * 8));
+  k_sgd<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, n, lr, weight_decay, grad_scale);
   MIL_LAUNCH_CHECK();
   return MILB200_OK;
 }

@@ -44,13 +44,17 @@ def flat_layout(L_feat, D):
 class AbmilTrainer:
     def __init__(self, L_feat=1024, D=192, compute_dtype=torch.bfloat16, lr=1e-5, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=1e-7, device="cuda", process_group=None, world_size=1, need_input_grad=False,
-                 save_gate=True):
+                 save_gate=True, optimizer="adam"):
         self.L, self.D = L_feat, D
         self.dtype = compute_dtype
         self.device = torch.device(device)
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.pg, self.world = process_group, world_size
         self.need_input_grad = need_input_grad
+        if optimizer not in ("adam", "sgd"):
+            raise ValueError("optimizer must be 'adam' (train_ddp.py:113-116) or 'sgd' (train_ddp.py:105-108)")
+        self.optimizer = optimizer
+        self.phase_hook = None
         self.save_gate = save_gate     # keep V,U from the forward (memory) instead of re-running the GEMM (time)
         n = 2 * D * L_feat + 3 * D + 1
         self.numel = n
@@ -112,18 +116,24 @@ class AbmilTrainer:
                                                   L.dtype_code(self._wcat_c), L.ptr(self._bcat_c), L.stream_ptr()),
                 "pack_gate_weights")
         Wcat, bcat = self._wcat_c, self._bcat_c
+        mark = self.phase_hook or (lambda name: None)     # measurement only: bench.py records a CUDA event per phase
+        mark("pack")
         if self.save_gate:
             s, act = F.gated_scores(X, Wcat, bcat, v["ww"], v["bw"], save=True)
         else:
             s, act = F.gated_scores(X, Wcat, bcat, v["ww"], v["bw"]), None
+        mark("gated_score_fwd")
         M, _, am, _ = F.segment_softmax_pool(X, s, offsets)
+        mark("segment_softmax_pool_fwd")
         if dM is None:
             if getattr(self, "_ones", None) is None or self._ones.shape != M.shape:
                 self._ones = torch.ones_like(M)
             dM = self._ones
         ds, attn = F.segment_softmax_pool_bwd(X, s, offsets, dM, M, want_attn=self.need_input_grad)
+        mark("segment_softmax_pool_bwd")
         dX, *_ = F.gated_scores_bwd(X, Wcat, bcat, v["ww"], v["bw"], ds, attn, dM, offsets,
                                     self.need_input_grad, grad_out=self.grads, gate_act=act)
+        mark("gate_bwd")
         self.last_argmax, self.last_scores = am, s
         return M, dX
 
@@ -133,9 +143,13 @@ class AbmilTrainer:
             torch.distributed.all_reduce(self.grads, group=self.pg)
 
     def reduce_and_update(self):
-        """all-reduce(sum) of the flat gradient over NCCL, then fused Adam with grad_scale = 1/world."""
+        """all-reduce(sum) of the flat gradient over NCCL, then the fused optimiser step with grad_scale = 1/world."""
         self.allreduce_grads()
         self.step_count += 1
+        if self.optimizer == "sgd":
+            L.check(L.lib().milb200_sgd_step(L.ptr(self.params), L.ptr(self.grads), self.numel, self.lr, self.wd,
+                                             1.0 / self.world, L.stream_ptr()), "sgd_step")
+            return
         L.check(L.lib().milb200_adam_step(L.ptr(self.params), L.ptr(self.grads), L.ptr(self.exp_avg),
                                           L.ptr(self.exp_avg_sq), self.numel, self.lr, self.betas[0], self.betas[1],
                                           self.eps, self.wd, 1.0 / self.world, self.step_count, L.stream_ptr()),

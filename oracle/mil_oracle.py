@@ -269,6 +269,12 @@ def adam_step(param, grad, m, v, step, lr=1e-5, b1=0.9, b2=0.999, eps=1e-8, wd=1
     return param - lr * mhat / (np.sqrt(vhat) + eps), m, v
 
 
+def sgd_step(param, grad, lr=1e-3, wd=1e-7):
+    """torch.optim.SGD(lr, weight_decay) without momentum, as train_ddp.py:103-108 builds it."""
+    param, grad = map(_f, (param, grad))
+    return param - lr * (grad + wd * param)
+
+
 # --------------------------------------------------------------------------------------
 # synthetic-data helpers shared by tests, golden generation and the bench (no reference analogue:
 # the real data are private, dataset.py:366-393 only fixes the shapes)

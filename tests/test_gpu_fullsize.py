@@ -100,3 +100,29 @@ def test_fullsize_trainer_step_matches_module_autograd(big):
     assert rel_err(gv["Wcat"][:192].detach().cpu().numpy(), m.attention_V[0].weight.grad.detach().cpu().numpy()) <= 1e-4
     assert rel_err(gv["Wcat"][192:].detach().cpu().numpy(), m.attention_U[0].weight.grad.detach().cpu().numpy()) <= 1e-4
     assert rel_err(gv["ww"].detach().cpu().numpy(), m.attention_weights.weight.grad.detach().cpu().numpy().reshape(-1)) <= 1e-4
+
+
+@pytest.mark.parametrize("optimizer", ["adam", "sgd"])
+def test_trainer_update_matches_optimizer_oracle(optimizer):
+    """Three update steps of the fused optimiser kernels (Adam: train_ddp.py:113-116; SGD: train_ddp.py:105-108)
+    over the flat buffer against the float64 restatement (itself pinned to torch.optim in the CPU suite)."""
+    from mil_b200.dp import AbmilTrainer
+    lr = 1e-5 if optimizer == "adam" else 1e-3
+    tr = AbmilTrainer(96, 192, torch.float32, device="cuda", lr=lr, optimizer=optimizer)
+    g = torch.Generator().manual_seed(5)
+    p0 = torch.randn(tr.numel, generator=g) * 0.05
+    tr.params.copy_(p0)
+    pn = p0.double().numpy()
+    m = np.zeros_like(pn)
+    v = np.zeros_like(pn)
+    for step in (1, 2, 3):
+        grad = torch.randn(tr.numel, generator=g)
+        tr.grads.copy_(grad)
+        tr.reduce_and_update()
+        if optimizer == "adam":
+            pn, m, v = mo.adam_step(pn, grad.double().numpy(), m, v, step, lr=lr)
+        else:
+            pn = mo.sgd_step(pn, grad.double().numpy(), lr=lr)
+    got = tr.params.detach().cpu().numpy()
+    assert np.abs(got - pn).max() <= 1e-6 * np.abs(pn).max()
+    assert rel_err(got - p0.numpy(), pn - p0.double().numpy()) <= 1e-3      # the update itself, not just the parameters

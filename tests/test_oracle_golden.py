@@ -333,6 +333,16 @@ def test_head_bce_and_adam_against_torch():
         opt.step()
         pn, m, v = mo.adam_step(pn, g, m, v, step)
     assert rel_err(pn, p.detach().numpy()) < 1e-12
+    # the learnable-prompt configuration's optimiser (train_ddp.py:103-108)
+    p = torch.nn.Parameter(_t(W).clone())
+    opt = torch.optim.SGD([p], lr=1e-3, weight_decay=1e-7)
+    pn = W.astype(np.float64)
+    for step in (1, 2, 3):
+        g = rnd(20 + step, 2, 512)
+        p.grad = _t(g)
+        opt.step()
+        pn = mo.sgd_step(pn, g)
+    assert rel_err(pn, p.detach().numpy()) < 1e-12
 
 
 def test_pe_matches_reference_formula():
