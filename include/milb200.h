@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MILB200_VERSION 103
+#define MILB200_VERSION 104
 
 enum { MILB200_F32 = 0, MILB200_BF16 = 1 };
 
@@ -264,6 +264,22 @@ int milb200_adam_step(float* param, const float* grad, float* exp_avg, float* ex
  * momentum): p -= lr * (grad_scale * g + weight_decay * p).                                          */
 int milb200_sgd_step(float* param, const float* grad, int64_t n, float lr, float weight_decay, float grad_scale,
                      void* stream);
+
+/* ---- feeder, host side (dataset.py:366-393) ---------------------------------------------------------
+ * Gathers the per-slide feature matrices of one step (what `np.load(<patient>.npy)` returns: [rows_b, L] row-major
+ * HOST memory, fp32/fp64/fp16/bf16) into the packed-CSR batch the kernels read: rows back to back in `dst` (normally
+ * pinned host memory, fp32 or bf16 with round-to-nearest-even) plus offsets[n_bags+1].  Replaces the reference's
+ * zero-padding to 15 592 rows (dataset.py:383-390) and its per-sample `.float()`; `keep_rows[b]` (optional, strictly
+ * increasing, keep_counts[b] entries) is the augmentation subset `sorted(random.sample(range(n), k))` of
+ * dataset.py:375-381.  bag_pitch_bytes (optional) gives the byte stride between rows of each source matrix.
+ * n_threads <= 0 uses every hardware thread.  No CUDA calls; usable without a GPU.                               */
+enum { MILB200_HOST_F32 = 0, MILB200_HOST_BF16 = 1, MILB200_HOST_F16 = 2, MILB200_HOST_F64 = 3 };
+int milb200_pack_bags_offsets(const int64_t* bag_rows, const int64_t* keep_counts, int n_bags, int32_t* offsets,
+                              int64_t* total_rows);
+int milb200_pack_bags_host(const void* const* bag_ptrs, const int64_t* bag_rows, const int64_t* bag_pitch_bytes,
+                           const int32_t* const* keep_rows, const int64_t* keep_counts, int n_bags, int L,
+                           int src_dtype, void* dst, int dst_dtype, int64_t dst_capacity_rows, int32_t* offsets,
+                           int n_threads);
 
 #ifdef __cplusplus
 }

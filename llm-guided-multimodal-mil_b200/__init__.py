@@ -9,6 +9,8 @@ from . import functional
 from .abmil import ABMIL, ABMIL_v2
 from . import model
 from . import clip_loss
+from . import feeder
+from .feeder import PackedBagFeeder, pack_bags_host
 from .clip_loss import CLIPLogits, CLIPloss_v1
 from .model.sam.transformer import Attention, TwoWayAttentionBlock, TwoWayTransformer
 from .model.sam.common import MLPBlock

@@ -15,6 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmilb200.so")
 
 F32, BF16 = 0, 1
+HOST_F32, HOST_BF16, HOST_F16, HOST_F64 = 0, 1, 2, 3
 ACT_NONE, ACT_TANH, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 
 _p, _i, _i64, _sz, _f = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
@@ -66,6 +67,8 @@ SIGNATURES = {
     "milb200_tape_backward": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p, _sz, _i, _p]),
     "milb200_adam_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _i, _p]),
     "milb200_sgd_step": (_i, [_p, _p, _i64, _f, _f, _f, _p]),
+    "milb200_pack_bags_offsets": (_i, [_p, _p, _i, _p, _p]),
+    "milb200_pack_bags_host": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _i64, _p, _i]),
     "milb200_sigmoid_bce_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _i, _p]),
 }
 
