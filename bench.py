@@ -160,9 +160,14 @@ def cpu_reference(lengths, steps, warmup, budget_s=20.0, per_step=4):
     p = mo.procedural_state(mo.abmil_shapes(L_FEAT, D_GATE), 1234)
     sd = {"a." + k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in p.items()}
     g = torch.Generator().manual_seed(1234)
+    pool_rows = max(int(v) for v in lengths) + 4096
+    big = torch.randn(1, pool_rows, L_FEAT, generator=g)      # one host buffer; each bag is a window of it (not timed)
+    cursor = [0]
 
     def one_bag(n):
-        x = torch.randn(1, n, L_FEAT, generator=g)
+        start = cursor[0] % (pool_rows - n + 1)
+        cursor[0] += 997
+        x = big[:, start:start + n]
         for t in sd.values():
             t.grad = None
         t0 = time.perf_counter()
@@ -607,9 +612,9 @@ def main():
     secondary = None
     if rank == 0 and world == 1 and not args.no_secondary:
         try:
-            secondary = secondary_fusion(dev)
+            secondary = {"fusion": secondary_fusion(dev)}
         except Exception as e:  # never let a secondary measurement break the contract line
-            secondary = {"error": repr(e)[:200]}
+            secondary = {"fusion": {"error": repr(e)[:200]}}
         try:    # cfg 2 with log-uniform bag lengths (skewed slide sizes), same trainer, device-resident
             ll = bag_lengths_loguniform(args.bags, 1234)
             off_l = torch.zeros(args.bags + 1, dtype=torch.int32)
@@ -630,6 +635,31 @@ def main():
                                                     "instances_per_s": n_l * 20 / (a.elapsed_time(b) / 1e3)}
         except Exception as e:
             secondary["cfg2_loguniform_lengths"] = {"error": repr(e)[:200]}
+        try:    # BASELINE configs[0] (the reference's CPU-runnable case): 32 bags x 512 instances x 1024, fp32, fwd+bwd
+            B1, N1 = 32, 512
+            tr1 = AbmilTrainer(L_FEAT, D_GATE, torch.float32, device=dev)
+            tr1.load_from(module)
+            g1 = torch.Generator(device=dev).manual_seed(1234)
+            X1 = torch.randn(B1 * N1, L_FEAT, device=dev, generator=g1)
+            off1 = (torch.arange(B1 + 1, device=dev, dtype=torch.int32) * N1).contiguous()
+            for _ in range(3):
+                tr1.step(X1, off1)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(20):
+                tr1.step(X1, off1)
+            b.record()
+            torch.cuda.synchronize()
+            cfg1 = {"gpu_bags_per_s": B1 * 20 / (a.elapsed_time(b) / 1e3), "gpu_ms_per_step": a.elapsed_time(b) / 20,
+                    "gpu_dtype": "f32 (SIMT FFMA kernels, the <=1e-5 parity path), 32 bags packed in one CSR batch"}
+            if not args.no_cpu_baseline:
+                c1 = cpu_reference(torch.full((B1,), N1), steps=3, warmup=2, budget_s=6.0, per_step=B1)
+                cfg1.update({"cpu_bags_per_s": c1["value"], "cpu_cores": c1["cores"], "cpu_sample": c1["sample"]})
+            secondary["cfg1_32x512x1024_fp32"] = cfg1
+            del tr1, X1
+        except Exception as e:
+            secondary["cfg1_32x512x1024_fp32"] = {"error": repr(e)[:200]}
         try:    # §8f rank 4: the same step fed from per-slide fp32 host matrices through the native packer + copy stream
             from mil_b200 import feeder as fd
             offs_l = [0] + lengths.cumsum(0).tolist()
