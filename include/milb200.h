@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MILB200_VERSION 104
+#define MILB200_VERSION 105
 
 enum { MILB200_F32 = 0, MILB200_BF16 = 1 };
 
@@ -232,6 +232,8 @@ int milb200_ct_tokens_bwd(const void* dtokens, void* dfmap, int c, int t, int hw
 enum { MILB200_OP_LINEAR = 1, MILB200_OP_ATTENTION = 2, MILB200_OP_LAYERNORM = 3, MILB200_OP_ADD = 4 };
 typedef struct milb200_tape_op {
   int32_t kind, in0, in1, in2, out, p0, p1, a0;
+  int32_t lane; /* 0 or 1: ops of different lanes may run concurrently (two streams / parallel graph branches); the
+                   executor orders every cross-lane use of a slot, slot gradient or parameter gradient */
 } milb200_tape_op;
 typedef struct milb200_tape_slot {
   int64_t rows;

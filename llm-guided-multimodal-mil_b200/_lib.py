@@ -75,7 +75,7 @@ SIGNATURES = {
 
 
 class TapeOp(C.Structure):
-    _fields_ = [(n, C.c_int32) for n in ("kind", "in0", "in1", "in2", "out", "p0", "p1", "a0")]
+    _fields_ = [(n, C.c_int32) for n in ("kind", "in0", "in1", "in2", "out", "p0", "p1", "a0", "lane")]
 
 
 class TapeSlot(C.Structure):

@@ -21,6 +21,7 @@ struct TapePlan {
   size_t arena_bytes = 0;
   size_t max_slot_bytes = 0;
   size_t scratch_fwd = 0, scratch_bwd = 0;
+  int lanes = 1;                  // 2 when any op asks for lane 1
 };
 
 static inline size_t slot_bytes(const milb200_tape_slot& s, int dtype) {
@@ -37,6 +38,7 @@ static int tape_validate(const milb200_tape_op* ops, int n_ops, const milb200_ta
   for (int i = 0; i < n_ops; ++i) {
     const milb200_tape_op& o = ops[i];
     MIL_CHECK_ARG(ok_slot(o.out, false) && ok_slot(o.in0, false), MILB200_EINVAL, "tape: op %d has a bad slot id", i);
+    MIL_CHECK_ARG(o.lane == 0 || o.lane == 1, MILB200_EINVAL, "tape: op %d asks for lane %d (two lanes: 0, 1)", i, o.lane);
     const milb200_tape_slot& so = slots[o.out];
     const milb200_tape_slot& s0 = slots[o.in0];
     switch (o.kind) {
@@ -123,6 +125,7 @@ static TapePlan tape_plan(const milb200_tape_op* ops, int n_ops, const milb200_t
     }
     p.scratch_fwd = std::max(p.scratch_fwd, f);
     p.scratch_bwd = std::max(p.scratch_bwd, b);
+    if (o.lane == 1) p.lanes = 2;
   }
   p.arena_bytes = align_up(off, 256) + 256;
   p.scratch_fwd = align_up(p.scratch_fwd, 256) + 256;
@@ -130,10 +133,85 @@ static TapePlan tape_plan(const milb200_tape_op* ops, int n_ops, const milb200_t
   return p;
 }
 
-// backward workspace image: [kernel scratch][3 temporaries of max_slot_bytes][gradient buffer of every internal slot]
-static size_t tape_bwd_ws_bytes(const TapePlan& p) {
-  return p.scratch_bwd + 3 * align_up(p.max_slot_bytes, 256) + p.arena_bytes;
-}
+// backward workspace image: per lane [kernel scratch][3 temporaries of max_slot_bytes], then [gradient buffer of every
+// internal slot]
+static size_t tape_bwd_lane_bytes(const TapePlan& p) { return p.scratch_bwd + 3 * align_up(p.max_slot_bytes, 256); }
+static size_t tape_bwd_ws_bytes(const TapePlan& p) { return p.lanes * tape_bwd_lane_bytes(p) + p.arena_bytes; }
+
+// ---- lanes: two streams, ordered through events wherever they share a resource -----------------------------------
+// Every op records an event on its lane's stream; a resource (slot value, slot gradient, parameter gradient) remembers
+// its last toucher, and an op on the other lane waits for that toucher's event first.  Touches of one resource are
+// thereby totally ordered (same lane: stream order; other lane: event), which is all the reverse-mode accumulation
+// needs.  Inside a stream capture the same calls become the edges of two parallel graph branches.
+struct LaneRun {
+  cudaStream_t st[2] = {nullptr, nullptr};
+  bool two = false;
+  std::vector<cudaEvent_t>* pool = nullptr;
+  size_t next_ev = 0;
+  struct Touch { int lane = -1; int64_t seq = -1; cudaEvent_t ev = nullptr; };
+  std::vector<Touch> touch;          // per resource
+  int64_t seq = 0;
+  int64_t waited[2] = {-1, -1};      // waited[l]: newest op (seq) of the OTHER lane that lane l has already waited for
+  bool used1 = false;
+
+  cudaEvent_t fresh() {
+    if (next_ev == pool->size()) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      pool->push_back(e);
+    }
+    return (*pool)[next_ev++];
+  }
+  int begin(cudaStream_t main, cudaStream_t aux, int n_resources, std::vector<cudaEvent_t>* p) {
+    st[0] = main;
+    st[1] = aux;
+    two = aux != nullptr;
+    pool = p;
+    touch.assign(n_resources, Touch{});
+    return MILB200_OK;
+  }
+  // call once the prologue (seeds, memsets) is enqueued on lane 0
+  int fork() {
+    if (!two) return MILB200_OK;
+    cudaEvent_t e = fresh();
+    MIL_CHECK_ARG(e != nullptr, MILB200_ECUDA, "tape: cannot create an event");
+    MIL_CUDA(cudaEventRecord(e, st[0]));
+    MIL_CUDA(cudaStreamWaitEvent(st[1], e, 0));
+    return MILB200_OK;
+  }
+  cudaStream_t stream_of(int lane) const { return two ? st[lane] : st[0]; }
+  int before(int lane, const int* res, int n) {
+    if (!two) return MILB200_OK;
+    if (lane == 1) used1 = true;
+    for (int i = 0; i < n; ++i) {
+      if (res[i] < 0) continue;
+      const Touch& t = touch[res[i]];
+      if (t.lane < 0 || t.lane == lane || t.seq <= waited[lane]) continue;
+      MIL_CUDA(cudaStreamWaitEvent(st[lane], t.ev, 0));
+      waited[lane] = t.seq;
+    }
+    return MILB200_OK;
+  }
+  int after(int lane, const int* res, int n) {
+    if (!two) return MILB200_OK;
+    cudaEvent_t e = fresh();
+    MIL_CHECK_ARG(e != nullptr, MILB200_ECUDA, "tape: cannot create an event");
+    MIL_CUDA(cudaEventRecord(e, st[lane]));
+    const int64_t s = seq++;
+    for (int i = 0; i < n; ++i)
+      if (res[i] >= 0) touch[res[i]] = Touch{lane, s, e};
+    return MILB200_OK;
+  }
+  int join() {
+    if (!two) return MILB200_OK;
+    cudaEvent_t e = fresh();      // always join: lane 1 was forked into the caller's stream / capture
+    MIL_CHECK_ARG(e != nullptr, MILB200_ECUDA, "tape: cannot create an event");
+    MIL_CUDA(cudaEventRecord(e, st[1]));
+    MIL_CUDA(cudaStreamWaitEvent(st[0], e, 0));
+    return MILB200_OK;
+  }
+};
+static thread_local std::vector<cudaEvent_t> t_lane_events;
 
 }  // namespace milb200
 
@@ -150,21 +228,25 @@ size_t milb200_tape_workspace_bytes(const milb200_tape_op* ops, int n_ops, const
                                     int dtype, int backward) {
   if (!ops || !slots || n_ops <= 0 || n_slots <= 0) return 256;
   TapePlan p = tape_plan(ops, n_ops, slots, n_slots, dtype);
-  return backward ? tape_bwd_ws_bytes(p) : p.scratch_fwd;
+  return backward ? tape_bwd_ws_bytes(p) : p.lanes * p.scratch_fwd;
 }
 
 static int tape_forward_run(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
                             const milb200_tape_param* params, int n_params, void* const* ext_ptrs, const void* w_compute,
                             const float* p_f32, void* arena, size_t arena_bytes, void* workspace, size_t ws_bytes, int dtype,
-                            void* stream) {
+                            void* stream_main, void* stream_aux) {
   int rc = tape_validate(ops, n_ops, slots, n_slots, params, n_params);
   if (rc) return rc;
   MIL_CHECK_ARG(dtype == MILB200_F32 || dtype == MILB200_BF16, MILB200_EINVAL, "tape: bad dtype %d", dtype);
   MIL_CHECK_ARG(ext_ptrs && w_compute && p_f32 && arena, MILB200_EINVAL, "tape_forward: null pointer");
   TapePlan pl = tape_plan(ops, n_ops, slots, n_slots, dtype);
   MIL_CHECK_ARG(arena_bytes >= pl.arena_bytes, MILB200_EWORKSPACE, "tape_forward: arena %zu < %zu", arena_bytes, pl.arena_bytes);
-  MIL_CHECK_ARG(workspace && ws_bytes >= pl.scratch_fwd, MILB200_EWORKSPACE, "tape_forward: workspace %zu < %zu", ws_bytes,
-                pl.scratch_fwd);
+  MIL_CHECK_ARG(workspace && ws_bytes >= pl.lanes * pl.scratch_fwd, MILB200_EWORKSPACE, "tape_forward: workspace %zu < %zu",
+                ws_bytes, pl.lanes * pl.scratch_fwd);
+  LaneRun lr;
+  lr.begin(static_cast<cudaStream_t>(stream_main), pl.lanes == 2 ? static_cast<cudaStream_t>(stream_aux) : nullptr, n_slots,
+           &t_lane_events);
+  if ((rc = lr.fork())) return rc;
   const size_t esz = elem_size(dtype);
   char* ar = static_cast<char*>(arena);
   std::vector<void*> ptr(n_slots);
@@ -177,15 +259,20 @@ static int tape_forward_run(const milb200_tape_op* ops, int n_ops, const milb200
     const milb200_tape_op& o = ops[i];
     const milb200_tape_slot& s0 = slots[o.in0];
     const milb200_tape_slot& so = slots[o.out];
+    const int res[4] = {o.in0, o.in1, o.in2, o.out};
+    if ((rc = lr.before(o.lane, res, 4))) return rc;
+    void* stream = lr.stream_of(o.lane);
+    void* workspace_l = static_cast<char*>(workspace) + (lr.two ? o.lane : 0) * pl.scratch_fwd;
+    const size_t ws_l = pl.scratch_fwd;
     switch (o.kind) {
       case MILB200_OP_LINEAR:
         rc = milb200_linear_fwd(ptr[o.in0], o.in1 >= 0 ? ptr[o.in1] : nullptr, wc + params[o.p0].offset * esz,
                                 o.p1 >= 0 ? p_f32 + params[o.p1].offset : nullptr, ptr[o.out], s0.rows, so.cols, s0.cols, o.a0,
-                                dtype, workspace, ws_bytes, stream);
+                                dtype, workspace_l, ws_l, stream);
         break;
       case MILB200_OP_ATTENTION:
         rc = milb200_attention_fwd(ptr[o.in0], ptr[o.in1], ptr[o.in2], ptr[o.out], reinterpret_cast<float*>(ar + pl.aux_off[i]),
-                                   s0.rows, slots[o.in1].rows, o.a0, s0.cols / o.a0, dtype, workspace, ws_bytes, stream);
+                                   s0.rows, slots[o.in1].rows, o.a0, s0.cols / o.a0, dtype, workspace_l, ws_l, stream);
         break;
       case MILB200_OP_LAYERNORM: {
         float* mean = reinterpret_cast<float*>(ar + pl.aux_off[i]);
@@ -202,14 +289,16 @@ static int tape_forward_run(const milb200_tape_op* ops, int n_ops, const milb200
         rc = MILB200_EINVAL;
     }
     if (rc) return rc;
+    if ((rc = lr.after(o.lane, res, 4))) return rc;
   }
-  return MILB200_OK;
+  return lr.join();
 }
 
 static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
                              const milb200_tape_param* params, int n_params, void* const* ext_ptrs, void* const* ext_grad_ptrs,
                              const void* const* seed_ptrs, const void* w_compute, const float* p_f32, float* g_f32,
-                             const void* arena, size_t arena_bytes, void* workspace, size_t ws_bytes, int dtype, void* stream) {
+                             const void* arena, size_t arena_bytes, void* workspace, size_t ws_bytes, int dtype,
+                             void* stream_main, void* stream_aux) {
   int rc = tape_validate(ops, n_ops, slots, n_slots, params, n_params);
   if (rc) return rc;
   MIL_CHECK_ARG(dtype == MILB200_F32 || dtype == MILB200_BF16, MILB200_EINVAL, "tape: bad dtype %d", dtype);
@@ -219,15 +308,20 @@ static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb20
   MIL_CHECK_ARG(arena_bytes >= pl.arena_bytes, MILB200_EWORKSPACE, "tape_backward: arena %zu < %zu", arena_bytes, pl.arena_bytes);
   const size_t need = tape_bwd_ws_bytes(pl);
   MIL_CHECK_ARG(workspace && ws_bytes >= need, MILB200_EWORKSPACE, "tape_backward: workspace %zu < %zu", ws_bytes, need);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  cudaStream_t st = static_cast<cudaStream_t>(stream_main);
   const size_t esz = elem_size(dtype);
   const char* ar = static_cast<const char*>(arena);
   char* ws = static_cast<char*>(workspace);
-  void* scratch = ws;
   const size_t scratch_bytes = pl.scratch_bwd;
   const size_t tmp_stride = align_up(pl.max_slot_bytes, 256);
+  const size_t lane_bytes = tape_bwd_lane_bytes(pl);
+  char* gbase = ws + pl.lanes * lane_bytes;
+  // the lane of the op being processed selects the stream, kernel scratch and temporaries the lambdas below use
+  void* stream = stream_main;
+  void* scratch = ws;
   char* tmp0 = ws + pl.scratch_bwd;
-  char* gbase = tmp0 + 3 * tmp_stride;
+  LaneRun lr;
+  lr.begin(st, pl.lanes == 2 ? static_cast<cudaStream_t>(stream_aux) : nullptr, n_slots + std::max(n_params, 0), &t_lane_events);
 
   std::vector<const void*> val(n_slots);
   std::vector<void*> grad(n_slots);
@@ -257,6 +351,7 @@ static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb20
       total = std::max<int64_t>(total, params[i].offset + static_cast<int64_t>(params[i].rows) * params[i].cols);
     if (total > 0) MIL_CUDA(cudaMemsetAsync(g_f32, 0, sizeof(float) * static_cast<size_t>(total), st));
   }
+  if ((rc = lr.fork())) return rc;
 
   // where an op should write its gradient w.r.t. slot s: straight into the slot's buffer if nothing is there yet,
   // else into temporary `t` (folded in by settle())
@@ -269,7 +364,8 @@ static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb20
     if (wrote == grad[s]) { has[s] = 1; return MILB200_OK; }
     const int64_t n = slots[s].rows * slots[s].cols;
     if (!has[s]) {
-      MIL_CUDA(cudaMemcpyAsync(grad[s], wrote, static_cast<size_t>(n) * esz, cudaMemcpyDeviceToDevice, st));
+      MIL_CUDA(cudaMemcpyAsync(grad[s], wrote, static_cast<size_t>(n) * esz, cudaMemcpyDeviceToDevice,
+                               static_cast<cudaStream_t>(stream)));
       count_launch();
       has[s] = 1;
       return MILB200_OK;
@@ -283,6 +379,14 @@ static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb20
     const milb200_tape_slot& s0 = slots[o.in0];
     const milb200_tape_slot& so = slots[o.out];
     const void* dY = grad[o.out];
+    const int res[6] = {o.out, o.in0, o.in1, o.in2, o.p0 >= 0 ? n_slots + o.p0 : -1, o.p1 >= 0 ? n_slots + o.p1 : -1};
+    if ((rc = lr.before(o.lane, res, 6))) return rc;
+    {
+      const int ln = lr.two ? o.lane : 0;
+      stream = lr.stream_of(o.lane);
+      scratch = ws + ln * lane_bytes;
+      tmp0 = ws + ln * lane_bytes + pl.scratch_bwd;
+    }
     switch (o.kind) {
       case MILB200_OP_LINEAR: {
         const bool need_dx = needs[o.in0] || (o.in1 >= 0 && needs[o.in1]);
@@ -371,8 +475,9 @@ static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb20
       default:
         return MILB200_EINVAL;
     }
+    if ((rc = lr.after(o.lane, res, 6))) return rc;
   }
-  return MILB200_OK;
+  return lr.join();
 }
 
 
@@ -403,6 +508,16 @@ std::mutex g_graph_mu;
 std::vector<GraphEntry> g_graph_cache;
 std::unordered_set<uint64_t> g_graph_seen;
 cudaStream_t g_capture_stream = nullptr;
+cudaStream_t g_capture_lane = nullptr;         // lane 1 while capturing
+thread_local cudaStream_t t_eager_lane = nullptr;   // lane 1 when the program runs eagerly on the caller's stream
+
+cudaStream_t eager_lane() {
+  if (!t_eager_lane && cudaStreamCreateWithFlags(&t_eager_lane, cudaStreamNonBlocking) != cudaSuccess) {
+    cudaGetLastError();
+    t_eager_lane = nullptr;      // no second stream: LaneRun then keeps everything on the main one
+  }
+  return t_eager_lane;
+}
 uint64_t g_graph_tick = 0;
 constexpr size_t GRAPH_CACHE_MAX = 32;
 
@@ -424,10 +539,10 @@ struct Hasher {
   template <typename T> void val(const T& v) { bytes(&v, sizeof(T)); }
 };
 
-// run `body(stream)` either eagerly, or as a captured / replayed graph keyed by `key`
+// run `body(stream, lane-1 stream)` either eagerly, or as a captured / replayed graph keyed by `key`
 template <class Body>
 int run_keyed(uint64_t key, cudaStream_t user_stream, Body body) {
-  if (!graphs_enabled()) return body(user_stream);
+  if (!graphs_enabled()) return body(user_stream, eager_lane());
   std::unique_lock<std::mutex> lock(g_graph_mu);
   ++g_graph_tick;
   for (auto& e : g_graph_cache) {
@@ -445,18 +560,19 @@ int run_keyed(uint64_t key, cudaStream_t user_stream, Body body) {
     if (g_graph_seen.size() > 8192) g_graph_seen.clear();
     g_graph_seen.insert(key);
     lock.unlock();
-    return body(user_stream);
+    return body(user_stream, eager_lane());
   }
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   if (cudaStreamIsCapturing(user_stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
     cudaGetLastError();
     lock.unlock();
-    return body(user_stream);  // the caller is capturing already: just enqueue into its capture
+    return body(user_stream, eager_lane());  // the caller is capturing already: just enqueue into its capture
   }
   if (!g_capture_stream) MIL_CUDA(cudaStreamCreateWithFlags(&g_capture_stream, cudaStreamNonBlocking));
+  if (!g_capture_lane) MIL_CUDA(cudaStreamCreateWithFlags(&g_capture_lane, cudaStreamNonBlocking));
   const int64_t before = milb200_launch_count();
   MIL_CUDA(cudaStreamBeginCapture(g_capture_stream, cudaStreamCaptureModeThreadLocal));
-  const int rc = body(g_capture_stream);
+  const int rc = body(g_capture_stream, g_capture_lane);
   cudaGraph_t graph = nullptr;
   cudaError_t ce = cudaStreamEndCapture(g_capture_stream, &graph);
   count_launch(-static_cast<int>(milb200_launch_count() - before));  // nothing ran yet
@@ -465,7 +581,7 @@ int run_keyed(uint64_t key, cudaStream_t user_stream, Body body) {
     cudaGetLastError();
     lock.unlock();
     if (rc != MILB200_OK) return rc;
-    return body(user_stream);  // capture refused: run eagerly
+    return body(user_stream, eager_lane());  // capture refused: run eagerly
   }
   size_t nodes = 0;
   cudaGraphGetNodes(graph, nullptr, &nodes);
@@ -475,7 +591,7 @@ int run_keyed(uint64_t key, cudaStream_t user_stream, Body body) {
   if (ce != cudaSuccess || exec == nullptr) {
     cudaGetLastError();
     lock.unlock();
-    return body(user_stream);
+    return body(user_stream, eager_lane());
   }
   if (g_graph_cache.size() >= GRAPH_CACHE_MAX) {
     size_t victim = 0;
@@ -508,9 +624,9 @@ int milb200_tape_forward(const milb200_tape_op* ops, int n_ops, const milb200_ta
   if (params && n_params > 0) h.bytes(params, sizeof(milb200_tape_param) * n_params);
   h.bytes(ext_ptrs, sizeof(void*) * n_slots);
   h.val(w_compute); h.val(p_f32); h.val(arena); h.val(arena_bytes); h.val(workspace); h.val(ws_bytes); h.val(dtype);
-  return run_keyed(h.h, static_cast<cudaStream_t>(stream), [&](cudaStream_t st) {
+  return run_keyed(h.h, static_cast<cudaStream_t>(stream), [&](cudaStream_t st, cudaStream_t lane1) {
     return tape_forward_run(ops, n_ops, slots, n_slots, params, n_params, ext_ptrs, w_compute, p_f32, arena, arena_bytes,
-                            workspace, ws_bytes, dtype, st);
+                            workspace, ws_bytes, dtype, st, lane1);
   });
 }
 
@@ -530,9 +646,9 @@ int milb200_tape_backward(const milb200_tape_op* ops, int n_ops, const milb200_t
   h.bytes(seed_ptrs, sizeof(void*) * n_slots);
   h.val(w_compute); h.val(p_f32); h.val(g_f32); h.val(arena); h.val(arena_bytes); h.val(workspace); h.val(ws_bytes);
   h.val(dtype);
-  return run_keyed(h.h, static_cast<cudaStream_t>(stream), [&](cudaStream_t st) {
+  return run_keyed(h.h, static_cast<cudaStream_t>(stream), [&](cudaStream_t st, cudaStream_t lane1) {
     return tape_backward_run(ops, n_ops, slots, n_slots, params, n_params, ext_ptrs, ext_grad_ptrs, seed_ptrs, w_compute,
-                             p_f32, g_f32, arena, arena_bytes, workspace, ws_bytes, dtype, st);
+                             p_f32, g_f32, arena, arena_bytes, workspace, ws_bytes, dtype, st, lane1);
   });
 }
 

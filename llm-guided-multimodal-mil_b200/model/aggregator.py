@@ -119,8 +119,11 @@ class aggregator(nn.Module):
             xp, pe_p = t.input("Np", 768), t.input("Np", E)
             txt = t.input("T", E)
             xin_p = t.linear(xp, self.fc_pathology[0], act="tanh")                                   # :141
-            q1, k1 = self.TwoWayTransformer_Both.emit(t, ct, pe_ct, t.linear(txt, self.fc_CI2CT[0], act="tanh"),
-                                                      single_token=single_token)                    # :160
+            # the CT branch (160 tokens: ~180 tiny kernels) is independent of the pathology branch until the bag is
+            # assembled: lane 1 runs it on a second stream / as a parallel branch of the replayed graph
+            with t.lane(1):
+                q1, k1 = self.TwoWayTransformer_Both.emit(t, ct, pe_ct, t.linear(txt, self.fc_CI2CT[0], act="tanh"),
+                                                          single_token=single_token)                # :160
             q2, k2 = self.TwoWayTransformer_Both.emit(t, xin_p, pe_p, t.linear(txt, self.fc_CI2Pth[0], act="tanh"),
                                                       single_token=single_token)                    # :168
             bag = t.buffer(lambda r: 2 * r["T"] + r["Nc"] + r["Np"], E)                             # :173 row order

@@ -23,7 +23,8 @@ _ACT = {None: L.ACT_NONE, "none": L.ACT_NONE, "tanh": L.ACT_TANH, "relu": L.ACT_
 
 class Tape:
     def __init__(self):
-        self.ops = []            # (kind, in0, in1, in2, out, p0, p1, a0)
+        self.ops = []            # (kind, in0, in1, in2, out, p0, p1, a0, lane)
+        self._lane = 0           # ops emitted now go to this lane (0 or 1); lanes run concurrently on two streams
         self.slot_rows = []      # symbolic row key per slot
         self.slot_cols = []
         self.slot_ext = []       # 0 internal, 1 external input, 2 external output (lives in an output buffer)
@@ -55,16 +56,36 @@ class Tape:
             self.params.append(p)
         return self._pidx[k]
 
+    def lane(self, n):
+        """Context manager: ops emitted inside run on lane `n` (0 or 1).  Lanes are executed on two streams (parallel
+        branches of the replayed CUDA graph); the executor orders every cross-lane use of a slot, a slot gradient or a
+        parameter gradient, so ANY assignment is correct — it only pays off for independent sub-programs such as the
+        CT and pathology branches of aggregator.py:160,168."""
+        tape = self
+
+        class _Lane:
+            def __enter__(self_inner):
+                self_inner.prev = tape._lane
+                tape._lane = int(n)
+
+            def __exit__(self_inner, *exc):
+                tape._lane = self_inner.prev
+        if n not in (0, 1):
+            raise L.MilB200Error("tape.lane: two lanes are available (0, 1)")
+        if os.environ.get("MILB200_TAPE_LANES", "1") == "0":      # switch: keep the whole program on one stream
+            n = 0
+        return _Lane()
+
     def linear(self, x, lin, act=None, add=None):
         """out = act((x [+ add]) W^T + b) for an ``nn.Linear`` parameter container."""
         out = self.slot(self.slot_rows[x], lin.weight.shape[0])
         self.ops.append((L.OP_LINEAR, x, -1 if add is None else add, -1, out, self.param(lin.weight), self.param(lin.bias),
-                         _ACT[act]))
+                         _ACT[act], self._lane))
         return out
 
     def attention(self, q, k, v, heads):
         out = self.slot(self.slot_rows[q], self.slot_cols[q])
-        self.ops.append((L.OP_ATTENTION, q, k, v, out, -1, -1, int(heads)))
+        self.ops.append((L.OP_ATTENTION, q, k, v, out, -1, -1, int(heads), self._lane))
         return out
 
     def layernorm(self, x, ln, residual=None):
@@ -72,14 +93,14 @@ class Tape:
             raise L.MilB200Error("layernorm kernels are built for eps = 1e-5 (nn.LayerNorm default)")
         out = self.slot(self.slot_rows[x], self.slot_cols[x])
         self.ops.append((L.OP_LAYERNORM, x, -1 if residual is None else residual, -1, out, self.param(ln.weight),
-                         self.param(ln.bias), 0))
+                         self.param(ln.bias), 0, self._lane))
         return out
 
     def add(self, a, b):
         """out = a + b as a slot of its own, for sums that several ops consume (keys + key_pe feeds two projections
         per block: materialise it once instead of once per consumer)."""
         out = self.slot(self.slot_rows[a], self.slot_cols[a])
-        self.ops.append((L.OP_ADD, a, b, -1, out, -1, -1, 0))
+        self.ops.append((L.OP_ADD, a, b, -1, out, -1, -1, 0, self._lane))
         return out
 
     def buffer(self, rows_fn, cols):

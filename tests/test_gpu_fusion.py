@@ -421,3 +421,43 @@ def test_graph_replay_tracks_new_inputs_and_parameter_updates(monkeypatch):
     m([x_ct, xa], x_t)[0][0, 0].backward()
     m([x_ct, xb], x_t)[0][0, 1].backward()
     assert _rel(ga, xa.grad) <= 1e-6 and _rel(gb, xb.grad) <= 1e-6
+
+
+@pytest.mark.parametrize("T,dtype", [(1, torch.float32), (10, torch.float32), (10, torch.bfloat16)])
+def test_two_lane_schedule_is_bit_identical_to_one_stream(monkeypatch, T, dtype):
+    """The CT branch runs on lane 1 (second stream / parallel graph branch).  Lanes only change WHEN kernels run, never
+    the order in which contributions are folded into a gradient, so outputs and every gradient must be bit-identical
+    to the single-stream schedule — eagerly (first call), while capturing (second) and on graph replay (third+)."""
+    import mil_b200
+    torch.manual_seed(21)
+    x_ct = torch.randn(1, 512, 160, 1, 1, device="cuda", dtype=dtype).requires_grad_(True)
+    x_p = torch.randn(1, 2311, 768, device="cuda", dtype=dtype).requires_grad_(True)
+    x_t = (torch.randn(1, T, 512, device="cuda") * 0.05).to(dtype).requires_grad_(True)
+    state = None
+    runs = {}
+    for lanes in ("0", "1"):
+        monkeypatch.setenv("MILB200_TAPE_LANES", lanes)
+        torch.manual_seed(3)
+        m = mil_b200.get_model(ARGS).cuda().to(dtype).eval()      # fresh module: its tape is recorded under this setting
+        if state is None:
+            state = {k: v.clone() for k, v in m.state_dict().items()}
+        m.load_state_dict(state)
+        assert {o[8] for o in m._fusion_tape(T == 1).ops} == ({0} if lanes == "0" else {0, 1})
+        outs = []
+        for call in range(4):
+            for t in (x_ct, x_p, x_t):
+                t.grad = None
+            m.zero_grad(set_to_none=True)
+            prob, a, b = m([x_ct, x_p], x_t)
+            (prob.float()[0, 1] + (a.float() * b.float()).sum()).backward()
+            torch.cuda.synchronize()
+            outs.append(dict(prob=prob.detach().clone(), a=a.detach().clone(), b=b.detach().clone(),
+                             dct=x_ct.grad.clone(), dp=x_p.grad.clone(), dt=x_t.grad.clone(),
+                             **{"g." + k: v.grad.clone() for k, v in m.named_parameters() if v.grad is not None}))
+        for call in range(1, 4):                                   # eager == captured == replayed
+            for k, v in outs[0].items():
+                assert torch.equal(v, outs[call][k]), (lanes, call, k)
+        runs[lanes] = outs[0]
+    assert runs["0"].keys() == runs["1"].keys()
+    for k, v in runs["0"].items():
+        assert torch.equal(v, runs["1"][k]), k

@@ -83,6 +83,39 @@ def test_native_validator_rejects_malformed_programs(model):
     rc = lib.milb200_tape_forward(ops, c["n_ops"], slots, n, c["params"], c["n_params"], ext, dummy, dummy, dummy, 1 << 30,
                                   dummy, 1 << 30, L.F32, None)
     assert rc != 0 and b"unknown kind" in lib.milb200_last_error()
+    # (4) only two lanes exist
+    ops = (L.TapeOp * c["n_ops"])(*c["ops"])
+    ops[3].lane = 2
+    rc = lib.milb200_tape_forward(ops, c["n_ops"], slots, n, c["params"], c["n_params"], ext, dummy, dummy, dummy, 1 << 30,
+                                  dummy, 1 << 30, L.F32, None)
+    assert rc != 0 and b"lane" in lib.milb200_last_error()
+
+
+def test_fusion_program_puts_the_ct_branch_on_its_own_lane(model):
+    """aggregator.py:160 (CT) and :168 (pathology) are independent until the bag is assembled: the CT branch's ops carry
+    lane 1, everything else lane 0, and a second lane doubles the per-lane scratch the executor asks for."""
+    import mil_b200
+    from mil_b200 import _lib as L
+    lib = mil_b200.lib()
+    t = model._fusion_tape()
+    lanes = [o[8] for o in t.ops]
+    assert set(lanes) == {0, 1}
+    ct_in = t.inputs[0]
+    reach = {ct_in}
+    for o in t.ops:                                   # everything computed from the CT tokens sits on lane 1
+        if any(x in reach for x in o[1:4] if x >= 0):
+            reach.add(o[4])
+            assert o[8] == 1
+    assert t.ops[0][8] == 0                           # fc_pathology
+    c = t._freeze()
+    rows = {"T": 1, "Nc": 160, "Np": 300}
+    slots = t._slots(rows)
+    two = lib.milb200_tape_workspace_bytes(c["ops"], c["n_ops"], slots, c["n_slots"], L.BF16, 0)
+    ops1 = (L.TapeOp * c["n_ops"])(*c["ops"])
+    for o in ops1:
+        o.lane = 0
+    one = lib.milb200_tape_workspace_bytes(ops1, c["n_ops"], slots, c["n_slots"], L.BF16, 0)
+    assert two == 2 * one
 
 
 def test_c_abi_argument_checks_launch_nothing():
