@@ -49,10 +49,12 @@ k_gate_fwd(const float* __restrict__ Z, const float* __restrict__ ww, const floa
 
 constexpr int GATE_MAX_DPL = 8;  // D <= 256 on the FFMA path
 
-// in place: Z (pre-activations, bias included) -> dZ = [dVpre | dUpre]; column sums accumulate atomically
+// in place: Z (pre-activations, bias included) -> dZ = [dVpre | dUpre]; the column sums leave as one record per CTA
+// [dVpre D | dUpre D | ds*V*U D | sum ds] that k_gate_bwd_fold adds up in CTA order (deterministic, no atomics)
 __global__ void __launch_bounds__(256)
 k_gate_bwd(float* __restrict__ Z, const float* __restrict__ ww, const float* __restrict__ dscores, int64_t rows, int D,
-           float* __restrict__ dbcat, float* __restrict__ dww, float* __restrict__ dbw) {
+           float* __restrict__ rec) {
+  __shared__ float red[8][3 * 32 * GATE_MAX_DPL + 1];
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * 8;
@@ -79,16 +81,38 @@ k_gate_bwd(float* __restrict__ Z, const float* __restrict__ ww, const float* __r
       }
     }
   }
+  const int wib = threadIdx.x >> 5;
 #pragma unroll
   for (int j = 0; j < GATE_MAX_DPL; ++j) {
     int d = lane + j * 32;
     if (d < D) {
-      atomicAdd(dbcat + d, sv[j]);
-      atomicAdd(dbcat + D + d, su[j]);
-      atomicAdd(dww + d, sw[j]);
+      red[wib][d] = sv[j];
+      red[wib][D + d] = su[j];
+      red[wib][2 * D + d] = sw[j];
     }
   }
-  if (lane == 0) atomicAdd(dbw, sds);
+  sds = warp_sum(sds);
+  if (lane == 0) red[wib][3 * D] = sds;
+  __syncthreads();
+  const int rl = 3 * D + 1;
+  for (int c = threadIdx.x; c < rl; c += blockDim.x) {
+    float a = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) a += red[w8][c];
+    rec[static_cast<int64_t>(blockIdx.x) * rl + c] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_gate_bwd_fold(const float* __restrict__ rec, int nrec, int D, float* __restrict__ dbcat, float* __restrict__ dww,
+                float* __restrict__ dbw, int accumulate) {
+  const int rl = 3 * D + 1;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= rl) return;
+  float a = 0.f;
+  for (int b = 0; b < nrec; ++b) a += rec[static_cast<int64_t>(b) * rl + c];
+  float* o = c < 2 * D ? dbcat + c : (c < 3 * D ? dww + (c - 2 * D) : dbw);
+  *o = accumulate ? *o + a : a;
 }
 
 // records: [ncta][8 epilogue warps e = half*4 + q][stride]; column d of each kind was produced by the warps whose
@@ -256,65 +280,69 @@ k_colsum(const T* __restrict__ A, int64_t rows, int cols, float* __restrict__ ou
   }
 }
 
-// same result, 128-bit loads: a CTA owns 32 x VN columns and a slab of rows; its 8 warps stride the rows with four
-// independent loads in flight each, fold in shared memory, one atomicAdd per column per CTA
+// Deterministic variant (what the library uses): one CTA owns ONE 16-byte vector column over ALL rows, so there is no
+// cross-CTA reduction and no atomics; threads stride the rows with four independent loads in flight, then fold through
+// a fixed shuffle tree and a fixed-order pass over the warps' partials.  `accumulate` is applied by the single writer
+// (no memset node in front).  The operand is the tensor the previous kernel just wrote (L2-resident), so the half-used
+// 32-byte sectors of the 16-byte-wide stripes cost L2 bandwidth, not HBM.
 template <typename T>
-__global__ void __launch_bounds__(256)
-k_colsum_vec(const T* __restrict__ A, int64_t rows, int cols, float* __restrict__ out, int rows_per_block) {
+__global__ void __launch_bounds__(1024)
+k_colsum_det(const T* __restrict__ A, int64_t rows, int cols, float* __restrict__ out, int accumulate) {
   constexpr int VN = Vec16<T>::N;
-  __shared__ float red[8][32 * VN + 1];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int vec = blockIdx.x * 32 + lane;           // vector column
+  __shared__ float red[32][VN];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int nvec = cols / VN;
-  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * rows_per_block;
-  const int64_t r1 = (r0 + rows_per_block < rows) ? r0 + rows_per_block : rows;
+  const uint4* base = reinterpret_cast<const uint4*>(A) + blockIdx.x;
   float acc[VN];
 #pragma unroll
   for (int e = 0; e < VN; ++e) acc[e] = 0.f;
-  if (vec < nvec) {
-    const uint4* base = reinterpret_cast<const uint4*>(A) + vec;
-    int64_t r = r0 + warp;
-    for (; r + 24 < r1; r += 32) {
-      uint4 v[4];
+  const int64_t step = blockDim.x;
+  int64_t r = threadIdx.x;
+  for (; r + 3 * step < rows; r += 4 * step) {
+    uint4 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = ldg_stream(base + (r + 8 * u) * nvec);
+    for (int u = 0; u < 4; ++u) v[u] = ldg_stream(base + (r + u * step) * nvec);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float f[VN];
-        Vec16<T>::unpack(v[u], f);
-#pragma unroll
-        for (int e = 0; e < VN; ++e) acc[e] += f[e];
-      }
-    }
-    for (; r < r1; r += 8) {
+    for (int u = 0; u < 4; ++u) {
       float f[VN];
-      Vec16<T>::unpack(ldg_stream(base + r * nvec), f);
+      Vec16<T>::unpack(v[u], f);
 #pragma unroll
       for (int e = 0; e < VN; ++e) acc[e] += f[e];
     }
   }
+  for (; r < rows; r += step) {
+    float f[VN];
+    Vec16<T>::unpack(ldg_stream(base + r * nvec), f);
 #pragma unroll
-  for (int e = 0; e < VN; ++e) red[warp][lane * VN + e] = acc[e];
+    for (int e = 0; e < VN; ++e) acc[e] += f[e];
+  }
+#pragma unroll
+  for (int e = 0; e < VN; ++e) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int e = 0; e < VN; ++e) red[warp][e] = acc[e];
+  }
   __syncthreads();
-  for (int c = threadIdx.x; c < 32 * VN; c += 256) {
-    const int col = blockIdx.x * 32 * VN + c;
-    if (col >= cols) continue;
+  if (threadIdx.x < VN) {
     float a = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) a += red[w][c];
-    atomicAdd(out + col, a);
+    for (int w = 0; w < nwarp; ++w) a += red[w][threadIdx.x];
+    float* o = out + static_cast<int64_t>(blockIdx.x) * VN + threadIdx.x;
+    *o = accumulate ? *o + a : a;
   }
 }
 
+// out[c] = (accumulate ? out[c] : 0) + sum_r A[r, c]
 template <typename T>
-static int colsum_launch(const T* A, int64_t rows, int cols, float* out, cudaStream_t st) {
+static int colsum_launch(const T* A, int64_t rows, int cols, float* out, int accumulate, cudaStream_t st) {
   constexpr int VN = Vec16<T>::N;
   if (cols % VN == 0 && aligned16(A)) {
-    int64_t slabs = std::max<int64_t>(1, std::min<int64_t>((rows + 63) / 64, (2 * sm_count() * 32 * VN + cols - 1) / cols));
-    int rpb = static_cast<int>((rows + slabs - 1) / slabs);
-    dim3 grid(static_cast<unsigned>((cols / VN + 31) / 32), static_cast<unsigned>((rows + rpb - 1) / rpb));
-    k_colsum_vec<T><<<grid, 256, 0, st>>>(A, rows, cols, out, rpb);
-  } else {
+    int threads = static_cast<int>(std::min<int64_t>(1024, ((rows + 31) / 32) * 32));
+    k_colsum_det<T><<<static_cast<unsigned>(cols / VN), threads, 0, st>>>(A, rows, cols, out, accumulate);
+  } else {   // odd widths (no caller on the shipped path): the atomic kernels
+    if (!accumulate) MIL_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
     int rpb = 128;
     k_colsum<T><<<static_cast<unsigned>((rows + rpb - 1) / rpb), 256, 0, st>>>(A, rows, cols, out, rpb);
   }
@@ -341,7 +369,7 @@ struct GateWs {
   // tensor-core path
   size_t dz, colsum, part, wT;
   // FFMA path
-  size_t z, spart;
+  size_t z, spart, rec;
   size_t total;
 };
 static GateWs gate_ws(int64_t total_n, int L, int D, int dtype, int backward) {
@@ -362,7 +390,10 @@ static GateWs gate_ws(int64_t total_n, int L, int D, int dtype, int backward) {
   } else {
     int64_t rows = std::min<int64_t>(total_n, SIMT_ROW_CHUNK);
     w.z = take(sizeof(float) * static_cast<size_t>(rows) * 2 * D);
-    if (backward) w.spart = take(sizeof(float) * simt_splits(rows) * 2 * D * L);
+    if (backward) {
+      w.spart = take(sizeof(float) * simt_splits(rows) * 2 * D * L);
+      w.rec = take(sizeof(float) * static_cast<size_t>(sm_count()) * 4 * (3 * D + 1));
+    }
   }
   w.total = align_up(off, 256) + 256;
   return w;
@@ -391,9 +422,7 @@ static int gate_bwd_simt(const T* X, const T* Wcat, const float* bcat, const flo
   MIL_CHECK_ARG(D <= 32 * GATE_MAX_DPL, MILB200_EUNSUPPORTED, "gated_score_bwd (FFMA path): D=%d > %d", D, 32 * GATE_MAX_DPL);
   float* Z = reinterpret_cast<float*>(ws + w.z);
   float* part = reinterpret_cast<float*>(ws + w.spart);
-  MIL_CUDA(cudaMemsetAsync(dbcat, 0, sizeof(float) * 2 * D, st));
-  MIL_CUDA(cudaMemsetAsync(dww, 0, sizeof(float) * D, st));
-  MIL_CUDA(cudaMemsetAsync(dbw, 0, sizeof(float), st));
+  float* rec = reinterpret_cast<float*>(ws + w.rec);
   int chunk = 0;
   for (int64_t r0 = 0; r0 < total_n; r0 += SIMT_ROW_CHUNK, ++chunk) {
     int64_t rows = std::min<int64_t>(SIMT_ROW_CHUNK, total_n - r0);
@@ -401,7 +430,9 @@ static int gate_bwd_simt(const T* X, const T* Wcat, const float* bcat, const flo
     int rc = simt::launch<T, T, true, true>(X + r0 * L, L, Wcat, L, rows, 2 * D, L, 1, ep, st);
     if (rc) return rc;
     unsigned blocks = static_cast<unsigned>(std::min<int64_t>((rows + 7) / 8, sm_count() * 4));
-    k_gate_bwd<<<blocks, 256, 0, st>>>(Z, ww, dscores + r0, rows, D, dbcat, dww, dbw);
+    k_gate_bwd<<<blocks, 256, 0, st>>>(Z, ww, dscores + r0, rows, D, rec);
+    MIL_LAUNCH_CHECK();
+    k_gate_bwd_fold<<<(3 * D + 1 + 255) / 256, 256, 0, st>>>(rec, static_cast<int>(blocks), D, dbcat, dww, dbw, chunk > 0);
     MIL_LAUNCH_CHECK();
     // dWcat[j, l] (+)= sum_i dZ[i, j] X[i, l]
     int splits = static_cast<int>(simt_splits(rows));
@@ -466,9 +497,9 @@ int milb200_add(const void* a, const void* b, void* out, int64_t n, int dtype, v
 int milb200_colsum(const void* A, int64_t rows, int cols, float* out, int dtype, int accumulate, void* stream) {
   MIL_CHECK_ARG(A && out && rows > 0 && cols > 0, MILB200_EINVAL, "colsum: bad arguments");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!accumulate) MIL_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * cols, st));
-  if (dtype == MILB200_BF16) return colsum_launch<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(A), rows, cols, out, st);
-  return colsum_launch<float>(static_cast<const float*>(A), rows, cols, out, st);
+  if (dtype == MILB200_BF16)
+    return colsum_launch<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(A), rows, cols, out, accumulate, st);
+  return colsum_launch<float>(static_cast<const float*>(A), rows, cols, out, accumulate, st);
 }
 
 int milb200_debug_trace(void* dev_u64x16) { return tc::debug_set_trace(dev_u64x16); }
@@ -658,8 +689,7 @@ static int linear_bwd_t(const T* Xin, const T* W, const T* Y, const T* dY, T* dX
     dypre = tmp;
   }
   if (dbias) {
-    if (!accumulate) MIL_CUDA(cudaMemsetAsync(dbias, 0, sizeof(float) * n, st));
-    int rcs = colsum_launch<T>(dypre, m, n, dbias, st);
+    int rcs = colsum_launch<T>(dypre, m, n, dbias, accumulate, st);
     if (rcs) return rcs;
   }
   float* part = reinterpret_cast<float*>(ws + w.part);

@@ -1,8 +1,6 @@
 set -x
 cd /root/repo
-timeout 600 python bench.py > gpurun_out/bench13.json 2> gpurun_out/bench13.err; echo "bench rc=$?" >> gpurun_out/bench13.err
-for T in 1 10; do
-for DT in bf16 f32; do
-MILB200_TAPE_GRAPHS=0 timeout 300 python tools/profile_fusion.py 15592 $T $DT 2 > gpurun_out/plain_pf_${T}_${DT}.log 2>&1 && \
-MILB200_TAPE_GRAPHS=0 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches_fusion_r1f_T${T}_${DT}.csv python tools/profile_fusion.py 15592 $T $DT 2 > gpurun_out/ncu_pf_${T}_${DT}.log 2>&1
-done; done
+timeout 900 python -m pytest tests/test_gpu_fusion.py tests/test_gpu_feeder.py -x -q -m gpu > gpurun_out/pytest_gpu14.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu14.log
+for L in 0 1; do
+MILB200_TAPE_LANES=$L timeout 300 python tools/bench_fusion.py > gpurun_out/bench_fusion_lanes$L.log 2>&1
+done
