@@ -91,8 +91,7 @@ k_gate_bwd(float* __restrict__ Z, const float* __restrict__ ww, const float* __r
       red[wib][2 * D + d] = sw[j];
     }
   }
-  sds = warp_sum(sds);
-  if (lane == 0) red[wib][3 * D] = sds;
+  if (lane == 0) red[wib][3 * D] = sds;   // every lane read the same ds values: sds is already the warp's total
   __syncthreads();
   const int rl = 3 * D + 1;
   for (int c = threadIdx.x; c < rl; c += blockDim.x) {
