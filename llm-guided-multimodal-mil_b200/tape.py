@@ -134,14 +134,24 @@ class Tape:
             params[i] = L.TapeParam(off, rows, cols)
             offsets.append(off)
             off += p.numel()
-        self._c = dict(ops=ops, n_ops=n_ops, n_slots=n_slots, params=params, n_params=n_params, offsets=offsets, total=off)
+        self._c = dict(ops=ops, n_ops=n_ops, n_slots=n_slots, params=params, n_params=n_params, offsets=offsets, total=off,
+                       sizes=[p.numel() for p in self.params],
+                       shapes=[None if p.dim() == 1 else tuple(p.shape) for p in self.params])
         return self._c
 
     def _slots(self, rows):
-        n = len(self.slot_cols)
-        arr = (L.TapeSlot * n)()
-        for i in range(n):
-            arr[i] = L.TapeSlot(int(rows[self.slot_rows[i]]), self.slot_cols[i], 1 if self.slot_ext[i] else 0)
+        key = tuple(sorted(rows.items()))
+        cache = self.__dict__.setdefault("_slots_cache", {})
+        arr = cache.get(key)
+        if arr is None or self._c is None:       # the slot table is final once the program is frozen
+            n = len(self.slot_cols)
+            arr = (L.TapeSlot * n)()
+            for i in range(n):
+                arr[i] = L.TapeSlot(int(rows[self.slot_rows[i]]), self.slot_cols[i], 1 if self.slot_ext[i] else 0)
+            if self._c is not None:
+                if len(cache) > 64:
+                    cache.clear()
+                cache[key] = arr
         return arr
 
     # ---- flat parameter images (cached while the parameters are unchanged) ------------------------------------
@@ -332,7 +342,9 @@ class _TapeFn(torch.autograd.Function):
         if pool is not None:
             gin = [g.clone() if g is not None else None for g in gin]
             pool.owner = None
-        gparams = []
-        for j, (p, off) in enumerate(zip(tape.params, c["offsets"])):
-            gparams.append(gflat[off:off + p.numel()].view(p.shape) if ctx.needs_input_grad[3 + n_in + j] else None)
+        need = ctx.needs_input_grad
+        base = 3 + n_in
+        pieces = gflat.split(c["sizes"])          # one call for the ~90 views; 2-D weights get their shape below
+        gparams = [(pc if sh is None else pc.view(sh)) if need[base + j] else None
+                   for j, (pc, sh) in enumerate(zip(pieces, c["shapes"]))]
         return (None, None, None, *gin, *gparams)

@@ -71,7 +71,7 @@ def test_native_validator_rejects_malformed_programs(model):
                                   0, L.F32, None)
     assert rc != 0 and b"null" in lib.milb200_last_error()
     # (2) a shape that contradicts the weights: shrink the column count of one linear's input slot
-    bad = t._slots(rows)
+    bad = type(slots).from_buffer_copy(slots)            # _slots() caches per shape: never edit its result
     lin = next(o for o in t.ops if o[0] == L.OP_LINEAR)
     bad[lin[1]].cols = 511
     rc = lib.milb200_tape_forward(c["ops"], c["n_ops"], bad, n, c["params"], c["n_params"], ext, dummy, dummy, dummy, 1 << 30,
