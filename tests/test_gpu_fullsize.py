@@ -126,3 +126,44 @@ def test_trainer_update_matches_optimizer_oracle(optimizer):
     got = tr.params.detach().cpu().numpy()
     assert np.abs(got - pn).max() <= 1e-6 * np.abs(pn).max()
     assert rel_err(got - p0.numpy(), pn - p0.double().numpy()) <= 1e-3      # the update itself, not just the parameters
+
+
+@pytest.mark.parametrize("total_n", [1, 2, 127, 128, 129, 255, 256, 257, 383, 385, 512, 513, 1025, 148 * 256 + 1])
+def test_tile_boundaries_of_the_tensor_core_step(total_n):
+    """The bench's trainer step (CTA-pair score GEMM with saved V,U, persistent pools, fused dW) at instance counts that
+    straddle the 128-row CTA tile, the 256-row pair tile and one full wave of pairs (+1), split into 1-3 ragged bags:
+    pooled vectors, scores, argmax and every parameter gradient against the float64 oracle on the same bf16 operands."""
+    from mil_b200.dp import AbmilTrainer
+    import mil_b200
+    L = 1024
+    p = mo.procedural_state(mo.abmil_shapes(L), 7)
+    m = mil_b200.ABMIL(None, L=L).cuda().eval()
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+    cuts = sorted({0, total_n // 3, (2 * total_n) // 3 + (1 if total_n > 2 else 0), total_n})
+    off = np.asarray(cuts, dtype=np.int32)
+    off = off[np.concatenate([[True], np.diff(off) > 0])]          # no empty bags
+    g = torch.Generator().manual_seed(total_n)
+    X = torch.randn(total_n, L, generator=g).to(torch.bfloat16)
+    dM = torch.randn(len(off) - 1, L, generator=g)
+    tr = AbmilTrainer(L, 192, torch.bfloat16, device="cuda")
+    tr.load_from(m)
+    Mt, _ = tr.forward_backward(X.cuda(), torch.from_numpy(off).cuda(), dM.cuda())
+    torch.cuda.synchronize()
+    pq = {k: (torch.from_numpy(v).to(torch.bfloat16).float().numpy() if k.endswith("0.weight") else v) for k, v in p.items()}
+    Xq = X.float().numpy()
+    Mr, sr, amr = mo.abmil_forward_csr(pq, Xq, off)
+    gr = mo.abmil_backward_csr(pq, Xq, off, dM.numpy())
+    assert rel_err(Mt.detach().cpu().numpy(), Mr) <= 1e-2
+    assert rel_err(tr.last_scores.detach().cpu().numpy(), sr) <= 1e-2
+    if mo.score_margin(sr, off) > 1e-3:
+        assert tr.last_argmax.detach().cpu().numpy().tolist() == amr.tolist()
+    gv = tr.grad_views()
+    got = {"attention_V.0.weight": gv["Wcat"][:192], "attention_U.0.weight": gv["Wcat"][192:],
+           "attention_V.0.bias": gv["bcat"][:192], "attention_U.0.bias": gv["bcat"][192:], "attention_weights.weight": gv["ww"]}
+    scale = max(float(np.abs(gr[k]).max()) for k in got)
+    for k, v in got.items():
+        a, b = v.detach().cpu().numpy().reshape(-1), np.asarray(gr[k]).reshape(-1)
+        if float(np.abs(b).max()) < 1e-6 * max(scale, 1e-30) or total_n <= 2:
+            assert float(np.abs(a - b).max()) <= 1e-2 * max(scale, 1e-6), k      # (near-)zero true gradient
+        else:
+            assert rel_err(a, b) <= 1e-2, k
