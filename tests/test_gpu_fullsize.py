@@ -163,7 +163,11 @@ def test_tile_boundaries_of_the_tensor_core_step(total_n):
     scale = max(float(np.abs(gr[k]).max()) for k in got)
     for k, v in got.items():
         a, b = v.detach().cpu().numpy().reshape(-1), np.asarray(gr[k]).reshape(-1)
-        if float(np.abs(b).max()) < 1e-6 * max(scale, 1e-30) or total_n <= 2:
+        if total_n <= 2:
+            # one-instance bags: softmax weight exactly 1, every attention gradient exactly 0 in exact arithmetic; the
+            # kernels leave float noise from g_i - dM.M (same bound as tests/test_gpu_abmil.py uses for N = 1)
+            assert float(np.abs(a - b).max()) <= 1e-5, k
+        elif float(np.abs(b).max()) < 1e-6 * max(scale, 1e-30):
             assert float(np.abs(a - b).max()) <= 1e-2 * max(scale, 1e-6), k      # (near-)zero true gradient
         else:
             assert rel_err(a, b) <= 1e-2, k

@@ -1,2 +1,3 @@
+set -x
 cd /root/repo
-timeout 300 python tools/pyprof_fusion.py > gpurun_out/pyprof_r1f.log 2>&1
+timeout 1200 python -m pytest tests -q -m gpu > gpurun_out/pytest_gpu17.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu17.log
