@@ -415,23 +415,24 @@ def main():
     value = total_bags / (ms_max / 1e3)
 
     # ---- the same steps again with a CUDA event between phases: per-kernel durations IN the step -------------------
+    # every rank runs them (the step contains the all-reduce); rank 0 records the events
     phase_ms = {}
-    if rank == 0:
-        marks = []
+    marks = []
 
-        def hook(name):
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            marks.append((name, ev))
+    def hook(name):
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks.append((name, ev))
+    if rank == 0:
         tr.phase_hook = hook
-        n_ph = max(3, min(args.steps, 10))
-        for _ in range(n_ph):
-            tr.step(X, offsets)
-        torch.cuda.synchronize()
-        tr.phase_hook = None
-        for (n0, a), (n1, b) in zip(marks[:-1], marks[1:]):
-            if n1 != "pack":
-                phase_ms[n1] = phase_ms.get(n1, 0.0) + a.elapsed_time(b) / n_ph
+    n_ph = max(3, min(args.steps, 10))
+    for _ in range(n_ph):
+        tr.step(X, offsets)
+    torch.cuda.synchronize()
+    tr.phase_hook = None
+    for (n0, a), (n1, b) in zip(marks[:-1], marks[1:]):
+        if n1 != "pack":
+            phase_ms[n1] = phase_ms.get(n1, 0.0) + a.elapsed_time(b) / n_ph
     barrier()
 
     # ---- end to end: host (pinned) inputs, H2D + D2H inside the timed region -----------------------------------
