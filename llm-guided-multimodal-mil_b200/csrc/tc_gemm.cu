@@ -990,12 +990,15 @@ constexpr int TNG_REC = 200;              // record: dVpre[64] | dUpre[64] | ds*
 constexpr int TNG_ASTAGES = 8;            // A ring (8 KB per stage): raw V,U land and are transformed well ahead of the MMA
 constexpr int TNG_BSTAGES = 4;            // B ring (32 KB per stage)
 constexpr int TNG_BAR_BYTES = 512;
-constexpr int TNG_RED_BYTES = static_cast<int>(sizeof(float)) * EPI_WARPS * 8 * 25;   // 6400: keeps ds_s 128-byte aligned
+constexpr int TNG_XW = 12;                // transform warps: three groups of four rotate over the stages (the in-place V,U ->
+                                          // dV,dU rewrite is latency-bound; with two groups it, not the MMA, set the pace)
+constexpr int TNG_THREADS = (EPI_WARP0 + TNG_XW) * 32;
+constexpr int TNG_RED_BYTES = static_cast<int>(sizeof(float)) * TNG_XW * 8 * 25;      // 9600: keeps ds_s 128-byte aligned
 constexpr size_t TNG_SMEM = 1024 + static_cast<size_t>(TNG_ASTAGES) * TN_A_BYTES + static_cast<size_t>(TNG_BSTAGES) * TN_B_BYTES +
                             TNG_BAR_BYTES + TNG_RED_BYTES + TNG_ASTAGES * TN_BK * sizeof(float);
 static_assert(TNG_SMEM <= 232448 && TNG_RED_BYTES % 128 == 0, "fused dW kernel smem budget");
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(TNG_THREADS, 1)
 k_gemm_tn_gate(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmD, const float* __restrict__ ww, int64_t Kr, int No, int n_tiles,
                int kb_per_split, float* __restrict__ part, float* __restrict__ rec_ws) {
@@ -1034,7 +1037,7 @@ k_gemm_tn_gate(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < TNG_ASTAGES; ++s) {
       mbar_init(araw_bar + s, 1);
-      mbar_init(afull_bar + s, EPI_WARPS / 2);   // one arrival per warp of the group that transforms the stage
+      mbar_init(afull_bar + s, 4);               // one arrival per warp of the group that transforms the stage
       mbar_init(aempty_bar + s, 1);
     }
     for (int s = 0; s < TNG_BSTAGES; ++s) {
@@ -1109,8 +1112,8 @@ k_gemm_tn_gate(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= EPI_WARP0) {
     // ===== in-place V,U -> dV,dU transform (main loop), then the accumulator epilogue =====
-    // Two groups of four warps alternate stages, so two stages are in transformation at any time and the latency of
-    // the proxy fence overlaps with the other group's work.  Thread (r, pc) of a group owns k-rows r and r + 16.
+    // Three groups of four warps rotate over the stages, so three stages are in transformation at any time and the
+    // latency of the proxy fence overlaps with the other groups' work.  Thread (r, pc) of a group owns k-rows r, r + 16.
     const int tid = threadIdx.x - EPI_WARP0 * 32;
     const int grp = tid >> 7, tg = tid & 127;
     const int r = tg >> 3, pc = tg & 7;
@@ -1123,7 +1126,7 @@ k_gemm_tn_gate(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float sdv[8], sdu[8], svu[8], sds = 0.f;
 #pragma unroll
     for (int e = 0; e < 8; ++e) sdv[e] = sdu[e] = svu[e] = 0.f;
-    for (int i = grp; i < nkb; i += 2) {
+    for (int i = grp; i < nkb; i += TNG_XW / 4) {
       const int s = i % TNG_ASTAGES;
       mbar_wait(araw_bar + s, static_cast<uint32_t>((i / TNG_ASTAGES) & 1));
       uint8_t* sa = a_ring + s * TN_A_BYTES;
@@ -1170,22 +1173,22 @@ k_gemm_tn_gate(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int e = 0; e < 8; ++e) { dst[e] = sdv[e]; dst[8 + e] = sdu[e]; dst[16 + e] = svu[e]; }
         dst[24] = sds;
       }
-      asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(TNG_XW * 32) : "memory");
       float* rec = rec_ws + (static_cast<int64_t>(split) * TNG_MT + mt) * TNG_REC;
       if (tid < 192) {
         const int k = tid / 64, j = tid % 64;
         float a = 0.f;
 #pragma unroll
-        for (int q = 0; q < EPI_WARPS; ++q) a += red[(q * 8 + j / 8) * 25 + k * 8 + j % 8];
+        for (int q = 0; q < TNG_XW; ++q) a += red[(q * 8 + j / 8) * 25 + k * 8 + j % 8];
         rec[tid] = a;
       } else if (tid == 192) {
         float a = 0.f;
 #pragma unroll
-        for (int q = 0; q < EPI_WARPS; ++q) a += red[(q * 8) * 25 + 24];
+        for (int q = 0; q < TNG_XW; ++q) a += red[(q * 8) * 25 + 24];
         rec[192] = a;
       }
     }
-    const int q = (warp - EPI_WARP0) & 3, half = (warp - EPI_WARP0) >> 2;
+    const int q = (warp - EPI_WARP0) & 3, third = (warp - EPI_WARP0) >> 2;
     const int m = mt * BM + q * 32 + lane;
     float* prow = part + (static_cast<int64_t>(split) * Mo + m) * No + nt * TN_BNO;
     if (nkb > 0) {
@@ -1194,7 +1197,7 @@ k_gemm_tn_gate(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     const uint32_t tacc = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-    for (int c = half * (TN_BNO / 2); c < (half + 1) * (TN_BNO / 2); c += 32) {
+    for (int c = third * 32; c < TN_BNO; c += 32 * (TNG_XW / 4)) {     // the three warps of a lane quarter interleave chunks
       if (nt * TN_BNO + c >= No) break;
       uint32_t rr[32];
       if (nkb > 0) {
@@ -1221,6 +1224,7 @@ k_gemm_tn_gate(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 }
 
+
 int gemm_tn_gate_max_records() { return sm_count(); }  // splits * 3 m-tiles <= resident CTAs
 int gemm_tn_gate_record_floats() { return TNG_REC; }
 
@@ -1246,7 +1250,7 @@ int gemm_tn_gate(const void* VU, const float* ds, const float* ww, const void* X
   splits = static_cast<int>((total_kb + kb_per_split - 1) / kb_per_split);
   if (splits_out) *splits_out = splits;
   MIL_CUDA(cudaFuncSetAttribute(k_gemm_tn_gate, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(TNG_SMEM)));
-  k_gemm_tn_gate<<<TNG_MT * n_tiles * splits, NUM_THREADS, TNG_SMEM, st>>>(tmA, tmB, tmD, ww, Kr, No, n_tiles, kb_per_split,
+  k_gemm_tn_gate<<<TNG_MT * n_tiles * splits, TNG_THREADS, TNG_SMEM, st>>>(tmA, tmB, tmD, ww, Kr, No, n_tiles, kb_per_split,
                                                                            part, rec_ws);
   MIL_LAUNCH_CHECK();
   return MILB200_OK;

@@ -128,14 +128,15 @@ def test_trainer_update_matches_optimizer_oracle(optimizer):
     assert rel_err(got - p0.numpy(), pn - p0.double().numpy()) <= 1e-3      # the update itself, not just the parameters
 
 
-@pytest.mark.parametrize("total_n", [1, 2, 127, 128, 129, 255, 256, 257, 383, 385, 512, 513, 1025, 148 * 256 + 1])
-def test_tile_boundaries_of_the_tensor_core_step(total_n):
+@pytest.mark.parametrize("total_n,L", [(n, 1024) for n in (1, 2, 127, 128, 129, 255, 256, 257, 383, 385, 512, 513, 1025,
+                                                            148 * 256 + 1)] +
+                         [(2500, 768), (2500, 512), (777, 256), (3001, 320), (40000, 768)])
+def test_tile_boundaries_of_the_tensor_core_step(total_n, L):
     """The bench's trainer step (CTA-pair score GEMM with saved V,U, persistent pools, fused dW) at instance counts that
     straddle the 128-row CTA tile, the 256-row pair tile and one full wave of pairs (+1), split into 1-3 ragged bags:
     pooled vectors, scores, argmax and every parameter gradient against the float64 oracle on the same bf16 operands."""
     from mil_b200.dp import AbmilTrainer
     import mil_b200
-    L = 1024
     p = mo.procedural_state(mo.abmil_shapes(L), 7)
     m = mil_b200.ABMIL(None, L=L).cuda().eval()
     m.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
