@@ -430,9 +430,13 @@ def main():
         tr.step(X, offsets)
     torch.cuda.synchronize()
     tr.phase_hook = None
+    per_phase = {}
     for (n0, a), (n1, b) in zip(marks[:-1], marks[1:]):
         if n1 != "pack":
-            phase_ms[n1] = phase_ms.get(n1, 0.0) + a.elapsed_time(b) / n_ph
+            per_phase.setdefault(n1, []).append(a.elapsed_time(b))
+    for name, vals in per_phase.items():      # median over the steps: one host hiccup must not colour a kernel's duration
+        vals.sort()
+        phase_ms[name] = vals[len(vals) // 2] if len(vals) % 2 else 0.5 * (vals[len(vals) // 2 - 1] + vals[len(vals) // 2])
     barrier()
 
     # ---- end to end: host (pinned) inputs, H2D + D2H inside the timed region -----------------------------------
@@ -711,7 +715,7 @@ def main():
                 "unit": dom["unit"], "frac": dom["frac"], "traffic": dom.get("traffic"),
                 "traffic_source": dom.get("traffic_source"), "peak_source": peak_src,
                 "ms_per_launch": dom["ms"], "algorithmic": dom.get("algorithmic"),
-                "timing": "CUDA events around the kernel inside the training step" if dom.get("ms_in_step")
+                "timing": "CUDA events around the kernel inside the training step (median over steps)" if dom.get("ms_in_step")
                           else "kernel looped alone, CUDA events",
                 "ms_alone_back_to_back": dom.get("ms_alone"), "frac_alone_back_to_back": dom.get("frac_alone"),
                 "frac_of_sustained_peak": dom.get("frac_of_sustained_peak"), "phase_ms_in_step": phase_ms}

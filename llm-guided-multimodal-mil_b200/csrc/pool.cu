@@ -241,44 +241,56 @@ k_pool_fwd(const T* __restrict__ X, const float* __restrict__ scores, const int3
 
 // ---- backward ------------------------------------------------------------------------------------
 // stats[b] = (lse_b, dM_b . M_b): softmax statistics are recomputed from the scores, not stored.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_pool_bwd_stats(const float* __restrict__ scores, const int32_t* __restrict__ offsets, int L,
                  const float* __restrict__ dM, const float* __restrict__ M, float2* __restrict__ stats) {
-  __shared__ float red[8];
+  __shared__ float red[32];
   __shared__ float bc;
-  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5, nt = blockDim.x, nw = blockDim.x >> 5;
   const int64_t ob = offsets[b], oe = offsets[b + 1];
+  // the bag's scores stay in registers between the two passes (up to 8 per thread; longer bags re-read from L2)
+  constexpr int KEEP = 8;
+  float sc[KEEP];
   float mx = -FLT_MAX;
-  for (int64_t i = ob + t; i < oe; i += 256) mx = fmaxf(mx, scores[i]);
+#pragma unroll
+  for (int k = 0; k < KEEP; ++k) {
+    const int64_t i = ob + t + static_cast<int64_t>(k) * nt;
+    sc[k] = i < oe ? scores[i] : -FLT_MAX;
+    mx = fmaxf(mx, sc[k]);
+  }
+  for (int64_t i = ob + t + static_cast<int64_t>(KEEP) * nt; i < oe; i += nt) mx = fmaxf(mx, scores[i]);
   mx = warp_max(mx);
   if (lane == 0) red[warp] = mx;
   __syncthreads();
   if (t == 0) {
     float v = red[0];
-    for (int w = 1; w < 8; ++w) v = fmaxf(v, red[w]);
+    for (int w = 1; w < nw; ++w) v = fmaxf(v, red[w]);
     bc = v;
   }
   __syncthreads();
   mx = bc;
   float sum = 0.f;
-  for (int64_t i = ob + t; i < oe; i += 256) sum += expf(scores[i] - mx);
+#pragma unroll
+  for (int k = 0; k < KEEP; ++k)
+    if (ob + t + static_cast<int64_t>(k) * nt < oe) sum += expf(sc[k] - mx);
+  for (int64_t i = ob + t + static_cast<int64_t>(KEEP) * nt; i < oe; i += nt) sum += expf(scores[i] - mx);
   sum = warp_sum(sum);
   __syncthreads();
   if (lane == 0) red[warp] = sum;
   __syncthreads();
   float tot = 0.f;
   if (t == 0) {
-    for (int w = 0; w < 8; ++w) tot += red[w];
+    for (int w = 0; w < nw; ++w) tot += red[w];
   }
   float dot = 0.f;
-  for (int c = t; c < L; c += 256) dot = fmaf(dM[static_cast<int64_t>(b) * L + c], M[static_cast<int64_t>(b) * L + c], dot);
+  for (int c = t; c < L; c += nt) dot = fmaf(dM[static_cast<int64_t>(b) * L + c], M[static_cast<int64_t>(b) * L + c], dot);
   dot = warp_sum(dot);
   __syncthreads();
   if (lane == 0) red[warp] = dot;
   __syncthreads();
   if (t == 0) {
     float d = 0.f;
-    for (int w = 0; w < 8; ++w) d += red[w];
+    for (int w = 0; w < nw; ++w) d += red[w];
     stats[b] = make_float2(oe > ob ? mx + logf(tot) : 0.f, d);
   }
 }
@@ -476,7 +488,7 @@ static int pool_bwd_t(const T* X, const float* scores, const int32_t* offsets, i
                       cudaStream_t st) {
   PoolWs w = pool_ws(workspace, total_n, B, L);
   MIL_CHECK_ARG(workspace && ws_bytes >= w.bytes, MILB200_EWORKSPACE, "pool_bwd: workspace %zu < %zu", ws_bytes, w.bytes);
-  k_pool_bwd_stats<<<B, 256, 0, st>>>(scores, offsets, L, dM, M, w.stats);
+  k_pool_bwd_stats<<<B, 1024, 0, st>>>(scores, offsets, L, dM, M, w.stats);
   MIL_LAUNCH_CHECK();
   int V = L * static_cast<int>(sizeof(T)) / 16;
   int nv = (V + 31) / 32;
