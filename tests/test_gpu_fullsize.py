@@ -172,3 +172,47 @@ def test_tile_boundaries_of_the_tensor_core_step(total_n, L):
             assert float(np.abs(a - b).max()) <= 1e-2 * max(scale, 1e-6), k      # (near-)zero true gradient
         else:
             assert rel_err(a, b) <= 1e-2, k
+
+
+@pytest.mark.parametrize("case", ["many_tiny_bags", "one_huge_bag", "huge_then_tiny"])
+def test_extreme_bag_shapes(case):
+    """Edge cases of the CSR machinery: thousands of 1-3 instance bags (every CTA slab holds hundreds of bag pieces),
+    one bag spread over every CTA of the persistent pools, and a huge bag followed by tiny ones."""
+    from mil_b200.dp import AbmilTrainer
+    import mil_b200
+    L = 512
+    rng = np.random.default_rng(11)
+    if case == "many_tiny_bags":
+        lens = rng.integers(1, 4, size=5000)
+    elif case == "one_huge_bag":
+        lens = np.asarray([150_001])
+    else:
+        lens = np.concatenate([[90_000], rng.integers(1, 5, size=700)])
+    off = mo.offsets_from_lengths(lens)
+    n = int(off[-1])
+    p = mo.procedural_state(mo.abmil_shapes(L), 3)
+    m = mil_b200.ABMIL(None, L=L).cuda().eval()
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+    g = torch.Generator().manual_seed(99)
+    X = torch.randn(n, L, generator=g).to(torch.bfloat16)
+    dM = torch.randn(len(lens), L, generator=g)
+    tr = AbmilTrainer(L, 192, torch.bfloat16, device="cuda")
+    tr.load_from(m)
+    Mt, _ = tr.forward_backward(X.cuda(), torch.from_numpy(off).cuda(), dM.cuda())
+    torch.cuda.synchronize()
+    pq = {k: (torch.from_numpy(v).to(torch.bfloat16).float().numpy() if k.endswith("0.weight") else v) for k, v in p.items()}
+    Xq = X.float().numpy()
+    Mr, sr, amr = mo.abmil_forward_csr(pq, Xq, off)
+    gr = mo.abmil_backward_csr(pq, Xq, off, dM.numpy())
+    assert rel_err(Mt.detach().cpu().numpy(), Mr) <= 1e-2
+    assert rel_err(tr.last_scores.detach().cpu().numpy(), sr) <= 1e-2
+    am = tr.last_argmax.detach().cpu().numpy()
+    assert am.shape == amr.shape and np.all((am >= 0) & (am < lens))          # index within the bag
+    for b in np.nonzero(am != amr)[0]:       # bf16 near-ties may pick another instance: its score must be the maximum too
+        seg = sr[off[b]:off[b + 1]]
+        assert seg[am[b]] >= seg.max() - 1e-2 * max(1.0, abs(seg.max())), b
+    gv = tr.grad_views()
+    got = {"attention_V.0.weight": gv["Wcat"][:192], "attention_U.0.weight": gv["Wcat"][192:],
+           "attention_V.0.bias": gv["bcat"][:192], "attention_U.0.bias": gv["bcat"][192:], "attention_weights.weight": gv["ww"]}
+    for k, v in got.items():
+        assert rel_err(v.detach().cpu().numpy().reshape(-1), np.asarray(gr[k]).reshape(-1)) <= 1e-2, k
