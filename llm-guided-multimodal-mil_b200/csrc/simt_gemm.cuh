@@ -125,12 +125,139 @@ k_gemm(const TA* __restrict__ A, int64_t lda, const TB* __restrict__ B, int64_t 
   }
 }
 
+// ---- 128 x 128 x 8 tiles, 8 x 8 outputs per thread, register-prefetched double buffering ---------------------------
+// Same contract as k_gemm; used when both output extents reach a full tile.  Per k step a thread issues four 128-bit
+// shared loads for 64 FMAs (the 64 x 64 kernel: two for 16), and the global loads of tile i+1 are in flight while tile i
+// is multiplied.
+constexpr int BM2 = 128, BN2 = 128, BK2 = 8;
+
+// four consecutive elements of `p` (guarded element-wise by `ok`), one 128-/64-bit load when the address allows it
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, bool ok0, bool ok1, bool ok2, bool ok3, bool vec, float (&v)[4]) {
+  if (vec && ok3) {   // ok3 implies ok0..ok2 (indices grow)
+    if (sizeof(T) == 4) {
+      float4 q = __ldg(reinterpret_cast<const float4*>(p));
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+      uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+      v[0] = __uint_as_float(q.x << 16); v[1] = __uint_as_float(q.x & 0xffff0000u);
+      v[2] = __uint_as_float(q.y << 16); v[3] = __uint_as_float(q.y & 0xffff0000u);
+    }
+    return;
+  }
+  v[0] = ok0 ? to_f32<T>(p[0]) : 0.f;
+  v[1] = ok1 ? to_f32<T>(p[1]) : 0.f;
+  v[2] = ok2 ? to_f32<T>(p[2]) : 0.f;
+  v[3] = ok3 ? to_f32<T>(p[3]) : 0.f;
+}
+
+// stage registers of one operand tile [128 (mn) x 8 (k)]: KCONTIG: thread -> (mn = t / 2, k = 4 (t % 2) ..+3);
+// otherwise thread -> (k = t / 32, mn = 4 (t % 32) ..+3)
+template <typename T, bool KCONTIG>
+__device__ __forceinline__ void fetch_tile(const T* __restrict__ P, int64_t ld, int64_t mn0, int64_t MN, int64_t k0,
+                                           int64_t kend, int t, bool vec, float (&v)[4]) {
+  if (KCONTIG) {
+    const int64_t mn = mn0 + (t >> 1), k = k0 + ((t & 1) << 2);
+    const bool in = mn < MN;
+    load4<T>(P + mn * ld + k, in && k < kend, in && k + 1 < kend, in && k + 2 < kend, in && k + 3 < kend, vec, v);
+  } else {
+    const int64_t k = k0 + (t >> 5), mn = mn0 + ((t & 31) << 2);
+    const bool in = k < kend;
+    load4<T>(P + k * ld + mn, in && mn < MN, in && mn + 1 < MN, in && mn + 2 < MN, in && mn + 3 < MN, vec, v);
+  }
+}
+template <bool KCONTIG>
+__device__ __forceinline__ void stash_tile(float (*S)[BM2 + 4], int t, const float (&v)[4]) {
+  if (KCONTIG) {
+    const int mn = t >> 1, k = (t & 1) << 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) S[k + j][mn] = v[j];
+  } else {
+    *reinterpret_cast<float4*>(&S[t >> 5][(t & 31) << 2]) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+template <typename TA, typename TB, bool A_KCONTIG, bool B_KCONTIG, class Epi>
+__global__ void __launch_bounds__(THREADS, 2)
+k_gemm128(const TA* __restrict__ A, int64_t lda, const TB* __restrict__ B, int64_t ldb, int64_t M, int N, int64_t K,
+          int64_t k_per_split, Epi epi) {
+  __shared__ __align__(16) float As[2][BK2][BM2 + 4];
+  __shared__ __align__(16) float Bs[2][BK2][BN2 + 4];
+  const int t = threadIdx.x;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * BM2;
+  const int n0 = blockIdx.y * BN2;
+  const int split = blockIdx.z;
+  const int64_t kbeg = split * k_per_split;
+  const int64_t kend = (kbeg + k_per_split < K) ? kbeg + k_per_split : K;
+  const int ty = t >> 4, tx = t & 15;
+  // vector loads need 16-byte (fp32) / 8-byte (bf16) aligned groups of four: base pointer, leading dimension, k origin
+  const bool vecA = (reinterpret_cast<uintptr_t>(A) % (4 * sizeof(TA)) == 0) && lda % 4 == 0 && (A_KCONTIG ? kbeg % 4 == 0 : true);
+  const bool vecB = (reinterpret_cast<uintptr_t>(B) % (4 * sizeof(TB)) == 0) && ldb % 4 == 0 && (B_KCONTIG ? kbeg % 4 == 0 : true);
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  float ra[4], rb[4];
+  if (kbeg < kend) {
+    fetch_tile<TA, A_KCONTIG>(A, lda, m0, M, kbeg, kend, t, vecA, ra);
+    fetch_tile<TB, B_KCONTIG>(B, ldb, n0, N, kbeg, kend, t, vecB, rb);
+    stash_tile<A_KCONTIG>(As[0], t, ra);
+    stash_tile<B_KCONTIG>(Bs[0], t, rb);
+  }
+  __syncthreads();
+  int buf = 0;
+  for (int64_t k0 = kbeg; k0 < kend; k0 += BK2) {
+    const bool more = k0 + BK2 < kend;
+    if (more) {
+      fetch_tile<TA, A_KCONTIG>(A, lda, m0, M, k0 + BK2, kend, t, vecA, ra);
+      fetch_tile<TB, B_KCONTIG>(B, ldb, n0, N, k0 + BK2, kend, t, vecB, rb);
+    }
+#pragma unroll
+    for (int kk = 0; kk < BK2; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (more) {
+      stash_tile<A_KCONTIG>(As[buf ^ 1], t, ra);
+      stash_tile<B_KCONTIG>(Bs[buf ^ 1], t, rb);
+    }
+    __syncthreads();
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+      if (n < N) epi(m, n, acc[i][j], split);
+    }
+  }
+}
+
 template <typename TA, typename TB, bool A_KCONTIG, bool B_KCONTIG, class Epi>
 inline int launch(const TA* A, int64_t lda, const TB* B, int64_t ldb, int64_t M, int N, int64_t K,
                   int splits, Epi epi, cudaStream_t st) {
   if (M <= 0 || N <= 0) return MILB200_OK;
   int64_t kps = (K + splits - 1) / splits;
   kps = (kps + TK - 1) / TK * TK;
+  if (M >= BM2 && N >= BN2) {
+    dim3 grid2(static_cast<unsigned>((M + BM2 - 1) / BM2), static_cast<unsigned>((N + BN2 - 1) / BN2),
+               static_cast<unsigned>(splits));
+    k_gemm128<TA, TB, A_KCONTIG, B_KCONTIG, Epi><<<grid2, THREADS, 0, st>>>(A, lda, B, ldb, M, N, K, kps, epi);
+    MIL_LAUNCH_CHECK();
+    return MILB200_OK;
+  }
   dim3 grid(static_cast<unsigned>((M + TM - 1) / TM), static_cast<unsigned>((N + TN - 1) / TN),
             static_cast<unsigned>(splits));
   k_gemm<TA, TB, A_KCONTIG, B_KCONTIG, Epi><<<grid, THREADS, 0, st>>>(A, lda, B, ldb, M, N, K, kps, epi);
