@@ -329,8 +329,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     config = {"workload": f"gated-attention MIL fwd+bwd, ragged bags {LEN_LO}-{LEN_HI} instances x {L_FEAT}-dim "
-                          f"(BASELINE configs[1]), {args.bags} bags/rank/step packed CSR, D={D_GATE}, "
-                          f"lengths randint seed 1234+rank",
+                          f"(BASELINE configs[1]), {args.bags} bags per rank per step on average, packed CSR, D={D_GATE}; the "
+                          f"step's {args.bags} x world bags (lengths randint seed 1234) are dealt to the ranks longest-first by "
+                          f"instance count (dp.shard_bags, SURVEY 8e); world = 1: exactly the 64-bag workload",
               "bags_per_rank": args.bags, "L": L_FEAT, "D": D_GATE, "parallelism": f"dp{world}",
               "input_grad": bool(args.input_grad),
               "cache": "inputs (~1.3 GB/rank) exceed the 126 MB L2, no flush needed",
@@ -368,8 +369,12 @@ def main():
         pg = dist.group.WORLD
 
     peaks, peak_src = load_peaks()
-    lengths = bag_lengths(args.bags, 1234 + rank)
-    offsets_h = torch.zeros(args.bags + 1, dtype=torch.int32)
+    from mil_b200.dp import shard_bags
+    all_lengths = bag_lengths(args.bags * world, 1234)            # world = 1: the 64 bags of the single-GPU workload
+    mine = shard_bags(all_lengths.tolist(), rank, world, balance=True)
+    lengths = all_lengths[mine]
+    n_bags = len(mine)
+    offsets_h = torch.zeros(n_bags + 1, dtype=torch.int32)
     offsets_h[1:] = lengths.cumsum(0).to(torch.int32)
     total_n = int(offsets_h[-1])
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -446,7 +451,7 @@ def main():
     X_h = torch.empty((total_n, L_FEAT), dtype=torch.bfloat16).pin_memory()
     X_h.copy_(X)
     off_pin = offsets_h.pin_memory()
-    M_h = [torch.empty((args.bags, L_FEAT), dtype=torch.float32).pin_memory() for _ in range(2)]
+    M_h = [torch.empty((n_bags, L_FEAT), dtype=torch.float32).pin_memory() for _ in range(2)]
     X_d = [torch.empty_like(X) for _ in range(2)]
     off_d = [torch.empty_like(offsets) for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
@@ -519,7 +524,7 @@ def main():
             torch.cuda.synchronize()
             return a.elapsed_time(b) / reps
 
-        n, Lf, D, B = total_n, L_FEAT, D_GATE, args.bags
+        n, Lf, D, B = total_n, L_FEAT, D_GATE, n_bags
         gemm_flops = 2.0 * n * Lf * 2 * D
         save = tr.save_gate and act is not None
         t_score = timeit(lambda: F.gated_scores(X, Wcat, bcat_c, v["ww"], v["bw"], save=save))
@@ -722,7 +727,8 @@ def main():
         line = {"metric": "bags/sec fwd+bwd", "value": value, "unit": "bags/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
-                "instances_per_step_per_rank": total_n, "instances_per_s": total_n * world * args.steps / (ms_max / 1e3),
+                "instances_per_step_per_rank": total_n, "bags_this_rank": n_bags,
+                "instances_per_s": int(all_lengths.sum()) * args.steps / (ms_max / 1e3),
                 "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "bags/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
