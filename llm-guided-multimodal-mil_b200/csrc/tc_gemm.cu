@@ -214,7 +214,9 @@ struct EpiScoreT {
     uint8_t* rowU = nullptr;
     uint8_t* boxV = nullptr;
     if (SAVE) {
-      // per warp: one V sub-box | one U sub-box, each a dense [32 rows][16 bf16] image (1 KB)
+      // per warp: one V sub-box | one U sub-box, each a [32 rows][16 bf16] image (1 KB) in the 32-byte-swizzled layout
+      // of the store's tensor map: the 16-byte halves of rows 4-7 (mod 8) are swapped, so that a quarter-warp's eight
+      // 128-bit stores (row pitch 32 B) hit all 32 banks instead of 16 of them twice
       boxV = staging + (cx.half * 4 + cx.q) * 2 * SUB_BYTES;
       rowV = boxV + cx.lane * 32;
       rowU = rowV + SUB_BYTES;
@@ -244,10 +246,11 @@ struct EpiScoreT {
       if (SAVE) {
         if (cx.lane == 0) tma_store_wait_read<0>();  // the previous chunk's sub-boxes have been read out
         __syncwarp();
-        *reinterpret_cast<uint4*>(rowV) = Vec16<__nv_bfloat16>::pack(fv);
-        *reinterpret_cast<uint4*>(rowV + 16) = Vec16<__nv_bfloat16>::pack(fv + 8);
-        *reinterpret_cast<uint4*>(rowU) = Vec16<__nv_bfloat16>::pack(fu);
-        *reinterpret_cast<uint4*>(rowU + 16) = Vec16<__nv_bfloat16>::pack(fu + 8);
+        const int sw = (cx.lane & 4) << 2;   // 16 for rows 4-7 (mod 8), else 0
+        *reinterpret_cast<uint4*>(rowV + sw) = Vec16<__nv_bfloat16>::pack(fv);
+        *reinterpret_cast<uint4*>(rowV + (sw ^ 16)) = Vec16<__nv_bfloat16>::pack(fv + 8);
+        *reinterpret_cast<uint4*>(rowU + sw) = Vec16<__nv_bfloat16>::pack(fu);
+        *reinterpret_cast<uint4*>(rowU + (sw ^ 16)) = Vec16<__nv_bfloat16>::pack(fu + 8);
         fence_proxy_async();
         __syncwarp();
         if (cx.lane == 0) {
@@ -809,7 +812,7 @@ int gated_score(const void* X, int64_t n, int L, const void* Wcat, const float* 
   if (gate_act) {
     EpiScoreT<true>::Params ep;
     ep.bcat = bcat; ep.ww = ww; ep.bw = bw; ep.scores = scores;
-    int rc0 = make_tmap_bf16_2d_linear(&ep.tmS, gate_act, static_cast<uint64_t>(n), 2 * GATE_D, 2 * GATE_D, 32, 16);
+    int rc0 = make_tmap_bf16_2d_sw32(&ep.tmS, gate_act, static_cast<uint64_t>(n), 2 * GATE_D, 2 * GATE_D, 32);
     if (rc0) return rc0;
     if (gate_2sm()) return launch_kmajor_2sm<GATE_BN, EpiScoreT<true>>(X, n, L, L, Wcat, 2 * GATE_D, L, ep, st);
     return launch_kmajor<GATE_BN, EpiScoreT<true>>(X, n, L, L, Wcat, 2 * GATE_D, L, ep, nullptr, st);
