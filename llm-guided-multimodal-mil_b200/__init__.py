@@ -11,6 +11,7 @@ from . import model
 from . import clip_loss
 from . import feeder
 from .feeder import PackedBagFeeder, pack_bags_host
+from .fusion_trainer import FusionTrainer
 from .clip_loss import CLIPLogits, CLIPloss_v1
 from .model.sam.transformer import Attention, TwoWayAttentionBlock, TwoWayTransformer
 from .model.sam.common import MLPBlock

@@ -105,9 +105,8 @@ class AbmilTrainer:
             torch.distributed.broadcast(self.params, src=0, group=self.pg)
 
     # ---- one training step ---------------------------------------------------------------------
-    def forward_backward(self, X, offsets, dM=None):
-        """Forward + backward of the pool over one packed CSR batch.  Upstream gradient dM defaults to ones
-        (loss = sum of the pooled vectors).  Returns (M fp32 [B, L], dX or None)."""
+    def forward(self, X, offsets):
+        """Forward of the pool over one packed CSR batch; keeps what `backward` needs.  Returns M fp32 [B, L]."""
         v = self._views(self.params)
         # fp32 master -> compute-dtype operand in the row order the kernels expect (one tiny kernel)
         D = self.D
@@ -125,17 +124,32 @@ class AbmilTrainer:
         mark("gated_score_fwd")
         M, _, am, _ = F.segment_softmax_pool(X, s, offsets)
         mark("segment_softmax_pool_fwd")
+        self._saved = (X, offsets, s, act, M, v)
+        self.last_argmax, self.last_scores = am, s
+        return M
+
+    def backward(self, dM):
+        """Backward of the last `forward` given dL/dM [B, L] fp32: parameter gradients go to the flat buffer; returns
+        dL/dX (or None when the trainer was built without need_input_grad)."""
+        X, offsets, s, act, M, v = self._saved
+        self._saved = None
+        mark = self.phase_hook or (lambda name: None)
+        ds, attn = F.segment_softmax_pool_bwd(X, s, offsets, dM, M, want_attn=self.need_input_grad)
+        mark("segment_softmax_pool_bwd")
+        dX, *_ = F.gated_scores_bwd(X, self._wcat_c, self._bcat_c, v["ww"], v["bw"], ds, attn, dM, offsets,
+                                    self.need_input_grad, grad_out=self.grads, gate_act=act)
+        mark("gate_bwd")
+        return dX
+
+    def forward_backward(self, X, offsets, dM=None):
+        """Forward + backward of the pool over one packed CSR batch.  Upstream gradient dM defaults to ones
+        (loss = sum of the pooled vectors).  Returns (M fp32 [B, L], dX or None)."""
+        M = self.forward(X, offsets)
         if dM is None:
             if getattr(self, "_ones", None) is None or self._ones.shape != M.shape:
                 self._ones = torch.ones_like(M)
             dM = self._ones
-        ds, attn = F.segment_softmax_pool_bwd(X, s, offsets, dM, M, want_attn=self.need_input_grad)
-        mark("segment_softmax_pool_bwd")
-        dX, *_ = F.gated_scores_bwd(X, Wcat, bcat, v["ww"], v["bw"], ds, attn, dM, offsets,
-                                    self.need_input_grad, grad_out=self.grads, gate_act=act)
-        mark("gate_bwd")
-        self.last_argmax, self.last_scores = am, s
-        return M, dX
+        return M, self.backward(dM)
 
     def allreduce_grads(self):
         """The path's only exchange: ONE all-reduce(sum) of the flat gradient buffer (NCCL on GPUs; any backend)."""

@@ -461,3 +461,57 @@ def test_two_lane_schedule_is_bit_identical_to_one_stream(monkeypatch, T, dtype)
     assert runs["0"].keys() == runs["1"].keys()
     for k, v in runs["0"].items():
         assert torch.equal(v, runs["1"][k]), k
+
+
+@pytest.mark.parametrize("T,dtype,tol", [(1, torch.float32, 2e-4), (10, torch.float32, 2e-4), (1, torch.bfloat16, 3e-2)])
+def test_fusion_trainer_matches_module_autograd(T, dtype, tol):
+    """FusionTrainer (flat parameter / gradient buffers, no autograd graph) against the nn.Module + torch.autograd path on
+    the same weights and inputs: losses, prob, every gradient; then one optimiser step against torch.optim.Adam."""
+    import mil_b200
+    from mil_b200 import functional as F
+    torch.manual_seed(31)
+    m = mil_b200.get_model(ARGS).cuda().to(dtype).eval()
+    x_ct = torch.randn(1, 512, 160, 1, 1, device="cuda", dtype=dtype)
+    x_p = torch.randn(1, 1203, 768, device="cuda", dtype=dtype)
+    x_t = (torch.randn(1, T, 512, device="cuda") * 0.05).to(dtype)
+    label = torch.tensor([[0.0, 1.0]], device="cuda")
+    prob, a, b = m([x_ct, x_p], x_t)
+    bce = torch.nn.functional.binary_cross_entropy(prob.float(), label)
+    cos = mil_b200.clip_loss.cosine_embedding_loss(a.squeeze(0), b.squeeze(0)).float()
+    (bce + cos).backward()
+    ref = {k: v.grad.detach().float().clone() for k, v in m.named_parameters() if v.grad is not None}
+    tr = mil_b200.FusionTrainer(m, n_text_tokens=T, compute_dtype=dtype, lr=1e-3)
+    loss, p2 = tr.forward_backward(F.ct_tokens(x_ct)[0], x_p[0], x_t[0], label[0])
+    torch.cuda.synchronize()
+    assert abs(float(loss[0]) - float(bce)) <= tol * max(1.0, abs(float(bce)))
+    assert abs(float(loss[1]) - float(cos)) <= max(tol, 1e-3 if dtype == torch.bfloat16 else 0) * max(1.0, abs(float(cos)))
+    assert _rel(p2, prob.float()) <= tol
+    got = tr.named_grads()
+    checked = 0
+    for k, g in ref.items():
+        if float(g.abs().max()) == 0.0 or k.endswith("attention_weights.bias") or k.endswith("k_proj.bias"):
+            continue                                       # unused / exactly-zero-gradient parameters (float noise at most)
+        assert k in got, k
+        if ".q_proj" in k or ".k_proj" in k:
+            scale = float(ref[k.replace(".q_proj", ".v_proj").replace(".k_proj", ".v_proj")].abs().max())
+            assert float((got[k].float() - g).abs().max()) <= 10 * tol * scale, k       # softmax-Jacobian cancellation class
+        else:
+            assert _fro(got[k].float(), g) <= tol, k
+        checked += 1
+    assert checked >= 40
+    if dtype == torch.float32:                             # the update: fused Adam over the flat buffer vs torch.optim.Adam
+        opt = torch.optim.Adam(m.parameters(), lr=1e-3, betas=(0.9, 0.999), weight_decay=1e-7)
+        opt.step()                                         # m's parameters move in place; tr.params still holds the old ones
+        tr.reduce_and_update()
+        compared = 0
+        for off, p in tr._module_tensors():
+            g = p.grad
+            if g is None:
+                continue
+            live = g.detach().abs().reshape(-1) > 1e-5     # first Adam step = lr * sign(g) wherever |g| >> eps
+            if int(live.sum()) == 0:
+                continue
+            new = tr.params[off:off + p.numel()]
+            assert float((new - p.detach().reshape(-1))[live].abs().max()) <= 2e-5, off
+            compared += int(live.sum())
+        assert compared > 100000
