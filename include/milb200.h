@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MILB200_VERSION 105
+#define MILB200_VERSION 106
 
 enum { MILB200_F32 = 0, MILB200_BF16 = 1 };
 
@@ -256,6 +256,18 @@ int milb200_tape_backward(const milb200_tape_op* ops, int n_ops, const milb200_t
                           void* const* ext_grad_ptrs, const void* const* seed_ptrs, const void* w_compute,
                           const float* p_f32, float* g_f32, const void* arena, size_t arena_bytes, void* workspace,
                           size_t ws_bytes, int dtype, void* stream);
+
+/* ---- single-pass forward of the gated pool (ABMIL.py:52-59 in one pass over X) ---------------------------------
+ * = milb200_gated_score_fwd (gate_act required) + milb200_segment_softmax_pool_fwd with the same outputs, reading X
+ * from HBM once: extra warps of the score GEMM reduce every finished 128-row tile to softmax-pooling records while it is
+ * L2-resident and the pooling kernel runs over the records.  milb200_gated_score_pool_supported() == 0 (other dtypes,
+ * L > 1024, the single-SM kernel selected): the entry returns MILB200_EUNSUPPORTED and the caller makes the two calls. */
+int milb200_gated_score_pool_supported(int L, int D, int dtype);
+size_t milb200_gated_score_pool_workspace_bytes(int64_t total_n, int B, int L);
+int milb200_gated_score_pool_fwd(const void* X, const void* Wcat, const float* bcat, const float* ww, const float* bw,
+                                 const int32_t* offsets, int B, float* scores, void* gate_act, float* M, int32_t* argmax,
+                                 float* lse, int64_t total_n, int L, int D, int dtype, void* workspace, size_t ws_bytes,
+                                 void* stream);
 
 /* ---- optimiser (train_ddp.py:111-118): fused Adam over one flat fp32 buffer -----------------------
  * g is first scaled by grad_scale (1/world after the NCCL sum = DDP's average).                      */

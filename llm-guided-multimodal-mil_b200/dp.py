@@ -117,13 +117,18 @@ class AbmilTrainer:
         Wcat, bcat = self._wcat_c, self._bcat_c
         mark = self.phase_hook or (lambda name: None)     # measurement only: bench.py records a CUDA event per phase
         mark("pack")
-        if self.save_gate:
-            s, act = F.gated_scores(X, Wcat, bcat, v["ww"], v["bw"], save=True)
+        fused = F.gated_scores_pool(X, Wcat, bcat, v["ww"], v["bw"], offsets) if self.save_gate else None
+        if fused is not None:
+            s, act, M, am, _ = fused          # one pass over X: scores, saved V,U and the pool
+            mark("gated_score_pool_fwd")
         else:
-            s, act = F.gated_scores(X, Wcat, bcat, v["ww"], v["bw"]), None
-        mark("gated_score_fwd")
-        M, _, am, _ = F.segment_softmax_pool(X, s, offsets)
-        mark("segment_softmax_pool_fwd")
+            if self.save_gate:
+                s, act = F.gated_scores(X, Wcat, bcat, v["ww"], v["bw"], save=True)
+            else:
+                s, act = F.gated_scores(X, Wcat, bcat, v["ww"], v["bw"]), None
+            mark("gated_score_fwd")
+            M, _, am, _ = F.segment_softmax_pool(X, s, offsets)
+            mark("segment_softmax_pool_fwd")
         self._saved = (X, offsets, s, act, M, v)
         self.last_argmax, self.last_scores = am, s
         return M

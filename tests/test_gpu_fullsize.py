@@ -131,7 +131,9 @@ def test_trainer_update_matches_optimizer_oracle(optimizer):
 @pytest.mark.parametrize("total_n,L", [(n, 1024) for n in (1, 2, 127, 128, 129, 255, 256, 257, 383, 385, 512, 513, 1025,
                                                             148 * 256 + 1)] +
                          [(2500, 768), (2500, 512), (777, 256), (3001, 320), (40000, 768)])
-def test_tile_boundaries_of_the_tensor_core_step(total_n, L):
+@pytest.mark.parametrize("single_pass", ["0", "1"])
+def test_tile_boundaries_of_the_tensor_core_step(total_n, L, single_pass, monkeypatch):
+    monkeypatch.setenv("MILB200_SINGLE_PASS", single_pass)      # "1": also through the opt-in one-pass forward
     """The bench's trainer step (CTA-pair score GEMM with saved V,U, persistent pools, fused dW) at instance counts that
     straddle the 128-row CTA tile, the 256-row pair tile and one full wave of pairs (+1), split into 1-3 ragged bags:
     pooled vectors, scores, argmax and every parameter gradient against the float64 oracle on the same bf16 operands."""
@@ -174,8 +176,10 @@ def test_tile_boundaries_of_the_tensor_core_step(total_n, L):
             assert rel_err(a, b) <= 1e-2, k
 
 
+@pytest.mark.parametrize("single_pass", ["0", "1"])
 @pytest.mark.parametrize("case", ["many_tiny_bags", "one_huge_bag", "huge_then_tiny"])
-def test_extreme_bag_shapes(case):
+def test_extreme_bag_shapes(case, single_pass, monkeypatch):
+    monkeypatch.setenv("MILB200_SINGLE_PASS", single_pass)      # "1": also through the opt-in one-pass forward
     """Edge cases of the CSR machinery: 3000 bags of 1-3 instances (every CTA slab holds hundreds of bag pieces),
     one bag spread over every CTA of the persistent pools, and a huge bag followed by tiny ones."""
     from mil_b200.dp import AbmilTrainer

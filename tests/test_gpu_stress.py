@@ -24,8 +24,11 @@ def _torch_reference(X, off, Wv, Wu, bv, bu, ww, bw, dM):
     return M.detach(), s.detach(), Wv.grad, Wu.grad
 
 
+@pytest.mark.parametrize("single_pass", ["0", "1"])
 @pytest.mark.parametrize("seed", list(range(24)))
-def test_random_batches_are_repeatable_and_correct(seed):
+def test_random_batches_are_repeatable_and_correct(seed, single_pass, monkeypatch):
+    # single_pass = "1": the opt-in one-pass forward (score GEMM + pooling records, milb200_gated_score_pool_fwd)
+    monkeypatch.setenv("MILB200_SINGLE_PASS", single_pass)
     import mil_b200
     from mil_b200.dp import AbmilTrainer
     rng = np.random.default_rng(1000 + seed)
