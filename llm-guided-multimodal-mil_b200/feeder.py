@@ -163,18 +163,32 @@ class PackedBagFeeder:
         q: "queue.Queue" = queue.Queue(maxsize=1)
         free = [threading.Semaphore(1), threading.Semaphore(1)]      # staging slot may be overwritten
 
+        stop = threading.Event()            # set when the consumer abandons the iteration: the worker must not block forever
+
+        def put(item):
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.2)
+                    return True
+                except queue.Full:
+                    continue
+            return False
+
         def worker():
             try:
                 for k, ids in enumerate(batches):
                     slot = k & 1
-                    free[slot].acquire()
+                    while not free[slot].acquire(timeout=0.2):
+                        if stop.is_set():
+                            return
                     if cuda:
                         self._staged_free[slot].synchronize()      # the H2D copy that last read this staging slot is done
                     n = self._pack(slot, ids, rng)
-                    q.put((slot, n, ids))
-                q.put(None)
+                    if not put((slot, n, ids)):
+                        return
+                put(None)
             except BaseException as e:       # surface packing errors in the consumer
-                q.put(e)
+                put(e)
 
         th = threading.Thread(target=worker, daemon=True)
         th.start()
@@ -182,6 +196,13 @@ class PackedBagFeeder:
             main = torch.cuda.current_stream(self.device)
             for ev in self._consumed:
                 ev.record(main)
+        try:
+            yield from self._consume(q, free, cuda)
+        finally:
+            stop.set()
+            th.join()
+
+    def _consume(self, q, free, cuda):
         while True:
             item = q.get()
             if item is None:
@@ -207,4 +228,3 @@ class PackedBagFeeder:
                 self._off_d[slot][:nb + 1].copy_(self._off_h[slot][:nb + 1])
                 free[slot].release()
                 yield self._dev[slot][:n], self._off_d[slot][:nb + 1], ids
-        th.join()

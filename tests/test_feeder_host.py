@@ -121,3 +121,16 @@ def test_feeder_batches_follow_distributed_sampler(tmp_path):
     a = f.order()
     f.set_epoch(1)
     assert sorted(a) == list(range(7)) and f.order() != a                 # reshuffled per epoch, still a permutation
+
+
+def test_abandoned_iteration_stops_the_worker_and_the_feeder_can_be_reused():
+    import threading
+    bags = _bags([5, 9, 3, 12, 7, 4, 8, 6], 16, np.float32, seed=2)
+    f = feeder.PackedBagFeeder(bags, batch_bags=2, L_feat=16, device="cpu", dtype=torch.float32)
+    before = threading.active_count()
+    it = iter(f)
+    X, off, ids = next(it)
+    assert ids == [0, 1] and off.tolist() == [0, 5, 14]
+    it.close()                                  # the consumer walks away after one batch
+    assert threading.active_count() == before   # ... and the packing thread is gone, not parked on a full queue
+    assert [ids for _, _, ids in f] == [[0, 1], [2, 3], [4, 5], [6, 7]]
