@@ -68,7 +68,7 @@ static EncodeTiledFn get_encoder() {
 
 static int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int esz, const void* base, uint64_t rows,
                      uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols, bool swizzle128 = true,
-                     bool swizzle32 = false) {
+                     int small_swizzle = 0) {
   EncodeTiledFn enc = get_encoder();
   MIL_CHECK_ARG(enc != nullptr, MILB200_ECUDA, "cuTensorMapEncodeTiled entry point unavailable");
   MIL_CHECK_ARG(aligned16(base) && (ld * esz) % 16 == 0, MILB200_EALIGN,
@@ -81,7 +81,9 @@ static int make_tmap(CUtensorMap* out, CUtensorMapDataType dt, int esz, const vo
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : (swizzle32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE),
+                   swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                              : (small_swizzle == 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                     : (small_swizzle == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE)),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MIL_CHECK_ARG(r == CUDA_SUCCESS, MILB200_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%llu cols=%llu ld=%llu box=%ux%u",
@@ -100,7 +102,12 @@ int make_tmap_bf16_2d_linear(CUtensorMap* out, const void* base, uint64_t rows, 
 // address is set (rows 4-7 of every 8) — lets 32 lanes write their rows with conflict-free 128-bit stores
 int make_tmap_bf16_2d_sw32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                            uint32_t box_rows) {
-  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, ld, box_rows, 16, false, true);
+  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, ld, box_rows, 16, false, 32);
+}
+// boxes whose rows are 64 bytes (32 bf16), 64-byte swizzle: 16-byte chunk index ^= bits 7-8 of the shared address
+int make_tmap_bf16_2d_sw64(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                           uint32_t box_rows) {
+  return make_tmap(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, rows, cols, ld, box_rows, 32, false, 64);
 }
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                      uint32_t box_rows, uint32_t box_cols) {

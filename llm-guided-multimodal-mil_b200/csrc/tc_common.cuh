@@ -22,6 +22,8 @@ int make_tmap_bf16_2d_linear(CUtensorMap* out, const void* base, uint64_t rows, 
                              uint32_t box_rows, uint32_t box_cols);
 int make_tmap_bf16_2d_sw32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                            uint32_t box_rows);
+int make_tmap_bf16_2d_sw64(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
+                           uint32_t box_rows);
 // same for fp32 (inner box 32 floats = 128 B), used by the TMA-store epilogues
 int make_tmap_f32_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld,
                      uint32_t box_rows, uint32_t box_cols = 32);

@@ -101,15 +101,29 @@ struct EpiStore {
     const float* dM;
     const int32_t* offsets;
     int nbags;
+    int tma_out;        // bf16 output through staged TMA stores ([32 x 32] boxes, 64-byte swizzle)
+    int bias_n;         // = N (length of bias)
+    CUtensorMap tmO;
   };
-  static constexpr int SMEM_FLOATS = 0;
-  static constexpr int STAGING_BYTES = 0;
+  static constexpr int BIAS_CACHE = 1024;       // bias[N] lives in shared memory for N <= 1024 (a global load per
+  static constexpr int SMEM_FLOATS = BIAS_CACHE;  // 32-column chunk put ~700 cycles of L2 latency on every chunk)
+  // one [32 rows x 32 cols] bf16 box per warp: a lane's 16-byte pieces of its own row would otherwise leave as 32
+  // partial-sector writes per store instruction (the epilogue of a 128 x 256 tile took 5.6 us of a 10 us kernel)
+  static constexpr int BOX_BYTES = 32 * 32 * 2;
+  static constexpr int STAGING_BYTES = EPI_WARPS * BOX_BYTES;
   static constexpr int POOL_WARPS = 0;
-  __device__ static void prologue(const Params&, float*, int) {}
+  __device__ static void prologue(const Params& p, float* esm, int tid) {
+    if (p.bias && p.bias_n <= BIAS_CACHE)
+      for (int i = tid; i < p.bias_n; i += NUM_THREADS) esm[i] = __ldg(p.bias + i);
+  }
   __device__ EpiStore() {}
   template <int BN>
-  __device__ __forceinline__ void tile(const Params& p, float*, uint8_t*, uint32_t tacc, const EpiCtx& cx) {
+  __device__ __forceinline__ void tile(const Params& p, float* esm, uint8_t* staging, uint32_t tacc, const EpiCtx& cx) {
     const int64_t row = cx.row;
+    const bool bias_smem = p.bias != nullptr && p.bias_n <= BIAS_CACHE;
+    uint8_t* box = staging + (cx.half * 4 + cx.q) * BOX_BYTES;
+    const uint32_t my_row = smem_u32(box) + static_cast<uint32_t>(cx.lane) * 64u;
+    const uint32_t sw = (my_row >> 7) & 3u;
     const int n0 = cx.n0, N = cx.N;
     const bool row_ok = row < cx.M;
     float a = 0.f;
@@ -125,13 +139,22 @@ struct EpiStore {
       uint32_t r[32];
       tmem_ld32(tacc + c, r);
       tmem_ld_wait();
-      if (!row_ok) continue;
+      if (!p.tma_out && !row_ok) continue;   // staged stores: every lane takes part, the TMA store clips rows >= M
       const int nvalid = (N - (n0 + c)) < 32 ? (N - (n0 + c)) : 32;  // multiple of 8 (N % 8 == 0)
       float v[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
       // bias: eight independent 128-bit loads (all lanes read the same addresses: one broadcast transaction each)
-      if (bias_vec) {
+      if (bias_smem) {
+        const float4* b4 = reinterpret_cast<const float4*>(esm + n0 + c);   // broadcast reads
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (j < nvalid) {
+            const float4 t = b4[j / 4];
+            v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+          }
+        }
+      } else if (bias_vec) {
         const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0 + c);
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -160,7 +183,23 @@ struct EpiStore {
         for (int j = 0; j < 32; ++j)
           if (j < nvalid) v[j] = fmaf(a, __ldg(dmrow + n0 + c + j), v[j]);
       }
-      if (p.out_bf16) {
+      if (p.tma_out) {
+        if (cx.lane == 0) tma_store_wait_read<0>();   // the previous chunk's box has been read out
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint4 pk = Vec16<__nv_bfloat16>::pack(v + 8 * k);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(my_row + ((static_cast<uint32_t>(k) ^ sw) << 4)),
+                       "r"(pk.x), "r"(pk.y), "r"(pk.z), "r"(pk.w)
+                       : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (cx.lane == 0) {
+          tma_store_2d(&p.tmO, box, n0 + c, static_cast<int32_t>(row));   // lane 0 holds the first row of the quarter
+          tma_store_commit();
+        }
+      } else if (p.out_bf16) {
         __nv_bfloat16* o = static_cast<__nv_bfloat16*>(p.out) + row * p.ldo + n0 + c;
 #pragma unroll
         for (int j = 0; j < 32; j += 8)
@@ -173,7 +212,9 @@ struct EpiStore {
       }
     }
   }
-  __device__ void finish(const Params&, int, int) {}
+  __device__ void finish(const Params& p, int, int lane) {
+    if (p.tma_out && lane == 0) tma_store_wait<0>();   // all boxes are globally visible before the kernel ends
+  }
 };
 
 // Gate tiles.  The packed weight rows (and bcat) are ordered [V 0..95 | U 0..95 | V 96..191 | U 96..191], so
@@ -932,7 +973,12 @@ int gemm_store(const void* A, int64_t M, int K, int64_t lda, const void* W, int 
                 (long long)M, N, K);
   MIL_CHECK_ARG(aligned16(out) && (ldo * (out_dtype == MILB200_BF16 ? 2 : 4)) % 16 == 0, MILB200_EALIGN,
                 "tc gemm_store: output must be 16-byte aligned");
-  EpiStore::Params ep{out, out_dtype == MILB200_BF16 ? 1 : 0, ldo, bias, act, attn, dM, offsets, nbags};
+  EpiStore::Params ep{out, out_dtype == MILB200_BF16 ? 1 : 0, ldo, bias, act, attn, dM, offsets, nbags, 0, N, {}};
+  if (out_dtype == MILB200_BF16 && M >= 32) {
+    int rc0 = make_tmap_bf16_2d_sw64(&ep.tmO, out, static_cast<uint64_t>(M), static_cast<uint64_t>(N), static_cast<uint64_t>(ldo), 32);
+    if (rc0) return rc0;
+    ep.tma_out = 1;
+  }
   if (N <= 128) return launch_kmajor<128, EpiStore>(A, M, K, lda, W, N, ldw, ep, nullptr, st);
   return launch_kmajor<256, EpiStore>(A, M, K, lda, W, N, ldw, ep, nullptr, st);
 }
