@@ -44,7 +44,7 @@ def flat_layout(L_feat, D):
 class AbmilTrainer:
     def __init__(self, L_feat=1024, D=192, compute_dtype=torch.bfloat16, lr=1e-5, betas=(0.9, 0.999), eps=1e-8,
                  weight_decay=1e-7, device="cuda", process_group=None, world_size=1, need_input_grad=False,
-                 save_gate=True, optimizer="adam"):
+                 save_gate=True, optimizer="adam", dropout_p=0.0):
         self.L, self.D = L_feat, D
         self.dtype = compute_dtype
         self.device = torch.device(device)
@@ -54,6 +54,10 @@ class AbmilTrainer:
         if optimizer not in ("adam", "sgd"):
             raise ValueError("optimizer must be 'adam' (train_ddp.py:113-116) or 'sgd' (train_ddp.py:105-108)")
         self.optimizer = optimizer
+        # train-mode semantics of ABMIL.forward (ABMIL.py:49: Dropout(p=0.5) on the INSTANCES before both GEMMs and the
+        # pool): the masked copy of X has to exist in memory because TMA feeds the GEMMs straight from it, so it costs
+        # one elementwise pass (Philox mask, seed drawn from torch's generator per step).  0 = eval-mode semantics.
+        self.dropout_p = float(dropout_p)
         self.phase_hook = None
         self.save_gate = save_gate     # keep V,U from the forward (memory) instead of re-running the GEMM (time)
         n = 2 * D * L_feat + 3 * D + 1
@@ -117,6 +121,10 @@ class AbmilTrainer:
         Wcat, bcat = self._wcat_c, self._bcat_c
         mark = self.phase_hook or (lambda name: None)     # measurement only: bench.py records a CUDA event per phase
         mark("pack")
+        if self.dropout_p > 0.0:
+            seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+            X = F._dropout_raw(X.contiguous(), self.dropout_p, seed, 0)
+            mark("dropout")
         fused = F.gated_scores_pool(X, Wcat, bcat, v["ww"], v["bw"], offsets) if self.save_gate else None
         if fused is not None:
             s, act, M, am, _ = fused          # one pass over X: scores, saved V,U and the pool

@@ -220,3 +220,32 @@ def test_extreme_bag_shapes(case, single_pass, monkeypatch):
            "attention_V.0.bias": gv["bcat"][:192], "attention_U.0.bias": gv["bcat"][192:], "attention_weights.weight": gv["ww"]}
     for k, v in got.items():
         assert rel_err(v.detach().cpu().numpy().reshape(-1), np.asarray(gr[k]).reshape(-1)) <= 1e-2, k
+
+
+def test_trainer_train_mode_dropout_matches_the_module_on_the_same_mask():
+    """AbmilTrainer(dropout_p=0.5) = ABMIL.forward in train mode (ABMIL.py:49): with the generator seeded identically both
+    draw the same Philox seed, hence the same mask, and must produce the same pooled vectors and weight gradients."""
+    import mil_b200
+    from mil_b200.dp import AbmilTrainer
+    L = 512
+    torch.manual_seed(3)
+    m = mil_b200.ABMIL(None, L=L).cuda().train()
+    lens = np.asarray([700, 33, 1500, 260])
+    off = torch.from_numpy(mo.offsets_from_lengths(lens)).cuda()
+    X = torch.randn(int(lens.sum()), L, device="cuda").to(torch.bfloat16)
+    dM = torch.randn(len(lens), L, device="cuda")
+    torch.manual_seed(77)
+    M_mod = m.forward_csr(X, off)
+    (M_mod.float() * dM).sum().backward()
+    tr = AbmilTrainer(L, 192, torch.bfloat16, device="cuda", dropout_p=m.dropout1.p)
+    tr.load_from(m)
+    torch.manual_seed(77)
+    M_tr, _ = tr.forward_backward(X, off, dM)
+    assert rel_err(M_tr.detach().cpu().numpy(), M_mod.detach().float().cpu().numpy()) <= 1e-2
+    gv = tr.grad_views()
+    assert rel_err(gv["Wcat"][:192].detach().cpu().numpy(), m.attention_V[0].weight.grad.detach().cpu().numpy()) <= 1e-3
+    # and it is dropout: about half of the instances' features are zeroed, the rest doubled
+    tr0 = AbmilTrainer(L, 192, torch.bfloat16, device="cuda")
+    tr0.load_from(m)
+    M0, _ = tr0.forward_backward(X, off, dM)
+    assert rel_err(M_tr.detach().cpu().numpy(), M0.detach().cpu().numpy()) > 0.05
