@@ -243,7 +243,7 @@ def test_trainer_train_mode_dropout_matches_the_module_on_the_same_mask():
     M_tr, _ = tr.forward_backward(X, off, dM)
     assert rel_err(M_tr.detach().cpu().numpy(), M_mod.detach().float().cpu().numpy()) <= 1e-2
     gv = tr.grad_views()
-    assert rel_err(gv["Wcat"][:192].detach().cpu().numpy(), m.attention_V[0].weight.grad.detach().cpu().numpy()) <= 1e-3
+    assert rel_err(gv["Wcat"][:192].detach().cpu().numpy(), m.attention_V[0].weight.grad.detach().cpu().numpy()) <= 1e-2
     # and it is dropout: about half of the instances' features are zeroed, the rest doubled
     tr0 = AbmilTrainer(L, 192, torch.bfloat16, device="cuda")
     tr0.load_from(m)
