@@ -663,6 +663,25 @@ def main():
                                                     "instances_per_s": n_l * 20 / (a.elapsed_time(b) / 1e3)}
         except Exception as e:
             secondary["cfg2_loguniform_lengths"] = {"error": repr(e)[:200]}
+        try:    # cfg 2 with train-mode semantics: Dropout(p=0.5) on the instances (ABMIL.py:49), one extra pass over X
+            trd = AbmilTrainer(L_FEAT, D_GATE, torch.bfloat16, lr=1e-5, weight_decay=1e-7, device=dev, dropout_p=0.5)
+            trd.load_from(module)
+            for _ in range(3):
+                trd.step(X, offsets)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(20):
+                trd.step(X, offsets)
+            b.record()
+            torch.cuda.synchronize()
+            secondary["cfg2_train_mode_dropout"] = {"bags_per_s": n_bags * 20 / (a.elapsed_time(b) / 1e3),
+                                                    "ms_per_step": a.elapsed_time(b) / 20,
+                                                    "what": "same step with Dropout(0.5) on the instances as the reference "
+                                                            "trains (masked copy of X: +2.7 GB of traffic per step)"}
+            del trd
+        except Exception as e:
+            secondary["cfg2_train_mode_dropout"] = {"error": repr(e)[:200]}
         try:    # BASELINE configs[0] (the reference's CPU-runnable case): 32 bags x 512 instances x 1024, fp32, fwd+bwd
             B1, N1 = 32, 512
             tr1 = AbmilTrainer(L_FEAT, D_GATE, torch.float32, device=dev)
