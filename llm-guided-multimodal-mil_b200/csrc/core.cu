@@ -370,22 +370,45 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   return ctr;
 }
 
+// One Philox call (128 random bits) serves EIGHT elements (16 bits each: keep-probability resolution 2^-16) and one
+// 128-bit (bf16) / two 128-bit (fp32) loads and stores; counter = index of the 8-element group (+ offset).
 template <typename T>
 __global__ void k_dropout(const T* __restrict__ x, T* __restrict__ out, int64_t n, float p, float scale,
                           uint64_t seed, uint64_t offset) {
-  int64_t blk = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const int64_t nblk = (n + 3) / 4, stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  int64_t grp = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t ngrp = (n + 7) / 8, stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
-  for (; blk < nblk; blk += stride) {
-    const uint64_t c = static_cast<uint64_t>(blk) + offset;
-    uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 32), 0u, 0u), key);
+  const uint32_t thr = static_cast<uint32_t>(fminf(fmaxf(p, 0.f), 1.f) * 65536.f);   // drop when u16 < thr
+  const bool vec = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+  for (; grp < ngrp; grp += stride) {
+    const uint64_t c = static_cast<uint64_t>(grp) + offset;
+    const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(c), static_cast<uint32_t>(c >> 32), 0u, 0u), key);
     const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+    const int64_t i0 = grp * 8;
+    float f[8];
+    if (vec && i0 + 8 <= n) {
+      if (sizeof(T) == 2) {
+        Vec16<__nv_bfloat16>::unpack(ldg_stream(reinterpret_cast<const uint4*>(x) + grp), f);
+      } else {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(x) + 2 * grp), b4 = __ldg(reinterpret_cast<const float4*>(x) + 2 * grp + 1);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b4.x; f[5] = b4.y; f[6] = b4.z; f[7] = b4.w;
+      }
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int64_t i = blk * 4 + j;
-      if (i < n) {
-        const float u = static_cast<float>(rr[j] >> 8) * (1.0f / 16777216.0f);  // [0, 1)
-        out[i] = from_f32<T>(u >= p ? to_f32<T>(x[i]) * scale : 0.f);
+      for (int j = 0; j < 8; ++j) f[j] = ((rr[j >> 1] >> (16 * (j & 1))) & 0xffffu) >= thr ? f[j] * scale : 0.f;
+      if (sizeof(T) == 2) {
+        reinterpret_cast<uint4*>(out)[grp] = Vec16<__nv_bfloat16>::pack(f);
+      } else {
+        reinterpret_cast<float4*>(out)[2 * grp] = make_float4(f[0], f[1], f[2], f[3]);
+        reinterpret_cast<float4*>(out)[2 * grp + 1] = make_float4(f[4], f[5], f[6], f[7]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int64_t i = i0 + j;
+        if (i < n) {
+          const bool keep = ((rr[j >> 1] >> (16 * (j & 1))) & 0xffffu) >= thr;
+          out[i] = from_f32<T>(keep ? to_f32<T>(x[i]) * scale : 0.f);
+        }
       }
     }
   }
@@ -454,7 +477,7 @@ int milb200_dropout(const void* x, void* out, int64_t n, float p, uint64_t seed,
   MIL_CHECK_ARG(x && out && n >= 0 && p >= 0.f && p < 1.f, MILB200_EINVAL, "dropout: bad arguments (p=%f)", p);
   if (n == 0) return MILB200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  unsigned blocks = static_cast<unsigned>(std::min<int64_t>(((n + 3) / 4 + 255) / 256, static_cast<int64_t>(sm_count()) * 16));
+  unsigned blocks = static_cast<unsigned>(std::min<int64_t>(((n + 7) / 8 + 255) / 256, static_cast<int64_t>(sm_count()) * 16));
   const float scale = 1.f / (1.f - p);
   if (dtype == MILB200_BF16)
     k_dropout<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, n, p, scale, seed, offset);
