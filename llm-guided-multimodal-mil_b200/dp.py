@@ -121,6 +121,7 @@ class AbmilTrainer:
         Wcat, bcat = self._wcat_c, self._bcat_c
         mark = self.phase_hook or (lambda name: None)     # measurement only: bench.py records a CUDA event per phase
         mark("pack")
+        seed = None
         if self.dropout_p > 0.0:
             seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
             X = F._dropout_raw(X.contiguous(), self.dropout_p, seed, 0)
@@ -137,14 +138,14 @@ class AbmilTrainer:
             mark("gated_score_fwd")
             M, _, am, _ = F.segment_softmax_pool(X, s, offsets)
             mark("segment_softmax_pool_fwd")
-        self._saved = (X, offsets, s, act, M, v)
+        self._saved = (X, offsets, s, act, M, v, seed)
         self.last_argmax, self.last_scores = am, s
         return M
 
     def backward(self, dM):
         """Backward of the last `forward` given dL/dM [B, L] fp32: parameter gradients go to the flat buffer; returns
         dL/dX (or None when the trainer was built without need_input_grad)."""
-        X, offsets, s, act, M, v = self._saved
+        X, offsets, s, act, M, v, seed = self._saved
         self._saved = None
         mark = self.phase_hook or (lambda name: None)
         ds, attn = F.segment_softmax_pool_bwd(X, s, offsets, dM, M, want_attn=self.need_input_grad)
@@ -152,6 +153,11 @@ class AbmilTrainer:
         dX, *_ = F.gated_scores_bwd(X, self._wcat_c, self._bcat_c, v["ww"], v["bw"], ds, attn, dM, offsets,
                                     self.need_input_grad, grad_out=self.grads, gate_act=act)
         mark("gate_bwd")
+        if dX is not None and seed is not None:
+            # dX above is the gradient w.r.t. the DROPPED instances; the dropout's own backward is the same Philox mask
+            # and 1/(1-p) scale applied to it (nothing was stored: the mask is a function of the step's seed)
+            dX = F._dropout_raw(dX, self.dropout_p, seed, 0)
+            mark("dropout_bwd")
         return dX
 
     def forward_backward(self, X, offsets, dM=None):

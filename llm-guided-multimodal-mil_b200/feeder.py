@@ -129,13 +129,21 @@ class PackedBagFeeder:
         self.epoch = int(epoch)
 
     def order(self):
-        """This rank's bag indices for the epoch: DistributedSampler's permutation + stride (train_ddp.py:191)."""
+        """This rank's bag indices for the epoch: DistributedSampler's permutation, padding and stride
+        (train_ddp.py:191, drop_last=False): the index list is extended with its own head to a multiple of `world`, so
+        every rank draws ceil(n / world) bags (and therefore the same number of batches — each step ends in one
+        all-reduce, a rank that ran out of batches would leave the others waiting in it)."""
         n = len(self.sources)
         if self.shuffle:
             g = torch.Generator().manual_seed(self.seed + self.epoch)
             idx = torch.randperm(n, generator=g).tolist()
         else:
             idx = list(range(n))
+        if self.world > 1 and n > 0:
+            total = (n + self.world - 1) // self.world * self.world
+            pad = total - n
+            if pad:
+                idx = idx + (idx * ((pad + n - 1) // n))[:pad]
         return idx[self.rank::self.world]
 
     def batches(self):

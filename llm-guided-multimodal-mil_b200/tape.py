@@ -166,6 +166,12 @@ class Tape:
         self._flat_cache = (key, wc, p32)
         return wc, p32
 
+    def invalidate(self):
+        """Drop the cached flat parameter images.  The cache key is (data_ptr, _version) per parameter, which versioned
+        in-place updates (optimiser steps, `p.copy_`, `load_state_dict`) change — but writes through `p.data` (EMA /
+        weight-sync code, some checkpoint loaders) do not bump `_version`: call this after such a write."""
+        self._flat_cache = None
+
     def _pool(self, rows, slots, dtype, dev, code):
         pools = getattr(self, "_pools", None)
         if pools is None:

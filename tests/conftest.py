@@ -15,9 +15,19 @@ def pytest_configure(config):
 
 
 def pytest_collection_modifyitems(config, items):
-    """GPU tests fail loudly (not skip) when selected on a box without a device or without the
-    built CUDA library — a silent skip would hide a missing native path."""
-    return
+    """GPU tests selected on a box without a device (or without the built CUDA library) must FAIL, not skip: a silent
+    skip would hide a missing native path.  Every `gpu` test gets a guard fixture that raises before the test body."""
+    for item in items:
+        if item.get_closest_marker("gpu") is not None:
+            item.fixturenames.insert(0, "_require_gpu_and_native_library")
+
+
+@pytest.fixture()
+def _require_gpu_and_native_library():
+    import torch
+    assert torch.cuda.is_available(), "a test marked `gpu` was selected but no CUDA device is visible (run with -m 'not gpu' on CPU boxes)"
+    import mil_b200
+    assert mil_b200.lib().milb200_version() > 0, "libmilb200.so did not load: build it with `python __graft_entry__.py build`"
 
 
 @pytest.fixture(scope="session")

@@ -108,14 +108,20 @@ def test_feeder_batches_follow_distributed_sampler(tmp_path):
     seen = []
     for rank in (0, 1):
         f = feeder.PackedBagFeeder(paths, batch_bags=2, L_feat=32, device="cpu", dtype=torch.bfloat16, rank=rank, world=2)
-        assert f.order() == list(range(7))[rank::2]                       # train_ddp.py:191 without shuffle
+        # train_ddp.py:191 without shuffle: DistributedSampler pads 7 -> 8 indices with the head of the list
+        assert f.order() == (list(range(7)) + [0])[rank::2]
+        assert len(f.batches()) == 2                                      # every rank runs the same number of steps
         for X, off, ids in f:
             assert off.dtype == torch.int32 and off[0] == 0
             assert off.tolist() == [0] + np.cumsum([lens[i] for i in ids]).tolist()
             want = _expect([bags[i] for i in ids], [None] * len(ids), torch.bfloat16)
             assert torch.equal(X.view(torch.int16), want.view(torch.int16))
             seen += ids
-    assert sorted(seen) == list(range(7))
+    assert sorted(seen) == [0] + list(range(7))                           # the padding index is seen twice
+    for world in (2, 3, 4, 8):                                            # equal step counts for any world size
+        counts = {len(feeder.PackedBagFeeder(paths, batch_bags=2, L_feat=32, device="cpu", rank=r, world=world,
+                                             shuffle=True, seed=5).batches()) for r in range(world)}
+        assert len(counts) == 1, (world, counts)
     f = feeder.PackedBagFeeder(paths, batch_bags=3, L_feat=32, device="cpu", shuffle=True, seed=3)
     f.set_epoch(0)
     a = f.order()
