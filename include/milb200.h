@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define MILB200_VERSION 106
+#define MILB200_VERSION 200
 
 enum { MILB200_F32 = 0, MILB200_BF16 = 1 };
 
@@ -227,9 +227,32 @@ int milb200_ct_tokens_bwd(const void* dtokens, void* dfmap, int c, int t, int hw
  *           ATTENTION out = softmax(Q K^T / sqrt(c)) V      in0/in1/in2 = Q/K/V (distinct slots), a0 = heads
  *           LAYERNORM out = LN(in0 [+ in1]) * gamma + beta  p0 = gamma, p1 = beta (eps 1e-5)
  *           ADD       out = in0 + in1                       (a sum several ops share, e.g. keys + key_pe)
- * Backward: seed_ptrs[s] != NULL gives dL/d(slot s) for program outputs; ext_grad_ptrs[s] != NULL asks for the
- * gradient of external input s (written there); internal slots' gradients live in the workspace.                  */
-enum { MILB200_OP_LINEAR = 1, MILB200_OP_ATTENTION = 2, MILB200_OP_LAYERNORM = 3, MILB200_OP_ADD = 4 };
+ *           JOIN      out = rows of in0 followed by rows of in1 (in0 is written in place: its producer's output IS the
+ *                     head of out; in1 is copied)           assembling the key stream / the token rows of all segments
+ *           HEADDIAG_U out[r*H + h, :] = sum_c in0[r, h*32 + c] W[h*32 + c, :]      p0 = W [256, 512] (fp32 slots)
+ *           HEADDIAG_O out[r, h*32 + c] = in0[r*H + h, :] . W[h*32 + c, :] + b      p0 = W [256, 512], p1 = b [256]
+ *           T2I_POOL  token -> image attention of transformer.py:290-295 with the key/value projections folded into
+ *                     the token side: in0 = keys, in1 = position table, in2 = U (HEADDIAG_U of the projected queries
+ *                     with k_proj.weight); out[(seg, t, h), :] = sum_n softmax_n(scale (keys + pe) . U) keys[n]
+ *                     a0 = 1: keys are addressed in the packed-bag layout (segment out_start), 0: key-stream layout
+ *           LN_SEG    out = LN(in0 + in1[segment]) * gamma + beta — image -> token attention with ONE token per
+ *                     segment (softmax over one key = 1: the attention output is one row per segment)
+ *                     a0 bit 0: write the rows at out_start (the packed bag of aggregator.py:173); in2 >= 0: also
+ *                     copy the token rows in2 [n_segs*T, 512] to tok_row (the x_CT2CI / x_Pth2CI rows of the bag)
+ *           TOK_SCATTER out = in1 with the token rows in0 [n_segs*T, 512] (fp32) written at tok_row, IN PLACE: out and in1
+ *                     must be external slots at the same address (value and gradient) — the x_CT2CI / x_Pth2CI rows of
+ *                     the packed bag, filled once the final token -> image attention has produced them
+ * Slots may be forced to fp32 inside a bf16 program (external bit 1): the text-token side (<= 16 rows) always runs in
+ * fp32 with the fp32 master weights; an op's arithmetic dtype is that of its in0.  The segment ops read the segment
+ * table handed to milb200_tape_forward/backward (host memory; NULL when the program has no segment ops).
+ * Backward: seed_ptrs[s] != NULL gives dL/d(slot s) for program outputs (copied into the slot's gradient buffer
+ * ext_grad_ptrs[s] unless the two pointers are equal: a caller-owned buffer may be seeded in place); ext_grad_ptrs[s] !=
+ * NULL asks for the gradient of external input s (written there); internal slots' gradients live in the workspace.  */
+enum { MILB200_OP_LINEAR = 1, MILB200_OP_ATTENTION = 2, MILB200_OP_LAYERNORM = 3, MILB200_OP_ADD = 4,
+       MILB200_OP_JOIN = 5, MILB200_OP_HEADDIAG_U = 6, MILB200_OP_HEADDIAG_O = 7, MILB200_OP_T2I_POOL = 8,
+       MILB200_OP_LN_SEG = 9, MILB200_OP_TOK_SCATTER = 10 };
+enum { MILB200_SLOT_EXTERNAL = 1, MILB200_SLOT_F32 = 2 };
+#define MILB200_MAX_SEGMENTS 16
 typedef struct milb200_tape_op {
   int32_t kind, in0, in1, in2, out, p0, p1, a0;
   int32_t lane; /* 0 or 1: ops of different lanes may run concurrently (two streams / parallel graph branches); the
@@ -237,25 +260,35 @@ typedef struct milb200_tape_op {
 } milb200_tape_op;
 typedef struct milb200_tape_slot {
   int64_t rows;
-  int32_t cols, external;
+  int32_t cols, external; /* external: MILB200_SLOT_* flags */
 } milb200_tape_slot;
 typedef struct milb200_tape_param {
   int64_t offset; /* elements from the start of the flat buffers; multiple of 8 */
   int32_t rows, cols;
 } milb200_tape_param;
+/* One image-side bag of the fusion path: `len` rows starting at row k_start of the key stream (JOIN output); the same
+ * rows start at out_start in the packed multi-modal bag, the segment's text-token rows at tok_row.                  */
+typedef struct milb200_segment {
+  int32_t k_start, len, out_start, tok_row;
+} milb200_segment;
+typedef struct milb200_segments {
+  const milb200_segment* seg; /* host memory, n_segs entries */
+  int32_t n_segs;
+  int32_t tokens; /* T: text tokens per segment */
+} milb200_segments;
 size_t milb200_tape_arena_bytes(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
-                                int dtype);
+                                int dtype, const milb200_segments* segs);
 size_t milb200_tape_workspace_bytes(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
-                                    int dtype, int backward);
+                                    int dtype, int backward, const milb200_segments* segs);
 int milb200_tape_forward(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
                          const milb200_tape_param* params, int n_params, void* const* ext_ptrs, const void* w_compute,
                          const float* p_f32, void* arena, size_t arena_bytes, void* workspace, size_t ws_bytes,
-                         int dtype, void* stream);
+                         int dtype, const milb200_segments* segs, void* stream);
 int milb200_tape_backward(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
                           const milb200_tape_param* params, int n_params, void* const* ext_ptrs,
                           void* const* ext_grad_ptrs, const void* const* seed_ptrs, const void* w_compute,
                           const float* p_f32, float* g_f32, const void* arena, size_t arena_bytes, void* workspace,
-                          size_t ws_bytes, int dtype, void* stream);
+                          size_t ws_bytes, int dtype, const milb200_segments* segs, void* stream);
 
 /* ---- single-pass forward of the gated pool (ABMIL.py:52-59 in one pass over X) ---------------------------------
  * = milb200_gated_score_fwd (gate_act required) + milb200_segment_softmax_pool_fwd with the same outputs, reading X

@@ -64,10 +64,10 @@ SIGNATURES = {
     "milb200_sinusoid_pe": (_i, [_p, _i64, _i, _i, _p]),
     "milb200_ct_tokens_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "milb200_ct_tokens_bwd": (_i, [_p, _p, _i, _i, _i, _i, _p]),
-    "milb200_tape_arena_bytes": (_sz, [_p, _i, _p, _i, _i]),
-    "milb200_tape_workspace_bytes": (_sz, [_p, _i, _p, _i, _i, _i]),
-    "milb200_tape_forward": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _sz, _p, _sz, _i, _p]),
-    "milb200_tape_backward": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p, _sz, _i, _p]),
+    "milb200_tape_arena_bytes": (_sz, [_p, _i, _p, _i, _i, _p]),
+    "milb200_tape_workspace_bytes": (_sz, [_p, _i, _p, _i, _i, _i, _p]),
+    "milb200_tape_forward": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _sz, _p, _sz, _i, _p, _p]),
+    "milb200_tape_backward": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p, _sz, _i, _p, _p]),
     "milb200_adam_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _i, _p]),
     "milb200_sgd_step": (_i, [_p, _p, _i64, _f, _f, _f, _p]),
     "milb200_pack_bags_offsets": (_i, [_p, _p, _i, _p, _p]),
@@ -89,7 +89,24 @@ class TapeParam(C.Structure):
     _fields_ = [("offset", C.c_int64), ("rows", C.c_int32), ("cols", C.c_int32)]
 
 
+class Segment(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("k_start", "len", "out_start", "tok_row")]
+
+
+class Segments(C.Structure):
+    _fields_ = [("seg", C.POINTER(Segment)), ("n_segs", C.c_int32), ("tokens", C.c_int32)]
+
+
+def make_segments(rows, tokens):
+    """rows: [(k_start, len, out_start, tok_row), ...] -> (Segments struct, keep-alive array).  Pass C.byref(struct)."""
+    arr = (Segment * len(rows))(*[Segment(*map(int, r)) for r in rows])
+    return Segments(arr, len(rows), int(tokens)), arr
+
+
 OP_LINEAR, OP_ATTENTION, OP_LAYERNORM, OP_ADD = 1, 2, 3, 4
+OP_JOIN, OP_HEADDIAG_U, OP_HEADDIAG_O, OP_T2I_POOL, OP_LN_SEG, OP_TOK_SCATTER = 5, 6, 7, 8, 9, 10
+SLOT_EXTERNAL, SLOT_F32 = 1, 2
+MAX_SEGMENTS = 16
 
 _lib = None
 _lock = threading.Lock()

@@ -37,13 +37,13 @@ class ABMIL(nn.Module):
         return (self.attention_V[0].weight, self.attention_V[0].bias, self.attention_U[0].weight,
                 self.attention_U[0].bias, self.attention_weights.weight, self.attention_weights.bias)
 
-    def forward_csr(self, X, offsets):
-        """X [total_n, L] packed instances, offsets int32 [B+1] on the device -> M [B, L]."""
+    def forward_csr(self, X, offsets, out_fp32=False):
+        """X [total_n, L] packed instances, offsets int32 [B+1] on the device -> M [B, L] (X.dtype; fp32 with out_fp32)."""
         if X.dim() != 2 or X.shape[1] != self.L:
             raise L.MilB200Error(f"ABMIL.forward_csr: expected [total_n, {self.L}], got {tuple(X.shape)}")
         if self.training and self.dropout1.p > 0:
             X = F.dropout(X, self.dropout1.p)                                  # ABMIL.py:49
-        M, am, s = F.abmil_pool_csr(X, offsets, *self._params())
+        M, am, s = F.abmil_pool_csr(X, offsets, *self._params(), out_fp32=out_fp32)
         self.last_argmax, self.last_scores = am, s
         return M
 

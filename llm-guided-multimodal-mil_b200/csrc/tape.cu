@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "xfusion.cuh"
 
 namespace milb200 {
 
@@ -22,14 +23,25 @@ struct TapePlan {
   size_t max_slot_bytes = 0;
   size_t scratch_fwd = 0, scratch_bwd = 0;
   int lanes = 1;                  // 2 when any op asks for lane 1
+  std::vector<int> alias_of;      // JOIN: slot whose storage (value and gradient) is the head of another slot's, else -1
+  bool has_segs = false;
+  xf::Segs sg;
 };
 
+static inline bool slot_ext(const milb200_tape_slot& s) { return (s.external & MILB200_SLOT_EXTERNAL) != 0; }
+// an op's arithmetic/storage dtype is its slots' own: the program dtype unless the slot is forced to fp32
+static inline int slot_dtype(const milb200_tape_slot& s, int dtype) { return (s.external & MILB200_SLOT_F32) ? MILB200_F32 : dtype; }
 static inline size_t slot_bytes(const milb200_tape_slot& s, int dtype) {
-  return static_cast<size_t>(s.rows) * static_cast<size_t>(s.cols) * elem_size(dtype);
+  return static_cast<size_t>(s.rows) * static_cast<size_t>(s.cols) * elem_size(slot_dtype(s, dtype));
+}
+static inline bool is_seg_op(int kind) {
+  return kind == MILB200_OP_T2I_POOL || kind == MILB200_OP_LN_SEG || kind == MILB200_OP_TOK_SCATTER;
 }
 
 static int tape_validate(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
-                         const milb200_tape_param* params, int n_params) {
+                         const milb200_tape_param* params, int n_params, int dtype, const milb200_segments* segs) {
+  auto dt = [&](int s) { return slot_dtype(slots[s], dtype); };
+  const int n_segs = segs ? segs->n_segs : 0, T = segs ? segs->tokens : 0;
   MIL_CHECK_ARG(ops && slots && n_ops > 0 && n_slots > 0, MILB200_EINVAL, "tape: empty program");
   auto ok_slot = [&](int s, bool optional) { return (optional && s < 0) || (s >= 0 && s < n_slots); };
   for (int i = 0; i < n_slots; ++i)
@@ -52,6 +64,8 @@ static int tape_validate(const milb200_tape_op* ops, int n_ops, const milb200_ta
         MIL_CHECK_ARG(o.in1 < 0 || (o.in1 != o.in0 && slots[o.in1].rows == s0.rows && slots[o.in1].cols == s0.cols),
                       MILB200_EINVAL, "tape: op %d `add` slot must differ from x and share its shape", i);
         MIL_CHECK_ARG(o.p1 < 0 || params[o.p1].rows * params[o.p1].cols == so.cols, MILB200_EINVAL, "tape: op %d bias size", i);
+        MIL_CHECK_ARG(dt(o.out) == dt(o.in0) && (o.in1 < 0 || dt(o.in1) == dt(o.in0)), MILB200_EINVAL,
+                      "tape: op %d linear operands must share one dtype", i);
         break;
       }
       case MILB200_OP_ATTENTION: {
@@ -80,6 +94,59 @@ static int tape_validate(const milb200_tape_op* ops, int n_ops, const milb200_ta
         MIL_CHECK_ARG(ok_slot(o.in1, false) && o.in1 != o.in0, MILB200_EINVAL, "tape: op %d add needs two distinct slots", i);
         MIL_CHECK_ARG(so.rows == s0.rows && so.cols == s0.cols && slots[o.in1].rows == s0.rows && slots[o.in1].cols == s0.cols,
                       MILB200_EINVAL, "tape: op %d add shape mismatch", i);
+        MIL_CHECK_ARG(dt(o.out) == dt(o.in0) && dt(o.in1) == dt(o.in0), MILB200_EINVAL, "tape: op %d add dtype mismatch", i);
+        break;
+      }
+      case MILB200_OP_JOIN: {
+        MIL_CHECK_ARG(ok_slot(o.in1, false) && o.in1 != o.in0 && o.out != o.in0 && o.out != o.in1, MILB200_EINVAL,
+                      "tape: op %d join needs three distinct slots", i);
+        MIL_CHECK_ARG(!slot_ext(so) && so.rows == s0.rows + slots[o.in1].rows && so.cols == s0.cols && slots[o.in1].cols == s0.cols &&
+                          dt(o.out) == dt(o.in0) && dt(o.in1) == dt(o.in0),
+                      MILB200_EINVAL, "tape: op %d join shape/dtype mismatch (the result must be an internal slot)", i);
+        break;
+      }
+      case MILB200_OP_HEADDIAG_U:
+      case MILB200_OP_HEADDIAG_O: {
+        const bool up = o.kind == MILB200_OP_HEADDIAG_U;
+        const milb200_tape_slot& small = up ? s0 : so;
+        const milb200_tape_slot& big = up ? so : s0;
+        MIL_CHECK_ARG(params && o.p0 >= 0 && o.p0 < n_params && o.p1 < n_params && params[o.p0].rows == xf::CI &&
+                          params[o.p0].cols == xf::E && (o.p1 < 0 || (!up && params[o.p1].rows * params[o.p1].cols == xf::CI)),
+                      MILB200_EINVAL, "tape: op %d head-diagonal product needs a [256, 512] weight", i);
+        MIL_CHECK_ARG(small.cols == xf::CI && big.cols == xf::E && big.rows == small.rows * xf::H && dt(o.in0) == MILB200_F32 &&
+                          dt(o.out) == MILB200_F32,
+                      MILB200_EINVAL, "tape: op %d head-diagonal product: [R, 256] <-> [R*8, 512] fp32 slots", i);
+        break;
+      }
+      case MILB200_OP_T2I_POOL: {
+        MIL_CHECK_ARG(ok_slot(o.in1, false) && ok_slot(o.in2, false) && n_segs > 0, MILB200_EINVAL,
+                      "tape: op %d t2i_pool needs keys, position table, U and a segment table", i);
+        MIL_CHECK_ARG(s0.cols == xf::E && slots[o.in1].cols == xf::E && dt(o.in1) == dt(o.in0) && slots[o.in2].cols == xf::E &&
+                          slots[o.in2].rows == static_cast<int64_t>(n_segs) * T * xf::H && so.rows == slots[o.in2].rows &&
+                          so.cols == xf::E && dt(o.in2) == MILB200_F32 && dt(o.out) == MILB200_F32,
+                      MILB200_EINVAL, "tape: op %d t2i_pool shape/dtype mismatch", i);
+        break;
+      }
+      case MILB200_OP_LN_SEG: {
+        MIL_CHECK_ARG(ok_slot(o.in1, false) && ok_slot(o.in2, true) && n_segs > 0 && T == 1, MILB200_EINVAL,
+                      "tape: op %d ln_seg needs keys, one row per segment and a segment table with one token per segment", i);
+        MIL_CHECK_ARG(params && o.p0 >= 0 && o.p0 < n_params && o.p1 >= 0 && o.p1 < n_params, MILB200_EINVAL,
+                      "tape: op %d bad param id", i);
+        MIL_CHECK_ARG(s0.cols == xf::E && so.cols == xf::E && dt(o.out) == dt(o.in0) && slots[o.in1].cols == xf::E &&
+                          slots[o.in1].rows == n_segs && dt(o.in1) == MILB200_F32 &&
+                          (o.in2 < 0 || (slots[o.in2].cols == xf::E && slots[o.in2].rows == static_cast<int64_t>(n_segs) * T &&
+                                         dt(o.in2) == MILB200_F32)) &&
+                          ((o.a0 & 1) || so.rows == s0.rows),
+                      MILB200_EINVAL, "tape: op %d ln_seg shape/dtype mismatch", i);
+        break;
+      }
+      case MILB200_OP_TOK_SCATTER: {
+        MIL_CHECK_ARG(ok_slot(o.in1, false) && n_segs > 0 && o.in1 != o.out, MILB200_EINVAL,
+                      "tape: op %d tok_scatter needs token rows, the bag and a segment table", i);
+        MIL_CHECK_ARG(s0.cols == xf::E && s0.rows == static_cast<int64_t>(n_segs) * T && dt(o.in0) == MILB200_F32 &&
+                          slot_ext(so) && slot_ext(slots[o.in1]) && so.cols == xf::E && slots[o.in1].cols == xf::E &&
+                          so.rows == slots[o.in1].rows && dt(o.out) == dt(o.in1),
+                      MILB200_EINVAL, "tape: op %d tok_scatter shape/dtype mismatch (bag slots must be external)", i);
         break;
       }
       default:
@@ -89,39 +156,60 @@ static int tape_validate(const milb200_tape_op* ops, int n_ops, const milb200_ta
   return MILB200_OK;
 }
 
-static TapePlan tape_plan(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots, int dtype) {
-  TapePlan p;
+static int tape_plan(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots, int dtype,
+                     const milb200_segments* segs, TapePlan* out) {
+  TapePlan& p = *out;
   p.slot_off.assign(n_slots, SIZE_MAX);
   p.aux_off.assign(n_ops, SIZE_MAX);
+  p.alias_of.assign(n_slots, -1);
+  if (segs && segs->n_segs > 0) {
+    int rc = xf::make_segs(segs->seg, segs->n_segs, segs->tokens, &p.sg);
+    if (rc) return rc;
+    p.has_segs = true;
+  }
+  // JOIN: an internal first operand is produced in place at the head of the result
+  for (int i = 0; i < n_ops; ++i)
+    if (ops[i].kind == MILB200_OP_JOIN && !slot_ext(slots[ops[i].in0]) && p.alias_of[ops[i].in0] < 0) p.alias_of[ops[i].in0] = ops[i].out;
   size_t off = 0;
   for (int i = 0; i < n_slots; ++i) {
     const size_t b = slot_bytes(slots[i], dtype);
     p.max_slot_bytes = std::max(p.max_slot_bytes, b);
-    if (slots[i].external) continue;
+    if (slot_ext(slots[i]) || p.alias_of[i] >= 0) continue;
     off = align_up(off, 256);
     p.slot_off[i] = off;
     off += b;
   }
+  for (int i = 0; i < n_slots; ++i)
+    if (p.alias_of[i] >= 0) p.slot_off[i] = p.slot_off[p.alias_of[i]];
   for (int i = 0; i < n_ops; ++i) {
     const milb200_tape_op& o = ops[i];
     size_t aux = 0;
     if (o.kind == MILB200_OP_ATTENTION) aux = sizeof(float) * static_cast<size_t>(o.a0) * slots[o.in0].rows;
     if (o.kind == MILB200_OP_LAYERNORM) aux = sizeof(float) * 2 * static_cast<size_t>(slots[o.in0].rows);
+    if (is_seg_op(o.kind)) MIL_CHECK_ARG(p.has_segs, MILB200_EINVAL, "tape: op %d needs a segment table", i);
+    if (o.kind == MILB200_OP_T2I_POOL)      // scores [rows, T*H] + lse [n_segs*T*H]
+      aux = sizeof(float) * (static_cast<size_t>(slots[o.in0].rows) * p.sg.T * xf::H + static_cast<size_t>(slots[o.out].rows));
+    if (o.kind == MILB200_OP_LN_SEG) aux = sizeof(float) * 2 * static_cast<size_t>(slots[o.in0].rows);
     if (aux) {
       off = align_up(off, 256);
       p.aux_off[i] = off;
       off += aux;
     }
     size_t f = 0, b = 0;
+    const int dt0 = slot_dtype(slots[o.in0], dtype);
     if (o.kind == MILB200_OP_LINEAR) {
-      f = milb200_linear_workspace_bytes(slots[o.in0].rows, slots[o.out].cols, slots[o.in0].cols, dtype, 0);
-      b = milb200_linear_workspace_bytes(slots[o.in0].rows, slots[o.out].cols, slots[o.in0].cols, dtype, 1);
+      f = milb200_linear_workspace_bytes(slots[o.in0].rows, slots[o.out].cols, slots[o.in0].cols, dt0, 0);
+      b = milb200_linear_workspace_bytes(slots[o.in0].rows, slots[o.out].cols, slots[o.in0].cols, dt0, 1);
     } else if (o.kind == MILB200_OP_ATTENTION) {
       const int c = slots[o.in0].cols / o.a0;
       f = milb200_attention_workspace_bytes(slots[o.in0].rows, slots[o.in1].rows, o.a0, c, 0);
       b = milb200_attention_workspace_bytes(slots[o.in0].rows, slots[o.in1].rows, o.a0, c, 1);
     } else if (o.kind == MILB200_OP_LAYERNORM) {
       b = milb200_layernorm_workspace_bytes(slots[o.in0].rows, slots[o.in0].cols) + 256 + sizeof(float) * slots[o.in0].cols;
+    } else if (o.kind == MILB200_OP_T2I_POOL) {
+      f = b = xf::t2i_ws_bytes(p.sg);
+    } else if (o.kind == MILB200_OP_LN_SEG) {
+      b = xf::ln_seg_ws_bytes(p.sg);
     }
     p.scratch_fwd = std::max(p.scratch_fwd, f);
     p.scratch_bwd = std::max(p.scratch_bwd, b);
@@ -130,7 +218,7 @@ static TapePlan tape_plan(const milb200_tape_op* ops, int n_ops, const milb200_t
   p.arena_bytes = align_up(off, 256) + 256;
   p.scratch_fwd = align_up(p.scratch_fwd, 256) + 256;
   p.scratch_bwd = align_up(p.scratch_bwd, 256) + 256;
-  return p;
+  return MILB200_OK;
 }
 
 // backward workspace image: per lane [kernel scratch][3 temporaries of max_slot_bytes], then [gradient buffer of every
@@ -219,27 +307,32 @@ using namespace milb200;
 
 extern "C" {
 
-size_t milb200_tape_arena_bytes(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots, int dtype) {
+size_t milb200_tape_arena_bytes(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots, int dtype,
+                                const milb200_segments* segs) {
   if (!ops || !slots || n_ops <= 0 || n_slots <= 0) return 256;
-  return tape_plan(ops, n_ops, slots, n_slots, dtype).arena_bytes;
+  TapePlan p;
+  if (tape_plan(ops, n_ops, slots, n_slots, dtype, segs, &p)) return 256;
+  return p.arena_bytes;
 }
 
 size_t milb200_tape_workspace_bytes(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
-                                    int dtype, int backward) {
+                                    int dtype, int backward, const milb200_segments* segs) {
   if (!ops || !slots || n_ops <= 0 || n_slots <= 0) return 256;
-  TapePlan p = tape_plan(ops, n_ops, slots, n_slots, dtype);
+  TapePlan p;
+  if (tape_plan(ops, n_ops, slots, n_slots, dtype, segs, &p)) return 256;
   return backward ? tape_bwd_ws_bytes(p) : p.lanes * p.scratch_fwd;
 }
 
 static int tape_forward_run(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
                             const milb200_tape_param* params, int n_params, void* const* ext_ptrs, const void* w_compute,
                             const float* p_f32, void* arena, size_t arena_bytes, void* workspace, size_t ws_bytes, int dtype,
-                            void* stream_main, void* stream_aux) {
-  int rc = tape_validate(ops, n_ops, slots, n_slots, params, n_params);
-  if (rc) return rc;
+                            const milb200_segments* segs, void* stream_main, void* stream_aux) {
   MIL_CHECK_ARG(dtype == MILB200_F32 || dtype == MILB200_BF16, MILB200_EINVAL, "tape: bad dtype %d", dtype);
+  int rc = tape_validate(ops, n_ops, slots, n_slots, params, n_params, dtype, segs);
+  if (rc) return rc;
   MIL_CHECK_ARG(ext_ptrs && w_compute && p_f32 && arena, MILB200_EINVAL, "tape_forward: null pointer");
-  TapePlan pl = tape_plan(ops, n_ops, slots, n_slots, dtype);
+  TapePlan pl;
+  if ((rc = tape_plan(ops, n_ops, slots, n_slots, dtype, segs, &pl))) return rc;
   MIL_CHECK_ARG(arena_bytes >= pl.arena_bytes, MILB200_EWORKSPACE, "tape_forward: arena %zu < %zu", arena_bytes, pl.arena_bytes);
   MIL_CHECK_ARG(workspace && ws_bytes >= pl.lanes * pl.scratch_fwd, MILB200_EWORKSPACE, "tape_forward: workspace %zu < %zu",
                 ws_bytes, pl.lanes * pl.scratch_fwd);
@@ -247,14 +340,18 @@ static int tape_forward_run(const milb200_tape_op* ops, int n_ops, const milb200
   lr.begin(static_cast<cudaStream_t>(stream_main), pl.lanes == 2 ? static_cast<cudaStream_t>(stream_aux) : nullptr, n_slots,
            &t_lane_events);
   if ((rc = lr.fork())) return rc;
-  const size_t esz = elem_size(dtype);
   char* ar = static_cast<char*>(arena);
   std::vector<void*> ptr(n_slots);
   for (int i = 0; i < n_slots; ++i) {
-    ptr[i] = slots[i].external ? ext_ptrs[i] : static_cast<void*>(ar + pl.slot_off[i]);
+    ptr[i] = slot_ext(slots[i]) ? ext_ptrs[i] : static_cast<void*>(ar + pl.slot_off[i]);
     MIL_CHECK_ARG(ptr[i] != nullptr && aligned16(ptr[i]), MILB200_EALIGN, "tape_forward: slot %d pointer is null or misaligned", i);
   }
-  const char* wc = static_cast<const char*>(w_compute);
+  auto dt = [&](int s) { return slot_dtype(slots[s], dtype); };
+  // weights of an op: the compute-dtype image for program-dtype operands, the fp32 master for fp32 slots
+  auto weight = [&](int p, int d) -> const void* {
+    return d == dtype ? static_cast<const void*>(static_cast<const char*>(w_compute) + params[p].offset * elem_size(dtype))
+                      : static_cast<const void*>(p_f32 + params[p].offset);
+  };
   for (int i = 0; i < n_ops; ++i) {
     const milb200_tape_op& o = ops[i];
     const milb200_tape_slot& s0 = slots[o.in0];
@@ -262,28 +359,70 @@ static int tape_forward_run(const milb200_tape_op* ops, int n_ops, const milb200
     const int res[4] = {o.in0, o.in1, o.in2, o.out};
     if ((rc = lr.before(o.lane, res, 4))) return rc;
     void* stream = lr.stream_of(o.lane);
+    cudaStream_t cst = static_cast<cudaStream_t>(stream);
     void* workspace_l = static_cast<char*>(workspace) + (lr.two ? o.lane : 0) * pl.scratch_fwd;
     const size_t ws_l = pl.scratch_fwd;
+    const int d0 = dt(o.in0);
     switch (o.kind) {
       case MILB200_OP_LINEAR:
-        rc = milb200_linear_fwd(ptr[o.in0], o.in1 >= 0 ? ptr[o.in1] : nullptr, wc + params[o.p0].offset * esz,
+        rc = milb200_linear_fwd(ptr[o.in0], o.in1 >= 0 ? ptr[o.in1] : nullptr, weight(o.p0, d0),
                                 o.p1 >= 0 ? p_f32 + params[o.p1].offset : nullptr, ptr[o.out], s0.rows, so.cols, s0.cols, o.a0,
-                                dtype, workspace_l, ws_l, stream);
+                                d0, workspace_l, ws_l, stream);
         break;
       case MILB200_OP_ATTENTION:
         rc = milb200_attention_fwd(ptr[o.in0], ptr[o.in1], ptr[o.in2], ptr[o.out], reinterpret_cast<float*>(ar + pl.aux_off[i]),
-                                   s0.rows, slots[o.in1].rows, o.a0, s0.cols / o.a0, dtype, workspace_l, ws_l, stream);
+                                   s0.rows, slots[o.in1].rows, o.a0, s0.cols / o.a0, d0, workspace_l, ws_l, stream);
         break;
       case MILB200_OP_LAYERNORM: {
         float* mean = reinterpret_cast<float*>(ar + pl.aux_off[i]);
         const int bcast = (o.in1 >= 0 && slots[o.in1].rows == 1 && s0.rows > 1) ? 1 : 0;
         rc = milb200_layernorm_fwd(ptr[o.in0], o.in1 >= 0 ? ptr[o.in1] : nullptr, p_f32 + params[o.p0].offset,
-                                   p_f32 + params[o.p1].offset, ptr[o.out], mean, mean + s0.rows, s0.rows, s0.cols, dtype,
+                                   p_f32 + params[o.p1].offset, ptr[o.out], mean, mean + s0.rows, s0.rows, s0.cols, d0,
                                    bcast, stream);
         break;
       }
       case MILB200_OP_ADD:
-        rc = milb200_add(ptr[o.in0], ptr[o.in1], ptr[o.out], s0.rows * s0.cols, dtype, stream);
+        rc = milb200_add(ptr[o.in0], ptr[o.in1], ptr[o.out], s0.rows * s0.cols, d0, stream);
+        break;
+      case MILB200_OP_JOIN: {
+        char* dst = static_cast<char*>(ptr[o.out]);
+        const size_t b0 = slot_bytes(s0, dtype);
+        if (pl.alias_of[o.in0] != o.out) {
+          MIL_CUDA(cudaMemcpyAsync(dst, ptr[o.in0], b0, cudaMemcpyDeviceToDevice, cst));
+          count_launch();
+        }
+        MIL_CUDA(cudaMemcpyAsync(dst + b0, ptr[o.in1], slot_bytes(slots[o.in1], dtype), cudaMemcpyDeviceToDevice, cst));
+        count_launch();
+        break;
+      }
+      case MILB200_OP_HEADDIAG_U:
+        rc = xf::headdiag_expand(static_cast<const float*>(ptr[o.in0]), p_f32 + params[o.p0].offset,
+                                 static_cast<float*>(ptr[o.out]), static_cast<int>(s0.rows), cst);
+        break;
+      case MILB200_OP_HEADDIAG_O:
+        rc = xf::headdiag_contract(static_cast<const float*>(ptr[o.in0]), p_f32 + params[o.p0].offset,
+                                   o.p1 >= 0 ? p_f32 + params[o.p1].offset : nullptr, static_cast<float*>(ptr[o.out]),
+                                   static_cast<int>(so.rows), cst);
+        break;
+      case MILB200_OP_T2I_POOL: {
+        MIL_CHECK_ARG(slots[o.in1].rows >= pl.sg.max_len, MILB200_EINVAL, "tape: op %d position table has %lld rows < longest segment %d",
+                      i, (long long)slots[o.in1].rows, pl.sg.max_len);
+        float* S = reinterpret_cast<float*>(ar + pl.aux_off[i]);
+        float* lse = S + static_cast<size_t>(s0.rows) * pl.sg.T * xf::H;
+        rc = xf::t2i_fwd(ptr[o.in0], ptr[o.in1], static_cast<const float*>(ptr[o.in2]), pl.sg, o.a0 & 1, S, lse,
+                         static_cast<float*>(ptr[o.out]), d0, workspace_l, ws_l, cst);
+        break;
+      }
+      case MILB200_OP_LN_SEG: {
+        float* mean = reinterpret_cast<float*>(ar + pl.aux_off[i]);
+        rc = xf::ln_seg_fwd(ptr[o.in0], static_cast<const float*>(ptr[o.in1]), p_f32 + params[o.p0].offset,
+                            p_f32 + params[o.p1].offset, o.in2 >= 0 ? static_cast<const float*>(ptr[o.in2]) : nullptr, pl.sg,
+                            o.a0 & 1, ptr[o.out], mean, mean + s0.rows, d0, cst);
+        break;
+      }
+      case MILB200_OP_TOK_SCATTER:
+        MIL_CHECK_ARG(ptr[o.out] == ptr[o.in1], MILB200_EINVAL, "tape: op %d tok_scatter works in place: out and in1 must share one address", i);
+        rc = xf::tok_scatter(static_cast<const float*>(ptr[o.in0]), pl.sg, ptr[o.out], dt(o.out), cst);
         break;
       default:
         rc = MILB200_EINVAL;
@@ -298,18 +437,18 @@ static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb20
                              const milb200_tape_param* params, int n_params, void* const* ext_ptrs, void* const* ext_grad_ptrs,
                              const void* const* seed_ptrs, const void* w_compute, const float* p_f32, float* g_f32,
                              const void* arena, size_t arena_bytes, void* workspace, size_t ws_bytes, int dtype,
-                             void* stream_main, void* stream_aux) {
-  int rc = tape_validate(ops, n_ops, slots, n_slots, params, n_params);
-  if (rc) return rc;
+                             const milb200_segments* segs, void* stream_main, void* stream_aux) {
   MIL_CHECK_ARG(dtype == MILB200_F32 || dtype == MILB200_BF16, MILB200_EINVAL, "tape: bad dtype %d", dtype);
+  int rc = tape_validate(ops, n_ops, slots, n_slots, params, n_params, dtype, segs);
+  if (rc) return rc;
   MIL_CHECK_ARG(ext_ptrs && ext_grad_ptrs && seed_ptrs && w_compute && p_f32 && g_f32 && arena, MILB200_EINVAL,
                 "tape_backward: null pointer");
-  TapePlan pl = tape_plan(ops, n_ops, slots, n_slots, dtype);
+  TapePlan pl;
+  if ((rc = tape_plan(ops, n_ops, slots, n_slots, dtype, segs, &pl))) return rc;
   MIL_CHECK_ARG(arena_bytes >= pl.arena_bytes, MILB200_EWORKSPACE, "tape_backward: arena %zu < %zu", arena_bytes, pl.arena_bytes);
   const size_t need = tape_bwd_ws_bytes(pl);
   MIL_CHECK_ARG(workspace && ws_bytes >= need, MILB200_EWORKSPACE, "tape_backward: workspace %zu < %zu", ws_bytes, need);
   cudaStream_t st = static_cast<cudaStream_t>(stream_main);
-  const size_t esz = elem_size(dtype);
   const char* ar = static_cast<const char*>(arena);
   char* ws = static_cast<char*>(workspace);
   const size_t scratch_bytes = pl.scratch_bwd;
@@ -322,12 +461,17 @@ static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb20
   char* tmp0 = ws + pl.scratch_bwd;
   LaneRun lr;
   lr.begin(st, pl.lanes == 2 ? static_cast<cudaStream_t>(stream_aux) : nullptr, n_slots + std::max(n_params, 0), &t_lane_events);
+  auto dt = [&](int s) { return slot_dtype(slots[s], dtype); };
+  auto weight = [&](int p, int d) -> const void* {
+    return d == dtype ? static_cast<const void*>(static_cast<const char*>(w_compute) + params[p].offset * elem_size(dtype))
+                      : static_cast<const void*>(p_f32 + params[p].offset);
+  };
 
   std::vector<const void*> val(n_slots);
   std::vector<void*> grad(n_slots);
   std::vector<char> has(n_slots, 0), needs(n_slots, 1);
   for (int i = 0; i < n_slots; ++i) {
-    if (slots[i].external) {
+    if (slot_ext(slots[i])) {
       val[i] = ext_ptrs[i];
       grad[i] = ext_grad_ptrs[i];
       needs[i] = grad[i] != nullptr;
@@ -341,7 +485,8 @@ static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb20
   for (int i = 0; i < n_slots; ++i) {
     if (!seed_ptrs[i]) continue;
     MIL_CHECK_ARG(grad[i] != nullptr, MILB200_EINVAL, "tape_backward: seeded slot %d has no gradient buffer", i);
-    MIL_CUDA(cudaMemcpyAsync(grad[i], seed_ptrs[i], slot_bytes(slots[i], dtype), cudaMemcpyDeviceToDevice, st));
+    if (grad[i] != seed_ptrs[i])     // equal pointers: the caller seeded its own gradient buffer in place
+      MIL_CUDA(cudaMemcpyAsync(grad[i], seed_ptrs[i], slot_bytes(slots[i], dtype), cudaMemcpyDeviceToDevice, st));
     has[i] = 1;
   }
   std::vector<char> ptouched(n_params > 0 ? n_params : 1, 0);
@@ -364,13 +509,13 @@ static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb20
     if (wrote == grad[s]) { has[s] = 1; return MILB200_OK; }
     const int64_t n = slots[s].rows * slots[s].cols;
     if (!has[s]) {
-      MIL_CUDA(cudaMemcpyAsync(grad[s], wrote, static_cast<size_t>(n) * esz, cudaMemcpyDeviceToDevice,
+      MIL_CUDA(cudaMemcpyAsync(grad[s], wrote, slot_bytes(slots[s], dtype), cudaMemcpyDeviceToDevice,
                                static_cast<cudaStream_t>(stream)));
       count_launch();
       has[s] = 1;
       return MILB200_OK;
     }
-    return milb200_add(grad[s], wrote, grad[s], n, dtype, stream);
+    return milb200_add(grad[s], wrote, grad[s], n, dt(s), stream);
   };
 
   for (int i = n_ops - 1; i >= 0; --i) {
@@ -387,16 +532,17 @@ static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb20
       scratch = ws + ln * lane_bytes;
       tmp0 = ws + ln * lane_bytes + pl.scratch_bwd;
     }
+    cudaStream_t cst = static_cast<cudaStream_t>(stream);
+    const int d0 = dt(o.in0);
     switch (o.kind) {
       case MILB200_OP_LINEAR: {
         const bool need_dx = needs[o.in0] || (o.in1 >= 0 && needs[o.in1]);
         void* dX = nullptr;
         if (need_dx) dX = needs[o.in0] ? target(o.in0, 0) : target(o.in1, 0);
         const int acc = ptouched[o.p0] ? 1 : 0;
-        rc = milb200_linear_bwd(val[o.in0], o.in1 >= 0 ? val[o.in1] : nullptr,
-                                static_cast<const char*>(w_compute) + params[o.p0].offset * esz, val[o.out], dY, dX,
+        rc = milb200_linear_bwd(val[o.in0], o.in1 >= 0 ? val[o.in1] : nullptr, weight(o.p0, d0), val[o.out], dY, dX,
                                 g_f32 + params[o.p0].offset, o.p1 >= 0 ? g_f32 + params[o.p1].offset : nullptr, s0.rows,
-                                so.cols, s0.cols, o.a0, dtype, acc, scratch, scratch_bytes, stream);
+                                so.cols, s0.cols, o.a0, d0, acc, scratch, scratch_bytes, stream);
         if (rc) return rc;
         ptouched[o.p0] = 1;
         if (o.p1 >= 0) ptouched[o.p1] = 1;
@@ -423,7 +569,7 @@ static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb20
         void* dVw = dV ? dV : static_cast<void*>(tmp0 + 2 * tmp_stride);
         rc = milb200_attention_bwd(val[o.in0], val[o.in1], val[o.in2], val[o.out],
                                    reinterpret_cast<const float*>(ar + pl.aux_off[i]), dY, dQw, dKw, dVw, s0.rows,
-                                   slots[o.in1].rows, o.a0, s0.cols / o.a0, dtype, scratch, scratch_bytes, stream);
+                                   slots[o.in1].rows, o.a0, s0.cols / o.a0, d0, scratch, scratch_bytes, stream);
         if (rc) return rc;
         if ((rc = settle(o.in0, dQ))) return rc;
         if ((rc = settle(o.in1, dK))) return rc;
@@ -441,7 +587,7 @@ static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb20
         const size_t ln_ws = milb200_layernorm_workspace_bytes(s0.rows, s0.cols);
         rc = milb200_layernorm_bwd(val[o.in0], o.in1 >= 0 ? val[o.in1] : nullptr, p_f32 + params[o.p0].offset, mean,
                                    mean + s0.rows, dY, dX, g_f32 + params[o.p0].offset, g_f32 + params[o.p1].offset, s0.rows,
-                                   s0.cols, dtype, acc, bcast, scratch, ln_ws, stream);
+                                   s0.cols, d0, acc, bcast, scratch, ln_ws, stream);
         if (rc) return rc;
         ptouched[o.p0] = ptouched[o.p1] = 1;
         if (need_dx) {
@@ -449,11 +595,11 @@ static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb20
             // gradient of the broadcast row = column sums of dXR (fp32), converted to the slot dtype; dX may live in tmp0,
             // so the converted row goes to temporary 1
             float* csum = reinterpret_cast<float*>(static_cast<char*>(scratch) + align_up(ln_ws, 256));
-            if ((rc = milb200_colsum(dX, s0.rows, s0.cols, csum, dtype, 0, stream))) return rc;
+            if ((rc = milb200_colsum(dX, s0.rows, s0.cols, csum, d0, 0, stream))) return rc;
             void* row = csum;  // fp32 slots take the sums as they are (consumed in stream order before scratch is reused)
-            if (dtype != MILB200_F32) {
+            if (d0 != MILB200_F32) {
               row = tmp0 + tmp_stride;
-              if ((rc = milb200_cast(csum, MILB200_F32, row, dtype, s0.cols, stream))) return rc;
+              if ((rc = milb200_cast(csum, MILB200_F32, row, d0, s0.cols, stream))) return rc;
             }
             if ((rc = settle(o.in1, row))) return rc;
           }
@@ -470,6 +616,88 @@ static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb20
         // d(in0) = d(in1) = dY: fold the op's gradient buffer into both operands (no kernel of its own)
         if ((rc = settle(o.in0, grad[o.out]))) return rc;
         if ((rc = settle(o.in1, grad[o.out]))) return rc;
+        break;
+      }
+      case MILB200_OP_JOIN: {
+        char* g = static_cast<char*>(grad[o.out]);
+        if (pl.alias_of[o.in0] == o.out) {
+          // the head of the result's gradient buffer IS in0's gradient buffer
+          MIL_CHECK_ARG(!has[o.in0], MILB200_EINVAL, "tape_backward: op %d: a JOIN operand produced in place has another consumer", i);
+          has[o.in0] = 1;
+        } else if ((rc = settle(o.in0, g))) {
+          return rc;
+        }
+        if ((rc = settle(o.in1, g + slot_bytes(s0, dtype)))) return rc;
+        break;
+      }
+      case MILB200_OP_HEADDIAG_U: {
+        // out = expand(in0, W):  d in0 = contract(dY, W),  dW += in0 (x) dY
+        float* dx = static_cast<float*>(target(o.in0, 0));
+        if (dx && (rc = xf::headdiag_contract(static_cast<const float*>(dY), p_f32 + params[o.p0].offset, nullptr, dx,
+                                              static_cast<int>(s0.rows), cst)))
+          return rc;
+        if ((rc = xf::headdiag_dw(static_cast<const float*>(val[o.in0]), static_cast<const float*>(dY),
+                                  g_f32 + params[o.p0].offset, nullptr, static_cast<int>(s0.rows), ptouched[o.p0] ? 1 : 0, cst)))
+          return rc;
+        ptouched[o.p0] = 1;
+        if ((rc = settle(o.in0, dx))) return rc;
+        break;
+      }
+      case MILB200_OP_HEADDIAG_O: {
+        // out = contract(in0, W) + b:  d in0 = expand(dY, W),  dW += dY (x) in0,  db += colsum(dY)
+        float* dy_big = static_cast<float*>(target(o.in0, 0));
+        if (dy_big && (rc = xf::headdiag_expand(static_cast<const float*>(dY), p_f32 + params[o.p0].offset, dy_big,
+                                                static_cast<int>(so.rows), cst)))
+          return rc;
+        if ((rc = xf::headdiag_dw(static_cast<const float*>(dY), static_cast<const float*>(val[o.in0]),
+                                  g_f32 + params[o.p0].offset, o.p1 >= 0 ? g_f32 + params[o.p1].offset : nullptr,
+                                  static_cast<int>(so.rows), ptouched[o.p0] ? 1 : 0, cst)))
+          return rc;
+        ptouched[o.p0] = 1;
+        if (o.p1 >= 0) ptouched[o.p1] = 1;
+        if ((rc = settle(o.in0, dy_big))) return rc;
+        break;
+      }
+      case MILB200_OP_T2I_POOL: {
+        const float* S = reinterpret_cast<const float*>(ar + pl.aux_off[i]);
+        const float* lse = S + static_cast<size_t>(s0.rows) * pl.sg.T * xf::H;
+        // dkeys is accumulated in place by the kernel (every row belongs to one warp): no temporary, no add pass
+        void* dK = needs[o.in0] ? grad[o.in0] : static_cast<void*>(tmp0);
+        const int acc = (needs[o.in0] && has[o.in0]) ? 1 : 0;
+        float* dU = static_cast<float*>(target(o.in2, 1));
+        float* dUw = dU ? dU : reinterpret_cast<float*>(tmp0 + tmp_stride);
+        rc = xf::t2i_bwd(val[o.in0], val[o.in1], static_cast<const float*>(val[o.in2]), S, lse,
+                         static_cast<const float*>(val[o.out]), static_cast<const float*>(dY), pl.sg, o.a0 & 1, dK, acc, dUw, d0,
+                         scratch, scratch_bytes, cst);
+        if (rc) return rc;
+        if (needs[o.in0]) has[o.in0] = 1;
+        if ((rc = settle(o.in2, dU))) return rc;
+        break;
+      }
+      case MILB200_OP_LN_SEG: {
+        const float* mean = reinterpret_cast<const float*>(ar + pl.aux_off[i]);
+        void* dK = needs[o.in0] ? grad[o.in0] : static_cast<void*>(tmp0);
+        const int acc = (needs[o.in0] && has[o.in0]) ? 1 : 0;
+        float* dR = static_cast<float*>(target(o.in1, 1));
+        float* dRw = dR ? dR : reinterpret_cast<float*>(tmp0 + tmp_stride);
+        float* dtok = o.in2 >= 0 ? static_cast<float*>(target(o.in2, 2)) : nullptr;
+        rc = xf::ln_seg_bwd(val[o.in0], static_cast<const float*>(val[o.in1]), p_f32 + params[o.p0].offset, mean,
+                            mean + s0.rows, dY, pl.sg, o.a0 & 1, dK, acc, dRw, g_f32 + params[o.p0].offset,
+                            g_f32 + params[o.p1].offset, ptouched[o.p0] ? 1 : 0, dtok, d0, scratch, scratch_bytes, cst);
+        if (rc) return rc;
+        ptouched[o.p0] = ptouched[o.p1] = 1;
+        if (needs[o.in0]) has[o.in0] = 1;
+        if ((rc = settle(o.in1, dR))) return rc;
+        if (o.in2 >= 0 && (rc = settle(o.in2, dtok))) return rc;
+        break;
+      }
+      case MILB200_OP_TOK_SCATTER: {
+        MIL_CHECK_ARG(grad[o.out] == grad[o.in1], MILB200_EINVAL,
+                      "tape_backward: op %d tok_scatter works in place: out and in1 must share one gradient buffer", i);
+        float* dtok = static_cast<float*>(target(o.in0, 0));
+        if (dtok && (rc = xf::tok_gather(dY, pl.sg, dtok, dt(o.out), cst))) return rc;
+        if ((rc = settle(o.in0, dtok))) return rc;
+        has[o.in1] = 1;        // same buffer: the key rows of the bag gradient are already in place
         break;
       }
       default:
@@ -612,11 +840,22 @@ int run_keyed(uint64_t key, cudaStream_t user_stream, Body body) {
 
 extern "C" {
 
+static void hash_segs(Hasher& h, const milb200_segments* segs) {
+  const int n = segs ? segs->n_segs : 0;
+  h.val(n);
+  if (n > 0) {
+    h.val(segs->tokens);
+    h.bytes(segs->seg, sizeof(milb200_segment) * n);
+  }
+}
+
 int milb200_tape_forward(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
                          const milb200_tape_param* params, int n_params, void* const* ext_ptrs, const void* w_compute,
                          const float* p_f32, void* arena, size_t arena_bytes, void* workspace, size_t ws_bytes, int dtype,
-                         void* stream) {
+                         const milb200_segments* segs, void* stream) {
   MIL_CHECK_ARG(ops && slots && n_ops > 0 && n_slots > 0 && ext_ptrs, MILB200_EINVAL, "tape_forward: null pointer");
+  MIL_CHECK_ARG(!segs || segs->n_segs == 0 || (segs->seg && segs->n_segs > 0 && segs->n_segs <= MILB200_MAX_SEGMENTS),
+                MILB200_EINVAL, "tape_forward: bad segment table");
   Hasher h;
   h.val(static_cast<int>(1));
   h.bytes(ops, sizeof(milb200_tape_op) * n_ops);
@@ -624,18 +863,22 @@ int milb200_tape_forward(const milb200_tape_op* ops, int n_ops, const milb200_ta
   if (params && n_params > 0) h.bytes(params, sizeof(milb200_tape_param) * n_params);
   h.bytes(ext_ptrs, sizeof(void*) * n_slots);
   h.val(w_compute); h.val(p_f32); h.val(arena); h.val(arena_bytes); h.val(workspace); h.val(ws_bytes); h.val(dtype);
+  hash_segs(h, segs);
   return run_keyed(h.h, static_cast<cudaStream_t>(stream), [&](cudaStream_t st, cudaStream_t lane1) {
     return tape_forward_run(ops, n_ops, slots, n_slots, params, n_params, ext_ptrs, w_compute, p_f32, arena, arena_bytes,
-                            workspace, ws_bytes, dtype, st, lane1);
+                            workspace, ws_bytes, dtype, segs, st, lane1);
   });
 }
 
 int milb200_tape_backward(const milb200_tape_op* ops, int n_ops, const milb200_tape_slot* slots, int n_slots,
                           const milb200_tape_param* params, int n_params, void* const* ext_ptrs, void* const* ext_grad_ptrs,
                           const void* const* seed_ptrs, const void* w_compute, const float* p_f32, float* g_f32,
-                          const void* arena, size_t arena_bytes, void* workspace, size_t ws_bytes, int dtype, void* stream) {
+                          const void* arena, size_t arena_bytes, void* workspace, size_t ws_bytes, int dtype,
+                          const milb200_segments* segs, void* stream) {
   MIL_CHECK_ARG(ops && slots && n_ops > 0 && n_slots > 0 && ext_ptrs && ext_grad_ptrs && seed_ptrs, MILB200_EINVAL,
                 "tape_backward: null pointer");
+  MIL_CHECK_ARG(!segs || segs->n_segs == 0 || (segs->seg && segs->n_segs > 0 && segs->n_segs <= MILB200_MAX_SEGMENTS),
+                MILB200_EINVAL, "tape_backward: bad segment table");
   Hasher h;
   h.val(static_cast<int>(2));
   h.bytes(ops, sizeof(milb200_tape_op) * n_ops);
@@ -646,9 +889,10 @@ int milb200_tape_backward(const milb200_tape_op* ops, int n_ops, const milb200_t
   h.bytes(seed_ptrs, sizeof(void*) * n_slots);
   h.val(w_compute); h.val(p_f32); h.val(g_f32); h.val(arena); h.val(arena_bytes); h.val(workspace); h.val(ws_bytes);
   h.val(dtype);
+  hash_segs(h, segs);
   return run_keyed(h.h, static_cast<cudaStream_t>(stream), [&](cudaStream_t st, cudaStream_t lane1) {
     return tape_backward_run(ops, n_ops, slots, n_slots, params, n_params, ext_ptrs, ext_grad_ptrs, seed_ptrs, w_compute,
-                             p_f32, g_f32, arena, arena_bytes, workspace, ws_bytes, dtype, st, lane1);
+                             p_f32, g_f32, arena, arena_bytes, workspace, ws_bytes, dtype, segs, st, lane1);
   });
 }
 

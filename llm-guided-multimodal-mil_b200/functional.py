@@ -151,7 +151,7 @@ class _AbmilPoolCSR(torch.autograd.Function):
     (ABMIL.py:47-64 applied bag by bag, which is how train_ddp.py:75 / test_ddp.py:73 run it)."""
 
     @staticmethod
-    def forward(ctx, X, offsets, Wv, bv, Wu, bu, ww, bw):
+    def forward(ctx, X, offsets, Wv, bv, Wu, bu, ww, bw, out_fp32=False):
         X = X.contiguous()
         Wcat, bcat = pack_gate_weights(Wv, bv, Wu, bu, X.dtype)
         wwf = _f32(ww).reshape(-1).contiguous()
@@ -160,7 +160,7 @@ class _AbmilPoolCSR(torch.autograd.Function):
         # MILB200_RECOMPUTE_GATE=1 trades that memory back for time
         need_grad = any(ctx.needs_input_grad) and not _recompute_gate()
         s, act = gated_scores(X, Wcat, bcat, wwf, bwf, save=True) if need_grad else (gated_scores(X, Wcat, bcat, wwf, bwf), None)
-        M, Ml, am, lse = segment_softmax_pool(X, s, offsets, want_lowp=X.dtype != torch.float32)
+        M, Ml, am, lse = segment_softmax_pool(X, s, offsets, want_lowp=(X.dtype != torch.float32 and not out_fp32))
         ctx.save_for_backward(X, offsets, Wcat, bcat, wwf, bwf, s, M, act)
         ctx.param_dtypes = (Wv.dtype, bv.dtype, Wu.dtype, bu.dtype, ww.dtype, bw.dtype)
         ctx.D = Wv.shape[0]
@@ -178,14 +178,16 @@ class _AbmilPoolCSR(torch.autograd.Function):
                                                       gate_act=act)
         dt = ctx.param_dtypes
         return (dX, None, dWcat[:D].to(dt[0]), dbcat[:D].to(dt[1]), dWcat[D:].to(dt[2]), dbcat[D:].to(dt[3]),
-                dww.view(1, D).to(dt[4]), dbw.view(1).to(dt[5]))
+                dww.view(1, D).to(dt[4]), dbw.view(1).to(dt[5]), None)
 
 
-def abmil_pool_csr(X, offsets, Wv, bv, Wu, bu, ww, bw):
-    """Returns (M [B,L] in X.dtype, argmax int32 [B] (index within the bag), scores fp32 [total_n])."""
+def abmil_pool_csr(X, offsets, Wv, bv, Wu, bu, ww, bw, out_fp32=False):
+    """Returns (M [B,L], argmax int32 [B] (index within the bag), scores fp32 [total_n]).  M is in X.dtype, or — with
+    out_fp32 — the fp32 accumulator itself (B x L values: callers that feed a small head keep it in fp32 so that the
+    bf16 storage of the instances is the only reduced-precision step on the path)."""
     if offsets.dtype != torch.int32:
         raise L.MilB200Error("offsets must be int32 CSR offsets on the device")
-    return _AbmilPoolCSR.apply(X, offsets, Wv, bv, Wu, bu, ww, bw)
+    return _AbmilPoolCSR.apply(X, offsets, Wv, bv, Wu, bu, ww, bw, out_fp32)
 
 
 # --------------------------------------------------------------------------------------------------

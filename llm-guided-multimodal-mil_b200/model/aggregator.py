@@ -20,7 +20,7 @@ from .. import functional as F
 from .._lib import MilB200Error
 from ..abmil import ABMIL, ABMIL_v2
 from .encoders import PrecomputedFeatures
-from .sam.transformer import TwoWayTransformer, _use_tape
+from .sam.transformer import TwoWayTransformer, _use_tape, _use_collapsed
 from ..tape import Tape
 
 _CT_MODELS = ("resnet2plus1d_18", "resnetMC3_18", "medicalNet", "SwinUNETR", "MViT")
@@ -134,6 +134,93 @@ class aggregator(nn.Module):
             object.__setattr__(self, name, t)
         return t
 
+    # ---- the same branch with the image-side projections folded into the token side (T = 1; csrc/xfusion.cu) ------------
+    def _fusion_tape_v2(self):
+        """fc_pathology, fc_CI2CT / fc_CI2Pth and BOTH TwoWayTransformer_Both calls as ONE segmented program: the CT bag and
+        the pathology bag (of one or several patients) are segments of one key stream; the token side (one row per
+        segment) runs in fp32; the final keys and token rows land in the packed multi-modal bag (aggregator.py:173)."""
+        t = getattr(self, "_tape_cache_v2", None)
+        if t is None:
+            t = Tape()
+            E = self.embedding_dim
+            xp, ct = t.input("NP", 768), t.input("NC", E)
+            pe = t.input("NPE", E)
+            txt = t.input("BT", E, f32=True)
+            keys = t.join(t.linear(xp, self.fc_pathology[0], act="tanh"), ct, "NK")                  # :141 | CT tokens
+            points = t.join(t.linear(txt, self.fc_CI2CT[0], act="tanh"),                             # :160 third argument
+                            t.linear(txt, self.fc_CI2Pth[0], act="tanh"), "ST")                      # :168 third argument
+            q, k = self.TwoWayTransformer_Both.emit_collapsed(t, keys, pe, points)
+            full = t.tok_scatter(q, k)
+            bag = t.buffer(lambda r: r["NBAG"], E)
+            t.output(k, bag, lambda r: 0)
+            t.output(full, bag, lambda r: 0)
+            object.__setattr__(self, "_tape_cache_v2", t)
+        return t
+
+    @staticmethod
+    def fusion_layout(n_ct, n_path_list, T=1):
+        """Row bookkeeping of the segmented program for B patients with n_ct CT tokens each and n_path_list[b] pathology
+        rows: (rows dict, segment table, per-patient bag offsets).  Bag b holds [T | n_ct | T | n_path_b] rows in the order
+        of aggregator.py:173; segments are ordered CT(0..B-1), pathology(0..B-1)."""
+        B = len(n_path_list)
+        n_p = int(sum(n_path_list))
+        bag_off = [0]
+        for n in n_path_list:
+            bag_off.append(bag_off[-1] + 2 * T + n_ct + int(n))
+        segs, pstart = [], 0
+        for b in range(B):
+            segs.append((n_p + b * n_ct, n_ct, bag_off[b] + T, bag_off[b]))
+        for b, n in enumerate(n_path_list):
+            segs.append((pstart, int(n), bag_off[b] + 2 * T + n_ct, bag_off[b] + T + n_ct))
+            pstart += int(n)
+        rows = {"NP": n_p, "NC": B * n_ct, "NK": n_p + B * n_ct, "BT": B * T, "ST": 2 * B * T, "SJ": 2 * B * T * 8,
+                "NBAG": bag_off[-1]}
+        return rows, (tuple(segs), T), bag_off
+
+    def _pe_table(self, n, like):
+        self._pe(n, like)
+        return self._pe_cache[(like.device, like.dtype)][0]          # the whole cached table: its address never changes
+
+    def _forward_fused_v2(self, x_ct_tokens, x_path, x_text):
+        Nc, Np = x_ct_tokens.shape[1], x_path.shape[1]
+        rows, segs, _ = self.fusion_layout(Nc, [Np], 1)
+        pe = self._pe_table(max(Nc, Np), x_path)
+        rows["NPE"] = pe.shape[0]
+        (bag,) = self._fusion_tape_v2().run(rows, [x_path[0], x_ct_tokens[0], pe, x_text[0].float()], segs=segs)
+        x0 = bag.unsqueeze(0)
+        return x0, x0[:, :1], x0[:, 1 + Nc:2 + Nc]
+
+    def forward_bags(self, ct_tokens, x_path, path_lens, x_text):
+        """The CT+pathology branch for B patients in ONE launch set (B200-native entry; the reference runs batch 1,
+        train_ddp.py:75).  ct_tokens (B, Nc, 512): per-slice CT tokens (F.ct_tokens of the encoder's feature map);
+        x_path (sum Np, 768): the patients' patch features packed row-wise; path_lens: their row counts (host ints);
+        x_text (B, 1, 512): one clinical-text embedding per patient.  Returns (prob (B, C) fp32, x_CT2CI (B, 1, 512),
+        x_Pth2CI (B, 1, 512)) — row b equals forward([ct_b, path_b], text_b)."""
+        B, Nc = int(ct_tokens.shape[0]), int(ct_tokens.shape[1])
+        path_lens = [int(n) for n in path_lens]
+        if len(path_lens) != B or x_text.shape[0] != B or x_text.shape[1] != 1 or 2 * B > 16:
+            raise MilB200Error("forward_bags: B patients (<= 8), one text token each, len(path_lens) == B")
+        if x_path.dim() != 2 or x_path.shape[0] != sum(path_lens) or min(path_lens) < 2 or Nc < 2:
+            raise MilB200Error("forward_bags: x_path must be the packed (sum Np, 768) matrix; bags need >= 2 rows")
+        rows, segs, bag_off = self.fusion_layout(Nc, path_lens, 1)
+        pe = self._pe_table(max(Nc, max(path_lens)), x_path)
+        rows["NPE"] = pe.shape[0]
+        E = self.embedding_dim
+        (bag,) = self._fusion_tape_v2().run(rows, [x_path, ct_tokens.reshape(B * Nc, E), pe, x_text.reshape(B, E).float()],
+                                            segs=segs)
+        key = (tuple(bag_off), bag.device)
+        cached = self.__dict__.setdefault("_bag_off_cache", {})
+        if key not in cached:
+            if len(cached) > 64:
+                cached.clear()
+            dev = bag.device
+            cached[key] = (torch.tensor(bag_off, dtype=torch.int32, device=dev),
+                           torch.tensor(bag_off[:-1], dtype=torch.int64, device=dev),
+                           torch.tensor([o + 1 + Nc for o in bag_off[:-1]], dtype=torch.int64, device=dev))
+        off, r_ct, r_p = cached[key]
+        prob = self._head(self.aggregator.forward_csr(bag, off, out_fp32=True))                   # :199-200
+        return prob, bag.index_select(0, r_ct).unsqueeze(1), bag.index_select(0, r_p).unsqueeze(1)
+
     def _forward_fused(self, x_ct_tokens, x_path, x_text):
         T, Nc, Np = x_text.shape[1], x_ct_tokens.shape[1], x_path.shape[1]
         like = x_text
@@ -152,6 +239,11 @@ class aggregator(nn.Module):
             x_text = self.clinic_extractor(x_CI)
             if x_ct.dim() == 5 and x_ct.shape[0] == 1 and x_list[1].dim() == 3 and x_list[1].shape[0] == 1 \
                     and x_text.dim() == 3 and x_text.shape[0] == 1 and x_ct.dtype == x_list[1].dtype == x_text.dtype:
+                if x_text.shape[1] == 1 and x_ct.shape[2] > 1 and x_list[1].shape[1] > 1 and _use_collapsed():
+                    x0, x_CT2CI, x_Pth2CI = self._forward_fused_v2(F.ct_tokens(x_ct), x_list[1], x_text)
+                    # pooled vector and head in fp32: with bf16 bags the storage of the bag is the only low-precision step
+                    off = torch.arange(0, 2, dtype=torch.int32, device=x0.device) * x0.shape[1]
+                    return self._head(self.aggregator.forward_csr(x0[0], off, out_fp32=True)), x_CT2CI, x_Pth2CI
                 x0, x_CT2CI, x_Pth2CI = self._forward_fused(F.ct_tokens(x_ct), x_list[1], x_text)
                 return self._head(self.aggregator(x0)), x_CT2CI, x_Pth2CI
         if has_ct:

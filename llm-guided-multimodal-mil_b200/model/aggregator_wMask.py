@@ -86,6 +86,8 @@ class aggregator_wMask(nn.Module):
         packed = x_padded.reshape(B * Nmax, Lf).index_select(0, rows)                 # compaction = data movement only
         offsets = torch.zeros(B + 1, dtype=torch.int32, device=x_padded.device)
         offsets[1:] = lengths.cumsum(0).to(torch.int32)
-        pooled = pool.forward_csr(packed, offsets)
-        x = torch.cat([pooled, *other_feats], dim=1) if other_feats else pooled
+        # the pooled vectors leave the kernel as fp32 and the (B x 1536 x 384) head runs in fp32: with bf16 bags the
+        # instances' storage is then the only reduced-precision step (a bf16 head costs ~3e-2 on dL/dX for nothing)
+        pooled = pool.forward_csr(packed, offsets, out_fp32=True)
+        x = torch.cat([pooled, *[f.float() for f in other_feats]], dim=1) if other_feats else pooled
         return self._head(x)

@@ -34,6 +34,12 @@ def _use_tape():
     return os.environ.get("MILB200_NO_TAPE", "0") != "1"
 
 
+def _use_collapsed():
+    """MILB200_FUSION_COLLAPSED=0 keeps the T = 1 CT+pathology branch on the projected-keys program (round-1 path: six
+    N x 512 x 256 GEMMs per TwoWayTransformer call) instead of the collapsed one (csrc/xfusion.cu)."""
+    return os.environ.get("MILB200_FUSION_COLLAPSED", "1") != "0"
+
+
 class Attention(nn.Module):
     """model/sam/transformer.py:395-450."""
 
@@ -183,6 +189,36 @@ class TwoWayTransformer(nn.Module):
             queries, keys = layer.emit(tape, queries, keys, points, image_pe, single_token=single_token)
         attn_out = self.final_attn_token_to_image.emit(tape, queries, keys, keys, q_add=points, k_add=image_pe)
         queries = tape.layernorm(queries, self.norm_final_attn, residual=attn_out)
+        return queries, keys
+
+    # ---- collapsed program: key/value projections folded into the token side (csrc/xfusion.cu) --------------------------
+    @staticmethod
+    def _emit_t2i(tape: Tape, att: "Attention", norm, queries: int, points: int, keys: int, pe: int, bag_layout: bool) -> int:
+        """queries = LN(queries + cross_attn_token_to_image(q=queries + points, k=keys + pe, v=keys))  (transformer.py:290-295,
+        114-118) without projecting the image tokens: the projected queries are pulled through k_proj.weight per head
+        (U = Wk_h^T q_h), ONE pass over the keys pools them per head, and v_proj is applied to the 8 pooled rows."""
+        qx = tape.linear(queries, att.q_proj, add=points)                       # [S*T, 256]
+        u = tape.headdiag_u(qx, att.k_proj, "SJ")                               # [S*T*8, 512]
+        tape.param(att.k_proj.bias)     # constant over the keys: cancels in the softmax, exactly-zero gradient (as upstream, up to noise)
+        pooled = tape.t2i_pool(keys, pe, u, bag_layout=bag_layout)              # [S*T*8, 512]
+        o = tape.headdiag_o(pooled, att.v_proj, "ST")                           # [S*T, 256]
+        return tape.layernorm(queries, norm, residual=tape.linear(o, att.out_proj))
+
+    def emit_collapsed(self, tape: Tape, keys: int, pe: int, points: int):
+        """forward() for ONE text token per segment over a segmented key stream (every image-side bag that shares these
+        weights is a segment: the CT bag and the pathology bag of aggregator.py:160,168, of one or several patients).
+        Returns (slot of the final token rows [S, E] fp32, slot of the final keys — written in the packed-bag layout)."""
+        queries = points
+        last = len(self.layers) - 1
+        for i, layer in enumerate(self.layers):
+            sa = layer.self_attn.emit_single_key(tape, queries)                              # :281-288, one key
+            queries = tape.layernorm(sa, layer.norm1) if layer.skip_first_layer_pe else \
+                tape.layernorm(queries, layer.norm1, residual=sa)
+            queries = self._emit_t2i(tape, layer.cross_attn_token_to_image, layer.norm2, queries, points, keys, pe, False)
+            queries = tape.layernorm(queries, layer.norm3, residual=layer.mlp.emit(tape, queries))   # :297-300
+            row = layer.cross_attn_image_to_token.emit_single_key(tape, queries)             # :302-307, one key per segment
+            keys = tape.ln_seg(keys, row, layer.norm4, out_rows_key="NBAG" if i == last else None)
+        queries = self._emit_t2i(tape, self.final_attn_token_to_image, self.norm_final_attn, queries, points, keys, pe, True)
         return queries, keys
 
     def _tape(self, single_token=False):

@@ -28,6 +28,7 @@ class Tape:
         self.slot_rows = []      # symbolic row key per slot
         self.slot_cols = []
         self.slot_ext = []       # 0 internal, 1 external input, 2 external output (lives in an output buffer)
+        self.slot_f32 = []       # True: the slot is fp32 whatever the program dtype (the text-token side)
         self.params = []         # nn.Parameter objects, in flat-buffer order
         self._pidx = {}
         self.inputs = []         # slot ids of external inputs, in call order
@@ -36,14 +37,15 @@ class Tape:
         self._c = None
 
     # ---- building ------------------------------------------------------------------------------------------
-    def slot(self, rows_key, cols, ext=0):
+    def slot(self, rows_key, cols, ext=0, f32=False):
         self.slot_rows.append(rows_key)
         self.slot_cols.append(int(cols))
         self.slot_ext.append(ext)
+        self.slot_f32.append(bool(f32))
         return len(self.slot_cols) - 1
 
-    def input(self, rows_key, cols):
-        s = self.slot(rows_key, cols, ext=1)
+    def input(self, rows_key, cols, f32=False):
+        s = self.slot(rows_key, cols, ext=1, f32=f32)
         self.inputs.append(s)
         return s
 
@@ -78,7 +80,7 @@ class Tape:
 
     def linear(self, x, lin, act=None, add=None):
         """out = act((x [+ add]) W^T + b) for an ``nn.Linear`` parameter container."""
-        out = self.slot(self.slot_rows[x], lin.weight.shape[0])
+        out = self.slot(self.slot_rows[x], lin.weight.shape[0], f32=self.slot_f32[x])
         self.ops.append((L.OP_LINEAR, x, -1 if add is None else add, -1, out, self.param(lin.weight), self.param(lin.bias),
                          _ACT[act], self._lane))
         return out
@@ -91,7 +93,7 @@ class Tape:
     def layernorm(self, x, ln, residual=None):
         if abs(ln.eps - 1e-5) > 1e-12:
             raise L.MilB200Error("layernorm kernels are built for eps = 1e-5 (nn.LayerNorm default)")
-        out = self.slot(self.slot_rows[x], self.slot_cols[x])
+        out = self.slot(self.slot_rows[x], self.slot_cols[x], f32=self.slot_f32[x])
         self.ops.append((L.OP_LAYERNORM, x, -1 if residual is None else residual, -1, out, self.param(ln.weight),
                          self.param(ln.bias), 0, self._lane))
         return out
@@ -99,8 +101,54 @@ class Tape:
     def add(self, a, b):
         """out = a + b as a slot of its own, for sums that several ops consume (keys + key_pe feeds two projections
         per block: materialise it once instead of once per consumer)."""
-        out = self.slot(self.slot_rows[a], self.slot_cols[a])
+        out = self.slot(self.slot_rows[a], self.slot_cols[a], f32=self.slot_f32[a])
         self.ops.append((L.OP_ADD, a, b, -1, out, -1, -1, 0, self._lane))
+        return out
+
+    # ---- segment ops of the collapsed cross-modal attention (csrc/xfusion.cu) ---------------------------------------
+    def join(self, a, b, rows_key):
+        """out = rows of a, then rows of b (`rows_key` names the total).  An internal `a` is produced in place at the head
+        of the result (no copy); `b` is copied."""
+        out = self.slot(rows_key, self.slot_cols[a], f32=self.slot_f32[a])
+        self.ops.append((L.OP_JOIN, a, b, -1, out, -1, -1, 0, self._lane))
+        return out
+
+    def headdiag_u(self, x, lin, rows_key):
+        """out[r*8 + h, :] = sum_c x[r, h*32 + c] W[h*32 + c, :] — the per-head image of the projected queries under the
+        key projection (U = Wk_h^T q_h).  x [R, 256] fp32, `lin` the k_proj container ([256, 512]); rows_key names R*8."""
+        out = self.slot(rows_key, lin.weight.shape[1], f32=True)
+        self.ops.append((L.OP_HEADDIAG_U, x, -1, -1, out, self.param(lin.weight), -1, 8, self._lane))
+        return out
+
+    def headdiag_o(self, y, lin, rows_key):
+        """out[r, h*32 + c] = y[r*8 + h, :] . W[h*32 + c, :] + b — the value projection applied to the per-head pooled
+        keys.  y [R*8, 512] fp32, `lin` the v_proj container; rows_key names R."""
+        out = self.slot(rows_key, lin.weight.shape[0], f32=True)
+        self.ops.append((L.OP_HEADDIAG_O, y, -1, -1, out, self.param(lin.weight), self.param(lin.bias), 8, self._lane))
+        return out
+
+    def t2i_pool(self, keys, pe, u, bag_layout=False):
+        """Pool[(seg, t, h), :] = sum_n softmax_n(scale (keys + pe) . U[(seg, t, h)]) keys[n] over each segment's rows."""
+        out = self.slot(self.slot_rows[u], self.slot_cols[u], f32=True)
+        self.ops.append((L.OP_T2I_POOL, keys, pe, u, out, -1, -1, 1 if bag_layout else 0, self._lane))
+        return out
+
+    def ln_seg(self, keys, rows, ln, out_rows_key=None, tokens=None):
+        """out = LN(keys + rows[segment]) (one residual row per segment).  out_rows_key: the result is written in the
+        packed-bag layout (segment out_start) into a slot of that many rows, with `tokens` copied to their rows."""
+        if abs(ln.eps - 1e-5) > 1e-12:
+            raise L.MilB200Error("layernorm kernels are built for eps = 1e-5 (nn.LayerNorm default)")
+        bag = out_rows_key is not None
+        out = self.slot(out_rows_key if bag else self.slot_rows[keys], self.slot_cols[keys], f32=self.slot_f32[keys])
+        self.ops.append((L.OP_LN_SEG, keys, rows, -1 if tokens is None else tokens, out, self.param(ln.weight),
+                         self.param(ln.bias), 1 if bag else 0, self._lane))
+        return out
+
+    def tok_scatter(self, tokens, bag):
+        """The token rows [n_segs*T, 512] written into their rows (segment tok_row) of the packed bag, in place: the result
+        names the same external memory as `bag` (declare both with Tape.output at the same buffer offset)."""
+        out = self.slot(self.slot_rows[bag], self.slot_cols[bag], f32=self.slot_f32[bag])
+        self.ops.append((L.OP_TOK_SCATTER, tokens, bag, -1, out, -1, -1, 0, self._lane))
         return out
 
     def buffer(self, rows_fn, cols):
@@ -147,7 +195,8 @@ class Tape:
             n = len(self.slot_cols)
             arr = (L.TapeSlot * n)()
             for i in range(n):
-                arr[i] = L.TapeSlot(int(rows[self.slot_rows[i]]), self.slot_cols[i], 1 if self.slot_ext[i] else 0)
+                arr[i] = L.TapeSlot(int(rows[self.slot_rows[i]]), self.slot_cols[i],
+                                    (L.SLOT_EXTERNAL if self.slot_ext[i] else 0) | (L.SLOT_F32 if self.slot_f32[i] else 0))
             if self._c is not None:
                 if len(cache) > 64:
                     cache.clear()
@@ -172,11 +221,24 @@ class Tape:
         weight-sync code, some checkpoint loaders) do not bump `_version`: call this after such a write."""
         self._flat_cache = None
 
-    def _pool(self, rows, slots, dtype, dev, code):
+    def _segments(self, segs):
+        """segs: None or (((k_start, len, out_start, tok_row), ...), T) -> ctypes pointer for the C calls (cached)."""
+        if segs is None:
+            return None
+        cache = self.__dict__.setdefault("_segs_cache", {})
+        hit = cache.get(segs)
+        if hit is None:
+            if len(cache) > 64:
+                cache.clear()
+            st, arr = L.make_segments(segs[0], segs[1])
+            hit = cache[segs] = (C.pointer(st), st, arr)
+        return hit[0]
+
+    def _pool(self, rows, slots, dtype, dev, code, segs=None):
         pools = getattr(self, "_pools", None)
         if pools is None:
             pools = self._pools = OrderedDict()
-        key = (tuple(sorted(rows.items())), dtype, str(dev))
+        key = (tuple(sorted(rows.items())), dtype, str(dev), segs)
         p = pools.get(key)
         if p is None:
             while len(pools) >= 3:                       # a few hundred MB each: keep the most recent shapes only
@@ -186,16 +248,24 @@ class Tape:
                 pools.pop(k_old)
             if len(pools) >= 3:
                 return None
-            p = pools[key] = _Pool(self, rows, slots, dtype, dev, code)
+            p = pools[key] = _Pool(self, rows, slots, dtype, dev, code, self._segments(segs))
         else:
             pools.move_to_end(key)
         return p
 
-    def run(self, rows, inputs):
-        """rows: {row key: int}; inputs: tensors for ``self.inputs`` (2-D, contiguous, one dtype).  Returns the output
-        buffers (one tensor per ``self.buffer``)."""
-        outs = _TapeFn.apply(self, dict(rows), len(inputs), *inputs, *self.params)
+    def run(self, rows, inputs, segs=None):
+        """rows: {row key: int}; inputs: tensors for ``self.inputs`` (2-D, contiguous; fp32 for slots declared f32, the
+        program dtype otherwise); segs: the segment table of programs with segment ops, as
+        (((k_start, len, out_start, tok_row), ...), tokens_per_segment).  Returns the output buffers (one tensor per
+        ``self.buffer``)."""
+        outs = _TapeFn.apply(self, dict(rows), segs, len(inputs), *inputs, *self.params)
         return outs if isinstance(outs, tuple) else (outs,)
+
+    def program_dtype(self, inputs):
+        for s, t in zip(self.inputs, inputs):
+            if not self.slot_f32[s]:
+                return t.dtype
+        return torch.float32
 
 
 def _ptr_array(n):
@@ -212,17 +282,16 @@ class _Pool:
     staging copies of inputs whose address changes from call to call, and the backward's gradient buffers.  Results
     are handed to autograd as fresh copies, so nothing the caller can hold aliases the pool."""
 
-    def __init__(self, tape, rows, slots, dtype, dev, code):
+    def __init__(self, tape, rows, slots, dtype, dev, code, segp=None):
         c = tape._freeze()
         lib = L.lib()
-        self.arena = torch.empty((lib.milb200_tape_arena_bytes(c["ops"], c["n_ops"], slots, c["n_slots"], code),),
+        self.arena = torch.empty((lib.milb200_tape_arena_bytes(c["ops"], c["n_ops"], slots, c["n_slots"], code, segp),),
                                  dtype=torch.uint8, device=dev)
         self.out = [torch.empty((int(fn(rows)), cols), dtype=dtype, device=dev) for fn, cols in tape.buffers]
         self.in_stage = [None] * len(tape.inputs)
         self.last_ptr = [0] * len(tape.inputs)
         self.seed = [torch.empty_like(b) for b in self.out]
         self.gin = [None] * len(tape.inputs)
-        self.gout = [torch.empty((slots[s].rows, slots[s].cols), dtype=dtype, device=dev) for s, _, _ in tape.outputs]
         self.g32 = torch.empty((c["total"],), dtype=torch.float32, device=dev)
         self.owner = None            # weakref to the autograd ctx whose backward still needs the arena
 
@@ -246,22 +315,27 @@ class _Pool:
 
 class _TapeFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, tape, rows, n_in, *tensors):
+    def forward(ctx, tape, rows, segs, n_in, *tensors):
         inputs = [t.contiguous() for t in tensors[:n_in]]
         c = tape._freeze()
-        dtype = inputs[0].dtype
+        dtype = tape.program_dtype(inputs)
         dev = inputs[0].device
-        if any(t.dtype != dtype for t in inputs):
-            raise L.MilB200Error("tape: all inputs must share one dtype")
-        code = L.dtype_code(inputs[0])
+        for s, t in zip(tape.inputs, inputs):
+            want = torch.float32 if tape.slot_f32[s] else dtype
+            if t.dtype != want:
+                raise L.MilB200Error(f"tape: input for slot {s} has dtype {t.dtype}, the program expects {want}")
+        code = L.BF16 if dtype == torch.bfloat16 else L.F32
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise L.MilB200Error(f"unsupported dtype {dtype}: mil_b200 kernels take float32 or bfloat16")
         slots = tape._slots(rows)
         for s, t in zip(tape.inputs, inputs):
             if tuple(t.shape) != (slots[s].rows, slots[s].cols):
                 raise L.MilB200Error(f"tape: input for slot {s} has shape {tuple(t.shape)}, expected "
                                      f"{(slots[s].rows, slots[s].cols)}")
+        segp = tape._segments(segs)
         wc, p32 = tape._flat(dtype)
         lib = L.lib()
-        pool = tape._pool(rows, slots, dtype, dev, code) if _pooling_enabled() else None
+        pool = tape._pool(rows, slots, dtype, dev, code, segs) if _pooling_enabled() else None
         if pool is not None and pool.busy():
             pool = None                      # a forward of the same shape is still waiting for its backward
         if pool is not None:
@@ -269,19 +343,19 @@ class _TapeFn(torch.autograd.Function):
             bufs, arena = pool.out, pool.arena
         else:
             bufs = [torch.empty((int(fn(rows)), cols), dtype=dtype, device=dev) for fn, cols in tape.buffers]
-            arena = torch.empty((lib.milb200_tape_arena_bytes(c["ops"], c["n_ops"], slots, c["n_slots"], code),),
+            arena = torch.empty((lib.milb200_tape_arena_bytes(c["ops"], c["n_ops"], slots, c["n_slots"], code, segp),),
                                 dtype=torch.uint8, device=dev)
         ext = _ptr_array(c["n_slots"])
         for s, t in zip(tape.inputs, inputs):
             ext[s] = t.data_ptr()
-        esz = inputs[0].element_size()
+        esz = bufs[0].element_size()
         for s, b, fn in tape.outputs:
             ext[s] = bufs[b].data_ptr() + int(fn(rows)) * tape.slot_cols[s] * esz
-        ws = L.workspace(lib.milb200_tape_workspace_bytes(c["ops"], c["n_ops"], slots, c["n_slots"], code, 0), dev)
+        ws = L.workspace(lib.milb200_tape_workspace_bytes(c["ops"], c["n_ops"], slots, c["n_slots"], code, 0, segp), dev)
         L.check(lib.milb200_tape_forward(c["ops"], c["n_ops"], slots, c["n_slots"], c["params"], c["n_params"], ext, L.ptr(wc),
-                                         L.ptr(p32), L.ptr(arena), arena.numel(), L.ptr(ws), ws.numel(), code,
+                                         L.ptr(p32), L.ptr(arena), arena.numel(), L.ptr(ws), ws.numel(), code, segp,
                                          L.stream_ptr()), "tape_forward")
-        ctx.tape, ctx.rows, ctx.n_in, ctx.code = tape, rows, n_in, code
+        ctx.tape, ctx.rows, ctx.n_in, ctx.code, ctx.segs = tape, rows, n_in, code, segs
         ctx.pool = pool
         ctx.save_for_backward(arena, wc, p32, *inputs, *bufs)
         if pool is not None:
@@ -301,20 +375,26 @@ class _TapeFn(torch.autograd.Function):
         bufs = saved[3 + n_in:]
         c = tape._freeze()
         slots = tape._slots(rows)
-        dev, dtype = inputs[0].device, inputs[0].dtype
-        esz = inputs[0].element_size()
+        segp = tape._segments(ctx.segs)
+        dev, dtype = bufs[0].device, bufs[0].dtype
+        esz = bufs[0].element_size()
         gouts = [(g.contiguous() if g is not None else torch.zeros_like(b)) for g, b in zip(gouts, bufs)]
         gouts = [g if g.dtype == dtype else F.cast(g, dtype) for g in gouts]
+        # the upstream gradients are copied once into buffers this call owns; every output slot's gradient buffer is its
+        # row range of that copy, seeded in place (seed pointer == gradient pointer: the C side skips its own copy)
         if pool is not None:
             for st, g in zip(pool.seed, gouts):
                 st.copy_(g)
             gouts = pool.seed
+        else:
+            gouts = [g.clone() for g in gouts]
         n_slots = c["n_slots"]
         ext, gext, seeds = _ptr_array(n_slots), _ptr_array(n_slots), _ptr_array(n_slots)
         gin = []
+        FIRST = 4                                  # tape, rows, segs, n_in precede the tensors in apply()
         for j, (s, t) in enumerate(zip(tape.inputs, inputs)):
             ext[s] = t.data_ptr()
-            if ctx.needs_input_grad[3 + j]:
+            if ctx.needs_input_grad[FIRST + j]:
                 if pool is not None:
                     if pool.gin[j] is None:
                         pool.gin[j] = torch.empty_like(t)
@@ -325,21 +405,16 @@ class _TapeFn(torch.autograd.Function):
                 gin.append(g)
             else:
                 gin.append(None)
-        scratch_out = []
         for i, (s, b, fn) in enumerate(tape.outputs):
             off = int(fn(rows)) * tape.slot_cols[s] * esz
             ext[s] = bufs[b].data_ptr() + off
-            seeds[s] = gouts[b].data_ptr() + off
-            # an output slot that also feeds later ops needs a writable gradient buffer of its own
-            g = pool.gout[i] if pool is not None else torch.empty((slots[s].rows, slots[s].cols), dtype=dtype, device=dev)
-            gext[s] = g.data_ptr()
-            scratch_out.append(g)
+            seeds[s] = gext[s] = gouts[b].data_ptr() + off
         g32 = pool.g32 if pool is not None else torch.empty((c["total"],), dtype=torch.float32, device=dev)
         lib = L.lib()
-        ws = L.workspace(lib.milb200_tape_workspace_bytes(c["ops"], c["n_ops"], slots, n_slots, code, 1), dev)
+        ws = L.workspace(lib.milb200_tape_workspace_bytes(c["ops"], c["n_ops"], slots, n_slots, code, 1, segp), dev)
         L.check(lib.milb200_tape_backward(c["ops"], c["n_ops"], slots, n_slots, c["params"], c["n_params"], ext, gext, seeds,
                                           L.ptr(wc), L.ptr(p32), L.ptr(g32), L.ptr(arena), arena.numel(), L.ptr(ws),
-                                          ws.numel(), code, L.stream_ptr()), "tape_backward")
+                                          ws.numel(), code, segp, L.stream_ptr()), "tape_backward")
         pdt = tape.params[0].dtype
         if pdt != torch.float32:
             gflat = F.cast(g32, pdt)
@@ -349,8 +424,8 @@ class _TapeFn(torch.autograd.Function):
             gin = [g.clone() if g is not None else None for g in gin]
             pool.owner = None
         need = ctx.needs_input_grad
-        base = 3 + n_in
+        base = FIRST + n_in
         pieces = gflat.split(c["sizes"])          # one call for the ~90 views; 2-D weights get their shape below
         gparams = [(pc if sh is None else pc.view(sh)) if need[base + j] else None
                    for j, (pc, sh) in enumerate(zip(pieces, c["shapes"]))]
-        return (None, None, None, *gin, *gparams)
+        return (None, None, None, None, *gin, *gparams)

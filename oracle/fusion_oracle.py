@@ -116,8 +116,10 @@ def sinusoid_pe(n_pos, dim, dtype=torch.float32):
     return pe.unsqueeze(0).to(dtype)
 
 
-def aggregator_fusion_forward(sd, x_ct_feat, x_path, x_text, num_heads=8, depth=2):
+def aggregator_fusion_forward(sd, x_ct_feat, x_path, x_text, num_heads=8, depth=2, pe_fn=None):
     """aggregator.py:134-203, CT+pathology branch, aggregator='ABMIL', eval mode.
+    pe_fn(n, E) -> (1, n, E) overrides the position table (tests of reduced-precision storage hand in the table the
+    kernels read, e.g. the bf16-rounded one).
     x_ct_feat: the CT extractor's output (1,512,c,h,w) (the encoder itself is out of scope);
     x_path (1,N,768); x_text: clinic_extractor output (1,T,512).
     Returns (prob (1,C), x_CT2CI (1,T,512), x_Pth2CI (1,T,512))."""
@@ -125,13 +127,14 @@ def aggregator_fusion_forward(sd, x_ct_feat, x_path, x_text, num_heads=8, depth=
     xin_path = torch.tanh(_lin(sd, "fc_pathology.0", x_path))                      # :141
     c = x_ct_feat.shape[2]                                                          # :156
     E = xin_path.shape[-1]
+    pe_of = (lambda n_: sinusoid_pe(n_, E, dt)) if pe_fn is None else (lambda n_: pe_fn(n_, E))
     ct2ci, ci2ct = two_way_transformer(sd, "TwoWayTransformer_Both", x_ct_feat,
-                                       sinusoid_pe(c, E, dt),
+                                       pe_of(c),
                                        torch.tanh(_lin(sd, "fc_CI2CT.0", x_text)),
                                        depth, num_heads)                            # :160
     n = xin_path.shape[1]
     pth2ci, ci2pth = two_way_transformer(sd, "TwoWayTransformer_Both", xin_path,
-                                         sinusoid_pe(n, E, dt),
+                                         pe_of(n),
                                          torch.tanh(_lin(sd, "fc_CI2Pth.0", x_text)),
                                          depth, num_heads)                          # :168
     bag = torch.cat([ct2ci, ci2ct, pth2ci, ci2pth], dim=1)                          # :173

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert len(names) >= 25
     missing = [n for n in names if not hasattr(h, n)]
     assert not missing, f"declared in include/milb200.h but not exported: {missing}"
-    assert h.milb200_version() == 106
+    assert h.milb200_version() == 200
     assert h.milb200_launch_count() >= 0
 
 

@@ -50,7 +50,8 @@ def test_cfg4_padded_bags_head_bce_all_gradients_vs_oracle(dtype, tol):
     sd = {}
     for k, v in sdn.items():
         t = torch.from_numpy(v)
-        sd[k] = (quant(t) if t.dim() == 2 else t.double()).requires_grad_(True)
+        # bf16 mode quantises what the tensor-core kernels consume: the gate weights; the small head stays fp32
+        sd[k] = (quant(t) if (t.dim() == 2 and "attention_" in k and k.endswith("0.weight")) else t.double()).requires_grad_(True)
     xd = xpad_t.detach().double().cpu().requires_grad_(True)
     pfd = pf_t.detach().double().cpu().requires_grad_(True)
     pooled = torch.cat([fo.abmil(sd, "extractor_pathology", xd[b, :int(n)]) for b, n in enumerate(lens)], dim=0)

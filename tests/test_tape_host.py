@@ -62,32 +62,32 @@ def test_native_validator_rejects_malformed_programs(model):
     c = t._freeze()
     rows = {"N": 100, "T": 2}
     slots = t._slots(rows)
-    assert lib.milb200_tape_arena_bytes(c["ops"], c["n_ops"], slots, c["n_slots"], L.F32) > 100 * 512 * 4
+    assert lib.milb200_tape_arena_bytes(c["ops"], c["n_ops"], slots, c["n_slots"], L.F32, None) > 100 * 512 * 4
     n = c["n_slots"]
     ext = (C.c_void_p * n)()
     dummy = C.c_void_p(256)
     # (1) missing pointers
     rc = lib.milb200_tape_forward(c["ops"], c["n_ops"], slots, n, c["params"], c["n_params"], ext, None, None, None, 0, None,
-                                  0, L.F32, None)
+                                  0, L.F32, None, None)
     assert rc != 0 and b"null" in lib.milb200_last_error()
     # (2) a shape that contradicts the weights: shrink the column count of one linear's input slot
     bad = type(slots).from_buffer_copy(slots)            # _slots() caches per shape: never edit its result
     lin = next(o for o in t.ops if o[0] == L.OP_LINEAR)
     bad[lin[1]].cols = 511
     rc = lib.milb200_tape_forward(c["ops"], c["n_ops"], bad, n, c["params"], c["n_params"], ext, dummy, dummy, dummy, 1 << 30,
-                                  dummy, 1 << 30, L.F32, None)
+                                  dummy, 1 << 30, L.F32, None, None)
     assert rc != 0 and b"shape mismatch" in lib.milb200_last_error()
     # (3) unknown op kind
     ops = (L.TapeOp * c["n_ops"])(*c["ops"])
     ops[0].kind = 99
     rc = lib.milb200_tape_forward(ops, c["n_ops"], slots, n, c["params"], c["n_params"], ext, dummy, dummy, dummy, 1 << 30,
-                                  dummy, 1 << 30, L.F32, None)
+                                  dummy, 1 << 30, L.F32, None, None)
     assert rc != 0 and b"unknown kind" in lib.milb200_last_error()
     # (4) only two lanes exist
     ops = (L.TapeOp * c["n_ops"])(*c["ops"])
     ops[3].lane = 2
     rc = lib.milb200_tape_forward(ops, c["n_ops"], slots, n, c["params"], c["n_params"], ext, dummy, dummy, dummy, 1 << 30,
-                                  dummy, 1 << 30, L.F32, None)
+                                  dummy, 1 << 30, L.F32, None, None)
     assert rc != 0 and b"lane" in lib.milb200_last_error()
 
 
@@ -110,12 +110,52 @@ def test_fusion_program_puts_the_ct_branch_on_its_own_lane(model):
     c = t._freeze()
     rows = {"T": 1, "Nc": 160, "Np": 300}
     slots = t._slots(rows)
-    two = lib.milb200_tape_workspace_bytes(c["ops"], c["n_ops"], slots, c["n_slots"], L.BF16, 0)
+    two = lib.milb200_tape_workspace_bytes(c["ops"], c["n_ops"], slots, c["n_slots"], L.BF16, 0, None)
     ops1 = (L.TapeOp * c["n_ops"])(*c["ops"])
     for o in ops1:
         o.lane = 0
-    one = lib.milb200_tape_workspace_bytes(ops1, c["n_ops"], slots, c["n_slots"], L.BF16, 0)
+    one = lib.milb200_tape_workspace_bytes(ops1, c["n_ops"], slots, c["n_slots"], L.BF16, 0, None)
     assert two == 2 * one
+
+
+def test_collapsed_fusion_program_and_segment_table(model):
+    """The T = 1 CT+pathology branch as a segmented program (csrc/xfusion.cu): no projected-keys ops on the image side, the
+    token side in fp32, and the native validator's view of the segment table."""
+    import mil_b200
+    from mil_b200 import _lib as L
+    lib = mil_b200.lib()
+    t = model._fusion_tape_v2()
+    kinds = [o[0] for o in t.ops]
+    assert kinds.count(L.OP_T2I_POOL) == 3 and kinds.count(L.OP_LN_SEG) == 2 and kinds.count(L.OP_TOK_SCATTER) == 1
+    assert L.OP_ATTENTION not in kinds and L.OP_ADD not in kinds
+    big = {t.inputs[0], t.inputs[1], t.inputs[2]}          # pathology rows, CT tokens, position table: program dtype
+    for o in t.ops:                                         # every LINEAR except fc_pathology runs on fp32 token rows
+        if o[0] == L.OP_LINEAR and o[1] not in big:
+            assert t.slot_f32[o[1]] and t.slot_f32[o[4]]
+    rows, segs, bag_off = model.fusion_layout(160, [300, 50], 1)
+    assert bag_off == [0, 462, 674]
+    assert segs[0] == ((350, 160, 1, 0), (510, 160, 463, 462), (0, 300, 162, 161), (300, 50, 624, 623))
+    rows["NPE"] = 4096
+    c = t._freeze()
+    slots = t._slots(rows)
+    segp = t._segments(segs)
+    assert lib.milb200_tape_arena_bytes(c["ops"], c["n_ops"], slots, c["n_slots"], L.BF16, segp) > 670 * 512 * 2
+    n = c["n_slots"]
+    ext = (C.c_void_p * n)()
+    for i in range(n):
+        ext[i] = 4096
+    dummy = C.c_void_p(4096)
+    # without a segment table the segment ops are rejected before anything is launched
+    l0 = lib.milb200_launch_count()
+    rc = lib.milb200_tape_forward(c["ops"], c["n_ops"], slots, n, c["params"], c["n_params"], ext, dummy, dummy, dummy, 1 << 40,
+                                  dummy, 1 << 40, L.BF16, None, None)
+    assert rc != 0 and b"segment table" in lib.milb200_last_error()
+    # a segment table whose row count contradicts the slots
+    bad_segs = t._segments((segs[0][:3], 1))
+    rc = lib.milb200_tape_forward(c["ops"], c["n_ops"], slots, n, c["params"], c["n_params"], ext, dummy, dummy, dummy, 1 << 40,
+                                  dummy, 1 << 40, L.BF16, bad_segs, None)
+    assert rc != 0 and b"mismatch" in lib.milb200_last_error()
+    assert lib.milb200_launch_count() == l0
 
 
 def test_c_abi_argument_checks_launch_nothing():
