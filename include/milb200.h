@@ -130,6 +130,16 @@ int milb200_linear_bwd(const void* X, const void* add, const void* W, const void
                        void* dX, float* dW, float* dbias, int64_t m, int n, int k, int act, int dtype,
                        int accumulate, void* workspace, size_t ws_bytes, void* stream);
 
+/* Mixed-precision variant for the head of the fusion path's key stream (fc_pathology, model/aggregator.py:141): X, W bf16
+ * on the tensor cores, Y fp32; backward takes fp32 dY (and the fp32 output Y), returns dW / dbias fp32 and dX bf16 (may be
+ * NULL).  Tensor-core shapes only (n % 16 == 0, k >= 64, k % 8 == 0).  Workspace (backward only):
+ * milb200_linear_workspace_bytes(m, n, k, MILB200_BF16, 1).                                                          */
+int milb200_linear_f32out_fwd(const void* X, const void* W, const float* bias, float* Y, int64_t m, int n, int k, int act,
+                              void* stream);
+int milb200_linear_f32out_bwd(const void* X, const void* W, const float* Y, const float* dY, void* dX, float* dW,
+                              float* dbias, int64_t m, int n, int k, int act, int accumulate, void* workspace,
+                              size_t ws_bytes, void* stream);
+
 /* ---- LayerNorm over the last dim (nn.LayerNorm, eps 1e-5; transformer.py:288,295,300,307,118) ----
  * Y = LN(X + R) * gamma + beta, R optional residual (may be NULL).  mean/rstd[m] fp32 are saved.
  * r_broadcast != 0: R is ONE row [n] added to every row of X — with a single text token the image->token attention of
@@ -235,6 +245,7 @@ int milb200_ct_tokens_bwd(const void* dtokens, void* dfmap, int c, int t, int hw
  *                     the token side: in0 = keys, in1 = position table, in2 = U (HEADDIAG_U of the projected queries
  *                     with k_proj.weight); out[(seg, t, h), :] = sum_n softmax_n(scale (keys + pe) . U) keys[n]
  *                     a0 = 1: keys are addressed in the packed-bag layout (segment out_start), 0: key-stream layout
+ *                     (the position table in1 is always fp32)
  *           LN_SEG    out = LN(in0 + in1[segment]) * gamma + beta — image -> token attention with ONE token per
  *                     segment (softmax over one key = 1: the attention output is one row per segment)
  *                     a0 bit 0: write the rows at out_start (the packed bag of aggregator.py:173); in2 >= 0: also
@@ -243,7 +254,9 @@ int milb200_ct_tokens_bwd(const void* dtokens, void* dfmap, int c, int t, int hw
  *                     must be external slots at the same address (value and gradient) — the x_CT2CI / x_Pth2CI rows of
  *                     the packed bag, filled once the final token -> image attention has produced them
  * Slots may be forced to fp32 inside a bf16 program (external bit 1): the text-token side (<= 16 rows) always runs in
- * fp32 with the fp32 master weights; an op's arithmetic dtype is that of its in0.  The segment ops read the segment
+ * fp32 with the fp32 master weights; an op's arithmetic dtype is that of its in0.  Two mixed ops exist for bf16 programs
+ * whose key stream is kept in fp32: LINEAR with a bf16 input and an fp32 result (milb200_linear_f32out_*), and LN_SEG
+ * with an fp32 input and a bf16 result (the last layer writes the bf16 packed bag).  The segment ops read the segment
  * table handed to milb200_tape_forward/backward (host memory; NULL when the program has no segment ops).
  * Backward: seed_ptrs[s] != NULL gives dL/d(slot s) for program outputs (copied into the slot's gradient buffer
  * ext_grad_ptrs[s] unless the two pointers are equal: a caller-owned buffer may be seeded in place); ext_grad_ptrs[s] !=

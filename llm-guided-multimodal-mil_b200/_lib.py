@@ -48,6 +48,8 @@ SIGNATURES = {
     "milb200_linear_workspace_bytes": (_sz, [_i64, _i, _i, _i, _i]),
     "milb200_linear_fwd": (_i, [_p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p, _sz, _p]),
     "milb200_linear_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _i, _p, _sz, _p]),
+    "milb200_linear_f32out_fwd": (_i, [_p, _p, _p, _p, _i64, _i, _i, _i, _p]),
+    "milb200_linear_f32out_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p, _sz, _p]),
     "milb200_layernorm_workspace_bytes": (_sz, [_i64, _i]),
     "milb200_layernorm_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _p]),
     "milb200_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _i, _i, _i, _i, _p, _sz, _p]),

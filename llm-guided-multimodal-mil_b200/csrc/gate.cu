@@ -266,6 +266,23 @@ __global__ void k_act_bwd(const T* __restrict__ Y, const T* __restrict__ dY, T* 
   }
 }
 
+// same with fp32 Y / dY and a bf16 result (the tensor-core operand of the mixed-precision linear's backward)
+__global__ void k_act_bwd_f32_bf16(const float* __restrict__ Y, const float* __restrict__ dY, __nv_bfloat16* __restrict__ out,
+                                   int64_t n4, int act) {
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (; i < n4; i += stride) {
+    float4 g = reinterpret_cast<const float4*>(dY)[i];
+    if (act != MILB200_ACT_NONE) {
+      const float4 y = reinterpret_cast<const float4*>(Y)[i];
+      if (act == MILB200_ACT_TANH) { g.x *= 1.f - y.x * y.x; g.y *= 1.f - y.y * y.y; g.z *= 1.f - y.z * y.z; g.w *= 1.f - y.w * y.w; }
+      else if (act == MILB200_ACT_RELU) { g.x = y.x > 0.f ? g.x : 0.f; g.y = y.y > 0.f ? g.y : 0.f; g.z = y.z > 0.f ? g.z : 0.f; g.w = y.w > 0.f ? g.w : 0.f; }
+      else { g.x *= y.x * (1.f - y.x); g.y *= y.y * (1.f - y.y); g.z *= y.z * (1.f - y.z); g.w *= y.w * (1.f - y.w); }
+    }
+    reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16(g.x, g.y), pack_bf16(g.z, g.w));
+  }
+}
+
 // out[c] (+)= sum_r A[r, c]
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -755,6 +772,58 @@ int milb200_linear_bwd(const void* X, const void* add, const void* W, const void
                                        accumulate, ws, w, st);
   return linear_bwd_t<float>((const float*)xin, (const float*)W, (const float*)Y, (const float*)dY, (float*)dX, dW, dbias,
                              m, n, k, act, dtype, accumulate, ws, w, st);
+}
+
+
+/* Mixed-precision linear for the head of the fusion path's key stream (fc_pathology, aggregator.py:141): X [m, k] and
+ * W [n, k] bf16 on the tensor cores, Y [m, n] fp32 — downstream the key stream stays fp32, so the bf16 storage of the patch
+ * features is the only reduced-precision step.  Backward: dY fp32 -> bf16 operand (one elementwise pass), dW / dbias fp32,
+ * dX bf16 (may be NULL).  Workspace: milb200_linear_workspace_bytes(m, n, k, MILB200_BF16, 1).                            */
+int milb200_linear_f32out_fwd(const void* X, const void* W, const float* bias, float* Y, int64_t m, int n, int k, int act,
+                              void* stream) {
+  int rc = linear_check(X, W, m, n, k, MILB200_BF16);
+  if (rc) return rc;
+  MIL_CHECK_ARG(Y != nullptr, MILB200_EINVAL, "linear_f32out_fwd: Y is null");
+  MIL_CHECK_ARG(tc::gemm_store_supported(m, n, k) && aligned16(X) && aligned16(W) && aligned16(Y), MILB200_EUNSUPPORTED,
+                "linear_f32out_fwd: shape m=%lld n=%d k=%d is outside the tensor-core kernel (n %% 16, k >= 64, k %% 8)",
+                (long long)m, n, k);
+  return tc::gemm_store(X, m, k, k, W, n, k, bias, act, Y, MILB200_F32, n, nullptr, nullptr, nullptr, 0,
+                        static_cast<cudaStream_t>(stream));
+}
+
+int milb200_linear_f32out_bwd(const void* X, const void* W, const float* Y, const float* dY, void* dX, float* dW, float* dbias,
+                              int64_t m, int n, int k, int act, int accumulate, void* workspace, size_t ws_bytes,
+                              void* stream) {
+  int rc = linear_check(X, W, m, n, k, MILB200_BF16);
+  if (rc) return rc;
+  MIL_CHECK_ARG(dY != nullptr && (act == MILB200_ACT_NONE || Y != nullptr), MILB200_EINVAL, "linear_f32out_bwd: null pointer");
+  MIL_CHECK_ARG(tc::gemm_store_supported(m, k, n) && tc::gemm_tn_supported(n, k) && (static_cast<int64_t>(m) * n) % 4 == 0,
+                MILB200_EUNSUPPORTED, "linear_f32out_bwd: shape m=%lld n=%d k=%d is outside the tensor-core kernels",
+                (long long)m, n, k);
+  LinWs w = linear_ws(m, n, k, MILB200_BF16, 1, 0);
+  MIL_CHECK_ARG(workspace && ws_bytes >= w.total, MILB200_EWORKSPACE, "linear_f32out_bwd: workspace %zu < %zu", ws_bytes, w.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* ws = static_cast<char*>(workspace);
+  __nv_bfloat16* dypre = reinterpret_cast<__nv_bfloat16*>(ws + w.dypre);
+  const int64_t n4 = m * n / 4;
+  const unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n4 + 255) / 256, sm_count() * 8));
+  k_act_bwd_f32_bf16<<<blocks, 256, 0, st>>>(Y, dY, dypre, n4, act);
+  MIL_LAUNCH_CHECK();
+  if (dbias && (rc = colsum_launch<__nv_bfloat16>(dypre, m, n, dbias, accumulate, st))) return rc;
+  if (dW) {
+    int splits = 0;
+    float* part = reinterpret_cast<float*>(ws + w.part);
+    if ((rc = tc::gemm_tn_splitk(dypre, n, X, k, m, n, k, part, &splits, st))) return rc;
+    if ((rc = splitk_reduce(part, splits, static_cast<int64_t>(n) * k, dW, accumulate, st))) return rc;
+  }
+  if (dX) {
+    void* wT = ws + w.wT;
+    if ((rc = transpose2d(W, wT, n, k, MILB200_BF16, st))) return rc;
+    if ((rc = tc::gemm_store(dypre, m, n, n, wT, k, n, nullptr, MILB200_ACT_NONE, dX, MILB200_BF16, k, nullptr, nullptr, nullptr,
+                             0, st)))
+      return rc;
+  }
+  return MILB200_OK;
 }
 
 }  // extern "C"

@@ -64,8 +64,9 @@ static int tape_validate(const milb200_tape_op* ops, int n_ops, const milb200_ta
         MIL_CHECK_ARG(o.in1 < 0 || (o.in1 != o.in0 && slots[o.in1].rows == s0.rows && slots[o.in1].cols == s0.cols),
                       MILB200_EINVAL, "tape: op %d `add` slot must differ from x and share its shape", i);
         MIL_CHECK_ARG(o.p1 < 0 || params[o.p1].rows * params[o.p1].cols == so.cols, MILB200_EINVAL, "tape: op %d bias size", i);
-        MIL_CHECK_ARG(dt(o.out) == dt(o.in0) && (o.in1 < 0 || dt(o.in1) == dt(o.in0)), MILB200_EINVAL,
-                      "tape: op %d linear operands must share one dtype", i);
+        MIL_CHECK_ARG((dt(o.out) == dt(o.in0) && (o.in1 < 0 || dt(o.in1) == dt(o.in0))) ||
+                          (dt(o.in0) == MILB200_BF16 && dt(o.out) == MILB200_F32 && o.in1 < 0),
+                      MILB200_EINVAL, "tape: op %d linear operands must share one dtype (or bf16 input -> fp32 result)", i);
         break;
       }
       case MILB200_OP_ATTENTION: {
@@ -121,7 +122,7 @@ static int tape_validate(const milb200_tape_op* ops, int n_ops, const milb200_ta
       case MILB200_OP_T2I_POOL: {
         MIL_CHECK_ARG(ok_slot(o.in1, false) && ok_slot(o.in2, false) && n_segs > 0, MILB200_EINVAL,
                       "tape: op %d t2i_pool needs keys, position table, U and a segment table", i);
-        MIL_CHECK_ARG(s0.cols == xf::E && slots[o.in1].cols == xf::E && dt(o.in1) == dt(o.in0) && slots[o.in2].cols == xf::E &&
+        MIL_CHECK_ARG(s0.cols == xf::E && slots[o.in1].cols == xf::E && dt(o.in1) == MILB200_F32 && slots[o.in2].cols == xf::E &&
                           slots[o.in2].rows == static_cast<int64_t>(n_segs) * T * xf::H && so.rows == slots[o.in2].rows &&
                           so.cols == xf::E && dt(o.in2) == MILB200_F32 && dt(o.out) == MILB200_F32,
                       MILB200_EINVAL, "tape: op %d t2i_pool shape/dtype mismatch", i);
@@ -132,7 +133,9 @@ static int tape_validate(const milb200_tape_op* ops, int n_ops, const milb200_ta
                       "tape: op %d ln_seg needs keys, one row per segment and a segment table with one token per segment", i);
         MIL_CHECK_ARG(params && o.p0 >= 0 && o.p0 < n_params && o.p1 >= 0 && o.p1 < n_params, MILB200_EINVAL,
                       "tape: op %d bad param id", i);
-        MIL_CHECK_ARG(s0.cols == xf::E && so.cols == xf::E && dt(o.out) == dt(o.in0) && slots[o.in1].cols == xf::E &&
+        MIL_CHECK_ARG(s0.cols == xf::E && so.cols == xf::E &&
+                          (dt(o.out) == dt(o.in0) || (dt(o.in0) == MILB200_F32 && dt(o.out) == MILB200_BF16)) &&
+                          slots[o.in1].cols == xf::E &&
                           slots[o.in1].rows == n_segs && dt(o.in1) == MILB200_F32 &&
                           (o.in2 < 0 || (slots[o.in2].cols == xf::E && slots[o.in2].rows == static_cast<int64_t>(n_segs) * T &&
                                          dt(o.in2) == MILB200_F32)) &&
@@ -365,6 +368,11 @@ static int tape_forward_run(const milb200_tape_op* ops, int n_ops, const milb200
     const int d0 = dt(o.in0);
     switch (o.kind) {
       case MILB200_OP_LINEAR:
+        if (d0 == MILB200_BF16 && dt(o.out) == MILB200_F32) {
+          rc = milb200_linear_f32out_fwd(ptr[o.in0], weight(o.p0, d0), o.p1 >= 0 ? p_f32 + params[o.p1].offset : nullptr,
+                                         static_cast<float*>(ptr[o.out]), s0.rows, so.cols, s0.cols, o.a0, stream);
+          break;
+        }
         rc = milb200_linear_fwd(ptr[o.in0], o.in1 >= 0 ? ptr[o.in1] : nullptr, weight(o.p0, d0),
                                 o.p1 >= 0 ? p_f32 + params[o.p1].offset : nullptr, ptr[o.out], s0.rows, so.cols, s0.cols, o.a0,
                                 d0, workspace_l, ws_l, stream);
@@ -409,7 +417,7 @@ static int tape_forward_run(const milb200_tape_op* ops, int n_ops, const milb200
                       i, (long long)slots[o.in1].rows, pl.sg.max_len);
         float* S = reinterpret_cast<float*>(ar + pl.aux_off[i]);
         float* lse = S + static_cast<size_t>(s0.rows) * pl.sg.T * xf::H;
-        rc = xf::t2i_fwd(ptr[o.in0], ptr[o.in1], static_cast<const float*>(ptr[o.in2]), pl.sg, o.a0 & 1, S, lse,
+        rc = xf::t2i_fwd(ptr[o.in0], static_cast<const float*>(ptr[o.in1]), static_cast<const float*>(ptr[o.in2]), pl.sg, o.a0 & 1, S, lse,
                          static_cast<float*>(ptr[o.out]), d0, workspace_l, ws_l, cst);
         break;
       }
@@ -417,7 +425,7 @@ static int tape_forward_run(const milb200_tape_op* ops, int n_ops, const milb200
         float* mean = reinterpret_cast<float*>(ar + pl.aux_off[i]);
         rc = xf::ln_seg_fwd(ptr[o.in0], static_cast<const float*>(ptr[o.in1]), p_f32 + params[o.p0].offset,
                             p_f32 + params[o.p1].offset, o.in2 >= 0 ? static_cast<const float*>(ptr[o.in2]) : nullptr, pl.sg,
-                            o.a0 & 1, ptr[o.out], mean, mean + s0.rows, d0, cst);
+                            o.a0 & 1, ptr[o.out], mean, mean + s0.rows, d0, dt(o.out), cst);
         break;
       }
       case MILB200_OP_TOK_SCATTER:
@@ -540,9 +548,15 @@ static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb20
         void* dX = nullptr;
         if (need_dx) dX = needs[o.in0] ? target(o.in0, 0) : target(o.in1, 0);
         const int acc = ptouched[o.p0] ? 1 : 0;
-        rc = milb200_linear_bwd(val[o.in0], o.in1 >= 0 ? val[o.in1] : nullptr, weight(o.p0, d0), val[o.out], dY, dX,
-                                g_f32 + params[o.p0].offset, o.p1 >= 0 ? g_f32 + params[o.p1].offset : nullptr, s0.rows,
-                                so.cols, s0.cols, o.a0, d0, acc, scratch, scratch_bytes, stream);
+        if (d0 == MILB200_BF16 && dt(o.out) == MILB200_F32)
+          rc = milb200_linear_f32out_bwd(val[o.in0], weight(o.p0, d0), static_cast<const float*>(val[o.out]),
+                                         static_cast<const float*>(dY), dX, g_f32 + params[o.p0].offset,
+                                         o.p1 >= 0 ? g_f32 + params[o.p1].offset : nullptr, s0.rows, so.cols, s0.cols, o.a0,
+                                         acc, scratch, scratch_bytes, stream);
+        else
+          rc = milb200_linear_bwd(val[o.in0], o.in1 >= 0 ? val[o.in1] : nullptr, weight(o.p0, d0), val[o.out], dY, dX,
+                                  g_f32 + params[o.p0].offset, o.p1 >= 0 ? g_f32 + params[o.p1].offset : nullptr, s0.rows,
+                                  so.cols, s0.cols, o.a0, d0, acc, scratch, scratch_bytes, stream);
         if (rc) return rc;
         ptouched[o.p0] = 1;
         if (o.p1 >= 0) ptouched[o.p1] = 1;
@@ -666,7 +680,7 @@ static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb20
         const int acc = (needs[o.in0] && has[o.in0]) ? 1 : 0;
         float* dU = static_cast<float*>(target(o.in2, 1));
         float* dUw = dU ? dU : reinterpret_cast<float*>(tmp0 + tmp_stride);
-        rc = xf::t2i_bwd(val[o.in0], val[o.in1], static_cast<const float*>(val[o.in2]), S, lse,
+        rc = xf::t2i_bwd(val[o.in0], static_cast<const float*>(val[o.in1]), static_cast<const float*>(val[o.in2]), S, lse,
                          static_cast<const float*>(val[o.out]), static_cast<const float*>(dY), pl.sg, o.a0 & 1, dK, acc, dUw, d0,
                          scratch, scratch_bytes, cst);
         if (rc) return rc;
@@ -683,7 +697,7 @@ static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb20
         float* dtok = o.in2 >= 0 ? static_cast<float*>(target(o.in2, 2)) : nullptr;
         rc = xf::ln_seg_bwd(val[o.in0], static_cast<const float*>(val[o.in1]), p_f32 + params[o.p0].offset, mean,
                             mean + s0.rows, dY, pl.sg, o.a0 & 1, dK, acc, dRw, g_f32 + params[o.p0].offset,
-                            g_f32 + params[o.p1].offset, ptouched[o.p0] ? 1 : 0, dtok, d0, scratch, scratch_bytes, cst);
+                            g_f32 + params[o.p1].offset, ptouched[o.p0] ? 1 : 0, dtok, d0, dt(o.out), scratch, scratch_bytes, cst);
         if (rc) return rc;
         ptouched[o.p0] = ptouched[o.p1] = 1;
         if (needs[o.in0]) has[o.in0] = 1;

@@ -90,6 +90,29 @@ __device__ __forceinline__ void load_f32_row(const float* row, int lane, float* 
     }
 }
 
+template <typename TK>
+__device__ __forceinline__ void store_f32_row(float* row, int lane, const float* v) {
+  constexpr int VN = Row<TK>::VN, NV = Row<TK>::NV, HV = Row<TK>::HV;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int h = 0; h < HV; ++h)
+      *reinterpret_cast<float4*>(row + (lane + 32 * i) * VN + h * 4) =
+          make_float4(v[i * VN + h * 4 + 0], v[i * VN + h * 4 + 1], v[i * VN + h * 4 + 2], v[i * VN + h * 4 + 3]);
+}
+// rows of storage type T handled in the lane order of the mapping type TM (TM = bf16 whenever either side of a kernel
+// stores bf16, so that one lane owns the same 16 columns of every operand)
+template <typename T, typename TM>
+__device__ __forceinline__ void rload(const T* row, int lane, float* v) {
+  if constexpr (sizeof(T) == sizeof(TM)) Row<T>::load(row, lane, v);
+  else load_f32_row<TM>(reinterpret_cast<const float*>(row), lane, v);
+}
+template <typename T, typename TM>
+__device__ __forceinline__ void rstore(T* row, int lane, const float* v) {
+  if constexpr (sizeof(T) == sizeof(TM)) Row<T>::store(row, lane, v);
+  else store_f32_row<TM>(reinterpret_cast<float*>(row), lane, v);
+}
+
 __device__ __forceinline__ int find_seg(const Segs& sg, int item) {
   int s = 0;
   while (s + 1 < sg.n && item >= sg.item0[s + 1]) ++s;
@@ -113,7 +136,7 @@ __device__ __forceinline__ void stage_rows(float* sm, const float* g, int rows) 
 // part_acc[(item*T + t)*8 + h][E], part_ml[(item*T + t)*8 + h] = (max, sum exp) of the item.
 template <typename TK>
 __global__ void __launch_bounds__(THREADS)
-k_t2i_fwd(const TK* __restrict__ K, const TK* __restrict__ PE, const float* __restrict__ U, const Segs sg, const int bag_layout,
+k_t2i_fwd(const TK* __restrict__ K, const float* __restrict__ PE, const float* __restrict__ U, const Segs sg, const int bag_layout,
           float* __restrict__ S, float* __restrict__ part_acc, float2* __restrict__ part_ml) {
   __shared__ __align__(16) float Us[H * E];
   __shared__ __align__(16) float red[WARPS * E];
@@ -138,7 +161,7 @@ k_t2i_fwd(const TK* __restrict__ K, const TK* __restrict__ PE, const float* __re
     const int64_t n = base + i;
     float kv[16], kp[16];
     Row<TK>::load(K + n * E, lane, kv);
-    Row<TK>::load(PE + static_cast<int64_t>(i) * E, lane, kp);
+    load_f32_row<TK>(PE + static_cast<int64_t>(i) * E, lane, kp);
 #pragma unroll
     for (int e = 0; e < 16; ++e) kp[e] += kv[e];
     float sc[H];
@@ -245,7 +268,7 @@ k_t2i_merge(const float* __restrict__ part_acc, const float2* __restrict__ part_
 // owns the row, dU partials go to part_du[(item*T + t)*8 + h][E].
 template <typename TK>
 __global__ void __launch_bounds__(THREADS)
-k_t2i_bwd(const TK* __restrict__ K, const TK* __restrict__ PE, const float* __restrict__ U, const float* __restrict__ S,
+k_t2i_bwd(const TK* __restrict__ K, const float* __restrict__ PE, const float* __restrict__ U, const float* __restrict__ S,
           const float* __restrict__ lse, const float* __restrict__ Pool, const float* __restrict__ dPool, const Segs sg,
           const int bag_layout, TK* __restrict__ dK, const int accumulate, float* __restrict__ part_du) {
   __shared__ __align__(16) float Us[H * E];
@@ -284,7 +307,7 @@ k_t2i_bwd(const TK* __restrict__ K, const TK* __restrict__ PE, const float* __re
       const int64_t n = base + i;
       float kv[16], kp[16], dk[16];
       Row<TK>::load(K + n * E, lane, kv);
-      Row<TK>::load(PE + static_cast<int64_t>(i) * E, lane, kp);
+      load_f32_row<TK>(PE + static_cast<int64_t>(i) * E, lane, kp);
       const float srow = (lane < H) ? S[n * J + t * H + lane] : 0.f;
       if (t > 0 || accumulate) {
         Row<TK>::load_cached(dK + n * E, lane, dk);
@@ -356,17 +379,18 @@ k_sum_items(const float* __restrict__ part, const Segs sg, float* __restrict__ o
 // LayerNorm(keys + row[segment])   (eps 1e-5)
 // ---------------------------------------------------------------------------------------------------------------------
 // grid (items [+ 1 when tokens are scattered]); rows are read at k_start, written at out_start when bag_layout_out.
-template <typename TK>
+// TI / TO: storage of the input rows and of the result (fp32 key stream -> bf16 packed bag on the last layer).
+template <typename TI, typename TO>
 __global__ void __launch_bounds__(THREADS)
-k_ln_seg_fwd(const TK* __restrict__ K, const float* __restrict__ R, const float* __restrict__ gamma, const float* __restrict__ beta,
-             const float* __restrict__ tokens, const Segs sg, const int bag_layout_out, TK* __restrict__ Y,
+k_ln_seg_fwd(const TI* __restrict__ K, const float* __restrict__ R, const float* __restrict__ gamma, const float* __restrict__ beta,
+             const float* __restrict__ tokens, const Segs sg, const int bag_layout_out, TO* __restrict__ Y,
              float* __restrict__ mean, float* __restrict__ rstd) {
   const int item = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (item >= sg.n_items) {         // the extra CTA: token rows of every segment -> their rows of the packed bag
     for (int r = warp; r < sg.n * sg.T; r += WARPS) {
       float v[16];
-      load_f32_row<TK>(tokens + static_cast<int64_t>(r) * E, lane, v);
-      Row<TK>::store(Y + static_cast<int64_t>(sg.tok_row[r / sg.T] + r % sg.T) * E, lane, v);
+      load_f32_row<TO>(tokens + static_cast<int64_t>(r) * E, lane, v);
+      Row<TO>::store(Y + static_cast<int64_t>(sg.tok_row[r / sg.T] + r % sg.T) * E, lane, v);
     }
     return;
   }
@@ -375,12 +399,12 @@ k_ln_seg_fwd(const TK* __restrict__ K, const float* __restrict__ R, const float*
   const int i1 = min(sg.len[s], i0 + sg.rows_per_item);
   const int64_t in0 = sg.k_start[s], out0 = bag_layout_out ? sg.out_start[s] : sg.k_start[s];
   float r[16], ga[16], be[16];
-  load_f32_row<TK>(R + static_cast<int64_t>(s) * E, lane, r);
-  load_f32_row<TK>(gamma, lane, ga);
-  load_f32_row<TK>(beta, lane, be);
+  load_f32_row<TO>(R + static_cast<int64_t>(s) * E, lane, r);
+  load_f32_row<TO>(gamma, lane, ga);
+  load_f32_row<TO>(beta, lane, be);
   for (int i = i0 + warp; i < i1; i += WARPS) {
     float v[16];
-    Row<TK>::load(K + (in0 + i) * E, lane, v);
+    rload<TI, TO>(K + (in0 + i) * E, lane, v);
     float sum = 0.f;
 #pragma unroll
     for (int e = 0; e < 16; ++e) { v[e] += r[e]; sum += v[e]; }
@@ -391,17 +415,18 @@ k_ln_seg_fwd(const TK* __restrict__ K, const float* __restrict__ R, const float*
     const float rs = rsqrtf(warp_sum(q) * (1.f / E) + 1e-5f);
 #pragma unroll
     for (int e = 0; e < 16; ++e) v[e] = (v[e] - mu) * rs * ga[e] + be[e];
-    Row<TK>::store(Y + (out0 + i) * E, lane, v);
+    Row<TO>::store(Y + (out0 + i) * E, lane, v);
     if (lane == 0) { mean[in0 + i] = mu; rstd[in0 + i] = rs; }
   }
 }
 
 // dXR = rstd (g - mean(g) - xhat mean(g xhat)), g = dY gamma; per item: part[item][0..2][E] = (dgamma, dbeta, sum dXR)
-template <typename TK>
+template <typename TI, typename TO>
 __global__ void __launch_bounds__(THREADS)
-k_ln_seg_bwd(const TK* __restrict__ K, const float* __restrict__ R, const float* __restrict__ gamma, const float* __restrict__ mean,
-             const float* __restrict__ rstd, const TK* __restrict__ dY, const Segs sg, const int bag_layout_out,
-             TK* __restrict__ dK, const int accumulate, float* __restrict__ part) {
+k_ln_seg_bwd(const TI* __restrict__ K, const float* __restrict__ R, const float* __restrict__ gamma, const float* __restrict__ mean,
+             const float* __restrict__ rstd, const TO* __restrict__ dY, const Segs sg, const int bag_layout_out,
+             TI* __restrict__ dK, const int accumulate, float* __restrict__ part) {
+  using TK = TO;      // lane order of every operand
   __shared__ __align__(16) float red[WARPS * E];
   const int item = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int s = find_seg(sg, item);
@@ -415,8 +440,8 @@ k_ln_seg_bwd(const TK* __restrict__ K, const float* __restrict__ R, const float*
   for (int e = 0; e < 16; ++e) dg[e] = db[e] = dr[e] = 0.f;
   for (int i = i0 + warp; i < i1; i += WARPS) {
     float x[16], dy[16], g[16];
-    Row<TK>::load(K + (in0 + i) * E, lane, x);
-    Row<TK>::load(dY + (out0 + i) * E, lane, dy);
+    rload<TI, TO>(K + (in0 + i) * E, lane, x);
+    Row<TO>::load(dY + (out0 + i) * E, lane, dy);
     const float mu = mean[in0 + i], rs = rstd[in0 + i];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
@@ -432,7 +457,7 @@ k_ln_seg_bwd(const TK* __restrict__ K, const float* __restrict__ R, const float*
     s2 = warp_sum(s2) * (1.f / E);
     float o[16];
     if (accumulate) {
-      Row<TK>::load_cached(dK + (in0 + i) * E, lane, o);
+      rload<TI, TO>(dK + (in0 + i) * E, lane, o);
     } else {
 #pragma unroll
       for (int e = 0; e < 16; ++e) o[e] = 0.f;
@@ -443,7 +468,7 @@ k_ln_seg_bwd(const TK* __restrict__ K, const float* __restrict__ R, const float*
       dr[e] += d;
       o[e] += d;
     }
-    Row<TK>::store(dK + (in0 + i) * E, lane, o);
+    rstore<TI, TO>(dK + (in0 + i) * E, lane, o);
   }
 #pragma unroll 1
   for (int k = 0; k < 3; ++k) {
@@ -641,7 +666,7 @@ int tok_gather(const void* dbag, const Segs& sg, float* dtokens, int dtype, cuda
   return MILB200_OK;
 }
 
-int t2i_fwd(const void* K, const void* PE, const float* U, const Segs& sg, int bag_layout, float* S, float* lse, float* Pool,
+int t2i_fwd(const void* K, const float* PE, const float* U, const Segs& sg, int bag_layout, float* S, float* lse, float* Pool,
             int dtype, void* ws, size_t ws_bytes, cudaStream_t st) {
   MIL_CHECK_ARG(K && PE && U && S && lse && Pool, MILB200_EINVAL, "t2i_fwd: null pointer");
   MIL_CHECK_ARG(ws && ws_bytes >= t2i_ws_bytes(sg), MILB200_EWORKSPACE, "t2i_fwd: workspace %zu < %zu", ws_bytes, t2i_ws_bytes(sg));
@@ -650,27 +675,27 @@ int t2i_fwd(const void* K, const void* PE, const float* U, const Segs& sg, int b
   float2* part_ml = reinterpret_cast<float2*>(static_cast<char*>(ws) + align_up(rows * E * sizeof(float), 256));
   const dim3 grid(sg.n_items, sg.T);
   if (dtype == MILB200_BF16)
-    k_t2i_fwd<__nv_bfloat16><<<grid, THREADS, 0, st>>>((const __nv_bfloat16*)K, (const __nv_bfloat16*)PE, U, sg, bag_layout, S,
+    k_t2i_fwd<__nv_bfloat16><<<grid, THREADS, 0, st>>>((const __nv_bfloat16*)K, PE, U, sg, bag_layout, S,
                                                        part_acc, part_ml);
   else
-    k_t2i_fwd<float><<<grid, THREADS, 0, st>>>((const float*)K, (const float*)PE, U, sg, bag_layout, S, part_acc, part_ml);
+    k_t2i_fwd<float><<<grid, THREADS, 0, st>>>((const float*)K, PE, U, sg, bag_layout, S, part_acc, part_ml);
   MIL_LAUNCH_CHECK();
   k_t2i_merge<<<sg.n * sg.T * H, 128, 0, st>>>(part_acc, part_ml, sg, Pool, lse);
   MIL_LAUNCH_CHECK();
   return MILB200_OK;
 }
 
-int t2i_bwd(const void* K, const void* PE, const float* U, const float* S, const float* lse, const float* Pool,
+int t2i_bwd(const void* K, const float* PE, const float* U, const float* S, const float* lse, const float* Pool,
             const float* dPool, const Segs& sg, int bag_layout, void* dK, int accumulate_dk, float* dU, int dtype, void* ws,
             size_t ws_bytes, cudaStream_t st) {
   MIL_CHECK_ARG(K && PE && U && S && lse && Pool && dPool && dK && dU, MILB200_EINVAL, "t2i_bwd: null pointer");
   MIL_CHECK_ARG(ws && ws_bytes >= t2i_ws_bytes(sg), MILB200_EWORKSPACE, "t2i_bwd: workspace %zu < %zu", ws_bytes, t2i_ws_bytes(sg));
   float* part = static_cast<float*>(ws);
   if (dtype == MILB200_BF16)
-    k_t2i_bwd<__nv_bfloat16><<<sg.n_items, THREADS, 0, st>>>((const __nv_bfloat16*)K, (const __nv_bfloat16*)PE, U, S, lse, Pool,
+    k_t2i_bwd<__nv_bfloat16><<<sg.n_items, THREADS, 0, st>>>((const __nv_bfloat16*)K, PE, U, S, lse, Pool,
                                                              dPool, sg, bag_layout, (__nv_bfloat16*)dK, accumulate_dk, part);
   else
-    k_t2i_bwd<float><<<sg.n_items, THREADS, 0, st>>>((const float*)K, (const float*)PE, U, S, lse, Pool, dPool, sg, bag_layout,
+    k_t2i_bwd<float><<<sg.n_items, THREADS, 0, st>>>((const float*)K, PE, U, S, lse, Pool, dPool, sg, bag_layout,
                                                      (float*)dK, accumulate_dk, part);
   MIL_LAUNCH_CHECK();
   k_sum_items<<<sg.n * sg.T * H, 128, 0, st>>>(part, sg, dU);
@@ -679,40 +704,50 @@ int t2i_bwd(const void* K, const void* PE, const float* U, const float* S, const
 }
 
 int ln_seg_fwd(const void* K, const float* R, const float* gamma, const float* beta, const float* tokens, const Segs& sg,
-               int bag_layout_out, void* Y, float* mean, float* rstd, int dtype, cudaStream_t st) {
+               int bag_layout_out, void* Y, float* mean, float* rstd, int in_dtype, int out_dtype, cudaStream_t st) {
   MIL_CHECK_ARG(K && R && gamma && beta && Y && mean && rstd, MILB200_EINVAL, "ln_seg_fwd: null pointer");
+  MIL_CHECK_ARG(in_dtype == out_dtype || (in_dtype == MILB200_F32 && out_dtype == MILB200_BF16), MILB200_EUNSUPPORTED,
+                "ln_seg_fwd: storage pair (in %d, out %d) is not built", in_dtype, out_dtype);
   const unsigned grid = sg.n_items + (tokens ? 1 : 0);
-  if (dtype == MILB200_BF16)
-    k_ln_seg_fwd<__nv_bfloat16><<<grid, THREADS, 0, st>>>((const __nv_bfloat16*)K, R, gamma, beta, tokens, sg, bag_layout_out,
-                                                          (__nv_bfloat16*)Y, mean, rstd);
+  using bf = __nv_bfloat16;
+  if (out_dtype == MILB200_F32)
+    k_ln_seg_fwd<float, float><<<grid, THREADS, 0, st>>>((const float*)K, R, gamma, beta, tokens, sg, bag_layout_out, (float*)Y,
+                                                         mean, rstd);
+  else if (in_dtype == MILB200_BF16)
+    k_ln_seg_fwd<bf, bf><<<grid, THREADS, 0, st>>>((const bf*)K, R, gamma, beta, tokens, sg, bag_layout_out, (bf*)Y, mean, rstd);
   else
-    k_ln_seg_fwd<float><<<grid, THREADS, 0, st>>>((const float*)K, R, gamma, beta, tokens, sg, bag_layout_out, (float*)Y, mean,
-                                                  rstd);
+    k_ln_seg_fwd<float, bf><<<grid, THREADS, 0, st>>>((const float*)K, R, gamma, beta, tokens, sg, bag_layout_out, (bf*)Y, mean,
+                                                      rstd);
   MIL_LAUNCH_CHECK();
   return MILB200_OK;
 }
 
 int ln_seg_bwd(const void* K, const float* R, const float* gamma, const float* mean, const float* rstd, const void* dY,
                const Segs& sg, int bag_layout_out, void* dK, int accumulate_dk, float* dR, float* dgamma, float* dbeta,
-               int accumulate_params, float* dtokens, int dtype, void* ws, size_t ws_bytes, cudaStream_t st) {
+               int accumulate_params, float* dtokens, int in_dtype, int out_dtype, void* ws, size_t ws_bytes, cudaStream_t st) {
   MIL_CHECK_ARG(K && R && gamma && mean && rstd && dY && dK && dR && dgamma && dbeta, MILB200_EINVAL, "ln_seg_bwd: null pointer");
+  MIL_CHECK_ARG(in_dtype == out_dtype || (in_dtype == MILB200_F32 && out_dtype == MILB200_BF16), MILB200_EUNSUPPORTED,
+                "ln_seg_bwd: storage pair (in %d, out %d) is not built", in_dtype, out_dtype);
   MIL_CHECK_ARG(ws && ws_bytes >= ln_seg_ws_bytes(sg), MILB200_EWORKSPACE, "ln_seg_bwd: workspace %zu < %zu", ws_bytes,
                 ln_seg_ws_bytes(sg));
   float* part = static_cast<float*>(ws);
   const unsigned rgrid = 2 + sg.n + (dtokens ? sg.n * sg.T : 0);
-  if (dtype == MILB200_BF16) {
-    k_ln_seg_bwd<__nv_bfloat16><<<sg.n_items, THREADS, 0, st>>>((const __nv_bfloat16*)K, R, gamma, mean, rstd,
-                                                                (const __nv_bfloat16*)dY, sg, bag_layout_out,
-                                                                (__nv_bfloat16*)dK, accumulate_dk, part);
-    MIL_LAUNCH_CHECK();
-    k_ln_seg_reduce<__nv_bfloat16><<<rgrid, 128, 0, st>>>(part, sg, dgamma, dbeta, accumulate_params, dR,
-                                                          (const __nv_bfloat16*)dY, dtokens);
+  using bf = __nv_bfloat16;
+  if (out_dtype == MILB200_F32) {
+    k_ln_seg_bwd<float, float><<<sg.n_items, THREADS, 0, st>>>((const float*)K, R, gamma, mean, rstd, (const float*)dY, sg,
+                                                               bag_layout_out, (float*)dK, accumulate_dk, part);
+  } else if (in_dtype == MILB200_BF16) {
+    k_ln_seg_bwd<bf, bf><<<sg.n_items, THREADS, 0, st>>>((const bf*)K, R, gamma, mean, rstd, (const bf*)dY, sg, bag_layout_out,
+                                                         (bf*)dK, accumulate_dk, part);
   } else {
-    k_ln_seg_bwd<float><<<sg.n_items, THREADS, 0, st>>>((const float*)K, R, gamma, mean, rstd, (const float*)dY, sg,
-                                                        bag_layout_out, (float*)dK, accumulate_dk, part);
-    MIL_LAUNCH_CHECK();
-    k_ln_seg_reduce<float><<<rgrid, 128, 0, st>>>(part, sg, dgamma, dbeta, accumulate_params, dR, (const float*)dY, dtokens);
+    k_ln_seg_bwd<float, bf><<<sg.n_items, THREADS, 0, st>>>((const float*)K, R, gamma, mean, rstd, (const bf*)dY, sg,
+                                                            bag_layout_out, (float*)dK, accumulate_dk, part);
   }
+  MIL_LAUNCH_CHECK();
+  if (out_dtype == MILB200_F32)
+    k_ln_seg_reduce<float><<<rgrid, 128, 0, st>>>(part, sg, dgamma, dbeta, accumulate_params, dR, (const float*)dY, dtokens);
+  else
+    k_ln_seg_reduce<bf><<<rgrid, 128, 0, st>>>(part, sg, dgamma, dbeta, accumulate_params, dR, (const bf*)dY, dtokens);
   MIL_LAUNCH_CHECK();
   return MILB200_OK;
 }

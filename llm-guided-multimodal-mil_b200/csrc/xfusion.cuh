@@ -37,24 +37,25 @@ int headdiag_dw(const float* x, const float* y, float* dW, float* db, int R, int
 
 // token -> image attention with the key / value projections folded into the token side (see xfusion.cu):
 //   S[n, j] = scale (K[n] + PE[pos(n)]) . U[seg(n), j],  a = softmax over the segment's rows,  Pool[seg, j] = sum_n a K[n]
-// K, PE in `dtype` (rows of E), U / Pool [n_segs*T*H, E] f32, S [rows, T*H] f32, lse [n_segs*T*H] f32.
-int t2i_fwd(const void* K, const void* PE, const float* U, const Segs& sg, int bag_layout, float* S, float* lse,
+// K in `dtype` (rows of E), PE fp32 (rows of E, row i = position i inside a segment), U / Pool [n_segs*T*H, E] f32, S [rows, T*H] f32, lse [n_segs*T*H] f32.
+int t2i_fwd(const void* K, const float* PE, const float* U, const Segs& sg, int bag_layout, float* S, float* lse,
             float* Pool, int dtype, void* ws, size_t ws_bytes, cudaStream_t st);
 // backward: dK (dtype; overwritten or accumulated in place) and dU [n_segs*T*H, E] f32 from dPool.
-int t2i_bwd(const void* K, const void* PE, const float* U, const float* S, const float* lse, const float* Pool,
+int t2i_bwd(const void* K, const float* PE, const float* U, const float* S, const float* lse, const float* Pool,
             const float* dPool, const Segs& sg, int bag_layout, void* dK, int accumulate_dk, float* dU, int dtype,
             void* ws, size_t ws_bytes, cudaStream_t st);
 
 // Y[out(n)] = LayerNorm(K[n] + R[seg(n)]) * gamma + beta  (R: ONE row per segment — the image -> token attention with
 // a single token).  bag_layout_out: rows are written at out_start (the packed bag) instead of k_start;
-// tokens != NULL additionally copies the T token rows of every segment to tok_row (cast to dtype).
+// tokens != NULL additionally copies the T token rows of every segment to tok_row (cast to out_dtype).  Storage pairs
+// (in, out): equal, or fp32 key stream -> bf16 packed bag (the last layer of a bf16 program).
 int ln_seg_fwd(const void* K, const float* R, const float* gamma, const float* beta, const float* tokens, const Segs& sg,
-               int bag_layout_out, void* Y, float* mean, float* rstd, int dtype, cudaStream_t st);
+               int bag_layout_out, void* Y, float* mean, float* rstd, int in_dtype, int out_dtype, cudaStream_t st);
 // dK (in place accumulate optional), dR [n_segs, E] f32, dgamma/dbeta (accumulate optional), dtokens [n_segs*T, E] f32
 // (= the token rows of dY; may be NULL)
 int ln_seg_bwd(const void* K, const float* R, const float* gamma, const float* mean, const float* rstd, const void* dY,
                const Segs& sg, int bag_layout_out, void* dK, int accumulate_dk, float* dR, float* dgamma, float* dbeta,
-               int accumulate_params, float* dtokens, int dtype, void* ws, size_t ws_bytes, cudaStream_t st);
+               int accumulate_params, float* dtokens, int in_dtype, int out_dtype, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // bag[tok_row[s] + t] = tokens[s*T + t] (cast to dtype) / dtokens[s*T + t] = dbag[tok_row[s] + t] (fp32)
 int tok_scatter(const float* tokens, const Segs& sg, void* bag, int dtype, cudaStream_t st);

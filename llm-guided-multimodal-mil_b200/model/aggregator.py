@@ -143,10 +143,13 @@ class aggregator(nn.Module):
         if t is None:
             t = Tape()
             E = self.embedding_dim
-            xp, ct = t.input("NP", 768), t.input("NC", E)
-            pe = t.input("NPE", E)
+            # Storage: the patch features (the big HBM stream) and the packed bag are in the program dtype; the key stream
+            # between them, the CT tokens, the position table and the whole token side are fp32 — in a bf16 program the
+            # only reduced-precision steps are then the tensor-core operands of fc_pathology and of the gated pool
+            xp, ct = t.input("NP", 768), t.input("NC", E, f32=True)
+            pe = t.input("NPE", E, f32=True)
             txt = t.input("BT", E, f32=True)
-            keys = t.join(t.linear(xp, self.fc_pathology[0], act="tanh"), ct, "NK")                  # :141 | CT tokens
+            keys = t.join(t.linear(xp, self.fc_pathology[0], act="tanh", out_f32=True), ct, "NK")    # :141 | CT tokens
             points = t.join(t.linear(txt, self.fc_CI2CT[0], act="tanh"),                             # :160 third argument
                             t.linear(txt, self.fc_CI2Pth[0], act="tanh"), "ST")                      # :168 third argument
             q, k = self.TwoWayTransformer_Both.emit_collapsed(t, keys, pe, points)
@@ -177,16 +180,18 @@ class aggregator(nn.Module):
                 "NBAG": bag_off[-1]}
         return rows, (tuple(segs), T), bag_off
 
-    def _pe_table(self, n, like):
+    def _pe_table(self, n, device):
+        """The cached fp32 position table (whole: its address never changes between calls), at least n rows."""
+        like = torch.empty(0, dtype=torch.float32, device=device)
         self._pe(n, like)
-        return self._pe_cache[(like.device, like.dtype)][0]          # the whole cached table: its address never changes
+        return self._pe_cache[(like.device, like.dtype)][0]
 
     def _forward_fused_v2(self, x_ct_tokens, x_path, x_text):
         Nc, Np = x_ct_tokens.shape[1], x_path.shape[1]
         rows, segs, _ = self.fusion_layout(Nc, [Np], 1)
-        pe = self._pe_table(max(Nc, Np), x_path)
+        pe = self._pe_table(max(Nc, Np), x_path.device)
         rows["NPE"] = pe.shape[0]
-        (bag,) = self._fusion_tape_v2().run(rows, [x_path[0], x_ct_tokens[0], pe, x_text[0].float()], segs=segs)
+        (bag,) = self._fusion_tape_v2().run(rows, [x_path[0], x_ct_tokens[0].float(), pe, x_text[0].float()], segs=segs)
         x0 = bag.unsqueeze(0)
         return x0, x0[:, :1], x0[:, 1 + Nc:2 + Nc]
 
@@ -203,11 +208,11 @@ class aggregator(nn.Module):
         if x_path.dim() != 2 or x_path.shape[0] != sum(path_lens) or min(path_lens) < 2 or Nc < 2:
             raise MilB200Error("forward_bags: x_path must be the packed (sum Np, 768) matrix; bags need >= 2 rows")
         rows, segs, bag_off = self.fusion_layout(Nc, path_lens, 1)
-        pe = self._pe_table(max(Nc, max(path_lens)), x_path)
+        pe = self._pe_table(max(Nc, max(path_lens)), x_path.device)
         rows["NPE"] = pe.shape[0]
         E = self.embedding_dim
-        (bag,) = self._fusion_tape_v2().run(rows, [x_path, ct_tokens.reshape(B * Nc, E), pe, x_text.reshape(B, E).float()],
-                                            segs=segs)
+        (bag,) = self._fusion_tape_v2().run(rows, [x_path, ct_tokens.reshape(B * Nc, E).float(), pe,
+                                                   x_text.reshape(B, E).float()], segs=segs)
         key = (tuple(bag_off), bag.device)
         cached = self.__dict__.setdefault("_bag_off_cache", {})
         if key not in cached:

@@ -78,9 +78,10 @@ class Tape:
             n = 0
         return _Lane()
 
-    def linear(self, x, lin, act=None, add=None):
-        """out = act((x [+ add]) W^T + b) for an ``nn.Linear`` parameter container."""
-        out = self.slot(self.slot_rows[x], lin.weight.shape[0], f32=self.slot_f32[x])
+    def linear(self, x, lin, act=None, add=None, out_f32=False):
+        """out = act((x [+ add]) W^T + b) for an ``nn.Linear`` parameter container.  out_f32: the result is an fp32 slot even
+        when x is stored in the program dtype (bf16 tensor-core operands, fp32 result: the head of an fp32 key stream)."""
+        out = self.slot(self.slot_rows[x], lin.weight.shape[0], f32=self.slot_f32[x] or out_f32)
         self.ops.append((L.OP_LINEAR, x, -1 if add is None else add, -1, out, self.param(lin.weight), self.param(lin.bias),
                          _ACT[act], self._lane))
         return out
@@ -139,7 +140,10 @@ class Tape:
         if abs(ln.eps - 1e-5) > 1e-12:
             raise L.MilB200Error("layernorm kernels are built for eps = 1e-5 (nn.LayerNorm default)")
         bag = out_rows_key is not None
-        out = self.slot(out_rows_key if bag else self.slot_rows[keys], self.slot_cols[keys], f32=self.slot_f32[keys])
+        # the packed bag is stored in the program dtype (it feeds the gated pool's tensor-core GEMMs); inside the stream the
+        # result keeps the storage of its input
+        out = self.slot(out_rows_key if bag else self.slot_rows[keys], self.slot_cols[keys],
+                        f32=False if bag else self.slot_f32[keys])
         self.ops.append((L.OP_LN_SEG, keys, rows, -1 if tokens is None else tokens, out, self.param(ln.weight),
                          self.param(ln.bias), 1 if bag else 0, self._lane))
         return out
