@@ -140,7 +140,7 @@ class FusionTrainer:
             b = dict(slots=slots, code=code, segp=segp,
                      arena=torch.empty(lib.milb200_tape_arena_bytes(c["ops"], c["n_ops"], slots, c["n_slots"], code, segp),
                                        dtype=torch.uint8, device=dev),
-                     out=[mk(fn(rows), cols) for fn, cols in t.buffers],
+                     out=[mk(fn(rows), cols, t.buffer_dtype(i, self.dtype)) for i, (fn, cols) in enumerate(t.buffers)],
                      stage=[mk(slots[s].rows, slots[s].cols, sdt(s)) for s in t.inputs],
                      z=torch.empty((B, Cn), dtype=f32, device=dev), prob=torch.empty((B, Cn), dtype=f32, device=dev),
                      dz=torch.empty((B, Cn), dtype=f32, device=dev), dM=torch.empty((B, E), dtype=f32, device=dev),
@@ -148,10 +148,8 @@ class FusionTrainer:
                      cos_rows=torch.empty(max(B * T, 1), dtype=f32, device=dev),
                      da=mk(B * T, E), db=mk(B * T, E),
                      offsets=torch.tensor(bag_off, dtype=torch.int32, device=dev))
-            if self.collapsed and B > 1:
-                Nc = rows["NC"] // B
-                b["r_ct"] = torch.tensor(bag_off[:-1], dtype=torch.int64, device=dev)
-                b["r_p"] = torch.tensor([o + 1 + Nc for o in bag_off[:-1]], dtype=torch.int64, device=dev)
+            if self.collapsed:      # gradient of the fp32 token rows [CT segments | pathology segments]: the cosine loss's
+                b["dtok"] = torch.zeros((2 * B * T, E), dtype=f32, device=dev)
             self._buf[key] = b
         return b
 
@@ -197,7 +195,7 @@ class FusionTrainer:
         ext = _ptrs(n_slots)
         for s, x in zip(t.inputs, inputs):
             ext[s] = x.data_ptr()
-        bag = b["out"][0]
+        bag, tok = b["out"][0], b["out"][1]
         for s, bi, fn in t.outputs:
             ext[s] = b["out"][bi].data_ptr()
         ws = L.workspace(lib.milb200_tape_workspace_bytes(c["ops"], c["n_ops"], slots, n_slots, code, 0, segp), self.device)
@@ -206,27 +204,22 @@ class FusionTrainer:
                                          code, segp, L.stream_ptr()), "tape_forward")
         self._set_targets(labels, B)
         dbag = self._pool_head_losses(b, bag, B)
-        if self.cosine_loss:
-            if B == 1:
-                a_rows, b_rows = bag[0:1], bag[1 + Nc:2 + Nc]                      # x_CT2CI, x_Pth2CI (aggregator.py:160,168)
-            else:
-                a_rows, b_rows = bag.index_select(0, b["r_ct"]), bag.index_select(0, b["r_p"])
-            L.check(lib.milb200_cosine_embedding_fwd_bwd(L.ptr(a_rows), L.ptr(b_rows), L.ptr(b["loss"][1:2]),
-                                                         L.ptr(b["cos_rows"]), L.ptr(b["da"]), L.ptr(b["db"]), B, E, code,
+        dtok = b["dtok"]
+        if not self.cosine_loss:
+            dtok.zero_()                  # the backward accumulates into the seeded buffers in place
+        else:
+            # x_CT2CI = token rows [0, B), x_Pth2CI = rows [B, 2B) of the fp32 token output (aggregator.py:160,168); the
+            # loss and its gradients stay fp32 and seed the token rows directly
+            L.check(lib.milb200_cosine_embedding_fwd_bwd(L.ptr(tok[:B]), L.ptr(tok[B:]), L.ptr(b["loss"][1:2]),
+                                                         L.ptr(b["cos_rows"]), L.ptr(dtok[:B]), L.ptr(dtok[B:]), B, E, L.F32,
                                                          L.stream_ptr()), "cosine_embedding")
-            if B == 1:
-                for rows_view, g in ((dbag[0:1], b["da"]), (dbag[1 + Nc:2 + Nc], b["db"])):   # both losses reach these rows
-                    L.check(lib.milb200_add(L.ptr(rows_view), L.ptr(g), L.ptr(rows_view), E, code, L.stream_ptr()), "add")
-            else:
-                dbag.index_add_(0, b["r_ct"], b["da"])
-                dbag.index_add_(0, b["r_p"], b["db"])
-        # backward of the fusion program: the gradient of the packed bag is seeded IN PLACE (seed == gradient buffer)
+        # backward of the fusion program: the gradients of the packed bag and of the token rows are seeded IN PLACE
         ext2, gext, seeds = _ptrs(n_slots), _ptrs(n_slots), _ptrs(n_slots)
         for s, x in zip(t.inputs, inputs):
             ext2[s] = x.data_ptr()
         for s, bi, fn in t.outputs:
             ext2[s] = b["out"][bi].data_ptr()
-            seeds[s] = gext[s] = dbag.data_ptr()
+            seeds[s] = gext[s] = (dbag if bi == 0 else dtok).data_ptr()
         ws = L.workspace(lib.milb200_tape_workspace_bytes(c["ops"], c["n_ops"], slots, n_slots, code, 1, segp), self.device)
         L.check(lib.milb200_tape_backward(c["ops"], c["n_ops"], slots, n_slots, c["params"], c["n_params"], ext2, gext, seeds,
                                           L.ptr(wcomp), L.ptr(self.params), L.ptr(self.grads), L.ptr(b["arena"]),

@@ -157,6 +157,9 @@ class aggregator(nn.Module):
             bag = t.buffer(lambda r: r["NBAG"], E)
             t.output(k, bag, lambda r: 0)
             t.output(full, bag, lambda r: 0)
+            # the final token rows also leave in fp32 (rows: CT segments, then pathology segments): x_CT2CI / x_Pth2CI and
+            # the cosine loss on them never see the packed bag's storage dtype
+            t.output(q, t.buffer(lambda r: r["ST"], E, f32=True), lambda r: 0)
             object.__setattr__(self, "_tape_cache_v2", t)
         return t
 
@@ -191,16 +194,15 @@ class aggregator(nn.Module):
         rows, segs, _ = self.fusion_layout(Nc, [Np], 1)
         pe = self._pe_table(max(Nc, Np), x_path.device)
         rows["NPE"] = pe.shape[0]
-        (bag,) = self._fusion_tape_v2().run(rows, [x_path[0], x_ct_tokens[0].float(), pe, x_text[0].float()], segs=segs)
-        x0 = bag.unsqueeze(0)
-        return x0, x0[:, :1], x0[:, 1 + Nc:2 + Nc]
+        bag, tok = self._fusion_tape_v2().run(rows, [x_path[0], x_ct_tokens[0].float(), pe, x_text[0].float()], segs=segs)
+        return bag.unsqueeze(0), tok[0:1].unsqueeze(0), tok[1:2].unsqueeze(0)          # x0, x_CT2CI, x_Pth2CI (fp32)
 
     def forward_bags(self, ct_tokens, x_path, path_lens, x_text):
         """The CT+pathology branch for B patients in ONE launch set (B200-native entry; the reference runs batch 1,
         train_ddp.py:75).  ct_tokens (B, Nc, 512): per-slice CT tokens (F.ct_tokens of the encoder's feature map);
         x_path (sum Np, 768): the patients' patch features packed row-wise; path_lens: their row counts (host ints);
-        x_text (B, 1, 512): one clinical-text embedding per patient.  Returns (prob (B, C) fp32, x_CT2CI (B, 1, 512),
-        x_Pth2CI (B, 1, 512)) — row b equals forward([ct_b, path_b], text_b)."""
+        x_text (B, 1, 512): one clinical-text embedding per patient.  Returns (prob (B, C), x_CT2CI (B, 1, 512),
+        x_Pth2CI (B, 1, 512)), all fp32 — row b equals forward([ct_b, path_b], text_b)."""
         B, Nc = int(ct_tokens.shape[0]), int(ct_tokens.shape[1])
         path_lens = [int(n) for n in path_lens]
         if len(path_lens) != B or x_text.shape[0] != B or x_text.shape[1] != 1 or 2 * B > 16:
@@ -211,20 +213,16 @@ class aggregator(nn.Module):
         pe = self._pe_table(max(Nc, max(path_lens)), x_path.device)
         rows["NPE"] = pe.shape[0]
         E = self.embedding_dim
-        (bag,) = self._fusion_tape_v2().run(rows, [x_path, ct_tokens.reshape(B * Nc, E).float(), pe,
-                                                   x_text.reshape(B, E).float()], segs=segs)
+        bag, tok = self._fusion_tape_v2().run(rows, [x_path, ct_tokens.reshape(B * Nc, E).float(), pe,
+                                                     x_text.reshape(B, E).float()], segs=segs)
         key = (tuple(bag_off), bag.device)
         cached = self.__dict__.setdefault("_bag_off_cache", {})
         if key not in cached:
             if len(cached) > 64:
                 cached.clear()
-            dev = bag.device
-            cached[key] = (torch.tensor(bag_off, dtype=torch.int32, device=dev),
-                           torch.tensor(bag_off[:-1], dtype=torch.int64, device=dev),
-                           torch.tensor([o + 1 + Nc for o in bag_off[:-1]], dtype=torch.int64, device=dev))
-        off, r_ct, r_p = cached[key]
-        prob = self._head(self.aggregator.forward_csr(bag, off, out_fp32=True))                   # :199-200
-        return prob, bag.index_select(0, r_ct).unsqueeze(1), bag.index_select(0, r_p).unsqueeze(1)
+            cached[key] = torch.tensor(bag_off, dtype=torch.int32, device=bag.device)
+        prob = self._head(self.aggregator.forward_csr(bag, cached[key], out_fp32=True))           # :199-200
+        return prob, tok[:B].unsqueeze(1), tok[B:].unsqueeze(1)
 
     def _forward_fused(self, x_ct_tokens, x_path, x_text):
         T, Nc, Np = x_text.shape[1], x_ct_tokens.shape[1], x_path.shape[1]

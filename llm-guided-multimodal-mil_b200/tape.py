@@ -155,9 +155,14 @@ class Tape:
         self.ops.append((L.OP_TOK_SCATTER, tokens, bag, -1, out, -1, -1, 0, self._lane))
         return out
 
-    def buffer(self, rows_fn, cols):
+    def buffer(self, rows_fn, cols, f32=False):
+        """An output buffer the caller receives; f32: fp32 whatever the program dtype (holds fp32 slots)."""
         self.buffers.append((rows_fn, int(cols)))
+        self.__dict__.setdefault("buffer_f32", []).append(bool(f32))
         return len(self.buffers) - 1
+
+    def buffer_dtype(self, i, dtype):
+        return torch.float32 if self.__dict__.get("buffer_f32", [False] * len(self.buffers))[i] else dtype
 
     def output(self, slot, buf, row_offset_fn):
         """Have `slot` written in place at row `row_offset_fn(rows)` of output buffer `buf`."""
@@ -165,6 +170,8 @@ class Tape:
             raise L.MilB200Error("tape.output: slot is already external")
         if self.slot_cols[slot] != self.buffers[buf][1]:
             raise L.MilB200Error("tape.output: column count differs from the buffer's")
+        if self.slot_f32[slot] != (self.buffer_dtype(buf, None) == torch.float32):
+            raise L.MilB200Error("tape.output: slot and buffer storage differ")
         self.slot_ext[slot] = 2
         self.outputs.append((slot, buf, row_offset_fn))
 
@@ -291,7 +298,8 @@ class _Pool:
         lib = L.lib()
         self.arena = torch.empty((lib.milb200_tape_arena_bytes(c["ops"], c["n_ops"], slots, c["n_slots"], code, segp),),
                                  dtype=torch.uint8, device=dev)
-        self.out = [torch.empty((int(fn(rows)), cols), dtype=dtype, device=dev) for fn, cols in tape.buffers]
+        self.out = [torch.empty((int(fn(rows)), cols), dtype=tape.buffer_dtype(i, dtype), device=dev)
+                    for i, (fn, cols) in enumerate(tape.buffers)]
         self.in_stage = [None] * len(tape.inputs)
         self.last_ptr = [0] * len(tape.inputs)
         self.seed = [torch.empty_like(b) for b in self.out]
@@ -346,15 +354,15 @@ class _TapeFn(torch.autograd.Function):
             inputs = [pool.stage_input(j, t) for j, t in enumerate(inputs)]
             bufs, arena = pool.out, pool.arena
         else:
-            bufs = [torch.empty((int(fn(rows)), cols), dtype=dtype, device=dev) for fn, cols in tape.buffers]
+            bufs = [torch.empty((int(fn(rows)), cols), dtype=tape.buffer_dtype(i, dtype), device=dev)
+                    for i, (fn, cols) in enumerate(tape.buffers)]
             arena = torch.empty((lib.milb200_tape_arena_bytes(c["ops"], c["n_ops"], slots, c["n_slots"], code, segp),),
                                 dtype=torch.uint8, device=dev)
         ext = _ptr_array(c["n_slots"])
         for s, t in zip(tape.inputs, inputs):
             ext[s] = t.data_ptr()
-        esz = bufs[0].element_size()
         for s, b, fn in tape.outputs:
-            ext[s] = bufs[b].data_ptr() + int(fn(rows)) * tape.slot_cols[s] * esz
+            ext[s] = bufs[b].data_ptr() + int(fn(rows)) * tape.slot_cols[s] * bufs[b].element_size()
         ws = L.workspace(lib.milb200_tape_workspace_bytes(c["ops"], c["n_ops"], slots, c["n_slots"], code, 0, segp), dev)
         L.check(lib.milb200_tape_forward(c["ops"], c["n_ops"], slots, c["n_slots"], c["params"], c["n_params"], ext, L.ptr(wc),
                                          L.ptr(p32), L.ptr(arena), arena.numel(), L.ptr(ws), ws.numel(), code, segp,
@@ -380,10 +388,9 @@ class _TapeFn(torch.autograd.Function):
         c = tape._freeze()
         slots = tape._slots(rows)
         segp = tape._segments(ctx.segs)
-        dev, dtype = bufs[0].device, bufs[0].dtype
-        esz = bufs[0].element_size()
+        dev = bufs[0].device
         gouts = [(g.contiguous() if g is not None else torch.zeros_like(b)) for g, b in zip(gouts, bufs)]
-        gouts = [g if g.dtype == dtype else F.cast(g, dtype) for g in gouts]
+        gouts = [g if g.dtype == b.dtype else F.cast(g, b.dtype) for g, b in zip(gouts, bufs)]
         # the upstream gradients are copied once into buffers this call owns; every output slot's gradient buffer is its
         # row range of that copy, seeded in place (seed pointer == gradient pointer: the C side skips its own copy)
         if pool is not None:
@@ -410,7 +417,7 @@ class _TapeFn(torch.autograd.Function):
             else:
                 gin.append(None)
         for i, (s, b, fn) in enumerate(tape.outputs):
-            off = int(fn(rows)) * tape.slot_cols[s] * esz
+            off = int(fn(rows)) * tape.slot_cols[s] * bufs[b].element_size()
             ext[s] = bufs[b].data_ptr() + off
             seeds[s] = gext[s] = gouts[b].data_ptr() + off
         g32 = pool.g32 if pool is not None else torch.empty((c["total"],), dtype=torch.float32, device=dev)
