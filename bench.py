@@ -197,6 +197,85 @@ def cpu_reference(lengths, steps, warmup, budget_s=20.0, per_step=4):
             "ms_per_step": 1e3 * total / len(times), "steps": len(times), "bags_per_step": per_step}
 
 
+def torch_eager_fusion_gpu(model, x_ct_tok, x_p, x_t, label, dtype, steps=5):
+    """BASELINE ONLY (the "real bar" for BASELINE configs[2]): the reference's CT+pathology `aggregator.forward`
+    (model/aggregator.py:134-203 over model/sam/transformer.py:58-120,278-309,418-450, eval mode) written with STOCK torch
+    ops on the same GPU — nn.functional.linear / layer_norm / softmax, projected K and V for every image token as upstream,
+    autograd backward, torch.optim.Adam — one patient per step as train_ddp.py:75 feeds it.  None of our kernels."""
+    import math
+    import torch
+    import torch.nn.functional as Fn
+    sd = {k: v.detach().to(dtype).clone().requires_grad_(True) for k, v in model.state_dict().items()
+          if v.is_floating_point() and not k.startswith(("TwoWayTransformer_CT", "TwoWayTransformer_Pth", "extractor_pathology",
+                                                         "fc_CI.", "prompt_embedding"))}
+    opt = torch.optim.Adam(list(sd.values()), lr=1e-5, betas=(0.9, 0.999), weight_decay=1e-7)
+    lin = lambda pre, x: Fn.linear(x, sd[pre + ".weight"], sd[pre + ".bias"])
+    ln = lambda pre, x: Fn.layer_norm(x, (x.shape[-1],), sd[pre + ".weight"], sd[pre + ".bias"], 1e-5)
+
+    def attn(pre, q, k, v, heads=8):
+        q, k, v = lin(pre + ".q_proj", q), lin(pre + ".k_proj", k), lin(pre + ".v_proj", v)
+        c = q.shape[-1] // heads
+        sp = lambda t: t.reshape(t.shape[0], heads, c).transpose(0, 1)
+        a = torch.softmax(sp(q) @ sp(k).transpose(1, 2) / math.sqrt(c), dim=-1)
+        return lin(pre + ".out_proj", (a @ sp(v)).transpose(0, 1).reshape(q.shape[0], heads * c))
+
+    def twoway(img, pe, pts):
+        pre = "TwoWayTransformer_Both"
+        qs, ks = pts, img
+        for i in range(2):
+            lp = f"{pre}.layers.{i}"
+            qs = ln(lp + ".norm1", attn(lp + ".self_attn", qs, qs, qs) if i == 0 else
+                    qs + attn(lp + ".self_attn", qs + pts, qs + pts, qs))
+            qs = ln(lp + ".norm2", qs + attn(lp + ".cross_attn_token_to_image", qs + pts, ks + pe, ks))
+            qs = ln(lp + ".norm3", qs + lin(lp + ".mlp.lin2", torch.relu(lin(lp + ".mlp.lin1", qs))))
+            ks = ln(lp + ".norm4", ks + attn(lp + ".cross_attn_image_to_token", ks + pe, qs + pts, qs))
+        qs = ln(pre + ".norm_final_attn", qs + attn(pre + ".final_attn_token_to_image", qs + pts, ks + pe, ks))
+        return qs, ks
+
+    pe_tab = model._pe_table(max(x_ct_tok.shape[0], x_p.shape[0]), x_p.device).to(dtype)
+    ct, xp, xt = x_ct_tok.to(dtype), x_p.to(dtype), x_t.to(dtype)
+
+    def one_step():
+        opt.zero_grad(set_to_none=True)
+        xin = torch.tanh(lin("fc_pathology.0", xp))
+        q1, k1 = twoway(ct, pe_tab[:ct.shape[0]], torch.tanh(lin("fc_CI2CT.0", xt)))
+        q2, k2 = twoway(xin, pe_tab[:xin.shape[0]], torch.tanh(lin("fc_CI2Pth.0", xt)))
+        bag = torch.cat([q1, k1, q2, k2], dim=0)
+        A = lin("aggregator.attention_weights", torch.tanh(lin("aggregator.attention_V.0", bag)) *
+                torch.sigmoid(lin("aggregator.attention_U.0", bag)))
+        M = torch.softmax(A.transpose(1, 0), dim=1) @ bag
+        prob = torch.sigmoid(lin("fc.1", M))
+        loss = Fn.binary_cross_entropy(prob.float(), label) + (1 - Fn.cosine_similarity(q1.float(), q2.float())).mean()
+        loss.backward()
+        opt.step()
+
+    one_step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        one_step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    return {"ms_per_bag": ms, "bags_per_s": 1e3 / ms, "dtype": str(dtype).replace("torch.", ""),
+            "what": "stock torch eager on the same GPU, one patient per step, fwd+bwd+Adam (baseline, not the product)"}
+
+
+# Work per patient of the CT+pathology fusion step, N pathology rows, 160 CT tokens, one text token (DESIGN.md §5b):
+#  * what the REFERENCE formulation executes (fc_pathology fwd + dW, 6 image-side K/V projection GEMMs fwd + dW + dX,
+#    gated pool L = 512 fwd + dW + dX): the figure the round-1 review used for "useful work"
+#  * HBM bytes of the COLLAPSED formulation (csrc/xfusion.cu; fp32 key stream, bf16 patch features and packed bag):
+#    every pass listed in DESIGN.md §5b, read + write
+def fusion_work_per_patient(n_path, n_ct=160):
+    n = n_path + n_ct
+    ref_flops = 2.0 * n_path * 768 * 512 * 2 + 6 * 2.0 * n * 512 * 256 * 3 + 12.0 * (n + 2) * 512 * 192
+    fwd = n_path * 768 * 2 + n_path * 512 * 4 + 2 * (n * 512 * 8) + (n * 512 * 8) + (n * 512 * 6) + (n * 512 * 6) + 2 * n * 512 * 2
+    bwd = (3 * n * 512 * 2) + (n * 512 * 10) + (n * 512 * 10) + (n * 512 * 16) + (n * 512 * 12) + (n * 512 * 16) + \
+          (n_path * 512 * 10) + n_path * 512 * 2 + n_path * 768 * 2
+    return ref_flops, float(fwd + bwd)
+
+
 def secondary_fusion(dev):
     """BASELINE configs[2]: the multimodal aggregator (fc_pathology -> two TwoWayTransformer calls -> packed bag -> gated
     pool -> head) forward+backward on ONE WSI-scale bag per call, as the reference trains (train_ddp.py:75), bf16, through
@@ -255,6 +334,48 @@ def secondary_fusion(dev):
                     "ms_per_bag": ms, "bags_per_s": 1e3 / ms, "kernels_per_bag": (mil_b200.launch_count() - l0) / 10,
                     "api": "FusionTrainer.step (flat parameter/gradient buffers, BCE + cosine loss, fused Adam)"})
         del tr
+        if T == 1:
+            # B patients per launch set (FusionTrainer.step_bags, collapsed program): the token side (~150 small launches) is
+            # shared by the B patients; roofline = HBM bytes of the collapsed formulation / time against the measured peak
+            peaks, _ = load_peaks()
+            hbm_peak = float(peaks.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"]))
+            tf_sus = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"])))
+            ref_flops, hbm_bytes = fusion_work_per_patient(N)
+            for Bp in (1, 4, 8):
+                trb = mil_b200.FusionTrainer(m, n_text_tokens=1, compute_dtype=torch.bfloat16)
+                ctb = tok.unsqueeze(0).repeat(Bp, 1, 1).contiguous()
+                xpb = x_p[0].repeat(Bp, 1).contiguous()
+                xtb = x_t[0].repeat(Bp, 1).contiguous()
+                lab = label.repeat(Bp, 1).contiguous()
+                lens_b = [N] * Bp
+                for _ in range(4):
+                    trb.step_bags(ctb, xpb, lens_b, xtb, lab)
+                torch.cuda.synchronize()
+                l0 = mil_b200.launch_count()
+                e0.record()
+                for _ in range(10):
+                    trb.step_bags(ctb, xpb, lens_b, xtb, lab)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 10
+                out.append({"workload": f"aggregator CT+pathology fwd+bwd+Adam, {Bp} patient(s) per step, N={N} x 768 + 160 CT "
+                                        f"tokens each, T=1, bf16 (fp32 key stream / token side)",
+                            "ms_per_step": ms, "ms_per_bag": ms / Bp, "bags_per_s": Bp * 1e3 / ms,
+                            "kernels_per_bag": (mil_b200.launch_count() - l0) / 10 / Bp,
+                            "api": "FusionTrainer.step_bags (collapsed program, csrc/xfusion.cu)",
+                            "roofline": {"bound": "hbm", "achieved": hbm_bytes * Bp / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                                         "frac": hbm_bytes * Bp / ms / 1e6 / hbm_peak,
+                                         "algorithmic": "HBM bytes of the collapsed formulation per patient (DESIGN 5b)",
+                                         "reference_formulation_tflops": ref_flops * Bp / ms / 1e9,
+                                         "reference_formulation_frac_of_sustained_tensor_peak": ref_flops * Bp / ms / 1e9 / tf_sus}})
+                del trb, xpb
+            try:
+                out.append(dict(torch_eager_fusion_gpu(m, tok, x_p[0], x_t[0], label, torch.float32),
+                                workload=f"same step, stock torch eager, fp32, N={N}"))
+                out.append(dict(torch_eager_fusion_gpu(m, tok, x_p[0], x_t[0], label, torch.bfloat16),
+                                workload=f"same step, stock torch eager, bf16, N={N}"))
+            except Exception as e:
+                out.append({"workload": "stock torch eager fusion step", "error": repr(e)[:200]})
 
     def timed(fn, reps=10):
         for _ in range(3):
@@ -317,6 +438,177 @@ def secondary_fusion(dev):
     return out
 
 
+def dp_equivalence_check(tr, module, X, offsets_h, lengths, rank, world, dev, pg):
+    """N > 1 correctness signal in every bench run (train_ddp.py:79): on a small verification batch (the first rows of two
+    bags per rank) the gradients after the exchange must equal those of ONE process over the union of all ranks' bags.
+    Uses fresh trainers with the bench's parameters; the exchange is the one the timed run uses."""
+    import torch
+    import torch.distributed as dist
+    from mil_b200.dp import AbmilTrainer
+    rows = 1500
+    offs = offsets_h.tolist()
+    picks = [b for b in range(len(lengths)) if int(lengths[b]) >= rows][:2]
+    mineX = torch.stack([X[offs[b]:offs[b] + rows] for b in picks])                        # [2, rows, L]
+    gathered = [torch.empty_like(mineX) for _ in range(world)]
+    dist.all_gather(gathered, mineX, group=pg)
+    off_local = torch.tensor([0, rows, 2 * rows], dtype=torch.int32, device=dev)
+    dpt = AbmilTrainer(tr.L, tr.D, tr.dtype, device=dev, process_group=pg, world_size=world)
+    dpt.params.copy_(tr.params)
+    symm = getattr(tr, "_symm", None) is not None and dpt.enable_symmetric_exchange()
+    dpt.forward_backward(mineX.reshape(2 * rows, tr.L), off_local)
+    if symm:
+        dpt.lr = 0.0                       # exchange kernel = reduce + update: a zero-step update leaves the summed gradients
+        dpt.wd = 0.0
+        dpt.reduce_and_update()
+    else:
+        dpt.allreduce_grads()
+    one = AbmilTrainer(tr.L, tr.D, tr.dtype, device=dev)
+    one.params.copy_(tr.params)
+    Xu = torch.cat([g.reshape(2 * rows, tr.L) for g in gathered])
+    offu = torch.arange(0, 2 * world + 1, dtype=torch.int32, device=dev) * rows
+    one.forward_backward(Xu, offu)
+    err = float((dpt.grads.double() - one.grads.double()).abs().max() / one.grads.double().abs().max())
+    hi, lo = dpt.grads.clone(), dpt.grads.clone()
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=pg)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=pg)
+    same = bool(torch.equal(hi, lo))
+    if err > 2e-3 or not same:
+        raise SystemExit(f"bench: data-parallel check failed: exchanged gradients vs single-process union rel err {err:.3e}, "
+                         f"identical across ranks: {same}")
+    return {"exchanged_grads_vs_single_process_union_rel_err": err, "grads_identical_across_ranks": same,
+            "batch": f"{2 * world} bags x {rows} rows (two per rank)", "exchange": "symmetric-memory kernel" if symm else "nccl"}
+
+
+def fusion_main(args, out):
+    """BASELINE configs[2] / configs[4]: data-parallel training step of the CT+pathology aggregator — FusionTrainer.step_bags,
+    `--patients` patients per rank per step (WSI-scale: 15 592 pathology rows x 768 + 160 CT tokens + one clinical-text
+    token each), bf16 storage, BCE + cosine loss, gradient exchange, fused Adam inside the timed region.  One JSON line."""
+    import torch
+    import torch.distributed as dist
+    from argparse import Namespace
+    import mil_b200
+    warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (B200); there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    N, Nc, Bp = 15592, 160, max(1, min(8, args.patients))
+    ns = Namespace(modality=["CT", "pathology"], model_CT="resnetMC3_18", model_pathology="ABMIL", model_CI="none",
+                   aggregator="ABMIL", num_classes=2, alignment_base="none", clinical_features=list("abcdefghi"))
+    torch.manual_seed(1234)
+    m = mil_b200.get_model(ns).to(dev).eval()
+    tr = mil_b200.FusionTrainer(m, n_text_tokens=1, compute_dtype=torch.bfloat16, process_group=pg, world_size=world)
+    tr.broadcast_params()
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    ct = torch.randn(Bp, Nc, 512, device=dev, generator=gen).to(torch.bfloat16)
+    xp = torch.randn(Bp * N, 768, device=dev, generator=gen).to(torch.bfloat16)
+    xt = (torch.randn(Bp, 512, device=dev, generator=gen) * 0.05).to(torch.bfloat16)
+    labels = torch.tensor([[0.0, 1.0], [1.0, 0.0]] * Bp, device=dev)[:Bp].contiguous()
+    lens = [N] * Bp
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        tr.step_bags(ct, xp, lens, xt, labels)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    l0 = mil_b200.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        tr.step_bags(ct, xp, lens, xt, labels)
+    e1.record()
+    barrier()
+    launches = mil_b200.launch_count() - l0
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = Bp * world * args.steps / (ms_max / 1e3)
+    # end to end: host (pinned) patient data, H2D inside the timed region, loss/prob read back every step
+    xp_h = torch.empty_like(xp, device="cpu").pin_memory()
+    xp_h.copy_(xp)
+    ct_h, xt_h = ct.cpu().pin_memory(), xt.cpu().pin_memory()
+    xp_d, ct_d, xt_d = torch.empty_like(xp), torch.empty_like(ct), torch.empty_like(xt)
+    res_h = torch.empty(2 + Bp * 2, dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, min(args.steps, 10))
+
+    def e2e_run(n):
+        s = 0.0
+        for _ in range(n):
+            xp_d.copy_(xp_h, non_blocking=True)
+            ct_d.copy_(ct_h, non_blocking=True)
+            xt_d.copy_(xt_h, non_blocking=True)
+            loss, prob = tr.step_bags(ct_d, xp_d, lens, xt_d, labels)
+            res_h[:2].copy_(loss, non_blocking=True)
+            res_h[2:].copy_(prob.reshape(-1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            s += float(res_h[0])
+        return s
+    e2e_run(2)
+    barrier()
+    e0.record()
+    e2e_run(e2e_steps)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    params_same = None
+    if world > 1:
+        hi, lo = tr.params.clone(), tr.params.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        params_same = bool(torch.equal(hi, lo))
+        if not params_same:
+            raise SystemExit("bench: parameters differ across ranks after the run — the gradient exchange is broken")
+    if rank == 0:
+        peaks, peak_src = load_peaks()
+        hbm_peak = float(peaks.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"]))
+        ref_flops, hbm_bytes = fusion_work_per_patient(N, Nc)
+        ms_step = ms_max / args.steps
+        line = {"metric": "bags/sec fwd+bwd", "value": value, "unit": "bags/s", "n_gpus": world, "steps": args.steps,
+                "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": f"data-parallel training step of the CT+pathology aggregator (BASELINE configs[2]/[4]): "
+                                       f"{Bp} patients per rank per step, {N} pathology rows x 768 + {Nc} CT tokens + 1 clinical-"
+                                       f"text token each, BCE + cosine loss, one all-reduce of the {tr.numel * 4 / 1e6:.0f} MB flat "
+                                       f"gradient buffer, fused Adam; FusionTrainer.step_bags (collapsed program, csrc/xfusion.cu)",
+                           "patients_per_rank": Bp, "parallelism": f"dp{world}",
+                           "storage": "bf16 patch features / packed bag / tensor-core operands, fp32 key stream and token side",
+                           "cache": "patient data (~96 MB/patient) cycles through HBM; parameters + optimiser state 160 MB > L2"},
+                "gpu_launches": int(launches), "kernels_per_bag": launches / args.steps / Bp,
+                "e2e": {"value": Bp * world * e2e_steps / (e2e_ms / 1e3), "unit": "bags/s",
+                        "h2d_bytes_per_step": int(xp_h.numel() * 2 + ct_h.numel() * 2 + xt_h.numel() * 2),
+                        "d2h_bytes_per_step": int(res_h.numel() * 4), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+                "roofline": {"bound": "hbm", "achieved": hbm_bytes * Bp / ms_step / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": hbm_bytes * Bp / ms_step / 1e6 / hbm_peak, "traffic": None, "peak_source": peak_src,
+                             "kernel": "whole step (HBM bytes of the collapsed formulation per patient, DESIGN 5b)",
+                             "reference_formulation_tflops": ref_flops * Bp / ms_step / 1e9},
+                "cpu_baseline": None, "clocks": clocks, "params_identical_across_ranks_after_run": params_same}
+        out.write(json.dumps(line) + "\n")
+        out.flush()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def _claim_stdout():
     """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner to stdout) must not add
     to it: point fd 1 at stderr for the whole run and return a writer on the original stdout for the final line."""
@@ -339,7 +631,16 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="skip the fusion-path (cfg 3) side measurement")
     ap.add_argument("--recompute-gate", action="store_true",
                     help="backward re-runs the gate GEMM instead of reading the V,U activations saved by the forward")
+    ap.add_argument("--workload", default="abmil", choices=["abmil", "fusion"],
+                    help="abmil: BASELINE configs[1] (the headline metric); fusion: BASELINE configs[2]/[4], the data-parallel "
+                         "training step of the CT+pathology aggregator (FusionTrainer.step_bags)")
+    ap.add_argument("--deal-bags", action="store_true",
+                    help="abmil, world > 1: deal ONE draw of bags x world lengths to the ranks longest-first (dp.shard_bags) "
+                         "instead of giving every rank the lengths of the single-GPU workload")
+    ap.add_argument("--patients", type=int, default=4, help="fusion: patients per rank per step (<= 8)")
     args = ap.parse_args()
+    if args.workload == "fusion" and args.impl == "ours":
+        return fusion_main(args, out)
     warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -347,9 +648,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     config = {"workload": f"gated-attention MIL fwd+bwd, ragged bags {LEN_LO}-{LEN_HI} instances x {L_FEAT}-dim "
-                          f"(BASELINE configs[1]), {args.bags} bags per rank per step on average, packed CSR, D={D_GATE}; the "
-                          f"step's {args.bags} x world bags (lengths randint seed 1234) are dealt to the ranks longest-first by "
-                          f"instance count (dp.shard_bags, SURVEY 8e); world = 1: exactly the 64-bag workload",
+                          f"(BASELINE configs[1]), {args.bags} bags per rank per step, packed CSR, D={D_GATE}; " +
+                          (f"the step's {args.bags} x world bags (lengths randint seed 1234) are dealt to the ranks longest-first "
+                           f"by instance count (dp.shard_bags, SURVEY 8e)" if args.deal_bags else
+                           f"every rank runs the bag LENGTHS of the single-GPU workload (randint seed 1234, its own data): "
+                           f"per-GPU work is identical at every N, so the scaling efficiency measures the exchange alone"),
               "bags_per_rank": args.bags, "L": L_FEAT, "D": D_GATE, "parallelism": f"dp{world}",
               "input_grad": bool(args.input_grad),
               "cache": "inputs (~1.3 GB/rank) exceed the 126 MB L2, no flush needed",
@@ -388,10 +691,14 @@ def main():
 
     peaks, peak_src = load_peaks()
     from mil_b200.dp import shard_bags
-    all_lengths = bag_lengths(args.bags * world, 1234)            # world = 1: the 64 bags of the single-GPU workload
-    mine = shard_bags(all_lengths.tolist(), rank, world, balance=True)
-    lengths = all_lengths[mine]
-    n_bags = len(mine)
+    if args.deal_bags:
+        all_lengths = bag_lengths(args.bags * world, 1234)
+        mine = shard_bags(all_lengths.tolist(), rank, world, balance=True)
+        lengths = all_lengths[mine]
+    else:
+        lengths = bag_lengths(args.bags, 1234)                    # the 64 bags of the single-GPU workload, on every rank
+        all_lengths = lengths.repeat(world)
+    n_bags = len(lengths)
     offsets_h = torch.zeros(n_bags + 1, dtype=torch.int32)
     offsets_h[1:] = lengths.cumsum(0).to(torch.int32)
     total_n = int(offsets_h[-1])
@@ -406,11 +713,19 @@ def main():
                       world_size=world, need_input_grad=args.input_grad, save_gate=not args.recompute_gate)
     tr.load_from(module)
     tr.broadcast_params()
+    exchange = "none (single GPU)"
+    if world > 1:
+        symm_on = os.environ.get("MILB200_SYMM", "1") != "0" and tr.enable_symmetric_exchange()
+        exchange = ("one kernel: multimem.ld_reduce/st over NVSwitch symmetric memory + fused Adam (csrc/exchange.cu)" if symm_on
+                    else "ncclAllReduce of the flat fp32 gradient buffer + fused Adam kernel")
+    config["exchange"] = exchange
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    dp_check = dp_equivalence_check(tr, module, X, offsets_h, lengths, rank, world, dev, pg) if world > 1 else None
 
     # ---- device-resident timing ----
     for _ in range(warmup):
@@ -746,6 +1061,15 @@ def main():
         except Exception as e:
             secondary["torch_eager_same_gpu"] = {"error": repr(e)[:200]}
 
+    params_same = None
+    if world > 1:      # the replicas must still be bit-identical after every timed step (a broken exchange would not be)
+        hi, lo = tr.params.clone(), tr.params.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        params_same = bool(torch.equal(hi, lo))
+        if not params_same:
+            raise SystemExit("bench: parameters differ across ranks after the run — the gradient exchange is broken")
+
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_base = cpu_reference(lengths, steps=10 ** 6, warmup=1, budget_s=12.0)   # ~12 s of CPU work over the same bags
@@ -769,7 +1093,8 @@ def main():
                 "gpu_launches": int(launches),
                 "e2e": {"value": e2e_value, "unit": "bags/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
-                "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_base, "clocks": clocks, "secondary": secondary}
+                "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_base, "clocks": clocks, "secondary": secondary,
+                "dp_check": dp_check, "params_identical_across_ranks_after_run": params_same}
         out.write(json.dumps(line) + "\n")
         out.flush()
     if world > 1:

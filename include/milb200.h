@@ -325,6 +325,20 @@ int milb200_adam_step(float* param, const float* grad, float* exp_avg, float* ex
 int milb200_sgd_step(float* param, const float* grad, int64_t n, float lr, float weight_decay, float grad_scale,
                      void* stream);
 
+/* ---- gradient exchange + optimiser as ONE kernel over NVLink / NVSwitch peer memory -------------------------------
+ * Replaces DDP's bucketed NCCL all-reduce + optimizer.step() (train_ddp.py:79,346-348) for one flat fp32 gradient buffer
+ * that lives in symmetric memory (the same allocation mapped on every rank of the node; the host side obtains the
+ * mappings from torch.distributed's symmetric memory): grad_local = this rank's mapping, grad_multicast = the multicast
+ * mapping, signal_pads_dev = device array of `world` pointers to the ranks' zero-initialised uint32 signal pads (at least
+ * pad_slot0 + 32 * world entries each).  Slice r of the buffer is reduced in the switch (multimem.ld_reduce) and
+ * broadcast (multimem.st) by rank r, between two flag barriers; then every rank applies the fused optimiser update
+ * (optimizer 0: Adam, 1: SGD) with grad_scale (1/world = DDP's average).  On return the gradient buffer holds the SUM over
+ * ranks — bit-identical on every rank.  The allocation must be padded to a multiple of 4 * world elements.              */
+int milb200_allreduce_update_symm(float* param, float* grad_local, void* grad_multicast, void* const* signal_pads_dev,
+                                  int pad_slot0, int rank, int world, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                  int optimizer, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                  float grad_scale, int step, void* stream);
+
 /* ---- feeder, host side (dataset.py:366-393) ---------------------------------------------------------
  * Gathers the per-slide feature matrices of one step (what `np.load(<patient>.npy)` returns: [rows_b, L] row-major
  * HOST memory, fp32/fp64/fp16/bf16) into the packed-CSR batch the kernels read: rows back to back in `dst` (normally

@@ -38,6 +38,30 @@ template <typename TK> __device__ __forceinline__ float xexp(float x);
 template <> __device__ __forceinline__ float xexp<float>(float x) { return expf(x); }
 template <> __device__ __forceinline__ float xexp<__nv_bfloat16>(float x) { return __expf(x); }
 
+// Sums of 8 per-lane values over the warp, every lane ends with all 8 sums: a halving butterfly (4 + 2 + 1 exchanges), two
+// plain steps and 8 broadcasts = 17 shuffles instead of 8 x 5.  After the butterfly lane l holds the sum of value
+// j = 4 bit4(l) + 2 bit3(l) + bit2(l).  The association is fixed, so results are reproducible.
+__device__ __forceinline__ void warp_sum8(float* v, int lane) {
+  const unsigned full = 0xffffffffu;
+  const bool h4 = lane & 16, h3 = lane & 8, h2 = lane & 4;
+  float a[4], b[2];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float send = h4 ? v[k] : v[k + 4], keep = h4 ? v[k + 4] : v[k];
+    a[k] = keep + __shfl_xor_sync(full, send, 16);
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    const float send = h3 ? a[k] : a[k + 2], keep = h3 ? a[k + 2] : a[k];
+    b[k] = keep + __shfl_xor_sync(full, send, 8);
+  }
+  float c = (h2 ? b[1] : b[0]) + __shfl_xor_sync(full, h2 ? b[0] : b[1], 4);
+  c += __shfl_xor_sync(full, c, 2);
+  c += __shfl_xor_sync(full, c, 1);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __shfl_sync(full, c, ((j & 4) ? 16 : 0) | ((j & 2) ? 8 : 0) | ((j & 1) ? 4 : 0));
+}
+
 // ---- a 512-wide row spread over a warp ------------------------------------------------------------------------------
 // Lane l owns the 16-byte vectors l, l+32, ... of the row: value idx = i*VN + e  <->  column (l + 32 i) * VN + e.
 template <typename TK> struct Row {
@@ -157,13 +181,24 @@ k_t2i_fwd(const TK* __restrict__ K, const float* __restrict__ PE, const float* _
 #pragma unroll
     for (int e = 0; e < 16; ++e) acc[j][e] = 0.f;
   }
-  for (int i = i0 + warp; i < i1; i += WARPS) {
+  // the next row's loads are issued before the current row's arithmetic (one CTA per SM at ~200 registers: the warp has
+  // to cover its own memory latency)
+  float kv[16], pe[16], kvn[16], pen[16];
+  int i = i0 + warp;
+  if (i < i1) {
+    Row<TK>::load(K + (base + i) * E, lane, kv);
+    load_f32_row<TK>(PE + static_cast<int64_t>(i) * E, lane, pe);
+  }
+  for (; i < i1; i += WARPS) {
     const int64_t n = base + i;
-    float kv[16], kp[16];
-    Row<TK>::load(K + n * E, lane, kv);
-    load_f32_row<TK>(PE + static_cast<int64_t>(i) * E, lane, kp);
+    const int inext = i + WARPS;
+    if (inext < i1) {
+      Row<TK>::load(K + (base + inext) * E, lane, kvn);
+      load_f32_row<TK>(PE + static_cast<int64_t>(inext) * E, lane, pen);
+    }
+    float kp[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) kp[e] += kv[e];
+    for (int e = 0; e < 16; ++e) kp[e] = pe[e] + kv[e];
     float sc[H];
 #pragma unroll
     for (int j = 0; j < H; ++j) {
@@ -172,8 +207,11 @@ k_t2i_fwd(const TK* __restrict__ K, const float* __restrict__ PE, const float* _
       float d = 0.f;
 #pragma unroll
       for (int e = 0; e < 16; ++e) d = fmaf(kp[e], u[e], d);
-      sc[j] = warp_sum(d) * SCALE;
+      sc[j] = d;
     }
+    warp_sum8(sc, lane);
+#pragma unroll
+    for (int j = 0; j < H; ++j) sc[j] *= SCALE;
     float mine = 0.f;
 #pragma unroll
     for (int j = 0; j < H; ++j) mine = (lane == j) ? sc[j] : mine;
@@ -192,6 +230,8 @@ k_t2i_fwd(const TK* __restrict__ K, const float* __restrict__ PE, const float* _
 #pragma unroll
       for (int e = 0; e < 16; ++e) acc[j][e] = fmaf(w, kv[e], acc[j][e]);
     }
+#pragma unroll
+    for (int e = 0; e < 16; ++e) { kv[e] = kvn[e]; pe[e] = pen[e]; }
   }
   if (lane == 0) {
 #pragma unroll
@@ -231,32 +271,92 @@ k_t2i_fwd(const TK* __restrict__ K, const float* __restrict__ PE, const float* _
   }
 }
 
-// grid (n_segs*T*H), 128 threads: merge the items of a segment in item order
-__global__ void __launch_bounds__(128)
+// Sum of per-item partial rows [E], optionally weighted: the block's 512 threads are 128 float4 columns x 4 item slices
+// (slice q takes items p0 + q, p0 + q + 4, ...; four loads in flight per thread), the slices are folded in fixed order.
+constexpr int MERGE_THREADS = 512;
+constexpr int MERGE_MAX_ITEMS = 2048;      // per segment (weights staged in shared memory)
+template <bool WEIGHTED>
+__device__ __forceinline__ float4 merge_items(const float* __restrict__ part, int64_t row_stride, int64_t row0, int p0, int p1,
+                                              const float* wsm, float4* red) {
+  const int c = (threadIdx.x & 127) * 4, q = threadIdx.x >> 7;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  int p = p0 + q;
+  for (; p + 12 < p1; p += 16) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float4*>(part + (row0 + (p + 4 * k) * row_stride) * E + c);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float f = WEIGHTED ? wsm[p + 4 * k - p0] : 1.f;
+      a.x = fmaf(f, v[k].x, a.x); a.y = fmaf(f, v[k].y, a.y); a.z = fmaf(f, v[k].z, a.z); a.w = fmaf(f, v[k].w, a.w);
+    }
+  }
+  for (; p < p1; p += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(part + (row0 + p * row_stride) * E + c);
+    const float f = WEIGHTED ? wsm[p - p0] : 1.f;
+    a.x = fmaf(f, v.x, a.x); a.y = fmaf(f, v.y, a.y); a.z = fmaf(f, v.z, a.z); a.w = fmaf(f, v.w, a.w);
+  }
+  red[threadIdx.x] = a;
+  __syncthreads();
+  if (q == 0) {
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+      const float4 o = red[threadIdx.x + 128 * k];
+      a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w;
+    }
+  }
+  return a;      // valid in slice 0
+}
+
+// grid (n_segs*T*H), 512 threads: merge the items of a segment (softmax statistics first, then the weighted rows)
+__global__ void __launch_bounds__(MERGE_THREADS)
 k_t2i_merge(const float* __restrict__ part_acc, const float2* __restrict__ part_ml, const Segs sg, float* __restrict__ Pool,
             float* __restrict__ lse) {
+  __shared__ float wsm[MERGE_MAX_ITEMS];
+  __shared__ float4 red[MERGE_THREADS];
+  __shared__ float wred[MERGE_THREADS / 32];
+  __shared__ float gm_s, gl_s;
   const int row = blockIdx.x;                    // (s*T + t)*H + h
   const int h = row % H, st = row / H, t = st % sg.T, s = st / sg.T;
   const int p0 = sg.item0[s], p1 = sg.item0[s + 1];
-  float gm = -FLT_MAX;
-  for (int p = p0; p < p1; ++p) gm = fmaxf(gm, part_ml[static_cast<int64_t>(p * sg.T + t) * H + h].x);
-  float gl = 0.f;
-  for (int p = p0; p < p1; ++p) {
-    const float2 ml = part_ml[static_cast<int64_t>(p * sg.T + t) * H + h];
-    gl = fmaf(ml.y, expf(ml.x - gm), gl);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t stride = static_cast<int64_t>(sg.T) * H, r0 = static_cast<int64_t>(t) * H + h;
+  float mx = -FLT_MAX;
+  for (int p = p0 + threadIdx.x; p < p1; p += MERGE_THREADS) mx = fmaxf(mx, part_ml[p * stride + r0].x);
+  mx = warp_max(mx);
+  if (lane == 0) wred[warp] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float g = wred[0];
+    for (int w = 1; w < MERGE_THREADS / 32; ++w) g = fmaxf(g, wred[w]);
+    gm_s = g;
   }
-  const float inv = 1.f / gl;
-  const int c = threadIdx.x * 4;
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int p = p0; p < p1; ++p) {
-    const int64_t pr = static_cast<int64_t>(p * sg.T + t) * H + h;
-    const float f = expf(part_ml[pr].x - gm);
-    const float4 v = *reinterpret_cast<const float4*>(part_acc + pr * E + c);
-    a.x = fmaf(f, v.x, a.x); a.y = fmaf(f, v.y, a.y); a.z = fmaf(f, v.z, a.z); a.w = fmaf(f, v.w, a.w);
+  __syncthreads();
+  const float gm = gm_s;
+  float ls = 0.f;
+  for (int p = p0 + threadIdx.x; p < p1; p += MERGE_THREADS) {
+    const float2 ml = part_ml[p * stride + r0];
+    const float f = expf(ml.x - gm);
+    wsm[p - p0] = f;
+    ls = fmaf(ml.y, f, ls);
   }
-  a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
-  *reinterpret_cast<float4*>(Pool + static_cast<int64_t>(row) * E + c) = a;
-  if (threadIdx.x == 0) lse[row] = gm + logf(gl);
+  ls = warp_sum(ls);
+  __syncthreads();                 // wred is reused
+  if (lane == 0) wred[warp] = ls;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float g = 0.f;
+    for (int w = 0; w < MERGE_THREADS / 32; ++w) g += wred[w];
+    gl_s = g;
+  }
+  __syncthreads();
+  float4 a = merge_items<true>(part_acc, stride, r0, p0, p1, wsm, red);
+  if (threadIdx.x < 128) {
+    const float inv = 1.f / gl_s;
+    a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
+    *reinterpret_cast<float4*>(Pool + static_cast<int64_t>(row) * E + threadIdx.x * 4) = a;
+  }
+  if (threadIdx.x == 0) lse[row] = gm + logf(gl_s);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -303,11 +403,12 @@ k_t2i_bwd(const TK* __restrict__ K, const float* __restrict__ PE, const float* _
     for (int j = 0; j < H; ++j)
 #pragma unroll
       for (int e = 0; e < 16; ++e) du[j][e] = 0.f;
+    // (no software prefetch here: 128 dU accumulators + the row leave no registers for a second row in flight)
     for (int i = i0 + warp; i < i1; i += WARPS) {
       const int64_t n = base + i;
-      float kv[16], kp[16], dk[16];
+      float kv[16], pe[16], dk[16];
       Row<TK>::load(K + n * E, lane, kv);
-      load_f32_row<TK>(PE + static_cast<int64_t>(i) * E, lane, kp);
+      load_f32_row<TK>(PE + static_cast<int64_t>(i) * E, lane, pe);
       const float srow = (lane < H) ? S[n * J + t * H + lane] : 0.f;
       if (t > 0 || accumulate) {
         Row<TK>::load_cached(dK + n * E, lane, dk);
@@ -316,7 +417,7 @@ k_t2i_bwd(const TK* __restrict__ K, const float* __restrict__ PE, const float* _
         for (int e = 0; e < 16; ++e) dk[e] = 0.f;
       }
 #pragma unroll
-      for (int e = 0; e < 16; ++e) kp[e] += kv[e];
+      for (int e = 0; e < 16; ++e) pe[e] += kv[e];          // keys + pe
 #pragma unroll
       for (int j = 0; j < H; ++j) {
         float d[16], u[16];
@@ -333,7 +434,7 @@ k_t2i_bwd(const TK* __restrict__ K, const float* __restrict__ PE, const float* _
         for (int e = 0; e < 16; ++e) {
           dk[e] = fmaf(a, d[e], dk[e]);
           dk[e] = fmaf(cs, u[e], dk[e]);
-          du[j][e] = fmaf(cs, kp[e], du[j][e]);
+          du[j][e] = fmaf(cs, pe[e], du[j][e]);
         }
       }
       Row<TK>::store(dK + n * E, lane, dk);
@@ -361,18 +462,15 @@ k_t2i_bwd(const TK* __restrict__ K, const float* __restrict__ PE, const float* _
   }
 }
 
-// out[(s*T + t)*H + h][:] = sum over the items of segment s (item order) of part[(item*T + t)*H + h][:]
-__global__ void __launch_bounds__(128)
+// out[(s*T + t)*H + h][:] = sum over the items of segment s of part[(item*T + t)*H + h][:]
+__global__ void __launch_bounds__(MERGE_THREADS)
 k_sum_items(const float* __restrict__ part, const Segs sg, float* __restrict__ out) {
+  __shared__ float4 red[MERGE_THREADS];
   const int row = blockIdx.x;
   const int h = row % H, st = row / H, t = st % sg.T, s = st / sg.T;
-  const int c = threadIdx.x * 4;
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int p = sg.item0[s]; p < sg.item0[s + 1]; ++p) {
-    const float4 v = *reinterpret_cast<const float4*>(part + (static_cast<int64_t>(p * sg.T + t) * H + h) * E + c);
-    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-  }
-  *reinterpret_cast<float4*>(out + static_cast<int64_t>(row) * E + c) = a;
+  const float4 a = merge_items<false>(part, static_cast<int64_t>(sg.T) * H, static_cast<int64_t>(t) * H + h, sg.item0[s],
+                                      sg.item0[s + 1], nullptr, red);
+  if (threadIdx.x < 128) *reinterpret_cast<float4*>(out + static_cast<int64_t>(row) * E + threadIdx.x * 4) = a;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -485,17 +583,18 @@ k_ln_seg_bwd(const TI* __restrict__ K, const float* __restrict__ R, const float*
   }
 }
 
-// grid (2 + n_segs + n_segs*T), 128 threads x float4:
+// grid (2 + n_segs + n_segs*T), 512 threads:
 //   block 0/1: dgamma / dbeta = sum over all items;  block 2+s: dR[s] = sum over the items of s;
 //   then one block per token row: dtokens[r] = dY[tok_row[r/T] + r%T] (fp32)
 template <typename TK>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(MERGE_THREADS)
 k_ln_seg_reduce(const float* __restrict__ part, const Segs sg, float* __restrict__ dgamma, float* __restrict__ dbeta,
                 const int accumulate, float* __restrict__ dR, const TK* __restrict__ dY, float* __restrict__ dtokens) {
-  const int b = blockIdx.x, c = threadIdx.x * 4;
+  __shared__ float4 red[MERGE_THREADS];
+  const int b = blockIdx.x, c = (threadIdx.x & 127) * 4;
   if (b >= 2 + sg.n) {
     const int r = b - 2 - sg.n;
-    if (dtokens == nullptr) return;
+    if (dtokens == nullptr || threadIdx.x >= 128) return;
     const TK* src = dY + static_cast<int64_t>(sg.tok_row[r / sg.T] + r % sg.T) * E + c;
     float4 o = make_float4(to_f32<TK>(src[0]), to_f32<TK>(src[1]), to_f32<TK>(src[2]), to_f32<TK>(src[3]));
     *reinterpret_cast<float4*>(dtokens + static_cast<int64_t>(r) * E + c) = o;
@@ -503,11 +602,8 @@ k_ln_seg_reduce(const float* __restrict__ part, const Segs sg, float* __restrict
   }
   const int k = b < 2 ? b : 2;
   const int p0 = b < 2 ? 0 : sg.item0[b - 2], p1 = b < 2 ? sg.n_items : sg.item0[b - 1];
-  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int p = p0; p < p1; ++p) {
-    const float4 v = *reinterpret_cast<const float4*>(part + (static_cast<int64_t>(p) * 3 + k) * E + c);
-    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-  }
+  float4 a = merge_items<false>(part, 3, k, p0, p1, nullptr, red);
+  if (threadIdx.x >= 128) return;
   float* dst = (b == 0 ? dgamma : (b == 1 ? dbeta : dR + static_cast<int64_t>(b - 2) * E)) + c;
   if (b < 2 && accumulate) {
     const float4 o = *reinterpret_cast<float4*>(dst);
@@ -610,15 +706,18 @@ int make_segs(const milb200_segment* segs, int n_segs, int T, Segs* out) {
     total += segs[s].len;
     g.max_len = std::max(g.max_len, segs[s].len);
   }
-  // ~2 items per SM, 32..256 rows each: every item folds 8 head accumulators through shared memory, so very small
-  // items pay mostly for the fold; very large ones leave SMs idle
-  int64_t rpi = (total + 2 * sm_count() - 1) / (2 * sm_count());
-  rpi = std::min<int64_t>(256, std::max<int64_t>(32, (rpi + 7) / 8 * 8));
+  // ~1 item per SM (the attention kernels hold ~200 registers per thread: one CTA per SM), 32..512 rows each: every
+  // item folds 8 head accumulators through shared memory and leaves a 16 KB partial for the merge kernels, so small
+  // items pay mostly for that; very large ones leave SMs idle
+  int64_t rpi = (total + sm_count() - 1) / sm_count();
+  rpi = std::min<int64_t>(512, std::max<int64_t>(32, (rpi + 7) / 8 * 8));
   g.rows_per_item = static_cast<int>(rpi);
   int items = 0;
   for (int s = 0; s < n_segs; ++s) {
     g.item0[s] = items;
     items += (g.len[s] + g.rows_per_item - 1) / g.rows_per_item;
+    MIL_CHECK_ARG((g.len[s] + g.rows_per_item - 1) / g.rows_per_item <= MERGE_MAX_ITEMS, MILB200_EUNSUPPORTED,
+                  "segments: segment %d has %d rows: more than %d work items", s, g.len[s], MERGE_MAX_ITEMS);
   }
   g.item0[n_segs] = items;
   for (int s = n_segs + 1; s <= MAXSEG; ++s) g.item0[s] = items;
@@ -626,11 +725,25 @@ int make_segs(const milb200_segment* segs, int n_segs, int T, Segs* out) {
   return MILB200_OK;
 }
 
+Segs finer(const Segs& sg, int factor) {
+  Segs g = sg;
+  g.rows_per_item = std::max(16, (sg.rows_per_item / factor + 7) / 8 * 8);
+  int items = 0;
+  for (int s = 0; s < g.n; ++s) {
+    g.item0[s] = items;
+    items += (g.len[s] + g.rows_per_item - 1) / g.rows_per_item;
+  }
+  for (int s = g.n; s <= MAXSEG; ++s) g.item0[s] = items;
+  g.n_items = items;
+  return g;
+}
+constexpr int LN_FINER = 4;
+
 size_t t2i_ws_bytes(const Segs& sg) {
   const size_t rows = static_cast<size_t>(sg.n_items) * sg.T * H;
   return align_up(rows * E * sizeof(float), 256) + align_up(rows * sizeof(float2), 256) + 256;
 }
-size_t ln_seg_ws_bytes(const Segs& sg) { return static_cast<size_t>(sg.n_items) * 3 * E * sizeof(float) + 256; }
+size_t ln_seg_ws_bytes(const Segs& sg) { return static_cast<size_t>(finer(sg, LN_FINER).n_items) * 3 * E * sizeof(float) + 256; }
 
 int headdiag_expand(const float* x, const float* W, float* y, int R, cudaStream_t st) {
   MIL_CHECK_ARG(x && W && y && R > 0, MILB200_EINVAL, "headdiag_expand: bad argument");
@@ -680,7 +793,7 @@ int t2i_fwd(const void* K, const float* PE, const float* U, const Segs& sg, int 
   else
     k_t2i_fwd<float><<<grid, THREADS, 0, st>>>((const float*)K, PE, U, sg, bag_layout, S, part_acc, part_ml);
   MIL_LAUNCH_CHECK();
-  k_t2i_merge<<<sg.n * sg.T * H, 128, 0, st>>>(part_acc, part_ml, sg, Pool, lse);
+  k_t2i_merge<<<sg.n * sg.T * H, MERGE_THREADS, 0, st>>>(part_acc, part_ml, sg, Pool, lse);
   MIL_LAUNCH_CHECK();
   return MILB200_OK;
 }
@@ -698,14 +811,15 @@ int t2i_bwd(const void* K, const float* PE, const float* U, const float* S, cons
     k_t2i_bwd<float><<<sg.n_items, THREADS, 0, st>>>((const float*)K, PE, U, S, lse, Pool, dPool, sg, bag_layout,
                                                      (float*)dK, accumulate_dk, part);
   MIL_LAUNCH_CHECK();
-  k_sum_items<<<sg.n * sg.T * H, 128, 0, st>>>(part, sg, dU);
+  k_sum_items<<<sg.n * sg.T * H, MERGE_THREADS, 0, st>>>(part, sg, dU);
   MIL_LAUNCH_CHECK();
   return MILB200_OK;
 }
 
-int ln_seg_fwd(const void* K, const float* R, const float* gamma, const float* beta, const float* tokens, const Segs& sg,
+int ln_seg_fwd(const void* K, const float* R, const float* gamma, const float* beta, const float* tokens, const Segs& sg_in,
                int bag_layout_out, void* Y, float* mean, float* rstd, int in_dtype, int out_dtype, cudaStream_t st) {
   MIL_CHECK_ARG(K && R && gamma && beta && Y && mean && rstd, MILB200_EINVAL, "ln_seg_fwd: null pointer");
+  const Segs sg = finer(sg_in, LN_FINER);
   MIL_CHECK_ARG(in_dtype == out_dtype || (in_dtype == MILB200_F32 && out_dtype == MILB200_BF16), MILB200_EUNSUPPORTED,
                 "ln_seg_fwd: storage pair (in %d, out %d) is not built", in_dtype, out_dtype);
   const unsigned grid = sg.n_items + (tokens ? 1 : 0);
@@ -723,13 +837,14 @@ int ln_seg_fwd(const void* K, const float* R, const float* gamma, const float* b
 }
 
 int ln_seg_bwd(const void* K, const float* R, const float* gamma, const float* mean, const float* rstd, const void* dY,
-               const Segs& sg, int bag_layout_out, void* dK, int accumulate_dk, float* dR, float* dgamma, float* dbeta,
+               const Segs& sg_in, int bag_layout_out, void* dK, int accumulate_dk, float* dR, float* dgamma, float* dbeta,
                int accumulate_params, float* dtokens, int in_dtype, int out_dtype, void* ws, size_t ws_bytes, cudaStream_t st) {
   MIL_CHECK_ARG(K && R && gamma && mean && rstd && dY && dK && dR && dgamma && dbeta, MILB200_EINVAL, "ln_seg_bwd: null pointer");
+  const Segs sg = finer(sg_in, LN_FINER);
   MIL_CHECK_ARG(in_dtype == out_dtype || (in_dtype == MILB200_F32 && out_dtype == MILB200_BF16), MILB200_EUNSUPPORTED,
                 "ln_seg_bwd: storage pair (in %d, out %d) is not built", in_dtype, out_dtype);
-  MIL_CHECK_ARG(ws && ws_bytes >= ln_seg_ws_bytes(sg), MILB200_EWORKSPACE, "ln_seg_bwd: workspace %zu < %zu", ws_bytes,
-                ln_seg_ws_bytes(sg));
+  MIL_CHECK_ARG(ws && ws_bytes >= ln_seg_ws_bytes(sg_in), MILB200_EWORKSPACE, "ln_seg_bwd: workspace %zu < %zu", ws_bytes,
+                ln_seg_ws_bytes(sg_in));
   float* part = static_cast<float*>(ws);
   const unsigned rgrid = 2 + sg.n + (dtokens ? sg.n * sg.T : 0);
   using bf = __nv_bfloat16;
@@ -745,9 +860,9 @@ int ln_seg_bwd(const void* K, const float* R, const float* gamma, const float* m
   }
   MIL_LAUNCH_CHECK();
   if (out_dtype == MILB200_F32)
-    k_ln_seg_reduce<float><<<rgrid, 128, 0, st>>>(part, sg, dgamma, dbeta, accumulate_params, dR, (const float*)dY, dtokens);
+    k_ln_seg_reduce<float><<<rgrid, MERGE_THREADS, 0, st>>>(part, sg, dgamma, dbeta, accumulate_params, dR, (const float*)dY, dtokens);
   else
-    k_ln_seg_reduce<bf><<<rgrid, 128, 0, st>>>(part, sg, dgamma, dbeta, accumulate_params, dR, (const bf*)dY, dtokens);
+    k_ln_seg_reduce<bf><<<rgrid, MERGE_THREADS, 0, st>>>(part, sg, dgamma, dbeta, accumulate_params, dR, (const bf*)dY, dtokens);
   MIL_LAUNCH_CHECK();
   return MILB200_OK;
 }

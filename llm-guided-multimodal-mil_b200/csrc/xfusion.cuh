@@ -21,6 +21,8 @@ struct Segs {
   int n, T, rows_per_item, n_items, max_len;
   int k_start[MAXSEG], len[MAXSEG], out_start[MAXSEG], tok_row[MAXSEG], item0[MAXSEG + 1];
 };
+// The LayerNorm kernels are light (100-160 registers): they take a finer cut of the same segments, ~4 CTAs per SM.
+Segs finer(const Segs& sg, int factor);
 
 int make_segs(const milb200_segment* segs, int n_segs, int T, Segs* out);
 

@@ -170,6 +170,41 @@ class AbmilTrainer:
             dM = self._ones
         return M, self.backward(dM)
 
+    # ---- latency-optimal exchange: symmetric memory + one kernel (csrc/exchange.cu) ------------------------------------
+    def enable_symmetric_exchange(self):
+        """Move the flat gradient buffer into symmetric memory (one allocation mapped on every rank of the node, with a
+        multicast mapping through the NVSwitch) so that `reduce_and_update` becomes ONE kernel: in-switch reduction +
+        broadcast of the gradients and the fused optimiser step (csrc/exchange.cu), instead of an NCCL all-reduce launch
+        followed by the optimiser launch.  torch.distributed's symmetric memory is the plumbing (allocation, handle
+        exchange, signal pads); returns False — and leaves the NCCL path in place — when the node has no multicast
+        support.  Collective: every rank of the group must call it."""
+        if self.world <= 1:
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.pg if self.pg is not None else torch.distributed.group.WORLD
+            pad = 4 * self.world
+            n_alloc = (self.numel + pad - 1) // pad * pad
+            buf = symm.empty(n_alloc, dtype=torch.float32, device=self.device)
+            buf.zero_()
+            hdl = symm.rendezvous(buf, group.group_name)
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            ok = torch.tensor([1 if mc else 0], device=self.device)
+        except Exception:
+            buf = hdl = None
+            mc = 0
+            ok = torch.tensor([0], device=self.device)
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN, group=self.pg)     # all ranks or none
+        if int(ok.item()) == 0:
+            return False
+        buf[:self.numel].copy_(self.grads)
+        self.grads = buf[:self.numel]
+        pads = torch.tensor([int(p) for p in hdl.signal_pad_ptrs], dtype=torch.int64, device=self.device)
+        self._symm = dict(hdl=hdl, buf=buf, pads=pads, mc=mc, rank=int(hdl.rank))
+        torch.cuda.synchronize()
+        torch.distributed.barrier(group=self.pg)       # every rank's buffer is zeroed and mapped before the first exchange
+        return True
+
     def allreduce_grads(self):
         """The path's only exchange: ONE all-reduce(sum) of the flat gradient buffer (NCCL on GPUs; any backend)."""
         if self.world > 1:
@@ -177,6 +212,15 @@ class AbmilTrainer:
 
     def reduce_and_update(self):
         """all-reduce(sum) of the flat gradient over NCCL, then the fused optimiser step with grad_scale = 1/world."""
+        sm = getattr(self, "_symm", None)
+        if sm is not None:
+            self.step_count += 1
+            L.check(L.lib().milb200_allreduce_update_symm(
+                L.ptr(self.params), L.ptr(self.grads), sm["mc"], L.ptr(sm["pads"]), 0, sm["rank"], self.world,
+                L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq), self.numel, 1 if self.optimizer == "sgd" else 0, self.lr,
+                self.betas[0], self.betas[1], self.eps, self.wd, 1.0 / self.world, self.step_count, L.stream_ptr()),
+                "allreduce_update_symm")
+            return
         self.allreduce_grads()
         self.step_count += 1
         if self.optimizer == "sgd":
