@@ -158,21 +158,39 @@ def cpu_reference(lengths, steps, warmup, budget_s=20.0, per_step=4):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     p = mo.procedural_state(mo.abmil_shapes(L_FEAT, D_GATE), 1234)
-    sd = {"a." + k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in p.items()}
     g = torch.Generator().manual_seed(1234)
     pool_rows = max(int(v) for v in lengths) + 4096
     big = torch.randn(1, pool_rows, L_FEAT, generator=g)      # one host buffer; each bag is a window of it (not timed)
     cursor = [0]
+    # the reference's own module when oracle/_ref holds it (oracle/make_ref.py copies model/dim1/ABMIL.py there, unmodified,
+    # at build time); otherwise the oracle's op-for-op restatement
+    from oracle import make_ref
+    RefABMIL = make_ref.load_reference_abmil()
+    if RefABMIL is not None:
+        kind = "reference"
+        ref = RefABMIL(None, L=L_FEAT, D=D_GATE).eval()       # eval(): dropout off, the semantics our headline step runs
+        ref.load_state_dict({k: torch.from_numpy(v) for k, v in p.items()})
+        params = list(ref.parameters())
+
+        def fwd_bwd(x):
+            for t in params:
+                t.grad = None
+            ref(x).sum().backward()
+    else:
+        kind = "port"
+        sd = {"a." + k: torch.from_numpy(v).clone().requires_grad_(True) for k, v in p.items()}
+
+        def fwd_bwd(x):
+            for t in sd.values():
+                t.grad = None
+            fo.abmil(sd, "a", x).sum().backward()
 
     def one_bag(n):
         start = cursor[0] % (pool_rows - n + 1)
         cursor[0] += 997
         x = big[:, start:start + n]
-        for t in sd.values():
-            t.grad = None
         t0 = time.perf_counter()
-        M = fo.abmil(sd, "a", x)
-        M.sum().backward()
+        fwd_bwd(x)
         return time.perf_counter() - t0
 
     lens = [int(v) for v in lengths]
@@ -190,10 +208,13 @@ def cpu_reference(lengths, steps, warmup, budget_s=20.0, per_step=4):
         if time.perf_counter() - t_begin > budget_s:
             break
     total = sum(times)
-    return {"value": done_bags / total, "unit": "bags/s", "cores": cores, "kind": "port",
+    what = ("the reference's own model/dim1/ABMIL.py (oracle/_ref, unmodified) in eval() mode" if kind == "reference"
+            else "the oracle's restatement of ABMIL.forward (eval-mode arithmetic)")
+    return {"value": done_bags / total, "unit": "bags/s", "cores": cores, "kind": kind,
             "sample": f"{done_bags} bags cycling through the workload's {len(lens)} bag lengths ({per_step} bags per step, "
                       f"{len(times)} steps, {total:.1f} s of CPU work), fp32, bag-at-a-time fwd+bwd (M.sum().backward()) as the "
-                      f"reference trains, torch {torch.__version__} with {cores} threads",
+                      f"reference trains, {what}; no dropout and NO optimiser step in the CPU figure (the GPU step includes "
+                      f"fused Adam), torch {torch.__version__} with {cores} threads",
             "ms_per_step": 1e3 * total / len(times), "steps": len(times), "bags_per_step": per_step}
 
 
