@@ -527,6 +527,7 @@ def fusion_main(args, out):
     m = mil_b200.get_model(ns).to(dev).eval()
     tr = mil_b200.FusionTrainer(m, n_text_tokens=1, compute_dtype=torch.bfloat16, process_group=pg, world_size=world)
     tr.broadcast_params()
+    symm_on = world > 1 and os.environ.get("MILB200_SYMM", "1") != "0" and tr.enable_symmetric_exchange()
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
     ct = torch.randn(Bp, Nc, 512, device=dev, generator=gen).to(torch.bfloat16)
     xp = torch.randn(Bp * N, 768, device=dev, generator=gen).to(torch.bfloat16)
@@ -560,6 +561,23 @@ def fusion_main(args, out):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = Bp * world * args.steps / (ms_max / 1e3)
+    # the exchange + optimiser part of the step alone (CUDA events around reduce_and_update, max over ranks)
+    ex_ms = []
+    for _ in range(5):
+        tr.forward_backward_bags(ct, xp, lens, xt, labels)
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        tr.reduce_and_update()
+        b.record()
+        torch.cuda.synchronize()
+        ex_ms.append(a.elapsed_time(b))
+    ex_ms.sort()
+    t = torch.tensor([ex_ms[len(ex_ms) // 2]], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    exchange_update_ms = float(t.item())
     # end to end: host (pinned) patient data, H2D inside the timed region, loss/prob read back every step
     xp_h = torch.empty_like(xp, device="cpu").pin_memory()
     xp_h.copy_(xp)
@@ -612,9 +630,13 @@ def fusion_main(args, out):
                                        f"text token each, BCE + cosine loss, one all-reduce of the {tr.numel * 4 / 1e6:.0f} MB flat "
                                        f"gradient buffer, fused Adam; FusionTrainer.step_bags (collapsed program, csrc/xfusion.cu)",
                            "patients_per_rank": Bp, "parallelism": f"dp{world}",
+                           "exchange": ("none (single GPU)" if world == 1 else
+                                        "multimem.ld_reduce/st over NVSwitch symmetric memory (csrc/exchange.cu) + fused Adam kernel"
+                                        if symm_on else "ncclAllReduce of the flat fp32 gradient buffer + fused Adam kernel"),
                            "storage": "bf16 patch features / packed bag / tensor-core operands, fp32 key stream and token side",
                            "cache": "patient data (~96 MB/patient) cycles through HBM; parameters + optimiser state 160 MB > L2"},
                 "gpu_launches": int(launches), "kernels_per_bag": launches / args.steps / Bp,
+                "exchange_plus_optimizer_ms": exchange_update_ms,
                 "e2e": {"value": Bp * world * e2e_steps / (e2e_ms / 1e3), "unit": "bags/s",
                         "h2d_bytes_per_step": int(xp_h.numel() * 2 + ct_h.numel() * 2 + xt_h.numel() * 2),
                         "d2h_bytes_per_step": int(res_h.numel() * 4), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},

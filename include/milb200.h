@@ -332,7 +332,8 @@ int milb200_sgd_step(float* param, const float* grad, int64_t n, float lr, float
  * mapping, signal_pads_dev = device array of `world` pointers to the ranks' zero-initialised uint32 signal pads (at least
  * pad_slot0 + 32 * world entries each).  Slice r of the buffer is reduced in the switch (multimem.ld_reduce) and
  * broadcast (multimem.st) by rank r, between two flag barriers; then every rank applies the fused optimiser update
- * (optimizer 0: Adam, 1: SGD) with grad_scale (1/world = DDP's average).  On return the gradient buffer holds the SUM over
+ * (optimizer 0: Adam, 1: SGD, -1: none — exchange only, for large buffers whose update wants a full-width grid: call
+ * milb200_adam_step afterwards) with grad_scale (1/world = DDP's average).  On return the gradient buffer holds the SUM over
  * ranks — bit-identical on every rank.  The allocation must be padded to a multiple of 4 * world elements.              */
 int milb200_allreduce_update_symm(float* param, float* grad_local, void* grad_multicast, void* const* signal_pads_dev,
                                   int pad_slot0, int rank, int world, float* exp_avg, float* exp_avg_sq, int64_t n,

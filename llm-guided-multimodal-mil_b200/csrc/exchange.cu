@@ -21,7 +21,7 @@
 namespace milb200 {
 
 constexpr int XCH_THREADS = 512;
-constexpr int XCH_MAX_BLOCKS = 32;
+constexpr int XCH_MAX_BLOCKS = 32;       // blocks that take part in the flag barriers (signal-pad slots: blocks x world)
 constexpr int XCH_MAX_WORLD = 16;
 
 __device__ __forceinline__ uint32_t cas_release_sys(uint32_t* addr, uint32_t cmp, uint32_t val) {
@@ -69,14 +69,23 @@ k_allreduce_update(float* __restrict__ p, float* __restrict__ g_local, float* g_
   peer_barrier(pads, rank, world, slot0);
   {
     const int64_t lo = rank * chunk4, hi = min((n + 3) / 4, lo + chunk4);
-    for (int64_t i = lo + static_cast<int64_t>(blockIdx.x) * XCH_THREADS + threadIdx.x; i < hi;
-         i += static_cast<int64_t>(gridDim.x) * XCH_THREADS) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * XCH_THREADS;
+    int64_t i = lo + static_cast<int64_t>(blockIdx.x) * XCH_THREADS + threadIdx.x;
+    for (; i + 3 * stride < hi; i += 4 * stride) {        // four switch round trips in flight per thread
+      float4 s[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s[k] = multimem_ld_reduce_add(g_mc + 4 * (i + k * stride));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) multimem_st(g_mc + 4 * (i + k * stride), s[k]);
+    }
+    for (; i < hi; i += stride) {
       const float4 s = multimem_ld_reduce_add(g_mc + 4 * i);
       multimem_st(g_mc + 4 * i, s);
     }
   }
   __threadfence_system();
   peer_barrier(pads, rank, world, slot0);
+  if (optimizer < 0) return;       // exchange only: the caller runs its own (wide) optimiser kernel on the summed gradients
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * XCH_THREADS + threadIdx.x; i < n; i += static_cast<int64_t>(gridDim.x) * XCH_THREADS) {
     const float pi = p[i];
     const float gi = fmaf(wd, pi, __ldcg(g_local + i) * gscale);
@@ -92,6 +101,30 @@ k_allreduce_update(float* __restrict__ p, float* __restrict__ g_local, float* g_
   }
 }
 
+// Large buffers (the 40 MB buffer of the aggregator trainer): the flag barrier as a one-block kernel on either side of a
+// full-width reduce + broadcast kernel (a barrier inside that kernel would tie the grid to the signal-pad slots).
+__global__ void __launch_bounds__(32) k_peer_barrier(uint32_t* const* __restrict__ pads, const int rank, const int world, const int slot0) {
+  peer_barrier(pads, rank, world, slot0);
+}
+__global__ void __launch_bounds__(XCH_THREADS)
+k_reduce_bcast(float* g_mc, const int rank, const int64_t n, const int64_t chunk4) {
+  const int64_t lo = rank * chunk4, hi = min((n + 3) / 4, lo + chunk4);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * XCH_THREADS;
+  int64_t i = lo + static_cast<int64_t>(blockIdx.x) * XCH_THREADS + threadIdx.x;
+  for (; i + 3 * stride < hi; i += 4 * stride) {
+    float4 s[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s[k] = multimem_ld_reduce_add(g_mc + 4 * (i + k * stride));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) multimem_st(g_mc + 4 * (i + k * stride), s[k]);
+  }
+  for (; i < hi; i += stride) {
+    const float4 s = multimem_ld_reduce_add(g_mc + 4 * i);
+    multimem_st(g_mc + 4 * i, s);
+  }
+  __threadfence_system();
+}
+
 }  // namespace milb200
 
 using namespace milb200;
@@ -102,7 +135,8 @@ extern "C" {
  * lives in symmetric memory: grad_local = this rank's mapping, grad_multicast = the multicast mapping of the same
  * allocation, signal_pads_dev = device array of `world` pointers to the ranks' uint32 signal pads (zero-initialised; at
  * least pad_slot0 + 32 * world entries).  n elements (the allocation must be padded to a multiple of 4 * world
- * elements).  optimizer: 0 Adam (exp_avg / exp_avg_sq updated), 1 SGD.  After the call every rank's gradient buffer holds
+ * elements).  optimizer: 0 Adam (exp_avg / exp_avg_sq updated), 1 SGD, -1 none (exchange only: large buffers, whose
+ * update wants a full-width grid, call milb200_adam_step afterwards).  After the call every rank's gradient buffer holds
  * the SUM over ranks and its parameters have taken the step with grad_scale (= 1/world for DDP's average).            */
 int milb200_allreduce_update_symm(float* param, float* grad_local, void* grad_multicast, void* const* signal_pads_dev,
                                   int pad_slot0, int rank, int world, float* exp_avg, float* exp_avg_sq, int64_t n,
@@ -111,13 +145,25 @@ int milb200_allreduce_update_symm(float* param, float* grad_local, void* grad_mu
   MIL_CHECK_ARG(param && grad_local && grad_multicast && signal_pads_dev && n > 0, MILB200_EINVAL, "allreduce_update: null pointer");
   MIL_CHECK_ARG(world >= 2 && world <= XCH_MAX_WORLD && rank >= 0 && rank < world && pad_slot0 >= 0, MILB200_EINVAL,
                 "allreduce_update: rank %d / world %d", rank, world);
-  MIL_CHECK_ARG(optimizer == 1 || (exp_avg && exp_avg_sq && step >= 1), MILB200_EINVAL, "allreduce_update: Adam needs its state and step >= 1");
+  MIL_CHECK_ARG(optimizer != 0 || (exp_avg && exp_avg_sq && step >= 1), MILB200_EINVAL, "allreduce_update: Adam needs its state and step >= 1");
   MIL_CHECK_ARG(aligned16(grad_local) && aligned16(grad_multicast), MILB200_EALIGN, "allreduce_update: buffers must be 16-byte aligned");
   const int64_t n4 = (n + 3) / 4;
   const int64_t chunk4 = (n4 + world - 1) / world;
+  if (optimizer < 0 && n > (1 << 20)) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    uint32_t* const* pads = reinterpret_cast<uint32_t* const*>(signal_pads_dev);
+    k_peer_barrier<<<1, 32, 0, st>>>(pads, rank, world, pad_slot0);
+    MIL_LAUNCH_CHECK();
+    const int wide = static_cast<int>(std::min<int64_t>(2 * sm_count(), (chunk4 + XCH_THREADS - 1) / XCH_THREADS));
+    k_reduce_bcast<<<std::max(wide, 1), XCH_THREADS, 0, st>>>(static_cast<float*>(grad_multicast), rank, n, chunk4);
+    MIL_LAUNCH_CHECK();
+    k_peer_barrier<<<1, 32, 0, st>>>(pads, rank, world, pad_slot0);
+    MIL_LAUNCH_CHECK();
+    return MILB200_OK;
+  }
   int blocks = static_cast<int>(std::min<int64_t>(XCH_MAX_BLOCKS, std::max<int64_t>(1, (n + XCH_THREADS * 8 - 1) / (XCH_THREADS * 8))));
-  const float bc1 = optimizer == 1 ? 1.f : 1.f - powf(beta1, static_cast<float>(step));
-  const float bc2 = optimizer == 1 ? 1.f : 1.f - powf(beta2, static_cast<float>(step));
+  const float bc1 = optimizer != 0 ? 1.f : 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2 = optimizer != 0 ? 1.f : 1.f - powf(beta2, static_cast<float>(step));
   k_allreduce_update<<<blocks, XCH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       param, grad_local, static_cast<float*>(grad_multicast), reinterpret_cast<uint32_t* const*>(signal_pads_dev), rank, world,
       pad_slot0, exp_avg, exp_avg_sq, n, chunk4, optimizer, lr, beta1, beta2, eps, weight_decay, grad_scale, bc1, bc2);

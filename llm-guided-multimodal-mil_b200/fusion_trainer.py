@@ -314,9 +314,47 @@ class FusionTrainer:
         return b["loss"], b["prob"]
 
     # ---- exchange + optimiser -------------------------------------------------------------------------------------------
+    def enable_symmetric_exchange(self):
+        """The flat gradient buffer moves into symmetric memory and the exchange becomes the in-switch reduce + broadcast
+        kernel of csrc/exchange.cu (see dp.AbmilTrainer.enable_symmetric_exchange); the 40 MB buffer keeps its own
+        full-width optimiser kernel.  Collective; returns False (NCCL stays) without multicast support."""
+        if self.world <= 1:
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm
+            group = self.pg if self.pg is not None else torch.distributed.group.WORLD
+            pad = 4 * self.world
+            n_alloc = (self.numel + pad - 1) // pad * pad
+            buf = symm.empty(n_alloc, dtype=torch.float32, device=self.device)
+            buf.zero_()
+            hdl = symm.rendezvous(buf, group.group_name)
+            mc = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            ok = torch.tensor([1 if mc else 0], device=self.device)
+        except Exception:
+            buf = hdl = None
+            mc = 0
+            ok = torch.tensor([0], device=self.device)
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN, group=self.pg)
+        if int(ok.item()) == 0:
+            return False
+        buf[:self.numel].copy_(self.grads)
+        self.grads = buf[:self.numel]
+        sl = slice(self.o_pool, self.o_pool + self.n_pool)
+        self.pool.grads = self.grads[sl]                   # the embedded pool trainer writes into the same buffer
+        pads = torch.tensor([int(p) for p in hdl.signal_pad_ptrs], dtype=torch.int64, device=self.device)
+        self._symm = dict(hdl=hdl, buf=buf, pads=pads, mc=mc, rank=int(hdl.rank))
+        torch.cuda.synchronize()
+        torch.distributed.barrier(group=self.pg)
+        return True
+
     def reduce_and_update(self):
-        """ONE all-reduce(sum) of the flat gradient, then the fused optimiser step with grad_scale = 1/world."""
-        if self.world > 1:
+        """ONE exchange (sum) of the flat gradient, then the fused optimiser step with grad_scale = 1/world."""
+        sm = getattr(self, "_symm", None)
+        if sm is not None:
+            L.check(L.lib().milb200_allreduce_update_symm(
+                L.ptr(self.params), L.ptr(self.grads), sm["mc"], L.ptr(sm["pads"]), 0, sm["rank"], self.world, None, None,
+                self.numel, -1, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 1, L.stream_ptr()), "allreduce_update_symm")
+        elif self.world > 1:
             torch.distributed.all_reduce(self.grads, group=self.pg)
         self.step_count += 1
         if self.optimizer == "sgd":
