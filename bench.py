@@ -680,7 +680,7 @@ def main():
     ap.add_argument("--deal-bags", action="store_true",
                     help="abmil, world > 1: deal ONE draw of bags x world lengths to the ranks longest-first (dp.shard_bags) "
                          "instead of giving every rank the lengths of the single-GPU workload")
-    ap.add_argument("--patients", type=int, default=4, help="fusion: patients per rank per step (<= 8)")
+    ap.add_argument("--patients", type=int, default=8, help="fusion: patients per rank per step (<= 8)")
     args = ap.parse_args()
     if args.workload == "fusion" and args.impl == "ours":
         return fusion_main(args, out)
