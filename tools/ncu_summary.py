@@ -73,7 +73,14 @@ def main():
         d["source"] = f"profiles/{tag}_ncu_full_summary.md"
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_summary.md"), "w").write("\n".join(lines))
-    json.dump(traffic, open(os.path.join(ROOT, "profiles", "kernel_traffic.json"), "w"), indent=1)
+    # merge: kernels of other captures (other tags) keep their entries
+    tpath = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    try:
+        merged = json.load(open(tpath))
+    except Exception:
+        merged = {}
+    merged.update(traffic)
+    json.dump(merged, open(tpath, "w"), indent=1)
     for k, d in traffic.items():
         print(k, d)
 
