@@ -76,7 +76,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 k_ln_bwd(const T* __restrict__ X, const T* __restrict__ R, const float* __restrict__ gamma, const float* __restrict__ mean,
          const float* __restrict__ rstd, const T* __restrict__ dY, T* __restrict__ dXR, float* __restrict__ part, int64_t m,
-         int n, int rows_per_cta, int r_bcast) {
+         int n, int rows_per_cta, int r_bcast, float* __restrict__ dgamma, float* __restrict__ dbeta, int final_mode) {
   constexpr int VN = LnCfg<T>::VN, MAXV = LnCfg<T>::MAXV;
   extern __shared__ float sm[];  // [8 warps][2][n]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -156,7 +156,12 @@ k_ln_bwd(const T* __restrict__ X, const T* __restrict__ R, const float* __restri
     int which = i / n, c = i % n;
     float a = 0.f;
     for (int w = 0; w < 8; ++w) a += sm[(w * 2 + which) * n + c];
-    part[static_cast<int64_t>(blockIdx.x) * 2 * n + i] = a;
+    if (final_mode) {      // a single CTA covers all rows (the <= 16-row token side): no partials, no reduce launch
+      float* dst = which == 0 ? dgamma + c : dbeta + c;
+      *dst = final_mode == 2 ? *dst + a : a;
+    } else {
+      part[static_cast<int64_t>(blockIdx.x) * 2 * n + i] = a;
+    }
   }
 }
 
@@ -433,19 +438,22 @@ int milb200_layernorm_bwd(const void* X, const void* R, const float* gamma, cons
   const int ctas = ln_ctas(m);
   const int rows_per_cta = static_cast<int>((m + ctas - 1) / ctas);
   float* part = static_cast<float*>(workspace);
+  const int final_mode = ctas == 1 ? (accumulate ? 2 : 1) : 0;
   size_t smem = sizeof(float) * 8 * 2 * n;
   if (dtype == MILB200_BF16) {
     auto kern = k_ln_bwd<__nv_bfloat16>;
     if (smem > 48 * 1024) MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<ctas, 256, smem, st>>>((const __nv_bfloat16*)X, (const __nv_bfloat16*)R, gamma, mean, rstd,
-                                  (const __nv_bfloat16*)dY, (__nv_bfloat16*)dXR, part, m, n, rows_per_cta, r_broadcast);
+                                  (const __nv_bfloat16*)dY, (__nv_bfloat16*)dXR, part, m, n, rows_per_cta, r_broadcast, dgamma,
+                                  dbeta, final_mode);
   } else {
     auto kern = k_ln_bwd<float>;
     if (smem > 48 * 1024) MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<ctas, 256, smem, st>>>((const float*)X, (const float*)R, gamma, mean, rstd, (const float*)dY, (float*)dXR, part, m,
-                                  n, rows_per_cta, r_broadcast);
+                                  n, rows_per_cta, r_broadcast, dgamma, dbeta, final_mode);
   }
   MIL_LAUNCH_CHECK();
+  if (final_mode) return MILB200_OK;
   k_ln_reduce<<<(2 * n + 31) / 32, 256, 0, st>>>(part, ctas, n, dgamma, dbeta, accumulate);
   MIL_LAUNCH_CHECK();
   return MILB200_OK;

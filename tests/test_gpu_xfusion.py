@@ -276,3 +276,64 @@ def test_fusion_trainer_train_mode_matches_module_train_mode_on_the_same_masks()
     _, p3 = tr_eval.forward_backward(F.ct_tokens(x_ct.detach())[0], x_p.detach()[0], x_t.detach()[0], label[0])
     assert _rel(p3, prob) > 1e-3                      # dropout really changed the result
     m.eval()
+
+
+@pytest.mark.parametrize("case", ["tiny_bags", "sixteen_segments", "one_huge_bag"])
+def test_collapsed_fusion_edge_shapes_vs_oracle(case):
+    """Segment machinery at its edges: 2-row bags (fewer rows than warps), 8 patients = 16 segments with lengths that are
+    not multiples of the row-item size, and one bag far above the per-item row cap next to a 3-row one; fp32 vs float64."""
+    import mil_b200
+    m, sdn = _model(seed=23)
+    if case == "tiny_bags":
+        lens, Nc = [2, 3, 2], 2
+    elif case == "sixteen_segments":
+        lens, Nc = [37, 1, 513, 64, 7, 1290, 255, 33], 160
+        lens = [max(2, n) for n in lens]
+    else:
+        lens, Nc = [41_003, 3], 5
+    B = len(lens)
+    g = torch.Generator(device="cuda").manual_seed(len(lens) * 7 + Nc)
+    ct = torch.randn(B, Nc, 512, device="cuda", generator=g).requires_grad_(True)
+    xp = torch.randn(sum(lens), 768, device="cuda", generator=g).requires_grad_(True)
+    xt = (torch.randn(B, 1, 512, device="cuda", generator=g) * 0.05).requires_grad_(True)
+    w = torch.randn(B, 2, device="cuda", generator=g)
+    wa = torch.randn(B, 1, 512, device="cuda", generator=g)
+    prob, a, b = m.forward_bags(ct, xp, lens, xt)
+    ((prob * w).sum() + (a * wa).sum() + (b * wa).sum()).backward()
+    torch.cuda.synchronize()
+    sd = _oracle_sd(sdn, torch.float32)
+    off = np.concatenate([[0], np.cumsum(lens)])
+    ctd, xpd, xtd = (t.detach().double().cpu().requires_grad_(True) for t in (ct, xp, xt))
+    total = 0
+    for i in range(B):
+        fmap = ctd[i].t().reshape(1, 512, Nc, 1, 1)
+        p_, a_, b_ = fo.aggregator_fusion_forward(sd, fmap, xpd[off[i]:off[i + 1]].unsqueeze(0), xtd[i:i + 1],
+                                                  pe_fn=lambda n, E: fo.sinusoid_pe(n, E, torch.float32).double())
+        assert _rel(prob[i:i + 1], p_) <= 1e-5 and _rel(a[i], a_[0]) <= 1e-5 and _rel(b[i], b_[0]) <= 1e-5, (case, i)
+        total = total + (p_ * w[i:i + 1].double().cpu()).sum() + (a_[0] * wa[i].double().cpu()).sum() + (b_[0] * wa[i].double().cpu()).sum()
+    total.backward()
+    assert _rel(xp.grad, xpd.grad) <= 2e-5 and _rel(ct.grad, ctd.grad) <= 2e-5 and _rel(xt.grad, xtd.grad) <= 2e-5
+    n = 0
+    for name, p in m.named_parameters():
+        ref = sd[name].grad
+        if ref is None or float(ref.abs().max()) == 0.0 or name.endswith("k_proj.bias") or name.endswith("attention_weights.bias"):
+            continue
+        qk = ".q_proj" in name or ".k_proj" in name
+        assert _rel(p.grad, ref) <= (4e-4 if qk else 2e-5), (case, name, _rel(p.grad, ref))
+        n += 1
+    assert n > 60
+
+
+def test_forward_bags_rejects_bad_arguments():
+    import mil_b200
+    m, _ = _model(seed=29)
+    ct = torch.randn(2, 160, 512, device="cuda")
+    xp = torch.randn(100, 768, device="cuda")
+    xt = torch.randn(2, 1, 512, device="cuda")
+    with pytest.raises(mil_b200.MilB200Error):
+        m.forward_bags(ct, xp, [60, 30], xt)              # lengths do not add up to the packed rows
+    with pytest.raises(mil_b200.MilB200Error):
+        m.forward_bags(ct, xp, [99, 1], xt)               # a 1-row bag (the one-key shortcut needs >= 2 rows)
+    with pytest.raises(mil_b200.MilB200Error):
+        m.forward_bags(torch.randn(9, 4, 512, device="cuda"), torch.randn(90, 768, device="cuda"), [10] * 9,
+                       torch.randn(9, 1, 512, device="cuda"))       # more than 8 patients = 16 segments
