@@ -13,6 +13,8 @@ Same ``args`` fields, forward signature, outputs and ``state_dict`` keys (``fc_p
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -142,14 +144,17 @@ class aggregator(nn.Module):
         t = getattr(self, "_tape_cache_v2", None)
         if t is None:
             t = Tape()
+            # MILB200_FUSION_STREAM=bf16 (experiment switch): the key stream and the CT tokens in the program dtype too
+            stream_f32 = os.environ.get("MILB200_FUSION_STREAM", "f32") != "bf16"
+            t.stream_f32 = stream_f32
             E = self.embedding_dim
             # Storage: the patch features (the big HBM stream) and the packed bag are in the program dtype; the key stream
             # between them, the CT tokens, the position table and the whole token side are fp32 — in a bf16 program the
             # only reduced-precision steps are then the tensor-core operands of fc_pathology and of the gated pool
-            xp, ct = t.input("NP", 768), t.input("NC", E, f32=True)
+            xp, ct = t.input("NP", 768), t.input("NC", E, f32=stream_f32)
             pe = t.input("NPE", E, f32=True)
             txt = t.input("BT", E, f32=True)
-            keys = t.join(t.linear(xp, self.fc_pathology[0], act="tanh", out_f32=True), ct, "NK")    # :141 | CT tokens
+            keys = t.join(t.linear(xp, self.fc_pathology[0], act="tanh", out_f32=stream_f32), ct, "NK")    # :141 | CT tokens
             points = t.join(t.linear(txt, self.fc_CI2CT[0], act="tanh"),                             # :160 third argument
                             t.linear(txt, self.fc_CI2Pth[0], act="tanh"), "ST")                      # :168 third argument
             q, k = self.TwoWayTransformer_Both.emit_collapsed(t, keys, pe, points)
@@ -194,7 +199,9 @@ class aggregator(nn.Module):
         rows, segs, _ = self.fusion_layout(Nc, [Np], 1)
         pe = self._pe_table(max(Nc, Np), x_path.device)
         rows["NPE"] = pe.shape[0]
-        bag, tok = self._fusion_tape_v2().run(rows, [x_path[0], x_ct_tokens[0].float(), pe, x_text[0].float()], segs=segs)
+        tape = self._fusion_tape_v2()
+        ct_in = x_ct_tokens[0].float() if tape.stream_f32 else x_ct_tokens[0]
+        bag, tok = tape.run(rows, [x_path[0], ct_in, pe, x_text[0].float()], segs=segs)
         return bag.unsqueeze(0), tok[0:1].unsqueeze(0), tok[1:2].unsqueeze(0)          # x0, x_CT2CI, x_Pth2CI (fp32)
 
     def forward_bags(self, ct_tokens, x_path, path_lens, x_text):
@@ -213,8 +220,10 @@ class aggregator(nn.Module):
         pe = self._pe_table(max(Nc, max(path_lens)), x_path.device)
         rows["NPE"] = pe.shape[0]
         E = self.embedding_dim
-        bag, tok = self._fusion_tape_v2().run(rows, [x_path, ct_tokens.reshape(B * Nc, E).float(), pe,
-                                                     x_text.reshape(B, E).float()], segs=segs)
+        tape = self._fusion_tape_v2()
+        ct_in = ct_tokens.reshape(B * Nc, E)
+        bag, tok = tape.run(rows, [x_path, ct_in.float() if tape.stream_f32 else ct_in, pe, x_text.reshape(B, E).float()],
+                            segs=segs)
         key = (tuple(bag_off), bag.device)
         cached = self.__dict__.setdefault("_bag_off_cache", {})
         if key not in cached:
