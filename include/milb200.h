@@ -248,8 +248,7 @@ int milb200_ct_tokens_bwd(const void* dtokens, void* dfmap, int c, int t, int hw
  *                     (the position table in1 is always fp32)
  *           LN_SEG    out = LN(in0 + in1[segment]) * gamma + beta — image -> token attention with ONE token per
  *                     segment (softmax over one key = 1: the attention output is one row per segment)
- *                     a0 bit 0: write the rows at out_start (the packed bag of aggregator.py:173); in2 >= 0: also
- *                     copy the token rows in2 [n_segs*T, 512] to tok_row (the x_CT2CI / x_Pth2CI rows of the bag)
+ *                     a0 bit 0: write the rows at out_start (the packed bag of aggregator.py:173)
  *           TOK_SCATTER out = in1 with the token rows in0 [n_segs*T, 512] (fp32) written at tok_row, IN PLACE: out and in1
  *                     must be external slots at the same address (value and gradient) — the x_CT2CI / x_Pth2CI rows of
  *                     the packed bag, filled once the final token -> image attention has produced them

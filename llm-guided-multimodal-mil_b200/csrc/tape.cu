@@ -129,17 +129,14 @@ static int tape_validate(const milb200_tape_op* ops, int n_ops, const milb200_ta
         break;
       }
       case MILB200_OP_LN_SEG: {
-        MIL_CHECK_ARG(ok_slot(o.in1, false) && ok_slot(o.in2, true) && n_segs > 0 && T == 1, MILB200_EINVAL,
+        MIL_CHECK_ARG(ok_slot(o.in1, false) && o.in2 < 0 && n_segs > 0 && T == 1, MILB200_EINVAL,
                       "tape: op %d ln_seg needs keys, one row per segment and a segment table with one token per segment", i);
         MIL_CHECK_ARG(params && o.p0 >= 0 && o.p0 < n_params && o.p1 >= 0 && o.p1 < n_params, MILB200_EINVAL,
                       "tape: op %d bad param id", i);
         MIL_CHECK_ARG(s0.cols == xf::E && so.cols == xf::E &&
                           (dt(o.out) == dt(o.in0) || (dt(o.in0) == MILB200_F32 && dt(o.out) == MILB200_BF16)) &&
                           slots[o.in1].cols == xf::E &&
-                          slots[o.in1].rows == n_segs && dt(o.in1) == MILB200_F32 &&
-                          (o.in2 < 0 || (slots[o.in2].cols == xf::E && slots[o.in2].rows == static_cast<int64_t>(n_segs) * T &&
-                                         dt(o.in2) == MILB200_F32)) &&
-                          ((o.a0 & 1) || so.rows == s0.rows),
+                          slots[o.in1].rows == n_segs && dt(o.in1) == MILB200_F32 && ((o.a0 & 1) || so.rows == s0.rows),
                       MILB200_EINVAL, "tape: op %d ln_seg shape/dtype mismatch", i);
         break;
       }
@@ -424,8 +421,7 @@ static int tape_forward_run(const milb200_tape_op* ops, int n_ops, const milb200
       case MILB200_OP_LN_SEG: {
         float* mean = reinterpret_cast<float*>(ar + pl.aux_off[i]);
         rc = xf::ln_seg_fwd(ptr[o.in0], static_cast<const float*>(ptr[o.in1]), p_f32 + params[o.p0].offset,
-                            p_f32 + params[o.p1].offset, o.in2 >= 0 ? static_cast<const float*>(ptr[o.in2]) : nullptr, pl.sg,
-                            o.a0 & 1, ptr[o.out], mean, mean + s0.rows, d0, dt(o.out), cst);
+                            p_f32 + params[o.p1].offset, pl.sg, o.a0 & 1, ptr[o.out], mean, mean + s0.rows, d0, dt(o.out), cst);
         break;
       }
       case MILB200_OP_TOK_SCATTER:
@@ -694,15 +690,13 @@ static int tape_backward_run(const milb200_tape_op* ops, int n_ops, const milb20
         const int acc = (needs[o.in0] && has[o.in0]) ? 1 : 0;
         float* dR = static_cast<float*>(target(o.in1, 1));
         float* dRw = dR ? dR : reinterpret_cast<float*>(tmp0 + tmp_stride);
-        float* dtok = o.in2 >= 0 ? static_cast<float*>(target(o.in2, 2)) : nullptr;
         rc = xf::ln_seg_bwd(val[o.in0], static_cast<const float*>(val[o.in1]), p_f32 + params[o.p0].offset, mean,
                             mean + s0.rows, dY, pl.sg, o.a0 & 1, dK, acc, dRw, g_f32 + params[o.p0].offset,
-                            g_f32 + params[o.p1].offset, ptouched[o.p0] ? 1 : 0, dtok, d0, dt(o.out), scratch, scratch_bytes, cst);
+                            g_f32 + params[o.p1].offset, ptouched[o.p0] ? 1 : 0, d0, dt(o.out), scratch, scratch_bytes, cst);
         if (rc) return rc;
         ptouched[o.p0] = ptouched[o.p1] = 1;
         if (needs[o.in0]) has[o.in0] = 1;
         if ((rc = settle(o.in1, dR))) return rc;
-        if (o.in2 >= 0 && (rc = settle(o.in2, dtok))) return rc;
         break;
       }
       case MILB200_OP_TOK_SCATTER: {

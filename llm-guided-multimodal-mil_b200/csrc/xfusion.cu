@@ -476,22 +476,13 @@ k_sum_items(const float* __restrict__ part, const Segs sg, float* __restrict__ o
 // ---------------------------------------------------------------------------------------------------------------------
 // LayerNorm(keys + row[segment])   (eps 1e-5)
 // ---------------------------------------------------------------------------------------------------------------------
-// grid (items [+ 1 when tokens are scattered]); rows are read at k_start, written at out_start when bag_layout_out.
+// grid (items); rows are read at k_start, written at out_start when bag_layout_out.
 // TI / TO: storage of the input rows and of the result (fp32 key stream -> bf16 packed bag on the last layer).
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(THREADS)
 k_ln_seg_fwd(const TI* __restrict__ K, const float* __restrict__ R, const float* __restrict__ gamma, const float* __restrict__ beta,
-             const float* __restrict__ tokens, const Segs sg, const int bag_layout_out, TO* __restrict__ Y,
-             float* __restrict__ mean, float* __restrict__ rstd) {
+             const Segs sg, const int bag_layout_out, TO* __restrict__ Y, float* __restrict__ mean, float* __restrict__ rstd) {
   const int item = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (item >= sg.n_items) {         // the extra CTA: token rows of every segment -> their rows of the packed bag
-    for (int r = warp; r < sg.n * sg.T; r += WARPS) {
-      float v[16];
-      load_f32_row<TO>(tokens + static_cast<int64_t>(r) * E, lane, v);
-      Row<TO>::store(Y + static_cast<int64_t>(sg.tok_row[r / sg.T] + r % sg.T) * E, lane, v);
-    }
-    return;
-  }
   const int s = find_seg(sg, item);
   const int i0 = (item - sg.item0[s]) * sg.rows_per_item;
   const int i1 = min(sg.len[s], i0 + sg.rows_per_item);
@@ -583,23 +574,12 @@ k_ln_seg_bwd(const TI* __restrict__ K, const float* __restrict__ R, const float*
   }
 }
 
-// grid (2 + n_segs + n_segs*T), 512 threads:
-//   block 0/1: dgamma / dbeta = sum over all items;  block 2+s: dR[s] = sum over the items of s;
-//   then one block per token row: dtokens[r] = dY[tok_row[r/T] + r%T] (fp32)
-template <typename TK>
+// grid (2 + n_segs), 512 threads: block 0/1: dgamma / dbeta = sum over all items;  block 2+s: dR[s] = sum over the items of s
 __global__ void __launch_bounds__(MERGE_THREADS)
 k_ln_seg_reduce(const float* __restrict__ part, const Segs sg, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                const int accumulate, float* __restrict__ dR, const TK* __restrict__ dY, float* __restrict__ dtokens) {
+                const int accumulate, float* __restrict__ dR) {
   __shared__ float4 red[MERGE_THREADS];
   const int b = blockIdx.x, c = (threadIdx.x & 127) * 4;
-  if (b >= 2 + sg.n) {
-    const int r = b - 2 - sg.n;
-    if (dtokens == nullptr || threadIdx.x >= 128) return;
-    const TK* src = dY + static_cast<int64_t>(sg.tok_row[r / sg.T] + r % sg.T) * E + c;
-    float4 o = make_float4(to_f32<TK>(src[0]), to_f32<TK>(src[1]), to_f32<TK>(src[2]), to_f32<TK>(src[3]));
-    *reinterpret_cast<float4*>(dtokens + static_cast<int64_t>(r) * E + c) = o;
-    return;
-  }
   const int k = b < 2 ? b : 2;
   const int p0 = b < 2 ? 0 : sg.item0[b - 2], p1 = b < 2 ? sg.n_items : sg.item0[b - 1];
   float4 a = merge_items<false>(part, 3, k, p0, p1, nullptr, red);
@@ -816,29 +796,27 @@ int t2i_bwd(const void* K, const float* PE, const float* U, const float* S, cons
   return MILB200_OK;
 }
 
-int ln_seg_fwd(const void* K, const float* R, const float* gamma, const float* beta, const float* tokens, const Segs& sg_in,
-               int bag_layout_out, void* Y, float* mean, float* rstd, int in_dtype, int out_dtype, cudaStream_t st) {
+int ln_seg_fwd(const void* K, const float* R, const float* gamma, const float* beta, const Segs& sg_in, int bag_layout_out,
+               void* Y, float* mean, float* rstd, int in_dtype, int out_dtype, cudaStream_t st) {
   MIL_CHECK_ARG(K && R && gamma && beta && Y && mean && rstd, MILB200_EINVAL, "ln_seg_fwd: null pointer");
   const Segs sg = finer(sg_in, LN_FINER);
   MIL_CHECK_ARG(in_dtype == out_dtype || (in_dtype == MILB200_F32 && out_dtype == MILB200_BF16), MILB200_EUNSUPPORTED,
                 "ln_seg_fwd: storage pair (in %d, out %d) is not built", in_dtype, out_dtype);
-  const unsigned grid = sg.n_items + (tokens ? 1 : 0);
+  const unsigned grid = sg.n_items;
   using bf = __nv_bfloat16;
   if (out_dtype == MILB200_F32)
-    k_ln_seg_fwd<float, float><<<grid, THREADS, 0, st>>>((const float*)K, R, gamma, beta, tokens, sg, bag_layout_out, (float*)Y,
-                                                         mean, rstd);
+    k_ln_seg_fwd<float, float><<<grid, THREADS, 0, st>>>((const float*)K, R, gamma, beta, sg, bag_layout_out, (float*)Y, mean, rstd);
   else if (in_dtype == MILB200_BF16)
-    k_ln_seg_fwd<bf, bf><<<grid, THREADS, 0, st>>>((const bf*)K, R, gamma, beta, tokens, sg, bag_layout_out, (bf*)Y, mean, rstd);
+    k_ln_seg_fwd<bf, bf><<<grid, THREADS, 0, st>>>((const bf*)K, R, gamma, beta, sg, bag_layout_out, (bf*)Y, mean, rstd);
   else
-    k_ln_seg_fwd<float, bf><<<grid, THREADS, 0, st>>>((const float*)K, R, gamma, beta, tokens, sg, bag_layout_out, (bf*)Y, mean,
-                                                      rstd);
+    k_ln_seg_fwd<float, bf><<<grid, THREADS, 0, st>>>((const float*)K, R, gamma, beta, sg, bag_layout_out, (bf*)Y, mean, rstd);
   MIL_LAUNCH_CHECK();
   return MILB200_OK;
 }
 
 int ln_seg_bwd(const void* K, const float* R, const float* gamma, const float* mean, const float* rstd, const void* dY,
                const Segs& sg_in, int bag_layout_out, void* dK, int accumulate_dk, float* dR, float* dgamma, float* dbeta,
-               int accumulate_params, float* dtokens, int in_dtype, int out_dtype, void* ws, size_t ws_bytes, cudaStream_t st) {
+               int accumulate_params, int in_dtype, int out_dtype, void* ws, size_t ws_bytes, cudaStream_t st) {
   MIL_CHECK_ARG(K && R && gamma && mean && rstd && dY && dK && dR && dgamma && dbeta, MILB200_EINVAL, "ln_seg_bwd: null pointer");
   const Segs sg = finer(sg_in, LN_FINER);
   MIL_CHECK_ARG(in_dtype == out_dtype || (in_dtype == MILB200_F32 && out_dtype == MILB200_BF16), MILB200_EUNSUPPORTED,
@@ -846,7 +824,7 @@ int ln_seg_bwd(const void* K, const float* R, const float* gamma, const float* m
   MIL_CHECK_ARG(ws && ws_bytes >= ln_seg_ws_bytes(sg_in), MILB200_EWORKSPACE, "ln_seg_bwd: workspace %zu < %zu", ws_bytes,
                 ln_seg_ws_bytes(sg_in));
   float* part = static_cast<float*>(ws);
-  const unsigned rgrid = 2 + sg.n + (dtokens ? sg.n * sg.T : 0);
+  const unsigned rgrid = 2 + sg.n;
   using bf = __nv_bfloat16;
   if (out_dtype == MILB200_F32) {
     k_ln_seg_bwd<float, float><<<sg.n_items, THREADS, 0, st>>>((const float*)K, R, gamma, mean, rstd, (const float*)dY, sg,
@@ -859,10 +837,7 @@ int ln_seg_bwd(const void* K, const float* R, const float* gamma, const float* m
                                                             bag_layout_out, (float*)dK, accumulate_dk, part);
   }
   MIL_LAUNCH_CHECK();
-  if (out_dtype == MILB200_F32)
-    k_ln_seg_reduce<float><<<rgrid, MERGE_THREADS, 0, st>>>(part, sg, dgamma, dbeta, accumulate_params, dR, (const float*)dY, dtokens);
-  else
-    k_ln_seg_reduce<bf><<<rgrid, MERGE_THREADS, 0, st>>>(part, sg, dgamma, dbeta, accumulate_params, dR, (const bf*)dY, dtokens);
+  k_ln_seg_reduce<<<rgrid, MERGE_THREADS, 0, st>>>(part, sg, dgamma, dbeta, accumulate_params, dR);
   MIL_LAUNCH_CHECK();
   return MILB200_OK;
 }

@@ -48,16 +48,14 @@ int t2i_bwd(const void* K, const float* PE, const float* U, const float* S, cons
             void* ws, size_t ws_bytes, cudaStream_t st);
 
 // Y[out(n)] = LayerNorm(K[n] + R[seg(n)]) * gamma + beta  (R: ONE row per segment — the image -> token attention with
-// a single token).  bag_layout_out: rows are written at out_start (the packed bag) instead of k_start;
-// tokens != NULL additionally copies the T token rows of every segment to tok_row (cast to out_dtype).  Storage pairs
-// (in, out): equal, or fp32 key stream -> bf16 packed bag (the last layer of a bf16 program).
-int ln_seg_fwd(const void* K, const float* R, const float* gamma, const float* beta, const float* tokens, const Segs& sg,
-               int bag_layout_out, void* Y, float* mean, float* rstd, int in_dtype, int out_dtype, cudaStream_t st);
-// dK (in place accumulate optional), dR [n_segs, E] f32, dgamma/dbeta (accumulate optional), dtokens [n_segs*T, E] f32
-// (= the token rows of dY; may be NULL)
+// a single token).  bag_layout_out: rows are written at out_start (the packed bag) instead of k_start.
+// Storage pairs (in, out): equal, or fp32 key stream -> bf16 packed bag (the last layer of a bf16 program).
+int ln_seg_fwd(const void* K, const float* R, const float* gamma, const float* beta, const Segs& sg, int bag_layout_out,
+               void* Y, float* mean, float* rstd, int in_dtype, int out_dtype, cudaStream_t st);
+// dK (in place accumulate optional), dR [n_segs, E] f32, dgamma/dbeta (accumulate optional)
 int ln_seg_bwd(const void* K, const float* R, const float* gamma, const float* mean, const float* rstd, const void* dY,
                const Segs& sg, int bag_layout_out, void* dK, int accumulate_dk, float* dR, float* dgamma, float* dbeta,
-               int accumulate_params, float* dtokens, int in_dtype, int out_dtype, void* ws, size_t ws_bytes, cudaStream_t st);
+               int accumulate_params, int in_dtype, int out_dtype, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // bag[tok_row[s] + t] = tokens[s*T + t] (cast to dtype) / dtokens[s*T + t] = dbag[tok_row[s] + t] (fp32)
 int tok_scatter(const float* tokens, const Segs& sg, void* bag, int dtype, cudaStream_t st);

@@ -122,36 +122,53 @@ class FusionTrainer:
             torch.distributed.broadcast(self.params, src=0, group=self.pg)
             self._refresh_compute_copy()
 
-    # ---- buffers of one step shape (pointer-stable, so the program replays as a CUDA graph) ---------------------------
+    # ---- buffers (pointer-stable, so a repeated step shape replays as a CUDA graph) ------------------------------------
+    CAP_ROWS = 4096        # pathology rows are rounded up to this granule when sizing buffers
+
     def _buffers(self, key, rows, segs, n_bags, bag_off):
+        """Buffers for a step.  Sized by CAPACITY (the packed pathology rows rounded up to CAP_ROWS), not by the exact shape:
+        real cohorts have a different row count per patient, and a fresh multi-hundred-MB arena per new shape would turn
+        every step into an allocation.  Steps whose shapes fall into the same capacity share one set of buffers (the
+        kernels get exact row counts and pointers to the heads of the buffers); exact repeats replay as CUDA graphs."""
         b = self._buf.get(key)
         if b is None:
             if len(self._buf) >= 4:
                 self._buf.pop(next(iter(self._buf)))
             t, c, lib = self.tape, self.tape._freeze(), L.lib()
-            slots = t._slots(rows)
-            segp = t._segments(segs)
             code = L.BF16 if self.dtype == torch.bfloat16 else L.F32
             dev = self.device
+            cap = dict(rows)
+            if self.collapsed:          # capacity image of the row counts: every slot at least as large as any shape of the bucket
+                extra = key[2] - rows["NP"]
+                for k in ("NP", "NK", "NBAG"):
+                    cap[k] = rows[k] + extra
+            slots_cap = t._slots(cap)
+            segp = t._segments(segs)
             mk = lambda r, cc, dt=None: torch.empty((int(r), int(cc)), dtype=dt or self.dtype, device=dev)
             sdt = lambda s: torch.float32 if t.slot_f32[s] else self.dtype
             B, Cn, T, E = n_bags, self.C, self.T, self.E
             f32 = torch.float32
-            b = dict(slots=slots, code=code, segp=segp,
-                     arena=torch.empty(lib.milb200_tape_arena_bytes(c["ops"], c["n_ops"], slots, c["n_slots"], code, segp),
+            b = dict(code=code,
+                     arena=torch.empty(lib.milb200_tape_arena_bytes(c["ops"], c["n_ops"], slots_cap, c["n_slots"], code, segp),
                                        dtype=torch.uint8, device=dev),
-                     out=[mk(fn(rows), cols, t.buffer_dtype(i, self.dtype)) for i, (fn, cols) in enumerate(t.buffers)],
-                     stage=[mk(slots[s].rows, slots[s].cols, sdt(s)) for s in t.inputs],
+                     out=[mk(fn(cap), cols, t.buffer_dtype(i, self.dtype)) for i, (fn, cols) in enumerate(t.buffers)],
+                     # (the cached position tables are used in place: no staging buffer for them)
+                     stage=[None if j in ((2,) if self.collapsed else (1, 3)) else mk(slots_cap[s].rows, slots_cap[s].cols, sdt(s))
+                            for j, s in enumerate(t.inputs)],
                      z=torch.empty((B, Cn), dtype=f32, device=dev), prob=torch.empty((B, Cn), dtype=f32, device=dev),
                      dz=torch.empty((B, Cn), dtype=f32, device=dev), dM=torch.empty((B, E), dtype=f32, device=dev),
                      loss=torch.zeros(2, dtype=f32, device=dev),
                      cos_rows=torch.empty(max(B * T, 1), dtype=f32, device=dev),
-                     da=mk(B * T, E), db=mk(B * T, E),
-                     offsets=torch.tensor(bag_off, dtype=torch.int32, device=dev))
+                     da=mk(B * T, E), db=mk(B * T, E), offsets={})
             if self.collapsed:      # gradient of the fp32 token rows [CT segments | pathology segments]: the cosine loss's
                 b["dtok"] = torch.zeros((2 * B * T, E), dtype=f32, device=dev)
             self._buf[key] = b
-        return b
+        off_key = tuple(bag_off)
+        if off_key not in b["offsets"]:
+            if len(b["offsets"]) > 256:
+                b["offsets"].clear()
+            b["offsets"][off_key] = torch.tensor(bag_off, dtype=torch.int32, device=self.device)
+        return b, self.tape._slots(rows), self.tape._segments(segs), b["offsets"][off_key]
 
     # ---- forward + backward ------------------------------------------------------------------------------------------
     def forward_backward(self, ct_tokens, x_path, x_text, label):
@@ -176,13 +193,15 @@ class FusionTrainer:
         rows, segs, bag_off = m.fusion_layout(Nc, path_lens, 1)
         pe = m._pe_table(max(Nc, max(path_lens)), self.device)
         rows["NPE"] = pe.shape[0]
-        key = (Nc, tuple(path_lens), pe.data_ptr())
-        b = self._buffers(key, rows, segs, B, bag_off)
+        n_p = rows["NP"]
+        key = (B, Nc, (n_p + self.CAP_ROWS - 1) // self.CAP_ROWS * self.CAP_ROWS, pe.data_ptr())
+        b, slots, segp, offsets = self._buffers(key, rows, segs, B, bag_off)
         c = t._freeze()
-        slots, code, segp, n_slots = b["slots"], b["code"], b["segp"], c["n_slots"]
+        code, n_slots = b["code"], c["n_slots"]
         E, Cn = self.E, self.C
         # inputs -> pointer-stable staging (program order: patch features, CT tokens fp32, position table, text fp32)
         st_xp, st_ct, _, st_txt = b["stage"]
+        st_xp = st_xp[:n_p]
         st_xp.copy_(x_path)
         for src, dst in ((ct_tokens.reshape(B * Nc, E), st_ct), (x_text.reshape(B, E), st_txt)):
             src = src.contiguous()
@@ -195,7 +214,7 @@ class FusionTrainer:
         ext = _ptrs(n_slots)
         for s, x in zip(t.inputs, inputs):
             ext[s] = x.data_ptr()
-        bag, tok = b["out"][0], b["out"][1]
+        bag, tok = b["out"][0][:rows["NBAG"]], b["out"][1]
         for s, bi, fn in t.outputs:
             ext[s] = b["out"][bi].data_ptr()
         ws = L.workspace(lib.milb200_tape_workspace_bytes(c["ops"], c["n_ops"], slots, n_slots, code, 0, segp), self.device)
@@ -203,7 +222,7 @@ class FusionTrainer:
                                          L.ptr(self.params), L.ptr(b["arena"]), b["arena"].numel(), L.ptr(ws), ws.numel(),
                                          code, segp, L.stream_ptr()), "tape_forward")
         self._set_targets(labels, B)
-        dbag = self._pool_head_losses(b, bag, B)
+        dbag = self._pool_head_losses(b, bag, B, offsets)
         dtok = b["dtok"]
         if not self.cosine_loss:
             dtok.zero_()                  # the backward accumulates into the seeded buffers in place
@@ -227,12 +246,12 @@ class FusionTrainer:
                 "tape_backward")
         return b["loss"], b["prob"]
 
-    def _pool_head_losses(self, b, bag, B):
+    def _pool_head_losses(self, b, bag, B, offsets):
         """Gated pool over the packed bag(s) (aggregator.py:199), head (:200) + BCE (train_ddp.py:99,319) and their
         backward; returns the gradient of the packed bag."""
         lib = L.lib()
         E, Cn = self.E, self.C
-        M = self.pool.forward(bag, b["offsets"])                              # (B, E) fp32
+        M = self.pool.forward(bag, offsets)                                   # (B, E) fp32
         Mh, seed_h = M, None
         if self.head_p > 0.0:                                                 # aggregator.py:128-131 Dropout(0.25), train mode
             seed_h = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
@@ -266,9 +285,9 @@ class FusionTrainer:
         if T != self.T:
             raise L.MilB200Error(f"FusionTrainer was built for {self.T} text token(s), got {T}")
         rows = {"T": T, "Nc": Nc, "Np": Np}
-        b = self._buffers(tuple(sorted(rows.items())), rows, None, 1, [0, 2 * T + Nc + Np])
+        b, slots, _, offsets = self._buffers(tuple(sorted(rows.items())), rows, None, 1, [0, 2 * T + Nc + Np])
         c = t._freeze()
-        slots, code, n_slots = b["slots"], b["code"], c["n_slots"]
+        code, n_slots = b["code"], c["n_slots"]
         like = x_text
         srcs = [ct_tokens, m._pe(Nc, like)[0], x_path, m._pe(Np, like)[0], x_text]
         inputs = []
@@ -291,7 +310,7 @@ class FusionTrainer:
                                          code, None, L.stream_ptr()), "tape_forward")
         bag = b["out"][0]                                                     # aggregator.py:173 row order
         self._set_targets(label, 1)
-        dbag = self._pool_head_losses(b, bag, 1)
+        dbag = self._pool_head_losses(b, bag, 1, offsets)
         if self.cosine_loss:
             a_rows, b_rows = bag[0:T], bag[T + Nc:2 * T + Nc]                 # x_CT2CI, x_Pth2CI (aggregator.py:160,168)
             L.check(lib.milb200_cosine_embedding_fwd_bwd(L.ptr(a_rows), L.ptr(b_rows), L.ptr(b["loss"][1:2]),

@@ -134,9 +134,9 @@ class Tape:
         self.ops.append((L.OP_T2I_POOL, keys, pe, u, out, -1, -1, 1 if bag_layout else 0, self._lane))
         return out
 
-    def ln_seg(self, keys, rows, ln, out_rows_key=None, tokens=None):
+    def ln_seg(self, keys, rows, ln, out_rows_key=None):
         """out = LN(keys + rows[segment]) (one residual row per segment).  out_rows_key: the result is written in the
-        packed-bag layout (segment out_start) into a slot of that many rows, with `tokens` copied to their rows."""
+        packed-bag layout (segment out_start) into a slot of that many rows."""
         if abs(ln.eps - 1e-5) > 1e-12:
             raise L.MilB200Error("layernorm kernels are built for eps = 1e-5 (nn.LayerNorm default)")
         bag = out_rows_key is not None
@@ -144,8 +144,8 @@ class Tape:
         # result keeps the storage of its input
         out = self.slot(out_rows_key if bag else self.slot_rows[keys], self.slot_cols[keys],
                         f32=False if bag else self.slot_f32[keys])
-        self.ops.append((L.OP_LN_SEG, keys, rows, -1 if tokens is None else tokens, out, self.param(ln.weight),
-                         self.param(ln.bias), 1 if bag else 0, self._lane))
+        self.ops.append((L.OP_LN_SEG, keys, rows, -1, out, self.param(ln.weight), self.param(ln.bias), 1 if bag else 0,
+                         self._lane))
         return out
 
     def tok_scatter(self, tokens, bag):

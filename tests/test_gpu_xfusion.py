@@ -337,3 +337,26 @@ def test_forward_bags_rejects_bad_arguments():
     with pytest.raises(mil_b200.MilB200Error):
         m.forward_bags(torch.randn(9, 4, 512, device="cuda"), torch.randn(90, 768, device="cuda"), [10] * 9,
                        torch.randn(9, 1, 512, device="cuda"))       # more than 8 patients = 16 segments
+
+
+def test_fusion_trainer_varying_shapes_share_buffers_and_stay_correct():
+    """Real cohorts have a different row count per patient: consecutive steps with different shapes (same capacity bucket,
+    then a larger one, then a repeat that replays its CUDA graph) must each equal a fresh trainer's result."""
+    import mil_b200
+    m, sdn = _model(seed=31)
+    tr = mil_b200.FusionTrainer(m, n_text_tokens=1, compute_dtype=torch.float32)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    shapes = [[700, 90], [650, 301], [5000, 40], [700, 90], [700, 90]]
+    for lens in shapes:
+        B = len(lens)
+        ct = torch.randn(B, 160, 512, device="cuda", generator=g)
+        xp = torch.randn(sum(lens), 768, device="cuda", generator=g)
+        xt = torch.randn(B, 512, device="cuda", generator=g) * 0.05
+        lab = torch.tensor([[0.0, 1.0], [1.0, 0.0]], device="cuda")
+        loss, prob = tr.forward_backward_bags(ct, xp, lens, xt, lab)
+        got = (loss.clone(), prob.clone(), tr.grads.clone())
+        fresh = mil_b200.FusionTrainer(m, n_text_tokens=1, compute_dtype=torch.float32)
+        l2, p2 = fresh.forward_backward_bags(ct, xp, lens, xt, lab)
+        assert torch.equal(got[0], l2) and torch.equal(got[1], p2), lens
+        assert torch.equal(got[2], fresh.grads), lens
+    assert len(tr._buf) == 2          # two capacity buckets: (4096 rows) and (8192 rows)
