@@ -194,7 +194,7 @@ class FusionTrainer:
         pe = m._pe_table(max(Nc, max(path_lens)), self.device)
         rows["NPE"] = pe.shape[0]
         n_p = rows["NP"]
-        key = (B, Nc, (n_p + self.CAP_ROWS - 1) // self.CAP_ROWS * self.CAP_ROWS, pe.data_ptr())
+        key = (B, Nc, (n_p + self.CAP_ROWS - 1) // self.CAP_ROWS * self.CAP_ROWS)
         b, slots, segp, offsets = self._buffers(key, rows, segs, B, bag_off)
         c = t._freeze()
         code, n_slots = b["code"], c["n_slots"]
