@@ -771,8 +771,13 @@ def main():
     dp_check = dp_equivalence_check(tr, module, X, offsets_h, lengths, rank, world, dev, pg) if world > 1 else None
 
     # ---- device-resident timing ----
+    # the whole step (forward, backward, exchange, optimiser) replays as ONE CUDA graph per input address
+    # (AbmilTrainer.step_graphed; MILB200_STEP_GRAPH=0 runs the ~10 launches eagerly)
+    use_graph = os.environ.get("MILB200_STEP_GRAPH", "1") != "0" and not args.input_grad
+    run_step = tr.step_graphed if use_graph else tr.step
+    config["step_launch"] = "one CUDA graph per step (AbmilTrainer.step_graphed)" if use_graph else "eager launches"
     for _ in range(warmup):
-        tr.step(X, offsets)
+        run_step(X, offsets)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -783,7 +788,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        tr.step(X, offsets)
+        run_step(X, offsets)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -846,7 +851,7 @@ def main():
                 off_d[b].copy_(off_pin, non_blocking=True)
                 copied[b].record(copy_stream)
             main_stream.wait_event(copied[b])
-            M = tr.step(X_d[b], off_d[b])
+            M = run_step(X_d[b], off_d[b])
             consumed[b].record(main_stream)
             M_h[b].copy_(M, non_blocking=True)
             read_back[b].record(main_stream)

@@ -319,6 +319,12 @@ int milb200_gated_score_pool_fwd(const void* X, const void* Wcat, const float* b
 int milb200_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
                       float lr, float beta1, float beta2, float eps, float weight_decay,
                       float grad_scale, int step, void* stream);
+/* The same update with the step number in device memory (bias corrections computed by the kernel): lets a captured CUDA
+ * graph of the whole training step be replayed.  milb200_step_counter_inc adds 1 to the counter (one-thread kernel).   */
+int milb200_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                          float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                          const int32_t* step_dev, void* stream);
+int milb200_step_counter_inc(int32_t* step_dev, void* stream);
 /* torch.optim.SGD(lr, weight_decay) as the learnable-prompt configuration builds it (train_ddp.py:103-108; no
  * momentum): p -= lr * (grad_scale * g + weight_decay * p).                                          */
 int milb200_sgd_step(float* param, const float* grad, int64_t n, float lr, float weight_decay, float grad_scale,
@@ -333,11 +339,13 @@ int milb200_sgd_step(float* param, const float* grad, int64_t n, float lr, float
  * broadcast (multimem.st) by rank r, between two flag barriers; then every rank applies the fused optimiser update
  * (optimizer 0: Adam, 1: SGD, -1: none — exchange only, for large buffers whose update wants a full-width grid: call
  * milb200_adam_step afterwards) with grad_scale (1/world = DDP's average).  On return the gradient buffer holds the SUM over
- * ranks — bit-identical on every rank.  The allocation must be padded to a multiple of 4 * world elements.              */
+ * ranks — bit-identical on every rank.  The allocation must be padded to a multiple of 4 * world elements.  step_dev
+ * (optional, device int32): the Adam step number is read from device memory instead of `step` — a training step that is
+ * replayed as a CUDA graph keeps its counter there (milb200_step_counter_inc).                                          */
 int milb200_allreduce_update_symm(float* param, float* grad_local, void* grad_multicast, void* const* signal_pads_dev,
                                   int pad_slot0, int rank, int world, float* exp_avg, float* exp_avg_sq, int64_t n,
                                   int optimizer, float lr, float beta1, float beta2, float eps, float weight_decay,
-                                  float grad_scale, int step, void* stream);
+                                  float grad_scale, int step, const int32_t* step_dev, void* stream);
 
 /* ---- feeder, host side (dataset.py:366-393) ---------------------------------------------------------
  * Gathers the per-slide feature matrices of one step (what `np.load(<patient>.npy)` returns: [rows_b, L] row-major

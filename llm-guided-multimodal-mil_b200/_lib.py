@@ -72,7 +72,9 @@ SIGNATURES = {
     "milb200_tape_backward": (_i, [_p, _i, _p, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p, _sz, _p, _sz, _i, _p, _p]),
     "milb200_adam_step": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _i, _p]),
     "milb200_sgd_step": (_i, [_p, _p, _i64, _f, _f, _f, _p]),
-    "milb200_allreduce_update_symm": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _i64, _i, _f, _f, _f, _f, _f, _f, _i, _p]),
+    "milb200_allreduce_update_symm": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _i64, _i, _f, _f, _f, _f, _f, _f, _i, _p, _p]),
+    "milb200_adam_step_dev": (_i, [_p, _p, _p, _p, _i64, _f, _f, _f, _f, _f, _f, _p, _p]),
+    "milb200_step_counter_inc": (_i, [_p, _p]),
     "milb200_pack_bags_offsets": (_i, [_p, _p, _i, _p, _p]),
     "milb200_pack_bags_host": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _i64, _p, _i]),
     "milb200_sigmoid_bce_fwd_bwd": (_i, [_p, _p, _p, _p, _p, _i, _p]),

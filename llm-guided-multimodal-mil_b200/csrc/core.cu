@@ -269,6 +269,28 @@ __global__ void k_adam(float* __restrict__ p, const float* __restrict__ g, float
   }
 }
 
+// same update with the step number read from device memory (so that a CUDA graph that contains the optimiser can be
+// replayed: the bias corrections must not be baked into the launch parameters)
+__global__ void k_adam_dev(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                           int64_t n, float lr, float b1, float b2, float eps, float wd, float gscale,
+                           const int32_t* __restrict__ step_dev) {
+  const float step = static_cast<float>(*step_dev);
+  const float bc1 = 1.f - powf(b1, step), bc2 = 1.f - powf(b2, step);
+  int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (; i < n; i += stride) {
+    float pi = p[i];
+    float gi = fmaf(wd, pi, g[i] * gscale);
+    float mi = fmaf(b1, m[i], (1.f - b1) * gi);
+    float vi = fmaf(b2, v[i], (1.f - b2) * gi * gi);
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+__global__ void k_counter_inc(int32_t* c) { *c += 1; }
+
 __global__ void k_sgd(float* __restrict__ p, const float* __restrict__ g, int64_t n, float lr, float wd, float gscale) {
   int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
@@ -560,6 +582,25 @@ int milb200_adam_step(float* param, const float* grad, float* exp_avg, float* ex
   unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 148 * 8));
   k_adam<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
                                                                 eps, weight_decay, grad_scale, bc1, bc2);
+  MIL_LAUNCH_CHECK();
+  return MILB200_OK;
+}
+
+int milb200_step_counter_inc(int32_t* step_dev, void* stream) {
+  MIL_CHECK_ARG(step_dev != nullptr, MILB200_EINVAL, "step_counter_inc: null pointer");
+  k_counter_inc<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(step_dev);
+  MIL_LAUNCH_CHECK();
+  return MILB200_OK;
+}
+
+int milb200_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                          float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                          const int32_t* step_dev, void* stream) {
+  MIL_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && n >= 0 && step_dev, MILB200_EINVAL, "adam_step_dev: bad arguments");
+  if (n == 0) return MILB200_OK;
+  unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n + 255) / 256, 148 * 8));
+  k_adam_dev<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                                    eps, weight_decay, grad_scale, step_dev);
   MIL_LAUNCH_CHECK();
   return MILB200_OK;
 }

@@ -65,7 +65,13 @@ __global__ void __launch_bounds__(XCH_THREADS)
 k_allreduce_update(float* __restrict__ p, float* __restrict__ g_local, float* g_mc, uint32_t* const* __restrict__ pads,
                    const int rank, const int world, const int slot0, float* __restrict__ m, float* __restrict__ v,
                    const int64_t n, const int64_t chunk4, const int optimizer, const float lr, const float b1, const float b2,
-                   const float eps, const float wd, const float gscale, const float bc1, const float bc2) {
+                   const float eps, const float wd, const float gscale, float bc1, float bc2,
+                   const int32_t* __restrict__ step_dev) {
+  if (step_dev != nullptr && optimizer == 0) {      // replayable graphs: the step number lives in device memory
+    const float step = static_cast<float>(*step_dev);
+    bc1 = 1.f - powf(b1, step);
+    bc2 = 1.f - powf(b2, step);
+  }
   peer_barrier(pads, rank, world, slot0);
   {
     const int64_t lo = rank * chunk4, hi = min((n + 3) / 4, lo + chunk4);
@@ -137,15 +143,16 @@ extern "C" {
  * least pad_slot0 + 32 * world entries).  n elements (the allocation must be padded to a multiple of 4 * world
  * elements).  optimizer: 0 Adam (exp_avg / exp_avg_sq updated), 1 SGD, -1 none (exchange only: large buffers, whose
  * update wants a full-width grid, call milb200_adam_step afterwards).  After the call every rank's gradient buffer holds
- * the SUM over ranks and its parameters have taken the step with grad_scale (= 1/world for DDP's average).            */
+ * the SUM over ranks and its parameters have taken the step with grad_scale (= 1/world for DDP's average).  step_dev
+ * (optional): the Adam step number in device memory, read by the kernel instead of `step` (replayable CUDA graphs).    */
 int milb200_allreduce_update_symm(float* param, float* grad_local, void* grad_multicast, void* const* signal_pads_dev,
                                   int pad_slot0, int rank, int world, float* exp_avg, float* exp_avg_sq, int64_t n,
                                   int optimizer, float lr, float beta1, float beta2, float eps, float weight_decay,
-                                  float grad_scale, int step, void* stream) {
+                                  float grad_scale, int step, const int32_t* step_dev, void* stream) {
   MIL_CHECK_ARG(param && grad_local && grad_multicast && signal_pads_dev && n > 0, MILB200_EINVAL, "allreduce_update: null pointer");
   MIL_CHECK_ARG(world >= 2 && world <= XCH_MAX_WORLD && rank >= 0 && rank < world && pad_slot0 >= 0, MILB200_EINVAL,
                 "allreduce_update: rank %d / world %d", rank, world);
-  MIL_CHECK_ARG(optimizer != 0 || (exp_avg && exp_avg_sq && step >= 1), MILB200_EINVAL, "allreduce_update: Adam needs its state and step >= 1");
+  MIL_CHECK_ARG(optimizer != 0 || (exp_avg && exp_avg_sq && (step >= 1 || step_dev)), MILB200_EINVAL, "allreduce_update: Adam needs its state and step >= 1");
   MIL_CHECK_ARG(aligned16(grad_local) && aligned16(grad_multicast), MILB200_EALIGN, "allreduce_update: buffers must be 16-byte aligned");
   const int64_t n4 = (n + 3) / 4;
   const int64_t chunk4 = (n4 + world - 1) / world;
@@ -166,7 +173,8 @@ int milb200_allreduce_update_symm(float* param, float* grad_local, void* grad_mu
   const float bc2 = optimizer != 0 ? 1.f : 1.f - powf(beta2, static_cast<float>(step));
   k_allreduce_update<<<blocks, XCH_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
       param, grad_local, static_cast<float*>(grad_multicast), reinterpret_cast<uint32_t* const*>(signal_pads_dev), rank, world,
-      pad_slot0, exp_avg, exp_avg_sq, n, chunk4, optimizer, lr, beta1, beta2, eps, weight_decay, grad_scale, bc1, bc2);
+      pad_slot0, exp_avg, exp_avg_sq, n, chunk4, optimizer, lr, beta1, beta2, eps, weight_decay, grad_scale, bc1, bc2,
+      step_dev);
   MIL_LAUNCH_CHECK();
   return MILB200_OK;
 }

@@ -213,16 +213,25 @@ class AbmilTrainer:
     def reduce_and_update(self):
         """all-reduce(sum) of the flat gradient over NCCL, then the fused optimiser step with grad_scale = 1/world."""
         sm = getattr(self, "_symm", None)
+        sd = getattr(self, "_step_dev", None)        # device-resident step counter (graphed steps), else None
+        if sd is not None:
+            L.check(L.lib().milb200_step_counter_inc(L.ptr(sd), L.stream_ptr()), "step_counter_inc")
         if sm is not None:
             self.step_count += 1
             L.check(L.lib().milb200_allreduce_update_symm(
                 L.ptr(self.params), L.ptr(self.grads), sm["mc"], L.ptr(sm["pads"]), 0, sm["rank"], self.world,
                 L.ptr(self.exp_avg), L.ptr(self.exp_avg_sq), self.numel, 1 if self.optimizer == "sgd" else 0, self.lr,
-                self.betas[0], self.betas[1], self.eps, self.wd, 1.0 / self.world, self.step_count, L.stream_ptr()),
-                "allreduce_update_symm")
+                self.betas[0], self.betas[1], self.eps, self.wd, 1.0 / self.world, self.step_count, L.ptr(sd),
+                L.stream_ptr()), "allreduce_update_symm")
             return
         self.allreduce_grads()
         self.step_count += 1
+        if self.optimizer == "adam" and sd is not None:
+            L.check(L.lib().milb200_adam_step_dev(L.ptr(self.params), L.ptr(self.grads), L.ptr(self.exp_avg),
+                                                  L.ptr(self.exp_avg_sq), self.numel, self.lr, self.betas[0], self.betas[1],
+                                                  self.eps, self.wd, 1.0 / self.world, L.ptr(sd), L.stream_ptr()),
+                    "adam_step_dev")
+            return
         if self.optimizer == "sgd":
             L.check(L.lib().milb200_sgd_step(L.ptr(self.params), L.ptr(self.grads), self.numel, self.lr, self.wd,
                                              1.0 / self.world, L.stream_ptr()), "sgd_step")
@@ -235,4 +244,39 @@ class AbmilTrainer:
     def step(self, X, offsets, dM=None):
         M, dX = self.forward_backward(X, offsets, dM)
         self.reduce_and_update()
+        return M
+
+    def step_graphed(self, X, offsets):
+        """`step(X, offsets)` replayed as ONE CUDA graph (forward, backward, exchange, optimiser: ~10 kernels, no host work
+        between them).  A graph is captured per (X, offsets) address and shape — the bench's device-resident loop and its
+        two rotating end-to-end buffers; data loaders that hand out fresh addresses should stage into fixed buffers first.
+        The Adam step number moves to device memory (the graph must not bake the bias corrections in).  Falls back to the
+        eager step for train-mode dropout (host-drawn seeds) and for an NCCL exchange (captured collectives are left to
+        the caller's NCCL settings).  The first call for an address runs two eager steps and then one captured step."""
+        if self.dropout_p > 0.0 or self.phase_hook is not None or (self.world > 1 and getattr(self, "_symm", None) is None):
+            return self.step(X, offsets)
+        if getattr(self, "_step_dev", None) is None:
+            self._step_dev = torch.full((1,), self.step_count, dtype=torch.int32, device=self.device)
+            self._graphs = {}
+        key = (X.data_ptr(), offsets.data_ptr(), tuple(X.shape), int(offsets.numel()))
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= 4:
+                self._graphs.pop(next(iter(self._graphs)))
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):                      # every lazily created buffer exists before the capture
+                for _ in range(2):
+                    self.step(X, offsets)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            count = self.step_count
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                M = self.step(X, offsets)
+            self.step_count = count                             # the capture enqueued nothing
+            ent = self._graphs[key] = (g, M, self.last_argmax, self.last_scores)
+        g, M, am, s = ent
+        g.replay()
+        self.step_count += 1
+        self.last_argmax, self.last_scores = am, s
         return M

@@ -372,7 +372,7 @@ class FusionTrainer:
         if sm is not None:
             L.check(L.lib().milb200_allreduce_update_symm(
                 L.ptr(self.params), L.ptr(self.grads), sm["mc"], L.ptr(sm["pads"]), 0, sm["rank"], self.world, None, None,
-                self.numel, -1, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 1, L.stream_ptr()), "allreduce_update_symm")
+                self.numel, -1, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 1, None, L.stream_ptr()), "allreduce_update_symm")
         elif self.world > 1:
             torch.distributed.all_reduce(self.grads, group=self.pg)
         self.step_count += 1
