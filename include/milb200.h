@@ -45,8 +45,10 @@ enum { MILB200_ACT_NONE = 0, MILB200_ACT_TANH = 1, MILB200_ACT_RELU = 2, MILB200
 
 int milb200_version(void);
 const char* milb200_last_error(void);
-/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches).  A host that replays a
+ * captured CUDA graph of library launches itself reports the graph's kernel count with milb200_count_launches. */
 int64_t milb200_launch_count(void);
+void milb200_count_launches(int64_t n);
 
 /* ---- gated-attention scores -------------------------------------------------------------------
  * Replaces ABMIL.forward's attention_V / attention_U / attention_weights chain

@@ -25,6 +25,7 @@ SIGNATURES = {
     "milb200_version": (_i, []),
     "milb200_last_error": (C.c_char_p, []),
     "milb200_launch_count": (_i64, []),
+    "milb200_count_launches": (None, [_i64]),
     "milb200_pack_gate_weights": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _i, _p, _p]),
     "milb200_cast": (_i, [_p, _i, _p, _i, _i64, _p]),
     "milb200_transpose": (_i, [_p, _p, _i, _i, _i, _p]),

@@ -586,6 +586,8 @@ int milb200_adam_step(float* param, const float* grad, float* exp_avg, float* ex
   return MILB200_OK;
 }
 
+void milb200_count_launches(int64_t n) { count_launch(static_cast<int>(n)); }
+
 int milb200_step_counter_inc(int32_t* step_dev, void* stream) {
   MIL_CHECK_ARG(step_dev != nullptr, MILB200_EINVAL, "step_counter_inc: null pointer");
   k_counter_inc<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(step_dev);

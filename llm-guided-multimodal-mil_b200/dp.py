@@ -252,7 +252,8 @@ class AbmilTrainer:
         two rotating end-to-end buffers; data loaders that hand out fresh addresses should stage into fixed buffers first.
         The Adam step number moves to device memory (the graph must not bake the bias corrections in).  Falls back to the
         eager step for train-mode dropout (host-drawn seeds) and for an NCCL exchange (captured collectives are left to
-        the caller's NCCL settings).  The first call for an address runs two eager steps and then one captured step."""
+        the caller's NCCL settings).  The first call for an address additionally runs two eager warm-up steps whose effect on the
+        parameters, the optimiser state and the step counters is undone before the capture: every call is ONE step."""
         if self.dropout_p > 0.0 or self.phase_hook is not None or (self.world > 1 and getattr(self, "_symm", None) is None):
             return self.step(X, offsets)
         if getattr(self, "_step_dev", None) is None:
@@ -260,23 +261,32 @@ class AbmilTrainer:
             self._graphs = {}
         key = (X.data_ptr(), offsets.data_ptr(), tuple(X.shape), int(offsets.numel()))
         ent = self._graphs.get(key)
-        if ent is None:
+        first = ent is None
+        if first:
             if len(self._graphs) >= 4:
                 self._graphs.pop(next(iter(self._graphs)))
+            # two eager steps on a side stream create every lazily allocated buffer; they must not count as training:
+            # parameters, optimiser state and both step counters are restored before the capture
+            state = [t.clone() for t in (self.params, self.exp_avg, self.exp_avg_sq, self._step_dev)]
+            count = self.step_count
             side = torch.cuda.Stream(device=self.device)
             side.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(side):                      # every lazily created buffer exists before the capture
+            with torch.cuda.stream(side):
                 for _ in range(2):
                     self.step(X, offsets)
+                for dst, src in zip((self.params, self.exp_avg, self.exp_avg_sq, self._step_dev), state):
+                    dst.copy_(src)
             torch.cuda.current_stream(self.device).wait_stream(side)
-            count = self.step_count
+            l0 = L.launch_count()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 M = self.step(X, offsets)
-            self.step_count = count                             # the capture enqueued nothing
-            ent = self._graphs[key] = (g, M, self.last_argmax, self.last_scores)
-        g, M, am, s = ent
+            self.step_count = count                             # nothing has run yet
+            ent = self._graphs[key] = (g, M, self.last_argmax, self.last_scores, L.launch_count() - l0)
+        g, M, am, s, n_kernels = ent
         g.replay()
+        if not first:
+            L.lib().milb200_count_launches(n_kernels)           # (the capture itself counted the first replay's kernels)
         self.step_count += 1
         self.last_argmax, self.last_scores = am, s
         return M
