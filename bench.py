@@ -800,6 +800,32 @@ def main():
     total_bags = args.bags * world * args.steps
     value = total_bags / (ms_max / 1e3)
 
+    # ---- N > 1: where the gap to N x single-GPU goes — the same ranks, same data, WITHOUT the exchange (forward +
+    # backward + a local optimiser step, no cross-rank synchronisation): fastest and slowest rank ----------------------
+    no_exchange = None
+    if world > 1:
+        solo = AbmilTrainer(L_FEAT, D_GATE, torch.bfloat16, lr=1e-5, weight_decay=1e-7, device=dev,
+                            need_input_grad=args.input_grad, save_gate=not args.recompute_gate)
+        solo.params.copy_(tr.params)
+        solo_step = solo.step_graphed if use_graph else solo.step
+        for _ in range(warmup):
+            solo_step(X, offsets)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            solo_step(X, offsets)
+        e1.record()
+        torch.cuda.synchronize()
+        t_solo = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+        hi, lo = t_solo.clone(), t_solo.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        no_exchange = {"ms_per_step_slowest_rank": float(hi.item()), "ms_per_step_fastest_rank": float(lo.item()),
+                       "what": "the same step on every rank without the gradient exchange (no cross-rank synchronisation): "
+                               "ms_per_step minus the slowest rank's figure is what the exchange and its barriers cost"}
+        del solo
+        barrier()
+
     # ---- the same steps again with a CUDA event between phases: per-kernel durations IN the step -------------------
     # every rank runs them (the step contains the all-reduce); rank 0 records the events
     phase_ms = {}
@@ -1142,7 +1168,8 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "bags/s", "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
                 "roofline": roof, "kernels": kernels, "cpu_baseline": cpu_base, "clocks": clocks, "secondary": secondary,
-                "dp_check": dp_check, "params_identical_across_ranks_after_run": params_same}
+                "dp_check": dp_check, "params_identical_across_ranks_after_run": params_same,
+                "step_without_exchange": no_exchange}
         out.write(json.dumps(line) + "\n")
         out.flush()
     if world > 1:
