@@ -775,7 +775,8 @@ def main():
     # (AbmilTrainer.step_graphed; MILB200_STEP_GRAPH=0 runs the ~10 launches eagerly)
     use_graph = os.environ.get("MILB200_STEP_GRAPH", "1") != "0" and not args.input_grad
     run_step = tr.step_graphed if use_graph else tr.step
-    config["step_launch"] = "one CUDA graph per step (AbmilTrainer.step_graphed)" if use_graph else "eager launches"
+    graphed = use_graph and (world == 1 or getattr(tr, "_symm", None) is not None)     # an NCCL exchange keeps the step eager
+    config["step_launch"] = "one CUDA graph per step (AbmilTrainer.step_graphed)" if graphed else "eager launches"
     for _ in range(warmup):
         run_step(X, offsets)
     barrier()
