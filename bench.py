@@ -986,6 +986,16 @@ def main():
                             "algorithmic": "2*n*L*2D flop", "hbm_gbs": (n * Lf * 2 + n * 2 * D * 2) / acc[1] / 1e6})
             kernels.append({"name": "split-K reduce (k_splitk_reduce)", "ms": acc[2], "bound": "hbm", "achieved": None,
                             "peak": hbm_peak, "unit": "GB/s"})
+        # The opt-in mirrored single-pass backward (MILB200_FUSED_BWD=1): pooling backward inside the dW kernel.  Timed
+        # here for the record (alone, same inputs); it is not in the default step, so it never becomes the dominant kernel.
+        if save and Lb.lib().milb200_gated_pool_bwd_supported(Lf, D, Lb.dtype_code(X)):
+            t_fb = timeit(lambda: F.gated_pool_bwd(X, s, offsets, dM, M, v["ww"], act, grad_out=tr.grads))
+            kernels.append({"name": "gated_pool_bwd, opt-in (k_gemm_tn_gate with the pooling backward in g warps + reduce)",
+                            "ms": t_fb, "bound": "tensor", "achieved": (gemm_flops + 2.0 * n * Lf) / t_fb / 1e9,
+                            "peak": tf_peak, "unit": "TFLOP/s", "algorithmic": "2*n*L*2D + 2*n*L flop",
+                            "in_step": bool(phase_ms.get("gated_pool_bwd")),
+                            "replaces_ms": t_pbwd + acc[0] + acc[1],
+                            "hbm_gbs": (n * Lf * 2 + n * 2 * D * 2 + n * 8) / t_fb / 1e6})
         # DRAM traffic per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu --set full
         # capture of this same workload (tools/ncu_summary.py -> profiles/kernel_traffic.json); null if absent
         try:
@@ -1002,7 +1012,8 @@ def main():
         # region") against the BURST peak (the conservative denominator); the alone-loop figures stay beside it.
         in_step = {"gated_score_fwd": phase_ms.get("gated_score_fwd"),
                    "segment_softmax_pool_fwd": phase_ms.get("segment_softmax_pool_fwd"),
-                   "segment_softmax_pool_bwd": phase_ms.get("segment_softmax_pool_bwd")}
+                   "segment_softmax_pool_bwd": phase_ms.get("segment_softmax_pool_bwd"),
+                   "gated_pool_bwd": phase_ms.get("gated_pool_bwd")}
         if fused and phase_ms.get("gate_bwd"):
             in_step["gate_bwd dW fused"] = phase_ms["gate_bwd"] - acc[1]
         for kinfo in kernels:
@@ -1151,7 +1162,7 @@ def main():
         cpu_base = {k: cpu_base[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
-        dom = max(kernels, key=lambda k: k["ms"])
+        dom = max((k for k in kernels if k.get("in_step", True)), key=lambda k: k["ms"])
         roof = {"kernel": dom["name"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
                 "unit": dom["unit"], "frac": dom["frac"], "traffic": dom.get("traffic"),
                 "traffic_source": dom.get("traffic_source"), "peak_source": peak_src,

@@ -148,6 +148,13 @@ class AbmilTrainer:
         X, offsets, s, act, M, v, seed = self._saved
         self._saved = None
         mark = self.phase_hook or (lambda name: None)
+        if act is not None and not self.need_input_grad and F.fused_backward_enabled():
+            # mirrored single-pass backward: the pooling backward runs inside the dW kernel (one pass over X)
+            fused = F.gated_pool_bwd(X, s, offsets, dM, M, v["ww"], act, grad_out=self.grads)
+            if fused is not None:
+                self.last_dscores = fused[0]
+                mark("gated_pool_bwd")
+                return None
         ds, attn = F.segment_softmax_pool_bwd(X, s, offsets, dM, M, want_attn=self.need_input_grad)
         mark("segment_softmax_pool_bwd")
         dX, *_ = F.gated_scores_bwd(X, self._wcat_c, self._bcat_c, v["ww"], v["bw"], ds, attn, dM, offsets,
