@@ -1100,7 +1100,8 @@ def main():
             b.record()
             torch.cuda.synchronize()
             cfg1 = {"gpu_bags_per_s": B1 * 20 / (a.elapsed_time(b) / 1e3), "gpu_ms_per_step": a.elapsed_time(b) / 20,
-                    "gpu_dtype": "f32 (SIMT FFMA kernels, the <=1e-5 parity path), 32 bags packed in one CSR batch"}
+                    "gpu_dtype": "f32 operands, 3xTF32 tcgen05 GEMMs (kind::tf32 over hi/lo splits; the <=1e-5 parity path), "
+                                 "32 bags packed in one CSR batch"}
             if not args.no_cpu_baseline:
                 c1 = cpu_reference(torch.full((B1,), N1), steps=3, warmup=2, budget_s=6.0, per_step=B1)
                 cfg1.update({"cpu_bags_per_s": c1["value"], "cpu_cores": c1["cores"], "cpu_sample": c1["sample"]})

@@ -382,12 +382,93 @@ static bool tc_gate_ok(int L, int D, int dtype) {
 // milb200_pack_gate_weights asks here so that packer and consumer always agree.
 bool gate_layout_interleaved(int L, int D, int dtype) { return tc_gate_ok(L, D, dtype); }
 
+// ---- 3xTF32: the fp32 path on the tensor cores -----------------------------------------------------
+// The reference computes in fp32 (no AMP anywhere in train_ddp.py); kind::tf32 MMAs over hi/lo operand splits give
+// fp32-grade products (see k_gemm_kmajor, KIND 1).  hi = the nearest tf32 value of x, lo = the nearest tf32 value of
+// x - hi: both are exact tf32 operands whether the tensor core truncates or rounds its inputs, the residual is 2^-22 |x|
+// with either sign (a truncating split biases every product the same way and showed up as 1.1e-5 on single scores).
+constexpr int TF32_CK = 512;   // k (= instance rows) per batch of the split-K dWcat product
+
+static bool tf32x3_enabled() {           // MILB200_TF32X3=0 keeps the FFMA kernels (read per call: tests flip it)
+  const char* e = getenv("MILB200_TF32X3");
+  return !(e && e[0] == '0');
+}
+// gate GEMMs in fp32: Z = X Wcat^T needs K = L, dWcat needs Mb = 2D (multiple of 128), N = L
+static bool tf32_gate_ok(int L, int D, int dtype) {
+  return dtype == MILB200_F32 && tf32x3_enabled() && !force_simt() && (2 * D) % 128 == 0 && L % 16 == 0 && L >= 32 &&
+         tc::gemm_tf32x3_supported(128, 2 * D, L);
+}
+
+__device__ __forceinline__ float tf32_rn(float x) {   // nearest tf32 value (ties away), returned as fp32
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+__global__ void __launch_bounds__(256)
+k_tf32_split(const float4* __restrict__ in, float4* __restrict__ hi, float4* __restrict__ lo, int64_t n4) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 x = __ldg(in + i);
+    const float4 h = make_float4(tf32_rn(x.x), tf32_rn(x.y), tf32_rn(x.z), tf32_rn(x.w));
+    hi[i] = h;
+    lo[i] = make_float4(tf32_rn(x.x - h.x), tf32_rn(x.y - h.y), tf32_rn(x.z - h.z), tf32_rn(x.w - h.w));
+  }
+}
+static int tf32_split(const float* in, float* hi, float* lo, int64_t n, cudaStream_t st) {   // n % 4 == 0
+  const int64_t n4 = n / 4;
+  unsigned blocks = static_cast<unsigned>(std::min<int64_t>((n4 + 255) / 256, static_cast<int64_t>(sm_count()) * 16));
+  k_tf32_split<<<blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(hi),
+                                       reinterpret_cast<float4*>(lo), n4);
+  MIL_LAUNCH_CHECK();
+  return MILB200_OK;
+}
+
+// in [rows, cols] -> hi/lo [batches][cols][TF32_CK] with row r at (batch r / CK, k = r % CK); rows past the end are zero:
+// the K-major operands of the batched dWcat product (contraction over the instance rows)
+__global__ void __launch_bounds__(256)
+k_tf32_transpose_split(const float* __restrict__ in, int64_t rows, int cols, float* __restrict__ hi, float* __restrict__ lo) {
+  __shared__ float t[32][33];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.y) * 32;
+  const int c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t r = r0 + ty + 8 * j;
+    const int c = c0 + tx;
+    t[ty + 8 * j][tx] = (r < rows && c < cols) ? __ldg(in + r * cols + c) : 0.f;
+  }
+  __syncthreads();
+  const int64_t batch = r0 / TF32_CK;
+  const int k0 = static_cast<int>(r0 % TF32_CK);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + ty + 8 * j;
+    if (c < cols) {
+      const float x = t[tx][ty + 8 * j];
+      const float h = tf32_rn(x);
+      const int64_t o = (batch * cols + c) * TF32_CK + k0 + tx;
+      hi[o] = h;
+      lo[o] = tf32_rn(x - h);
+    }
+  }
+}
+static int tf32_transpose_split(const float* in, int64_t rows, int cols, float* hi, float* lo, cudaStream_t st) {
+  const int64_t rows_pad = (rows + TF32_CK - 1) / TF32_CK * TF32_CK;
+  dim3 grid(static_cast<unsigned>((cols + 31) / 32), static_cast<unsigned>(rows_pad / 32));
+  k_tf32_transpose_split<<<grid, 256, 0, st>>>(in, rows, cols, hi, lo);
+  MIL_LAUNCH_CHECK();
+  return MILB200_OK;
+}
+
 // ---- workspace layouts ---------------------------------------------------------------------------
 struct GateWs {
   // tensor-core path
   size_t dz, colsum, part, wT;
   // FFMA path
   size_t z, spart, rec;
+  // 3xTF32 path (fp32 operands): hi/lo splits of Wcat and of the row chunk, transposed splits for dWcat, partials
+  size_t whi, wlo, xhi, xlo, dzt_hi, dzt_lo, xt_hi, xt_lo, tpart;
   size_t total;
 };
 static GateWs gate_ws(int64_t total_n, int L, int D, int dtype, int backward) {
@@ -411,6 +492,20 @@ static GateWs gate_ws(int64_t total_n, int L, int D, int dtype, int backward) {
     if (backward) {
       w.spart = take(sizeof(float) * simt_splits(rows) * 2 * D * L);
       w.rec = take(sizeof(float) * static_cast<size_t>(sm_count()) * 4 * (3 * D + 1));
+    }
+    if (tf32_gate_ok(L, D, dtype)) {
+      const size_t rows_pad = static_cast<size_t>((rows + TF32_CK - 1) / TF32_CK * TF32_CK);
+      w.whi = take(sizeof(float) * 2 * D * L);
+      w.wlo = take(sizeof(float) * 2 * D * L);
+      w.xhi = take(sizeof(float) * static_cast<size_t>(rows) * L);
+      w.xlo = take(sizeof(float) * static_cast<size_t>(rows) * L);
+      if (backward) {
+        w.dzt_hi = take(sizeof(float) * rows_pad * 2 * D);
+        w.dzt_lo = take(sizeof(float) * rows_pad * 2 * D);
+        w.xt_hi = take(sizeof(float) * rows_pad * L);
+        w.xt_lo = take(sizeof(float) * rows_pad * L);
+        w.tpart = take(sizeof(float) * (rows_pad / TF32_CK) * 2 * D * L);
+      }
     }
   }
   w.total = align_up(off, 256) + 256;
@@ -463,6 +558,78 @@ static int gate_bwd_simt(const T* X, const T* Wcat, const float* bcat, const flo
       // dX[i, l] = sum_j dZ[i, j] Wcat[j, l]  (+ attn_i * dM[bag(i), l])
       simt::EpiStore<T> ex{dX + r0 * L, L, nullptr, MILB200_ACT_NONE, attn, dM, offsets, B, r0};
       rc = simt::launch<float, T, true, false>(Z, 2 * D, Wcat, L, rows, L, 2 * D, 1, ex, st);
+      if (rc) return rc;
+    }
+  }
+  return MILB200_OK;
+}
+
+// fp32 operands on the tensor cores (3xTF32): same sequence as the FFMA path with the GEMMs replaced
+static int gate_fwd_tf32(const float* X, const float* Wcat, const float* bcat, const float* ww, const float* bw, float* scores,
+                         int64_t total_n, int L, int D, char* ws, const GateWs& w, cudaStream_t st) {
+  float* Z = reinterpret_cast<float*>(ws + w.z);
+  float* whi = reinterpret_cast<float*>(ws + w.whi);
+  float* wlo = reinterpret_cast<float*>(ws + w.wlo);
+  float* xhi = reinterpret_cast<float*>(ws + w.xhi);
+  float* xlo = reinterpret_cast<float*>(ws + w.xlo);
+  int rc = tf32_split(Wcat, whi, wlo, static_cast<int64_t>(2) * D * L, st);
+  if (rc) return rc;
+  for (int64_t r0 = 0; r0 < total_n; r0 += SIMT_ROW_CHUNK) {
+    int64_t rows = std::min<int64_t>(SIMT_ROW_CHUNK, total_n - r0);
+    rc = tf32_split(X + r0 * L, xhi, xlo, rows * L, st);
+    if (rc) return rc;
+    rc = tc::gemm_store_tf32x3(xhi, xlo, rows, L, L, whi, wlo, 2 * D, L, bcat, MILB200_ACT_NONE, Z, 2 * D, st);
+    if (rc) return rc;
+    k_gate_fwd<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(Z, ww, bw, scores + r0, rows, D);
+    MIL_LAUNCH_CHECK();
+  }
+  return MILB200_OK;
+}
+
+static int gate_bwd_tf32(const float* X, const float* Wcat, const float* bcat, const float* ww, const float* dscores,
+                         const float* attn, const float* dM, const int32_t* offsets, int B, int64_t total_n, int L,
+                         int D, float* dWcat, float* dbcat, float* dww, float* dbw, float* dX, char* ws, const GateWs& w,
+                         cudaStream_t st) {
+  MIL_CHECK_ARG(D <= 32 * GATE_MAX_DPL, MILB200_EUNSUPPORTED, "gated_score_bwd (3xTF32 path): D=%d > %d", D, 32 * GATE_MAX_DPL);
+  float* Z = reinterpret_cast<float*>(ws + w.z);
+  float* rec = reinterpret_cast<float*>(ws + w.rec);
+  float* whi = reinterpret_cast<float*>(ws + w.whi);
+  float* wlo = reinterpret_cast<float*>(ws + w.wlo);
+  float* xhi = reinterpret_cast<float*>(ws + w.xhi);
+  float* xlo = reinterpret_cast<float*>(ws + w.xlo);
+  float* dzt_hi = reinterpret_cast<float*>(ws + w.dzt_hi);
+  float* dzt_lo = reinterpret_cast<float*>(ws + w.dzt_lo);
+  float* xt_hi = reinterpret_cast<float*>(ws + w.xt_hi);
+  float* xt_lo = reinterpret_cast<float*>(ws + w.xt_lo);
+  float* part = reinterpret_cast<float*>(ws + w.tpart);
+  int rc = tf32_split(Wcat, whi, wlo, static_cast<int64_t>(2) * D * L, st);
+  if (rc) return rc;
+  int chunk = 0;
+  for (int64_t r0 = 0; r0 < total_n; r0 += SIMT_ROW_CHUNK, ++chunk) {
+    int64_t rows = std::min<int64_t>(SIMT_ROW_CHUNK, total_n - r0);
+    rc = tf32_split(X + r0 * L, xhi, xlo, rows * L, st);
+    if (rc) return rc;
+    rc = tc::gemm_store_tf32x3(xhi, xlo, rows, L, L, whi, wlo, 2 * D, L, bcat, MILB200_ACT_NONE, Z, 2 * D, st);
+    if (rc) return rc;
+    unsigned blocks = static_cast<unsigned>(std::min<int64_t>((rows + 7) / 8, sm_count() * 4));
+    k_gate_bwd<<<blocks, 256, 0, st>>>(Z, ww, dscores + r0, rows, D, rec);          // Z becomes dZ in place
+    MIL_LAUNCH_CHECK();
+    k_gate_bwd_fold<<<(3 * D + 1 + 255) / 256, 256, 0, st>>>(rec, static_cast<int>(blocks), D, dbcat, dww, dbw, chunk > 0);
+    MIL_LAUNCH_CHECK();
+    // dWcat[j, l] (+)= sum_i dZ[i, j] X[i, l]: K-major operands = the transposes, split-K over batches of TF32_CK rows
+    const int batches = static_cast<int>((rows + TF32_CK - 1) / TF32_CK);
+    rc = tf32_transpose_split(Z, rows, 2 * D, dzt_hi, dzt_lo, st);
+    if (rc) return rc;
+    rc = tf32_transpose_split(X + r0 * L, rows, L, xt_hi, xt_lo, st);
+    if (rc) return rc;
+    rc = tc::gemm_batched_tf32x3(dzt_hi, dzt_lo, batches, 2 * D, TF32_CK, xt_hi, xt_lo, L, part, st);
+    if (rc) return rc;
+    rc = splitk_reduce(part, batches, static_cast<int64_t>(2) * D * L, dWcat, chunk > 0, st);
+    if (rc) return rc;
+    if (dX) {
+      // dX[i, l] = sum_j dZ[i, j] Wcat[j, l]  (+ attn_i * dM[bag(i), l]): FFMA kernel (the pooling term rides in its epilogue)
+      simt::EpiStore<float> ex{dX + r0 * L, L, nullptr, MILB200_ACT_NONE, attn, dM, offsets, B, r0};
+      rc = simt::launch<float, float, true, false>(Z, 2 * D, Wcat, L, rows, L, 2 * D, 1, ex, st);
       if (rc) return rc;
     }
   }
@@ -559,6 +726,8 @@ int milb200_gated_score_fwd(const void* X, const void* Wcat, const float* bcat, 
   if (dtype == MILB200_BF16)
     return gate_fwd_simt<__nv_bfloat16>((const __nv_bfloat16*)X, (const __nv_bfloat16*)Wcat, bcat, ww, bw, scores, total_n,
                                         L, D, ws, w, st);
+  if (tf32_gate_ok(L, D, dtype))
+    return gate_fwd_tf32((const float*)X, (const float*)Wcat, bcat, ww, bw, scores, total_n, L, D, ws, w, st);
   return gate_fwd_simt<float>((const float*)X, (const float*)Wcat, bcat, ww, bw, scores, total_n, L, D, ws, w, st);
 }
 
@@ -641,6 +810,9 @@ int milb200_gated_score_bwd(const void* X, const void* Wcat, const float* bcat, 
   if (dtype == MILB200_BF16)
     return gate_bwd_simt<__nv_bfloat16>((const __nv_bfloat16*)X, (const __nv_bfloat16*)Wcat, bcat, ww, dscores, attn, dM,
                                         offsets, B, total_n, L, D, dWcat, dbcat, dww, dbw, (__nv_bfloat16*)dX, ws, w, st);
+  if (tf32_gate_ok(L, D, dtype))
+    return gate_bwd_tf32((const float*)X, (const float*)Wcat, bcat, ww, dscores, attn, dM, offsets, B, total_n, L, D,
+                         dWcat, dbcat, dww, dbw, (float*)dX, ws, w, st);
   return gate_bwd_simt<float>((const float*)X, (const float*)Wcat, bcat, ww, dscores, attn, dM, offsets, B, total_n, L, D,
                               dWcat, dbcat, dww, dbw, (float*)dX, ws, w, st);
 }

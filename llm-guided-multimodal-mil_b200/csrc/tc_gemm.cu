@@ -576,10 +576,19 @@ struct EpiDz {
 // K-major persistent GEMM.  A CTA owns row tiles mt = blockIdx.x, blockIdx.x + gridDim.x, ... and sweeps
 // the N tiles of each (the A tile's second pass comes from L2).
 // ---------------------------------------------------------------------------------------------
-template <int BN, class Epi>
+// KIND 1 = "3xTF32": fp32 operands pre-split into hi (tf32-exact) and lo (= x - hi) arrays; the k loop runs three times
+// (hi.lo, lo.hi, hi.hi — the lo.lo term is below fp32 rounding) into the same accumulator with kind::tf32 MMAs, which
+// gives fp32-grade products (error ~2^-21 per term) at a sixth of the bf16 rate instead of the FFMA path's fortieth.
+// The shared-memory image is byte-for-byte the bf16 one (128-byte swizzle rows = 32 floats, 32 bytes of K per MMA).
+// batch_mtiles > 0: batched mode for split-K products — m-tile mt belongs to batch mt / batch_mtiles and reads the B rows
+// [batch * N, batch * N + N) (A = [batches * M_b, K], B = [batches * N, K], out = [batches * M_b, N] partials).
+template <int BN, class Epi, int KIND = 0>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int64_t M, int N, int K,
-              uint32_t b_box_bytes, const __grid_constant__ typename Epi::Params ep) {
+              uint32_t b_box_bytes, const __grid_constant__ typename Epi::Params ep,
+              const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, int batch_mtiles) {
+  constexpr int BKE = KIND ? 32 : BK;          // elements per 128-byte swizzle row
+  constexpr int PHASES = KIND ? 3 : 1;
   using Cfg = TileCfg<BN>;
   constexpr int STAGES = kmajor_stages<BN, Epi>();
   static_assert(STAGES >= 3, "pipeline too shallow");
@@ -600,12 +609,17 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t m_tiles = (M + BM - 1) / BM;
   const int n_tiles = (N + BN - 1) / BN;
-  const int num_kb = (K + BK - 1) / BK;
+  const int num_kb = (K + BKE - 1) / BKE;
+  const int num_it = num_kb * PHASES;
   if (threadIdx.x == 0) trace(0);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (KIND) {
+      prefetch_tmap(&tmA2);
+      prefetch_tmap(&tmB2);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -633,20 +647,28 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       uint32_t ph = 0;
       const uint32_t stage_tx = Cfg::A_BYTES + Cfg::N_MMA * b_box_bytes;
       for (int64_t mt = blockIdx.x; mt < m_tiles; mt += gridDim.x) {
+        const int b_row0 = batch_mtiles > 0 ? static_cast<int>(mt / batch_mtiles) * N : 0;
         for (int nt = 0; nt < n_tiles; ++nt) {
-          for (int kb = 0; kb < num_kb; ++kb) {
+          for (int ki = 0; ki < num_it; ++ki) {
+            const int kb = KIND ? ki % num_kb : ki;
+            const int phase = KIND ? ki / num_kb : 0;
+            // small terms first (hi.lo, lo.hi, then hi.hi): the accumulator rounds toward zero on every MMA, so adding
+            // 2 x K/8 tiny terms to an already large accumulator costs ~1e-5 (measured); into a still small one, nothing
+            const CUtensorMap* mA = (KIND && phase == 1) ? &tmA2 : &tmA;
+            const CUtensorMap* mB = (KIND && phase == 0) ? &tmB2 : &tmB;
             mbar_wait(empty_bar + s, ph ^ 1);
             uint8_t* sa = stage_base + s * Cfg::STAGE_BYTES;
             uint8_t* sb = sa + Cfg::A_BYTES;
             mbar_arrive_expect_tx(full_bar + s, stage_tx);
             // the A tile is read n_tiles times back to back: keep it in L2 until the last sweep
-            tma_load_2d(sa, &tmA, full_bar + s, kb * BK, static_cast<int32_t>(mt * BM),
-                        nt == n_tiles - 1 ? kEvictFirst : kEvictNormal);
+            tma_load_2d(sa, mA, full_bar + s, kb * BKE, static_cast<int32_t>(mt * BM),
+                        (!KIND && nt == n_tiles - 1) ? kEvictFirst : kEvictNormal);
 #pragma unroll
             for (int j = 0; j < Cfg::N_MMA; ++j)
-              tma_load_2d(sb + j * Cfg::UMMA_N * 128, &tmB, full_bar + s, kb * BK, nt * BN + j * Cfg::UMMA_N, kEvictLast);
-            if (kb == 0 && nt == 0 && mt == blockIdx.x) trace(2);
-            if (kb == num_kb - 1 && nt == 0 && mt == blockIdx.x) trace(3);
+              tma_load_2d(sb + j * Cfg::UMMA_N * 128, mB, full_bar + s, kb * BKE, b_row0 + nt * BN + j * Cfg::UMMA_N,
+                          batch_mtiles > 0 ? kEvictNormal : kEvictLast);
+            if (ki == 0 && nt == 0 && mt == blockIdx.x) trace(2);
+            if (ki == num_it - 1 && nt == 0 && mt == blockIdx.x) trace(3);
             if (++s == STAGES) { s = 0; ph ^= 1; }
           }
         }
@@ -655,7 +677,7 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else if (warp == 1) {
     // ===== MMA issuer: the whole warp walks the loop (so addresses stay in uniform registers); one elected
     // lane issues tcgen05.mma / tcgen05.commit =====
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, Cfg::UMMA_N, 0, 0);
+    constexpr uint32_t idesc = KIND ? umma_idesc_tf32(BM, Cfg::UMMA_N, 0, 0) : umma_idesc_bf16(BM, Cfg::UMMA_N, 0, 0);
     const uint64_t desc0 = umma_desc_sw128(smem_u32(stage_base), 16, 1024);
     const uint32_t d_hi = static_cast<uint32_t>(desc0 >> 32);
     const uint32_t a_lo0 = static_cast<uint32_t>(desc0);
@@ -670,22 +692,28 @@ k_gemm_kmajor(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         mbar_wait(tempty_bar + acc, acc_ph ^ 1);
         tc_fence_after();
         const uint32_t tacc = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = 0; kb < num_it; ++kb) {
           mbar_wait(full_bar + s, ph);
           tc_fence_after();
-          if (it == 0 && lane == 0) { if (kb == 0) trace(4); if (kb == num_kb - 1) trace(5); }
+          if (it == 0 && lane == 0) { if (kb == 0) trace(4); if (kb == num_it - 1) trace(5); }
           if (elect_one()) {
             const uint32_t so = static_cast<uint32_t>(s) * (Cfg::STAGE_BYTES >> 4);
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) {
+            for (int k = 0; k < BK / UMMA_K; ++k) {      // four MMAs of 32 bytes of K each (16 bf16 or 8 tf32)
 #pragma unroll
-              for (int j = 0; j < Cfg::N_MMA; ++j)
-                umma_bf16_lohi(tacc + j * Cfg::UMMA_N, a_lo0 + so + k * (UMMA_K * 2 >> 4), d_hi,
-                               b_lo0 + so + ((j * Cfg::UMMA_N * 128) >> 4) + k * (UMMA_K * 2 >> 4), d_hi, idesc,
-                               (kb | k) != 0 ? 1u : 0u);
+              for (int j = 0; j < Cfg::N_MMA; ++j) {
+                if (KIND)
+                  umma_tf32_lohi(tacc + j * Cfg::UMMA_N, a_lo0 + so + k * (UMMA_K * 2 >> 4), d_hi,
+                                 b_lo0 + so + ((j * Cfg::UMMA_N * 128) >> 4) + k * (UMMA_K * 2 >> 4), d_hi, idesc,
+                                 (kb | k) != 0 ? 1u : 0u);
+                else
+                  umma_bf16_lohi(tacc + j * Cfg::UMMA_N, a_lo0 + so + k * (UMMA_K * 2 >> 4), d_hi,
+                                 b_lo0 + so + ((j * Cfg::UMMA_N * 128) >> 4) + k * (UMMA_K * 2 >> 4), d_hi, idesc,
+                                 (kb | k) != 0 ? 1u : 0u);
+              }
             }
             tc_commit(empty_bar + s);  // frees the smem stage once these MMAs have read it
-            if (kb == num_kb - 1) tc_commit(tfull_bar + acc);  // accumulator complete -> epilogue
+            if (kb == num_it - 1) tc_commit(tfull_bar + acc);  // accumulator complete -> epilogue
           }
           __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
@@ -959,9 +987,57 @@ static int launch_kmajor(const void* A, int64_t M, int K, int64_t lda, const voi
   const int64_t m_tiles = (M + BM - 1) / BM;
   const int grid = static_cast<int>(m_tiles < sm_count() ? m_tiles : sm_count());
   if (grid_out) *grid_out = grid;
-  kern<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, M, N, K, box_rows * 128u, ep);
+  kern<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, M, N, K, box_rows * 128u, ep, tmA, tmB, 0);
   MIL_LAUNCH_CHECK();
   return MILB200_OK;
+}
+
+// 3xTF32 launch: fp32 operands given as (hi, lo) pairs (see tf32_split); fp32 output through EpiStore
+static int launch_kmajor_tf32x3(const float* Ahi, const float* Alo, int64_t M, int K, int64_t lda, const float* Bhi,
+                                const float* Blo, int N, int64_t ldb, int64_t b_rows, EpiStore::Params ep, int batch_mtiles,
+                                cudaStream_t st) {
+  constexpr int BN = 256;
+  using Cfg = TileCfg<BN>;
+  CUtensorMap tmA, tmA2, tmB, tmB2;
+  int rc = make_tmap_f32_2d(&tmA, Ahi, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), BM);
+  if (rc) return rc;
+  rc = make_tmap_f32_2d(&tmA2, Alo, static_cast<uint64_t>(M), static_cast<uint64_t>(K), static_cast<uint64_t>(lda), BM);
+  if (rc) return rc;
+  const uint32_t box_rows = static_cast<uint32_t>(N < Cfg::UMMA_N ? N : Cfg::UMMA_N);
+  rc = make_tmap_f32_2d(&tmB, Bhi, static_cast<uint64_t>(b_rows), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), box_rows);
+  if (rc) return rc;
+  rc = make_tmap_f32_2d(&tmB2, Blo, static_cast<uint64_t>(b_rows), static_cast<uint64_t>(K), static_cast<uint64_t>(ldb), box_rows);
+  if (rc) return rc;
+  auto kern = k_gemm_kmajor<BN, EpiStore, 1>;
+  constexpr size_t smem = kmajor_smem_bytes<BN, EpiStore>();
+  MIL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int64_t m_tiles = (M + BM - 1) / BM;
+  const int grid = static_cast<int>(m_tiles < sm_count() ? m_tiles : sm_count());
+  kern<<<grid, NUM_THREADS, smem, st>>>(tmA, tmB, M, N, K, box_rows * 128u, ep, tmA2, tmB2, batch_mtiles);
+  MIL_LAUNCH_CHECK();
+  return MILB200_OK;
+}
+
+bool gemm_tf32x3_supported(int64_t M, int N, int K) { return M >= 1 && N >= 16 && N % 16 == 0 && K >= 32 && K % 4 == 0; }
+
+// out[M, N] fp32 = act(A[M, K] . B[N, K]^T + bias), A = Ahi + Alo, B = Bhi + Blo (fp32 arrays from tf32_split)
+int gemm_store_tf32x3(const float* Ahi, const float* Alo, int64_t M, int K, int64_t lda, const float* Bhi, const float* Blo,
+                      int N, int64_t ldb, const float* bias, int act, float* out, int64_t ldo, cudaStream_t st) {
+  MIL_CHECK_ARG(gemm_tf32x3_supported(M, N, K), MILB200_EUNSUPPORTED, "tc gemm_store_tf32x3: unsupported shape M=%lld N=%d K=%d",
+                (long long)M, N, K);
+  MIL_CHECK_ARG(aligned16(out) && (ldo * 4) % 16 == 0, MILB200_EALIGN, "tc gemm_store_tf32x3: output must be 16-byte aligned");
+  EpiStore::Params ep{out, 0, ldo, bias, act, nullptr, nullptr, nullptr, 0, 0, N, {}};
+  return launch_kmajor_tf32x3(Ahi, Alo, M, K, lda, Bhi, Blo, N, ldb, N, ep, 0, st);
+}
+
+// Batched split-K form: part[b * Mb + m, n] = sum_k A[b * Mb + m, k] * B[b * N + n, k] for b < batches (Mb % 128 == 0)
+int gemm_batched_tf32x3(const float* Ahi, const float* Alo, int batches, int Mb, int K, const float* Bhi, const float* Blo,
+                        int N, float* part, cudaStream_t st) {
+  MIL_CHECK_ARG(Mb % BM == 0 && gemm_tf32x3_supported(static_cast<int64_t>(batches) * Mb, N, K), MILB200_EUNSUPPORTED,
+                "tc gemm_batched_tf32x3: unsupported shape Mb=%d N=%d K=%d", Mb, N, K);
+  EpiStore::Params ep{part, 0, N, nullptr, MILB200_ACT_NONE, nullptr, nullptr, nullptr, 0, 0, N, {}};
+  return launch_kmajor_tf32x3(Ahi, Alo, static_cast<int64_t>(batches) * Mb, K, K, Bhi, Blo, N, K,
+                              static_cast<int64_t>(batches) * N, ep, Mb / BM, st);
 }
 
 bool gemm_store_supported(int64_t M, int N, int K) { return M >= 1 && N >= 16 && N % 16 == 0 && K >= 64 && K % 8 == 0; }

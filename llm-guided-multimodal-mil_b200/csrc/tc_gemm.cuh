@@ -58,6 +58,13 @@ int gemm_tn_gate(const void* VU, const float* ds, const float* ww, const void* X
 bool gemm_tn_gate_pool_supported(int No);
 int gemm_tn_gate_max_records();
 int gemm_tn_gate_record_floats();
+// 3xTF32 tensor-core products for fp32 operands (kind::tf32 MMAs over hi/lo splits, fp32-grade results); operands are
+// (hi, lo) pairs of fp32 arrays with 16-byte aligned rows.
+bool gemm_tf32x3_supported(int64_t M, int N, int K);
+int gemm_store_tf32x3(const float* Ahi, const float* Alo, int64_t M, int K, int64_t lda, const float* Bhi, const float* Blo,
+                      int N, int64_t ldb, const float* bias, int act, float* out, int64_t ldo, cudaStream_t st);
+int gemm_batched_tf32x3(const float* Ahi, const float* Alo, int batches, int Mb, int K, const float* Bhi, const float* Blo,
+                        int N, float* part, cudaStream_t st);
 int debug_set_trace(void* dev_ptr);
 bool gemm_tn_supported(int Mo, int No);
 
