@@ -61,10 +61,13 @@ int milb200_pack_gate_weights(const void* Wv, const void* Wu, const void* bv, co
 
 size_t milb200_gated_score_workspace_bytes(int64_t total_n, int L, int D, int dtype, int backward);
 
-/* gate_act (optional, may be NULL): receives the gate activations [total_n, 2D] in X's dtype (V = tanh(.), U =
- * sigmoid(.), column order of Wcat's packed rows) for the backward.  Only the tensor-core path writes it
- * (milb200_gated_score_saves_activations() == 1); passing it to milb200_gated_score_bwd replaces the recompute
- * GEMM by an elementwise pass (+0.77 KB/instance of memory for -35 % of the backward time at L = 1024).      */
+/* gate_act (optional, may be NULL): receives what the backward needs of the gate, [total_n, 2D] in X's dtype — bf16: the
+ * activations V = tanh(.), U = sigmoid(.) (column order of Wcat's packed rows); fp32 (3xTF32 tensor-core path): the
+ * pre-activations X Wcat^T + bcat.  Only the tensor-core paths write it (milb200_gated_score_saves_activations() == 1);
+ * passing it to milb200_gated_score_bwd replaces the recompute GEMM by an elementwise pass (bf16: +0.77 KB/instance of
+ * memory for -35 % of the backward time at L = 1024).  fp32 inputs run on the tensor cores as three kind::tf32 MMAs
+ * over hi/lo operand splits ("3xTF32", fp32-grade results: <= 1e-5 of the float64 oracle); MILB200_TF32X3=0 in the
+ * environment, D % 64 != 0 or L % 16 != 0 select the FFMA kernels.                                                    */
 int milb200_gated_score_saves_activations(int L, int D, int dtype);
 int milb200_gated_score_fwd(const void* X, const void* Wcat, const float* bcat, const float* ww,
                             const float* bw, float* scores, void* gate_act, int64_t total_n, int L, int D,

@@ -54,8 +54,8 @@ constexpr int GATE_MAX_DPL = 8;  // D <= 256 on the FFMA path
 // in place: Z (pre-activations, bias included) -> dZ = [dVpre | dUpre]; the column sums leave as one record per CTA
 // [dVpre D | dUpre D | ds*V*U D | sum ds] that k_gate_bwd_fold adds up in CTA order (deterministic, no atomics)
 __global__ void __launch_bounds__(256)
-k_gate_bwd(float* __restrict__ Z, const float* __restrict__ ww, const float* __restrict__ dscores, int64_t rows, int D,
-           float* __restrict__ rec) {
+k_gate_bwd(const float* Zin, float* Z, const float* __restrict__ ww, const float* __restrict__ dscores, int64_t rows, int D,
+           float* __restrict__ rec) {     // Zin == Z: in place; Zin = the pre-activations the forward saved otherwise
   __shared__ float red[8][3 * 32 * GATE_MAX_DPL + 1];
   const int lane = threadIdx.x & 31;
   const int64_t warp0 = static_cast<int64_t>(blockIdx.x) * 8 + (threadIdx.x >> 5);
@@ -66,13 +66,14 @@ k_gate_bwd(float* __restrict__ Z, const float* __restrict__ ww, const float* __r
   float sds = 0.f;
   for (int64_t r = warp0; r < rows; r += nwarps) {
     float* z = Z + r * 2 * D;
+    const float* zi = Zin + r * 2 * D;
     const float ds = __ldg(dscores + r);
     sds += ds;
 #pragma unroll
     for (int j = 0; j < GATE_MAX_DPL; ++j) {
       int d = lane + j * 32;
       if (d < D) {
-        float V = tanhf(z[d]), U = sigmoid_precise(z[D + d]);
+        float V = tanhf(zi[d]), U = sigmoid_precise(zi[D + d]);
         float g = ds * __ldg(ww + d);
         float dv = g * U * (1.f - V * V), du = g * V * U * (1.f - U);
         z[d] = dv;
@@ -107,13 +108,23 @@ k_gate_bwd(float* __restrict__ Z, const float* __restrict__ ww, const float* __r
 __global__ void __launch_bounds__(256)
 k_gate_bwd_fold(const float* __restrict__ rec, int nrec, int D, float* __restrict__ dbcat, float* __restrict__ dww,
                 float* __restrict__ dbw, int accumulate) {
+  // 32 columns x 8 record slices per CTA (coalesced 128-byte rows of the records); slices folded in fixed order
+  __shared__ float red[8][33];
   const int rl = 3 * D + 1;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= rl) return;
+  const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float a = 0.f;
-  for (int b = 0; b < nrec; ++b) a += rec[static_cast<int64_t>(b) * rl + c];
-  float* o = c < 2 * D ? dbcat + c : (c < 3 * D ? dww + (c - 2 * D) : dbw);
-  *o = accumulate ? *o + a : a;
+  if (c < rl)
+    for (int b = sl; b < nrec; b += 8) a += rec[static_cast<int64_t>(b) * rl + c];
+  red[sl][cx] = a;
+  __syncthreads();
+  if (sl == 0 && c < rl) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][cx];
+    float* o = c < 2 * D ? dbcat + c : (c < 3 * D ? dww + (c - 2 * D) : dbw);
+    *o = accumulate ? *o + t : t;
+  }
 }
 
 // records: [ncta][8 epilogue warps e = half*4 + q][stride]; column d of each kind was produced by the warps whose
@@ -543,9 +554,9 @@ static int gate_bwd_simt(const T* X, const T* Wcat, const float* bcat, const flo
     int rc = simt::launch<T, T, true, true>(X + r0 * L, L, Wcat, L, rows, 2 * D, L, 1, ep, st);
     if (rc) return rc;
     unsigned blocks = static_cast<unsigned>(std::min<int64_t>((rows + 7) / 8, sm_count() * 4));
-    k_gate_bwd<<<blocks, 256, 0, st>>>(Z, ww, dscores + r0, rows, D, rec);
+    k_gate_bwd<<<blocks, 256, 0, st>>>(Z, Z, ww, dscores + r0, rows, D, rec);
     MIL_LAUNCH_CHECK();
-    k_gate_bwd_fold<<<(3 * D + 1 + 255) / 256, 256, 0, st>>>(rec, static_cast<int>(blocks), D, dbcat, dww, dbw, chunk > 0);
+    k_gate_bwd_fold<<<(3 * D + 1 + 31) / 32, 256, 0, st>>>(rec, static_cast<int>(blocks), D, dbcat, dww, dbw, chunk > 0);
     MIL_LAUNCH_CHECK();
     // dWcat[j, l] (+)= sum_i dZ[i, j] X[i, l]
     int splits = static_cast<int>(simt_splits(rows));
@@ -566,8 +577,8 @@ static int gate_bwd_simt(const T* X, const T* Wcat, const float* bcat, const flo
 
 // fp32 operands on the tensor cores (3xTF32): same sequence as the FFMA path with the GEMMs replaced
 static int gate_fwd_tf32(const float* X, const float* Wcat, const float* bcat, const float* ww, const float* bw, float* scores,
-                         int64_t total_n, int L, int D, char* ws, const GateWs& w, cudaStream_t st) {
-  float* Z = reinterpret_cast<float*>(ws + w.z);
+                         float* zsave, int64_t total_n, int L, int D, char* ws, const GateWs& w, cudaStream_t st) {
+  float* Zws = reinterpret_cast<float*>(ws + w.z);
   float* whi = reinterpret_cast<float*>(ws + w.whi);
   float* wlo = reinterpret_cast<float*>(ws + w.wlo);
   float* xhi = reinterpret_cast<float*>(ws + w.xhi);
@@ -578,6 +589,7 @@ static int gate_fwd_tf32(const float* X, const float* Wcat, const float* bcat, c
     int64_t rows = std::min<int64_t>(SIMT_ROW_CHUNK, total_n - r0);
     rc = tf32_split(X + r0 * L, xhi, xlo, rows * L, st);
     if (rc) return rc;
+    float* Z = zsave ? zsave + r0 * 2 * D : Zws;       // saved pre-activations (bias included): the backward skips this GEMM
     rc = tc::gemm_store_tf32x3(xhi, xlo, rows, L, L, whi, wlo, 2 * D, L, bcat, MILB200_ACT_NONE, Z, 2 * D, st);
     if (rc) return rc;
     k_gate_fwd<<<static_cast<unsigned>((rows + 7) / 8), 256, 0, st>>>(Z, ww, bw, scores + r0, rows, D);
@@ -587,7 +599,7 @@ static int gate_fwd_tf32(const float* X, const float* Wcat, const float* bcat, c
 }
 
 static int gate_bwd_tf32(const float* X, const float* Wcat, const float* bcat, const float* ww, const float* dscores,
-                         const float* attn, const float* dM, const int32_t* offsets, int B, int64_t total_n, int L,
+                         const float* zsaved, const float* attn, const float* dM, const int32_t* offsets, int B, int64_t total_n, int L,
                          int D, float* dWcat, float* dbcat, float* dww, float* dbw, float* dX, char* ws, const GateWs& w,
                          cudaStream_t st) {
   MIL_CHECK_ARG(D <= 32 * GATE_MAX_DPL, MILB200_EUNSUPPORTED, "gated_score_bwd (3xTF32 path): D=%d > %d", D, 32 * GATE_MAX_DPL);
@@ -602,19 +614,24 @@ static int gate_bwd_tf32(const float* X, const float* Wcat, const float* bcat, c
   float* xt_hi = reinterpret_cast<float*>(ws + w.xt_hi);
   float* xt_lo = reinterpret_cast<float*>(ws + w.xt_lo);
   float* part = reinterpret_cast<float*>(ws + w.tpart);
-  int rc = tf32_split(Wcat, whi, wlo, static_cast<int64_t>(2) * D * L, st);
-  if (rc) return rc;
+  int rc = MILB200_OK;
+  if (!zsaved) {
+    rc = tf32_split(Wcat, whi, wlo, static_cast<int64_t>(2) * D * L, st);
+    if (rc) return rc;
+  }
   int chunk = 0;
   for (int64_t r0 = 0; r0 < total_n; r0 += SIMT_ROW_CHUNK, ++chunk) {
     int64_t rows = std::min<int64_t>(SIMT_ROW_CHUNK, total_n - r0);
-    rc = tf32_split(X + r0 * L, xhi, xlo, rows * L, st);
-    if (rc) return rc;
-    rc = tc::gemm_store_tf32x3(xhi, xlo, rows, L, L, whi, wlo, 2 * D, L, bcat, MILB200_ACT_NONE, Z, 2 * D, st);
-    if (rc) return rc;
+    if (!zsaved) {       // nothing saved: recompute the pre-activations of the chunk
+      rc = tf32_split(X + r0 * L, xhi, xlo, rows * L, st);
+      if (rc) return rc;
+      rc = tc::gemm_store_tf32x3(xhi, xlo, rows, L, L, whi, wlo, 2 * D, L, bcat, MILB200_ACT_NONE, Z, 2 * D, st);
+      if (rc) return rc;
+    }
     unsigned blocks = static_cast<unsigned>(std::min<int64_t>((rows + 7) / 8, sm_count() * 4));
-    k_gate_bwd<<<blocks, 256, 0, st>>>(Z, ww, dscores + r0, rows, D, rec);          // Z becomes dZ in place
+    k_gate_bwd<<<blocks, 256, 0, st>>>(zsaved ? zsaved + r0 * 2 * D : Z, Z, ww, dscores + r0, rows, D, rec);   // -> dZ
     MIL_LAUNCH_CHECK();
-    k_gate_bwd_fold<<<(3 * D + 1 + 255) / 256, 256, 0, st>>>(rec, static_cast<int>(blocks), D, dbcat, dww, dbw, chunk > 0);
+    k_gate_bwd_fold<<<(3 * D + 1 + 31) / 32, 256, 0, st>>>(rec, static_cast<int>(blocks), D, dbcat, dww, dbw, chunk > 0);
     MIL_LAUNCH_CHECK();
     // dWcat[j, l] (+)= sum_i dZ[i, j] X[i, l]: K-major operands = the transposes, split-K over batches of TF32_CK rows
     const int batches = static_cast<int>((rows + TF32_CK - 1) / TF32_CK);
@@ -703,7 +720,9 @@ size_t milb200_gated_score_workspace_bytes(int64_t total_n, int L, int D, int dt
   return gate_ws(total_n, L, D, dtype, backward).total;
 }
 
-int milb200_gated_score_saves_activations(int L, int D, int dtype) { return tc_gate_ok(L, D, dtype) ? 1 : 0; }
+int milb200_gated_score_saves_activations(int L, int D, int dtype) {
+  return (tc_gate_ok(L, D, dtype) || tf32_gate_ok(L, D, dtype)) ? 1 : 0;
+}
 
 int milb200_gated_score_fwd(const void* X, const void* Wcat, const float* bcat, const float* ww, const float* bw,
                             float* scores, void* gate_act, int64_t total_n, int L, int D, int dtype, void* workspace,
@@ -727,7 +746,8 @@ int milb200_gated_score_fwd(const void* X, const void* Wcat, const float* bcat, 
     return gate_fwd_simt<__nv_bfloat16>((const __nv_bfloat16*)X, (const __nv_bfloat16*)Wcat, bcat, ww, bw, scores, total_n,
                                         L, D, ws, w, st);
   if (tf32_gate_ok(L, D, dtype))
-    return gate_fwd_tf32((const float*)X, (const float*)Wcat, bcat, ww, bw, scores, total_n, L, D, ws, w, st);
+    return gate_fwd_tf32((const float*)X, (const float*)Wcat, bcat, ww, bw, scores, static_cast<float*>(gate_act), total_n, L,
+                         D, ws, w, st);
   return gate_fwd_simt<float>((const float*)X, (const float*)Wcat, bcat, ww, bw, scores, total_n, L, D, ws, w, st);
 }
 
@@ -811,7 +831,8 @@ int milb200_gated_score_bwd(const void* X, const void* Wcat, const float* bcat, 
     return gate_bwd_simt<__nv_bfloat16>((const __nv_bfloat16*)X, (const __nv_bfloat16*)Wcat, bcat, ww, dscores, attn, dM,
                                         offsets, B, total_n, L, D, dWcat, dbcat, dww, dbw, (__nv_bfloat16*)dX, ws, w, st);
   if (tf32_gate_ok(L, D, dtype))
-    return gate_bwd_tf32((const float*)X, (const float*)Wcat, bcat, ww, dscores, attn, dM, offsets, B, total_n, L, D,
+    return gate_bwd_tf32((const float*)X, (const float*)Wcat, bcat, ww, dscores, static_cast<const float*>(gate_act), attn, dM,
+                         offsets, B, total_n, L, D,
                          dWcat, dbcat, dww, dbw, (float*)dX, ws, w, st);
   return gate_bwd_simt<float>((const float*)X, (const float*)Wcat, bcat, ww, dscores, attn, dM, offsets, B, total_n, L, D,
                               dWcat, dbcat, dww, dbw, (float*)dX, ws, w, st);
