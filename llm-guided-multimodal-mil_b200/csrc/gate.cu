@@ -2,6 +2,7 @@
 // the dense linear layers (nn.Linear sites of aggregator.py / sam/transformer.py), dispatching between
 // the tcgen05 kernels (bf16) and the FFMA kernels (fp32, or shapes the tensor-core tiles do not cover).
 #include <algorithm>
+#include <type_traits>
 
 #include "simt_gemm.cuh"
 #include "tc_gemm.cuh"
@@ -655,8 +656,21 @@ static int gate_bwd_tf32(const float* X, const float* Wcat, const float* bcat, c
 
 // ---- linear workspace ------------------------------------------------------------------------------
 struct LinWs {
-  size_t xin, dypre, wT, part, smallm, total;
+  size_t xin, dypre, wT, part, smallm;
+  // 3xTF32 path (fp32 operands, m >= 256): hi/lo splits of X and W; backward: transposed splits of dYpre and X and the
+  // batched partials (dW), splits of dYpre and of W^T padded to 512 columns (dX)
+  size_t t_xhi, t_xlo, t_whi, t_wlo, t_dyt_hi, t_dyt_lo, t_xt_hi, t_xt_lo, t_part, t_dyhi, t_dylo, t_wt_hi, t_wt_lo;
+  size_t total;
 };
+static bool tf32_linear_ok(int64_t m, int n, int k, int dtype) {
+  return dtype == MILB200_F32 && tf32x3_enabled() && !force_simt() && m >= 256 && tc::gemm_tf32x3_supported(m, n, k);
+}
+static bool tf32_linear_dw_ok(int64_t m, int n, int k, int dtype) {   // dW[n, k] = dYpre^T X: Mb = n, N = k
+  return tf32_linear_ok(m, n, k, dtype) && n % 128 == 0 && k % 16 == 0;
+}
+static bool tf32_linear_dx_ok(int64_t m, int n, int k, int dtype) {   // dX[m, k] = dYpre W: K = n (one 512-column batch of W^T)
+  return tf32_linear_ok(m, n, k, dtype) && n <= TF32_CK && tc::gemm_tf32x3_supported(m, k, n);
+}
 static bool tc_linear_ok(int64_t m, int n, int k, int dtype) {
   return dtype == MILB200_BF16 && !force_simt() && tc::gemm_store_supported(m, n, k);
 }
@@ -680,6 +694,29 @@ static LinWs linear_ws(int64_t m, int n, int k, int dtype, int backward, int has
     size_t splits = tc_linear_bwd_ok(m, n, k, dtype) ? static_cast<size_t>(tc::gemm_tn_max_splits(n, k)) : simt_splits(m);
     w.part = take(sizeof(float) * splits * n * k);
     if (smallm_ok(m, n, k, dtype)) w.smallm = take(smallm_ws_bytes(m, k));
+  }
+  if (tf32_linear_ok(m, n, k, dtype)) {
+    const size_t f = sizeof(float);
+    const size_t m_pad = static_cast<size_t>((m + TF32_CK - 1) / TF32_CK * TF32_CK);
+    w.t_xhi = take(f * m * k);
+    w.t_xlo = take(f * m * k);
+    w.t_whi = take(f * n * k);
+    w.t_wlo = take(f * n * k);
+    if (backward) {
+      if (tf32_linear_dw_ok(m, n, k, dtype)) {
+        w.t_dyt_hi = take(f * m_pad * n);
+        w.t_dyt_lo = take(f * m_pad * n);
+        w.t_xt_hi = take(f * m_pad * k);
+        w.t_xt_lo = take(f * m_pad * k);
+        w.t_part = take(f * (m_pad / TF32_CK) * n * k);
+      }
+      if (tf32_linear_dx_ok(m, n, k, dtype)) {
+        w.t_dyhi = take(f * m * n);
+        w.t_dylo = take(f * m * n);
+        w.t_wt_hi = take(f * static_cast<size_t>(k) * TF32_CK);
+        w.t_wt_lo = take(f * static_cast<size_t>(k) * TF32_CK);
+      }
+    }
   }
   w.total = align_up(off, 256) + 256;
   return w;
@@ -945,6 +982,21 @@ int milb200_linear_fwd(const void* X, const void* add, const void* W, const floa
   }
   if (tc_linear_ok(m, n, k, dtype) && aligned16(xin) && aligned16(W) && aligned16(Y))
     return tc::gemm_store(xin, m, k, k, W, n, k, bias, act, Y, MILB200_BF16, n, nullptr, nullptr, nullptr, 0, st);
+  if (tf32_linear_ok(m, n, k, dtype) && aligned16(xin) && aligned16(W) && aligned16(Y)) {
+    // fp32 operands on the tensor cores (3xTF32)
+    LinWs w = linear_ws(m, n, k, dtype, 0, add != nullptr);
+    MIL_CHECK_ARG(workspace && ws_bytes >= w.total, MILB200_EWORKSPACE, "linear_fwd: workspace %zu < %zu", ws_bytes, w.total);
+    char* ws = static_cast<char*>(workspace);
+    float* xhi = reinterpret_cast<float*>(ws + w.t_xhi);
+    float* xlo = reinterpret_cast<float*>(ws + w.t_xlo);
+    float* whi = reinterpret_cast<float*>(ws + w.t_whi);
+    float* wlo = reinterpret_cast<float*>(ws + w.t_wlo);
+    rc = tf32_split(static_cast<const float*>(xin), xhi, xlo, m * k, st);
+    if (rc) return rc;
+    rc = tf32_split(static_cast<const float*>(W), whi, wlo, static_cast<int64_t>(n) * k, st);
+    if (rc) return rc;
+    return tc::gemm_store_tf32x3(xhi, xlo, m, k, k, whi, wlo, n, k, bias, act, static_cast<float*>(Y), n, st);
+  }
   if (dtype == MILB200_BF16)
     return linear_fwd_simt<__nv_bfloat16>((const __nv_bfloat16*)xin, (const __nv_bfloat16*)W, bias, (__nv_bfloat16*)Y, m,
                                           n, k, act, st);
@@ -972,6 +1024,43 @@ static int linear_bwd_t(const T* Xin, const T* W, const T* Y, const T* dY, T* dX
   float* part = reinterpret_cast<float*>(ws + w.part);
   const bool use_tc = tc_linear_bwd_ok(m, n, k, dtype) && aligned16(dypre) && aligned16(Xin) && aligned16(W);
   int rc;
+  if constexpr (std::is_same<T, float>::value) {
+    // fp32 operands on the tensor cores (3xTF32): dW through the transposed splits (split-K over batches of rows), dX with
+    // W^T as one zero-padded 512-column batch
+    const bool dw_tc = dW && tf32_linear_dw_ok(m, n, k, dtype) && aligned16(dypre) && aligned16(Xin);
+    const bool dx_tc = dX && tf32_linear_dx_ok(m, n, k, dtype) && aligned16(dypre) && aligned16(W) && aligned16(dX);
+    if (dw_tc) {
+      float* dyt_hi = reinterpret_cast<float*>(ws + w.t_dyt_hi);
+      float* dyt_lo = reinterpret_cast<float*>(ws + w.t_dyt_lo);
+      float* xt_hi = reinterpret_cast<float*>(ws + w.t_xt_hi);
+      float* xt_lo = reinterpret_cast<float*>(ws + w.t_xt_lo);
+      float* tpart = reinterpret_cast<float*>(ws + w.t_part);
+      const int batches = static_cast<int>((m + TF32_CK - 1) / TF32_CK);
+      rc = tf32_transpose_split(dypre, m, n, dyt_hi, dyt_lo, st);
+      if (rc) return rc;
+      rc = tf32_transpose_split(Xin, m, k, xt_hi, xt_lo, st);
+      if (rc) return rc;
+      rc = tc::gemm_batched_tf32x3(dyt_hi, dyt_lo, batches, n, TF32_CK, xt_hi, xt_lo, k, tpart, st);
+      if (rc) return rc;
+      rc = splitk_reduce(tpart, batches, static_cast<int64_t>(n) * k, dW, accumulate, st);
+      if (rc) return rc;
+      dW = nullptr;
+    }
+    if (dx_tc) {
+      float* dyhi = reinterpret_cast<float*>(ws + w.t_dyhi);
+      float* dylo = reinterpret_cast<float*>(ws + w.t_dylo);
+      float* wt_hi = reinterpret_cast<float*>(ws + w.t_wt_hi);
+      float* wt_lo = reinterpret_cast<float*>(ws + w.t_wt_lo);
+      rc = tf32_split(dypre, dyhi, dylo, m * n, st);
+      if (rc) return rc;
+      rc = tf32_transpose_split(W, n, k, wt_hi, wt_lo, st);     // W [n, k] -> [k][512], columns >= n zero
+      if (rc) return rc;
+      // K = n: the operands' rows are n (dYpre, ld n) and 512 (W^T, ld 512) floats long; TMA zero-fills dYpre past n
+      rc = tc::gemm_store_tf32x3(dyhi, dylo, m, n, n, wt_hi, wt_lo, k, TF32_CK, nullptr, MILB200_ACT_NONE, dX, k, st);
+      if (rc) return rc;
+      dX = nullptr;
+    }
+  }
   if (dW) {
     int splits = 0;
     if (use_tc) {

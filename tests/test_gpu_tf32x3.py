@@ -114,3 +114,42 @@ def test_fp32_module_matches_reference_fixture_through_tensor_cores():
             assert abs(got[0] - want[0]) <= 1e-5
         else:
             assert rel_err(got, want) <= 1e-5, k
+
+
+@pytest.mark.parametrize("m,k,n,act,use_add", [(1000, 768, 512, "relu", False), (15592, 768, 512, None, False),
+                                                (700, 512, 256, "tanh", True), (513, 512, 2048, "relu", False),
+                                                (300, 64, 128, None, False)])
+def test_fp32_linear_on_tensor_cores(m, k, n, act, use_add, monkeypatch):
+    """nn.Linear (+ReLU/Tanh, + the fused input add) with fp32 operands and m >= 256 rows: forward, dX, dW and dbias through
+    the 3xTF32 kernels against float64 torch and against the FFMA kernels (aggregator.py:44,47,66; transformer.py:430-448)."""
+    from mil_b200 import functional as F
+    gen = torch.Generator(device="cuda").manual_seed(m + n)
+    x = torch.randn(m, k, device="cuda", generator=gen)
+    add = torch.randn(m, k, device="cuda", generator=gen) if use_add else None
+    W = torch.randn(n, k, device="cuda", generator=gen) / k ** 0.5
+    b = torch.randn(n, device="cuda", generator=gen) * 0.1
+    dy = torch.randn(m, n, device="cuda", generator=gen)
+
+    def run():
+        xs = [t.clone().requires_grad_(True) for t in ((x, add, W, b) if use_add else (x, W, b))]
+        if use_add:
+            y = F.linear(xs[0], xs[2], xs[3], act=act, add=xs[1])
+        else:
+            y = F.linear(xs[0], xs[1], xs[2], act=act)
+        y.backward(dy)
+        return [y.detach()] + [t.grad for t in xs]
+
+    got = run()
+    monkeypatch.setenv("MILB200_TF32X3", "0")
+    ffma = run()
+    xd = [t.double().clone().requires_grad_(True) for t in ((x, add, W, b) if use_add else (x, W, b))]
+    xin = xd[0] + xd[1] if use_add else xd[0]
+    Wd, bd = (xd[2], xd[3]) if use_add else (xd[1], xd[2])
+    yd = xin @ Wd.t() + bd
+    yd = torch.relu(yd) if act == "relu" else (torch.tanh(yd) if act == "tanh" else yd)
+    yd.backward(dy.double())
+    want = [yd.detach()] + [t.grad for t in xd]
+    torch.cuda.synchronize()
+    for i, (a, f, w) in enumerate(zip(got, ffma, want)):
+        e_tc, e_ffma = rel_err(a.cpu().numpy(), w.cpu().numpy()), rel_err(f.cpu().numpy(), w.cpu().numpy())
+        assert e_tc <= 1e-5, (i, e_tc, e_ffma)
