@@ -400,14 +400,16 @@ bool gate_layout_interleaved(int L, int D, int dtype) { return tc_gate_ok(L, D, 
 // x - hi: both are exact tf32 operands whether the tensor core truncates or rounds its inputs, the residual is 2^-22 |x|
 // with either sign (a truncating split biases every product the same way and showed up as 1.1e-5 on single scores).
 constexpr int TF32_CK = 512;   // k (= instance rows) per batch of the split-K dWcat product
+constexpr int64_t TF32_MIN_ROWS = 4096;   // below this the row-tile-persistent GEMM leaves most SMs idle and the splits /
+                                          // transposes cost more than the FFMA kernels (measured: 1 000 rows 2.2 vs 1.8 ms)
 
 static bool tf32x3_enabled() {           // MILB200_TF32X3=0 keeps the FFMA kernels (read per call: tests flip it)
   const char* e = getenv("MILB200_TF32X3");
   return !(e && e[0] == '0');
 }
 // gate GEMMs in fp32: Z = X Wcat^T needs K = L, dWcat needs Mb = 2D (multiple of 128), N = L
-static bool tf32_gate_ok(int L, int D, int dtype) {
-  return dtype == MILB200_F32 && tf32x3_enabled() && !force_simt() && (2 * D) % 128 == 0 && L % 16 == 0 && L >= 32 &&
+static bool tf32_gate_ok(int L, int D, int dtype, int64_t rows = TF32_MIN_ROWS) {
+  return rows >= TF32_MIN_ROWS && dtype == MILB200_F32 && tf32x3_enabled() && !force_simt() && (2 * D) % 128 == 0 && L % 16 == 0 && L >= 32 &&
          tc::gemm_tf32x3_supported(128, 2 * D, L);
 }
 
@@ -505,7 +507,7 @@ static GateWs gate_ws(int64_t total_n, int L, int D, int dtype, int backward) {
       w.spart = take(sizeof(float) * simt_splits(rows) * 2 * D * L);
       w.rec = take(sizeof(float) * static_cast<size_t>(sm_count()) * 4 * (3 * D + 1));
     }
-    if (tf32_gate_ok(L, D, dtype)) {
+    if (tf32_gate_ok(L, D, dtype, total_n)) {
       const size_t rows_pad = static_cast<size_t>((rows + TF32_CK - 1) / TF32_CK * TF32_CK);
       w.whi = take(sizeof(float) * 2 * D * L);
       w.wlo = take(sizeof(float) * 2 * D * L);
@@ -657,13 +659,13 @@ static int gate_bwd_tf32(const float* X, const float* Wcat, const float* bcat, c
 // ---- linear workspace ------------------------------------------------------------------------------
 struct LinWs {
   size_t xin, dypre, wT, part, smallm;
-  // 3xTF32 path (fp32 operands, m >= 256): hi/lo splits of X and W; backward: transposed splits of dYpre and X and the
+  // 3xTF32 path (fp32 operands, m >= TF32_MIN_ROWS): hi/lo splits of X and W; backward: transposed splits of dYpre and X and the
   // batched partials (dW), splits of dYpre and of W^T padded to 512 columns (dX)
   size_t t_xhi, t_xlo, t_whi, t_wlo, t_dyt_hi, t_dyt_lo, t_xt_hi, t_xt_lo, t_part, t_dyhi, t_dylo, t_wt_hi, t_wt_lo;
   size_t total;
 };
 static bool tf32_linear_ok(int64_t m, int n, int k, int dtype) {
-  return dtype == MILB200_F32 && tf32x3_enabled() && !force_simt() && m >= 256 && tc::gemm_tf32x3_supported(m, n, k);
+  return dtype == MILB200_F32 && tf32x3_enabled() && !force_simt() && m >= TF32_MIN_ROWS && tc::gemm_tf32x3_supported(m, n, k);
 }
 static bool tf32_linear_dw_ok(int64_t m, int n, int k, int dtype) {   // dW[n, k] = dYpre^T X: Mb = n, N = k
   return tf32_linear_ok(m, n, k, dtype) && n % 128 == 0 && k % 16 == 0;
@@ -782,7 +784,7 @@ int milb200_gated_score_fwd(const void* X, const void* Wcat, const float* bcat, 
   if (dtype == MILB200_BF16)
     return gate_fwd_simt<__nv_bfloat16>((const __nv_bfloat16*)X, (const __nv_bfloat16*)Wcat, bcat, ww, bw, scores, total_n,
                                         L, D, ws, w, st);
-  if (tf32_gate_ok(L, D, dtype))
+  if (tf32_gate_ok(L, D, dtype, total_n))
     return gate_fwd_tf32((const float*)X, (const float*)Wcat, bcat, ww, bw, scores, static_cast<float*>(gate_act), total_n, L,
                          D, ws, w, st);
   return gate_fwd_simt<float>((const float*)X, (const float*)Wcat, bcat, ww, bw, scores, total_n, L, D, ws, w, st);
@@ -867,7 +869,7 @@ int milb200_gated_score_bwd(const void* X, const void* Wcat, const float* bcat, 
   if (dtype == MILB200_BF16)
     return gate_bwd_simt<__nv_bfloat16>((const __nv_bfloat16*)X, (const __nv_bfloat16*)Wcat, bcat, ww, dscores, attn, dM,
                                         offsets, B, total_n, L, D, dWcat, dbcat, dww, dbw, (__nv_bfloat16*)dX, ws, w, st);
-  if (tf32_gate_ok(L, D, dtype))
+  if (tf32_gate_ok(L, D, dtype, total_n))
     return gate_bwd_tf32((const float*)X, (const float*)Wcat, bcat, ww, dscores, static_cast<const float*>(gate_act), attn, dM,
                          offsets, B, total_n, L, D,
                          dWcat, dbcat, dww, dbw, (float*)dX, ws, w, st);
