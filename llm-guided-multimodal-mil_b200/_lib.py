@@ -12,7 +12,8 @@ import threading
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmilb200.so")
+# MILB200_LIB: developer hook for A/B runs of kernel variants (tools/build_variant.py); the product loads the in-tree build
+LIB_PATH = os.environ.get("MILB200_LIB") or os.path.join(HERE, "libmilb200.so")
 
 F32, BF16 = 0, 1
 HOST_F32, HOST_BF16, HOST_F16, HOST_F64 = 0, 1, 2, 3
