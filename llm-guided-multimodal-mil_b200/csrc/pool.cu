@@ -56,12 +56,28 @@ k_pool_fwd(const T* __restrict__ X, const float* __restrict__ scores, const int3
   const uint4* Xv = reinterpret_cast<const uint4*>(X);
 
   int b = find_bag(offsets, B, r0);
+  while (b > 0 && __ldg(offsets + b - 1) == r0) --b;   // empty bags that sit exactly at the start of this slab
   for (; b < B; ++b) {
     const int64_t ob = __ldg(offsets + b), oe = __ldg(offsets + b + 1);
-    if (ob >= r1) break;
+    const bool empty = oe == ob;
+    if (ob >= r1 && !(empty && r1 == total_n)) break;  // (trailing empty bags belong to the last CTA)
     const int64_t s0 = ob > r0 ? ob : r0, s1 = oe < r1 ? oe : r1;
     const int nseg = static_cast<int>(s1 - s0);
-    if (nseg <= 0) continue;  // empty bag: nothing to pool (contract: bags are non-empty)
+    if (nseg <= 0) {
+      // an empty bag has no rows, so no piece would ever write its outputs: the CTA whose slab contains its position does
+      // (pooled vector 0, argmax -1, lse -inf; torch gives NaN for a softmax over nothing — the reference never builds one)
+      if (empty && ob >= r0) {
+        for (int c = t; c < L; c += POOL_THREADS) {
+          M[static_cast<int64_t>(b) * L + c] = 0.f;
+          if (M_lowp) M_lowp[static_cast<int64_t>(b) * L + c] = from_f32<T>(0.f);
+        }
+        if (t == 0) {
+          if (argmax_out) argmax_out[b] = -1;
+          if (lse_out) lse_out[b] = -INFINITY;
+        }
+      }
+      continue;
+    }
 
     // ---- (1) piece max and first argmax ----
     float pm = 0.f;

@@ -157,3 +157,40 @@ def test_trainer_step_with_fused_backward_matches_the_default_step(monkeypatch):
     scale = float(g0.abs().max())
     assert float((g0 - g1).abs().max()) <= 2e-4 * scale + 2e-5 * X.shape[0]
     assert float((p0 - p1).abs().max()) <= 2.1e-3          # Adam moves every weight by at most lr; sign flips of ~0 gradients
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_empty_bags_have_defined_outputs_and_zero_gradient_share(dtype):
+    """Zero-length bags at the start, in the middle (also exactly on a slab boundary of the persistent pool kernel) and at
+    the end of a packed batch: pooled vector 0, argmax -1, lse -inf; the other bags and every gradient are what the batch
+    without the empty bags gives (both backward routes)."""
+    from mil_b200 import functional as F
+    lens_full = [0, 0, 700, 0, 4096, 0, 33, 0]
+    lens = [l for l in lens_full if l > 0]
+    off_full = torch.from_numpy(mo.offsets_from_lengths(np.asarray(lens_full))).cuda()
+    off = torch.from_numpy(mo.offsets_from_lengths(np.asarray(lens))).cuda()
+    gen = torch.Generator(device="cuda").manual_seed(13)
+    X = torch.randn(sum(lens), L_FEAT, device="cuda", generator=gen).to(dtype)
+    Wv = torch.randn(D, L_FEAT, device="cuda", generator=gen) * 0.03
+    Wu = torch.randn(D, L_FEAT, device="cuda", generator=gen) * 0.03
+    bv = torch.zeros(D, device="cuda")
+    ww = torch.randn(D, device="cuda", generator=gen) * 0.3
+    bw = torch.zeros(1, device="cuda")
+    Wcat, bcat = F.pack_gate_weights(Wv, bv, Wu, bv, dtype)
+    s, act = F.gated_scores(X, Wcat, bcat, ww, bw, save=True)
+    M, _, am, lse = F.segment_softmax_pool(X, s, off)
+    Mf, _, amf, lsef = F.segment_softmax_pool(X, s, off_full)
+    keep = torch.tensor([i for i, l in enumerate(lens_full) if l > 0], device="cuda")
+    gone = torch.tensor([i for i, l in enumerate(lens_full) if l == 0], device="cuda")
+    assert torch.equal(Mf[keep], M) and torch.equal(amf[keep], am) and torch.equal(lsef[keep], lse)
+    assert float(Mf[gone].abs().max()) == 0.0 and bool((amf[gone] == -1).all()) and bool(torch.isinf(lsef[gone]).all())
+    dMf = torch.randn(len(lens_full), L_FEAT, device="cuda", generator=gen)
+    dM = dMf[keep].contiguous()
+    ds, _ = F.segment_softmax_pool_bwd(X, s, off, dM, M, want_attn=False)
+    dsf, _ = F.segment_softmax_pool_bwd(X, s, off_full, dMf, Mf, want_attn=False)
+    assert torch.equal(ds, dsf)
+    if dtype == torch.bfloat16:
+        a = F.gated_pool_bwd(X, s, off, dM, M, ww, act)
+        b = F.gated_pool_bwd(X, s, off_full, dMf, Mf, ww, act)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
