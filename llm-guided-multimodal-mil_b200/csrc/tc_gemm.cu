@@ -1597,8 +1597,12 @@ k_gemm_tn_gate(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t c0 = static_cast<uint32_t>(clock64());
         {
           uint32_t spins = 0;
-          while (*prog + gp.lead < i) {
-            __nanosleep(128);
+          const uint32_t prog_addr = smem_u32(const_cast<int*>(prog));
+          for (;;) {
+            int pv;
+            asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(pv) : "r"(prog_addr) : "memory");
+            if (pv + gp.lead >= i) break;
+            __nanosleep(256);
             if (++spins > TNG_SPIN_LIMIT) asm volatile("trap;");
           }
         }
