@@ -1026,11 +1026,20 @@ def main():
                     kinfo["ms_in_step"] = t_in
                     kinfo["achieved"] = kinfo["achieved"] * kinfo["ms"] / t_in
                     kinfo["ms"] = t_in
+        # Denominators (the bench contract): a kernel timed INSIDE the long step is measured against the SUSTAINED tensor
+        # peak (cuBLAS bf16 back to back for seconds: the chip is power-limited there, ~1335 MHz at ~1 kW), a kernel timed
+        # alone against the BURST figure.  Both fractions are kept; HBM has one measured figure.
+        sustained = float(peaks["bf16_tflops_sustained"]) if peaks.get("bf16_tflops_sustained") else None
         for kinfo in kernels:
+            burst_peak = kinfo["peak"]
+            kinfo["frac_alone"] = (kinfo["achieved_alone"] / burst_peak) if kinfo.get("achieved_alone") else None
+            if kinfo["bound"] == "tensor" and kinfo.get("achieved") and sustained:
+                kinfo["frac_of_sustained_peak"] = kinfo["achieved"] / sustained
+                kinfo["frac_of_burst_peak"] = kinfo["achieved"] / burst_peak
+                if kinfo.get("ms_in_step"):
+                    kinfo["peak"] = sustained
+                    kinfo["peak_kind"] = "sustained (kernel timed inside the step); burst %.1f" % burst_peak
             kinfo["frac"] = (kinfo["achieved"] / kinfo["peak"]) if kinfo.get("achieved") else None
-            kinfo["frac_alone"] = (kinfo["achieved_alone"] / kinfo["peak"]) if kinfo.get("achieved_alone") else None
-            if kinfo["bound"] == "tensor" and kinfo.get("achieved") and peaks.get("bf16_tflops_sustained"):
-                kinfo["frac_of_sustained_peak"] = kinfo["achieved"] / float(peaks["bf16_tflops_sustained"])
             kinfo["traffic"] = None
             for prefix, key in ncu_keys.items():
                 if kinfo["name"].startswith(prefix) and key in ncu_traffic:
@@ -1171,7 +1180,8 @@ def main():
                 "timing": "CUDA events around the kernel inside the training step (median over steps)" if dom.get("ms_in_step")
                           else "kernel looped alone, CUDA events",
                 "ms_alone_back_to_back": dom.get("ms_alone"), "frac_alone_back_to_back": dom.get("frac_alone"),
-                "frac_of_sustained_peak": dom.get("frac_of_sustained_peak"), "phase_ms_in_step": phase_ms}
+                "frac_of_sustained_peak": dom.get("frac_of_sustained_peak"), "frac_of_burst_peak": dom.get("frac_of_burst_peak"),
+                "peak_kind": dom.get("peak_kind", "measured burst / copy peak"), "phase_ms_in_step": phase_ms}
         line = {"metric": "bags/sec fwd+bwd", "value": value, "unit": "bags/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
