@@ -307,9 +307,39 @@ def secondary_fusion(dev):
     ns = Namespace(modality=["CT", "pathology"], model_CT="resnetMC3_18", model_pathology="ABMIL", model_CI="none",
                    aggregator="ABMIL", num_classes=2, alignment_base="none", clinical_features=list("abcdefghi"))
     torch.manual_seed(1234)
+    out = []
+    # fp32 (the reference's own arithmetic): same module, fp32 operands — the big GEMMs run as 3xTF32 on the tensor cores
+    m32 = mil_b200.get_model(ns).to(dev).train(False)
+    p32 = list(m32.parameters())
+    for T, N in ((1, 15592),):
+        x_ct = torch.randn(1, 512, 160, 1, 1, device=dev)
+        x_p = torch.randn(1, N, 768, device=dev)
+        x_t = torch.randn(1, T, 512, device=dev) * 0.05
+        label = torch.tensor([[0.0, 1.0]], device=dev)
+
+        def step32():
+            for p in p32:
+                p.grad = None
+            prob, a, b = m32([x_ct, x_p], x_t)
+            loss = torch.nn.functional.binary_cross_entropy(prob.float(), label) + \
+                mil_b200.clip_loss.cosine_embedding_loss(a.squeeze(0), b.squeeze(0)).float()
+            loss.backward()
+
+        for _ in range(4):
+            step32()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            step32()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        out.append({"workload": f"aggregator CT+pathology fwd+bwd, 1 bag, N={N} x 768 + 160 CT tokens, T={T}, fp32 (3xTF32 GEMMs)",
+                    "ms_per_bag": ms, "bags_per_s": 1e3 / ms, "api": "nn.Module + torch.autograd (no optimiser step in the figure)"})
+    del m32, p32
     m = mil_b200.get_model(ns).to(dev).to(torch.bfloat16).train(False)
     plist = list(m.parameters())
-    out = []
     for T, N in ((1, 15592), (10, 15592)):
         x_ct = torch.randn(1, 512, 160, 1, 1, device=dev, dtype=torch.bfloat16)
         x_p = torch.randn(1, N, 768, device=dev, dtype=torch.bfloat16)
