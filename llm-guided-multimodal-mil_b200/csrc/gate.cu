@@ -647,10 +647,21 @@ static int gate_bwd_tf32(const float* X, const float* Wcat, const float* bcat, c
     rc = splitk_reduce(part, batches, static_cast<int64_t>(2) * D * L, dWcat, chunk > 0, st);
     if (rc) return rc;
     if (dX) {
-      // dX[i, l] = sum_j dZ[i, j] Wcat[j, l]  (+ attn_i * dM[bag(i), l]): FFMA kernel (the pooling term rides in its epilogue)
-      simt::EpiStore<float> ex{dX + r0 * L, L, nullptr, MILB200_ACT_NONE, attn, dM, offsets, B, r0};
-      rc = simt::launch<float, float, true, false>(Z, 2 * D, Wcat, L, rows, L, 2 * D, 1, ex, st);
-      if (rc) return rc;
+      // dX[i, l] = sum_j dZ[i, j] Wcat[j, l]  (+ attn_i * dM[bag(i), l], in the epilogue): A = dZ (K = 2D), B = Wcat^T as one
+      // zero-padded 512-column batch (2D <= 512); dZ's splits reuse the X-split buffers (X's are not needed any more)
+      if (2 * D <= TF32_CK && 2 * D <= L) {
+        rc = tf32_transpose_split(Wcat, 2 * D, L, xt_hi, xt_lo, st);        // [L][512]; the dW product above is done with xt_*
+        if (rc) return rc;
+        rc = tf32_split(Z, xhi, xlo, rows * 2 * D, st);
+        if (rc) return rc;
+        rc = tc::gemm_store_tf32x3(xhi, xlo, rows, 2 * D, 2 * D, xt_hi, xt_lo, L, TF32_CK, nullptr, MILB200_ACT_NONE,
+                                   dX + r0 * L, L, st, attn, dM, offsets, B, r0);
+        if (rc) return rc;
+      } else {
+        simt::EpiStore<float> ex{dX + r0 * L, L, nullptr, MILB200_ACT_NONE, attn, dM, offsets, B, r0};
+        rc = simt::launch<float, float, true, false>(Z, 2 * D, Wcat, L, rows, L, 2 * D, 1, ex, st);
+        if (rc) return rc;
+      }
     }
   }
   return MILB200_OK;

@@ -104,6 +104,7 @@ struct EpiStore {
     int tma_out;        // bf16 output through staged TMA stores ([32 x 32] boxes, 64-byte swizzle)
     int bias_n;         // = N (length of bias)
     CUtensorMap tmO;
+    int64_t row0 = 0;   // global row of the A operand's first row (row chunks of a longer batch: attn / bag lookups)
   };
   static constexpr int BIAS_CACHE = 1024;       // bias[N] lives in shared memory for N <= 1024 (a global load per
   static constexpr int SMEM_FLOATS = BIAS_CACHE;  // 32-column chunk put ~700 cycles of L2 latency on every chunk)
@@ -129,8 +130,8 @@ struct EpiStore {
     float a = 0.f;
     const float* dmrow = nullptr;
     if (p.attn && row_ok) {
-      a = __ldg(p.attn + row);
-      dmrow = p.dM + static_cast<int64_t>(find_bag(p.offsets, p.nbags, row)) * p.ldo;
+      a = __ldg(p.attn + p.row0 + row);
+      dmrow = p.dM + static_cast<int64_t>(find_bag(p.offsets, p.nbags, p.row0 + row)) * p.ldo;
     }
     const bool bias_vec = p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15u) == 0;
 #pragma unroll 1
@@ -1022,11 +1023,13 @@ bool gemm_tf32x3_supported(int64_t M, int N, int K) { return M >= 1 && N >= 16 &
 
 // out[M, N] fp32 = act(A[M, K] . B[N, K]^T + bias), A = Ahi + Alo, B = Bhi + Blo (fp32 arrays from tf32_split)
 int gemm_store_tf32x3(const float* Ahi, const float* Alo, int64_t M, int K, int64_t lda, const float* Bhi, const float* Blo,
-                      int N, int64_t ldb, const float* bias, int act, float* out, int64_t ldo, cudaStream_t st) {
+                      int N, int64_t ldb, const float* bias, int act, float* out, int64_t ldo, cudaStream_t st,
+                      const float* attn, const float* dM, const int32_t* offsets, int nbags, int64_t row0) {
   MIL_CHECK_ARG(gemm_tf32x3_supported(M, N, K), MILB200_EUNSUPPORTED, "tc gemm_store_tf32x3: unsupported shape M=%lld N=%d K=%d",
                 (long long)M, N, K);
   MIL_CHECK_ARG(aligned16(out) && (ldo * 4) % 16 == 0, MILB200_EALIGN, "tc gemm_store_tf32x3: output must be 16-byte aligned");
-  EpiStore::Params ep{out, 0, ldo, bias, act, nullptr, nullptr, nullptr, 0, 0, N, {}};
+  EpiStore::Params ep{out, 0, ldo, bias, act, attn, dM, offsets, nbags, 0, N, {}};
+  ep.row0 = row0;
   return launch_kmajor_tf32x3(Ahi, Alo, M, K, lda, Bhi, Blo, N, ldb, N, ep, 0, st);
 }
 

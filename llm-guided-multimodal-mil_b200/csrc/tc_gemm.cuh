@@ -62,7 +62,9 @@ int gemm_tn_gate_record_floats();
 // (hi, lo) pairs of fp32 arrays with 16-byte aligned rows.
 bool gemm_tf32x3_supported(int64_t M, int N, int K);
 int gemm_store_tf32x3(const float* Ahi, const float* Alo, int64_t M, int K, int64_t lda, const float* Bhi, const float* Blo,
-                      int N, int64_t ldb, const float* bias, int act, float* out, int64_t ldo, cudaStream_t st);
+                      int N, int64_t ldb, const float* bias, int act, float* out, int64_t ldo, cudaStream_t st,
+                      const float* attn = nullptr, const float* dM = nullptr, const int32_t* offsets = nullptr, int nbags = 0,
+                      int64_t row0 = 0);     // attn != NULL: + attn[row0 + i] * dM[bag(row0 + i), :] (pooling term of the gate's dX)
 int gemm_batched_tf32x3(const float* Ahi, const float* Alo, int batches, int Mb, int K, const float* Bhi, const float* Blo,
                         int N, float* part, cudaStream_t st);
 int debug_set_trace(void* dev_ptr);

@@ -161,3 +161,36 @@ def test_fp32_linear_on_tensor_cores(m, k, n, act, use_add, monkeypatch):
     e_tc, e_ffma = check(got), check(ffma)
     for i, e in enumerate(e_tc):
         assert e <= 1e-5, (i, e_tc, e_ffma)
+
+
+@pytest.mark.parametrize("lens", [[3000, 1200, 5], [20000, 15000, 3000]])
+def test_fp32_gate_input_gradient_on_tensor_cores(lens, monkeypatch):
+    """dX of the gated pool with fp32 operands (the packed bag of the fusion path requires it): the GEMM term runs as 3xTF32
+    with the pooling term a_i dM_b in its epilogue — also across the 32768-row chunking — against the FFMA kernels and,
+    for the small case, the float64 oracle."""
+    from mil_b200 import functional as F
+    gen, Wv, bv, Wu, bu, ww, bw = _params(1024, 17)
+    off = mo.offsets_from_lengths(np.asarray(lens))
+    n = int(off[-1])
+    X = torch.randn(n, 1024, device="cuda", generator=gen)
+    offt = torch.from_numpy(off).cuda()
+    dM = torch.randn(len(lens), 1024, device="cuda", generator=gen)
+    Wcat, bcat = F.pack_gate_weights(Wv, bv, Wu, bu, X.dtype)
+
+    def run():
+        s, act = F.gated_scores(X, Wcat, bcat, ww, bw, save=True)
+        M, _, _, _ = F.segment_softmax_pool(X, s, offt)
+        ds, attn = F.segment_softmax_pool_bwd(X, s, offt, dM, M, want_attn=True)
+        dX, dWcat, _, _, _ = F.gated_scores_bwd(X, Wcat, bcat, ww, bw, ds, attn, dM, offt, True, gate_act=act)
+        return dX.clone(), dWcat.clone()
+
+    dX, dW = run()
+    monkeypatch.setenv("MILB200_TF32X3", "0")
+    dX0, dW0 = run()
+    torch.cuda.synchronize()
+    assert rel_err(dX.cpu().numpy(), dX0.cpu().numpy()) <= 1e-5
+    assert rel_err(dW.cpu().numpy(), dW0.cpu().numpy()) <= 2e-5
+    if n <= 10000:
+        g = mo.abmil_backward_csr(_oracle_params(Wv, bv, Wu, bu, ww, bw), X.double().cpu().numpy(), off,
+                                  dM.double().cpu().numpy(), need_dx=True)
+        assert rel_err(dX.cpu().numpy(), g["x"]) <= 1e-5
